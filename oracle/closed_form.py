@@ -1,0 +1,98 @@
+"""Vectorised closed-form restatement of the WSWGAT path (TEST INFRASTRUCTURE).
+
+Independent of oracle/wswgat_ref.py: instead of replaying DGL's per-head,
+degree-bucketed execution it evaluates the formula of SURVEY.md §8-a directly
+on CSC arrays with scatter ops, all heads at once:
+
+    e      = leaky_relu(p_src + q_bin)                 (dst z is DGL's zero fill)
+    sh_v   = sum_act exp(e-m) z_u / (sum_act exp(e-m) + x_v exp(-m)),
+    m      = max(max_act e, 0 if x_v > 0)              (x_v extra in-edges, e = 0, z = 0)
+
+Used (i) as a cross-check of wswgat_ref (tests), (ii) as the fast oracle for
+large inputs, (iii) as the stronger CPU baseline "B-cf-cpu" in bench.py.
+Follows GATLayer.py:88-102,127-140, GATStackLayer.py:55-59, GAT.py:56-58,
+HiGraph.py:98-106 of the reference.
+"""
+import torch
+import torch.nn.functional as F
+
+LEAKY_SLOPE = 0.01
+
+
+def pack_layer(params, prefix, n_heads):
+    """per-head state_dict keys -> packed (W [F,in], Wf [F,fe], bf [F], a [H,3d])."""
+    W = torch.cat([params[prefix + "heads.%d.fc.weight" % k] for k in range(n_heads)], 0)
+    Wf = torch.cat([params[prefix + "heads.%d.feat_fc.weight" % k] for k in range(n_heads)], 0)
+    key = prefix + "heads.0.feat_fc.bias"
+    if key in params:
+        bf = torch.cat([params[prefix + "heads.%d.feat_fc.bias" % k] for k in range(n_heads)], 0)
+    else:
+        bf = torch.zeros(W.shape[0], dtype=W.dtype)
+    a = torch.cat([params[prefix + "heads.%d.attn_fc.weight" % k] for k in range(n_heads)], 0)
+    return W, Wf, bf, a
+
+
+def n_heads_of(params, prefix):
+    n = 0
+    while (prefix + "heads.%d.fc.weight" % n) in params:
+        n += 1
+    return n
+
+
+def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T):
+    """All heads of one MultiHeadLayer application on a CSC (dst-major) edge list."""
+    H = a.shape[0]
+    d = a.shape[1] // 3
+    indptr = torch.as_tensor(indptr, dtype=torch.int64)
+    src = torch.as_tensor(src, dtype=torch.int64)
+    bins = torch.as_tensor(bins, dtype=torch.int64)
+    extra = torch.as_tensor(extra_cnt, dtype=h_src.dtype).reshape(-1, 1)
+    deg = indptr[1:] - indptr[:-1]
+    dst = torch.repeat_interleave(torch.arange(n_dst), deg)
+    z = (h_src @ W.t()).reshape(-1, H, d)
+    p = (z * a[:, :d].unsqueeze(0)).sum(-1)                                   # [N_src, H]
+    dfeat = (T @ Wf.t() + bf).reshape(-1, H, d)                               # [10, H, d]
+    q = (dfeat * a[:, 2 * d:].unsqueeze(0)).sum(-1)                           # [10, H]
+    e = F.leaky_relu(p[src] + q[bins], LEAKY_SLOPE)                           # [E, H]
+    neg = torch.full((n_dst, H), float("-inf"), dtype=e.dtype)
+    m = neg.scatter_reduce(0, dst.reshape(-1, 1).expand(-1, H), e, "amax", include_self=True)
+    m = torch.where(extra > 0, torch.clamp(m, min=0.0), m)
+    m = torch.where(torch.isinf(m), torch.zeros_like(m), m)
+    w = torch.exp(e - m[dst])
+    den = torch.zeros(n_dst, H, dtype=e.dtype).index_add(0, dst, w) + extra * torch.exp(-m)
+    den_safe = torch.where(den > 0, den, torch.ones_like(den))
+    alpha = w / den_safe[dst]
+    sh = torch.zeros(n_dst, H, d, dtype=e.dtype).index_add(0, dst, alpha.unsqueeze(-1) * z[src])
+    return sh.reshape(n_dst, H * d)
+
+
+def ffn_cf(x, w1, b1, w2, b2, gamma, beta):
+    y = F.relu(x @ w1.reshape(w1.shape[0], -1).t() + b1) @ w2.reshape(w2.shape[0], -1).t() + b2
+    return F.layer_norm(y + x, (x.shape[-1],), gamma, beta, 1e-5)
+
+
+def wswgat_cf(csc, w, s, params, prefix, kind, T):
+    H = n_heads_of(params, prefix + "layer.")
+    W, Wf, bf, a = pack_layer(params, prefix + "layer.", H)
+    if kind == "W2S":
+        origin, neighbor = s, w
+        sh = multi_head_cf(neighbor, s.shape[0], csc["super_indptr"], csc["super_src"], csc["super_bin"],
+                           csc["extra_cnt"], W, Wf, bf, a, T)
+    else:
+        origin, neighbor = w, s
+        sh = multi_head_cf(neighbor, w.shape[0], csc["word_indptr"], csc["word_src"], csc["word_bin"],
+                           csc["extra_cnt_word"], W, Wf, bf, a, T)
+    h = F.elu(sh) + origin
+    return ffn_cf(h, params[prefix + "ffn.w_1.weight"], params[prefix + "ffn.w_1.bias"],
+                  params[prefix + "ffn.w_2.weight"], params[prefix + "ffn.w_2.bias"],
+                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"])
+
+
+def update_loop_cf(csc, word_feature, super_feature, params, n_iter):
+    T = params["_TFembed.weight"]
+    word_state = word_feature
+    sent_state = wswgat_cf(csc, word_feature, super_feature, params, "word2sent.", "W2S", T)
+    for _ in range(n_iter):
+        word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T)
+        sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T)
+    return word_state, sent_state
