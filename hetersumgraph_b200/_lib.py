@@ -1,0 +1,135 @@
+"""ctypes binding of libhsg_b200.so (the C ABI declared in include/hsg_b200.h).
+
+The product path has NO fallback: if the library is missing it is built in-tree
+with nvcc (hetersumgraph_b200/build.py); if that fails, or the device is not a
+B200, every op raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i32p = C.c_void_p   # device pointers are passed as integers (tensor.data_ptr())
+c_f32p = C.c_void_p
+
+
+class TokenBatchC(C.Structure):
+    _fields_ = [("n_graphs", C.c_int32), ("n_sent", C.c_int32), ("sent_len", C.c_int32), ("hdsg", C.c_int32),
+                ("vocab_size", C.c_int32), ("n_doc", C.c_int32), ("n_doc_tok", C.c_int32),
+                ("max_sent_per_graph", C.c_int32),
+                ("tokens", C.c_void_p), ("sent_bin", C.c_void_p), ("graph_sent_ptr", C.c_void_p),
+                ("filter_bitmap", C.c_void_p), ("graph_doc_ptr", C.c_void_p), ("sent_doc", C.c_void_p),
+                ("doc_tok_ptr", C.c_void_p), ("doc_tokens", C.c_void_p), ("doc_bin", C.c_void_p)]
+
+
+class GraphOffsetsC(C.Structure):
+    _fields_ = [("word_ptr", C.c_void_p), ("super_ptr", C.c_void_p), ("node_ptr", C.c_void_p),
+                ("edge_ptr", C.c_void_p), ("pair_ptr", C.c_void_p)]
+
+
+class CscC(C.Structure):
+    _fields_ = [("n_dst", C.c_int32), ("n_src", C.c_int32), ("n_edges", C.c_int32), ("reserved", C.c_int32),
+                ("indptr", C.c_void_p), ("nbr", C.c_void_p), ("bin", C.c_void_p), ("extra", C.c_void_p)]
+
+
+class GraphOutC(C.Structure):
+    _fields_ = [("cap_word", C.c_int32), ("cap_super", C.c_int32), ("cap_pair", C.c_int32), ("reserved", C.c_int32),
+                ("off", GraphOffsetsC),
+                ("word_wid", C.c_void_p), ("word_nid", C.c_void_p), ("super_nid", C.c_void_p),
+                ("super_type", C.c_void_p), ("super_graph", C.c_void_p), ("super_indptr", C.c_void_p),
+                ("super_src", C.c_void_p), ("super_bin", C.c_void_p), ("super_eid", C.c_void_p),
+                ("super_extra", C.c_void_p), ("word_indptr", C.c_void_p), ("word_src", C.c_void_p),
+                ("word_bin", C.c_void_p), ("word_eid", C.c_void_p), ("status", C.c_void_p)]
+
+
+_I, _P, _Z = C.c_int, C.c_void_p, C.c_size_t
+
+_PROTOS = {
+    "hsg_version": (C.c_int, []),
+    "hsg_strerror": (C.c_char_p, [_I]),
+    "hsg_device_check": (C.c_int, []),
+    "hsg_num_sms": (C.c_int, []),
+    "hsg_profile_enable": (C.c_int, [_I]),
+    "hsg_profile_reset": (C.c_int, []),
+    "hsg_profile_num_slots": (C.c_int, []),
+    "hsg_profile_slot_name": (C.c_char_p, [_I]),
+    "hsg_profile_read": (C.c_int, [_I, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "hsg_launch_count": (C.c_longlong, []),
+    "hsg_build_workspace_bytes": (_Z, [C.POINTER(TokenBatchC)]),
+    "hsg_build_count": (C.c_int, [C.POINTER(TokenBatchC), GraphOffsetsC, _P, _P, _Z, _P]),
+    "hsg_build_fill": (C.c_int, [C.POINTER(TokenBatchC), C.POINTER(GraphOutC), _P, _Z, _P]),
+    "hsg_attn_prep_fwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_attn_prep_bwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_gemm_nt": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
+    "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
+    "hsg_gemm_tn_workspace_bytes": (_Z, [_I, _I, _I]),
+    "hsg_gemm_tn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _Z, _P]),
+    "hsg_edge_fwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "hsg_edge_bwd_prep": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "hsg_edge_bwd_workspace_bytes": (_Z, [_I]),
+    "hsg_edge_bwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),
+    "hsg_layernorm_bwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS.keys())
+
+EPI_BIAS, EPI_RELU, EPI_ADD, EPI_RELU_MASK = 1, 2, 4, 8
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) the shared library; raises if impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError("libhsg_b200.so is missing and could not be built; the WSWGAT path has no fallback")
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().hsg_strerror(int(rc)).decode()
+        raise RuntimeError("hsg_b200: %s (status %d)" % (msg, rc))
+
+
+_DEVICE_OK = False
+
+
+def require_device():
+    """Fail loudly unless a sm_100 device is current."""
+    global _DEVICE_OK
+    if _DEVICE_OK:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("hsg_b200: no CUDA device - the WSWGAT path runs only on B200 (sm_100a), no CPU fallback")
+    check(load().hsg_device_check())
+    _DEVICE_OK = True
+
+
+def profile_snapshot():
+    """{kernel name: (launches, total ms)} since the last reset."""
+    lib = load()
+    out = {}
+    cnt, ms = C.c_int(0), C.c_float(0.0)
+    for i in range(lib.hsg_profile_num_slots()):
+        check(lib.hsg_profile_read(i, C.byref(cnt), C.byref(ms)))
+        if cnt.value:
+            out[lib.hsg_profile_slot_name(i).decode()] = (cnt.value, float(ms.value))
+    return out

@@ -1,0 +1,58 @@
+// Shared helpers for the sm_100a WSWGAT kernels: launch bookkeeping, per-kernel
+// CUDA-event profiling, small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hsg_b200.h"
+
+namespace hsg {
+
+enum Slot {
+  SLOT_BUILD_COUNT = 0,
+  SLOT_BUILD_SCAN,
+  SLOT_BUILD_FILL,
+  SLOT_PREP_FWD,
+  SLOT_PREP_BWD,
+  SLOT_GEMM_NT,
+  SLOT_GEMM_NN,
+  SLOT_GEMM_TN,
+  SLOT_GEMM_TN_REDUCE,
+  SLOT_EDGE_FWD,
+  SLOT_EDGE_BWD_PREP,
+  SLOT_EDGE_BWD,
+  SLOT_EDGE_BWD_DQ,
+  SLOT_LN_FWD,
+  SLOT_LN_BWD,
+  SLOT_LN_BWD_REDUCE,
+  SLOT_COUNT
+};
+
+// implemented in hsg_abi.cu
+void prof_begin(int slot, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+int num_sms();
+
+struct LaunchScope {
+  int slot;
+  cudaStream_t s;
+  LaunchScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_) { prof_begin(slot, s); }
+  ~LaunchScope() { prof_end(slot, s); }
+};
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? HSG_OK : HSG_ERR_CUDA; }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : HSG_LEAKY_SLOPE * x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace hsg

@@ -1,0 +1,373 @@
+// Tall-skinny dense products of the WSWGAT path (projections K1/K6 and the FFN
+// products of K4) in exact fp32 (FFMA) - the parity mode that meets the 1e-5
+// bound of BASELINE.json.  M (nodes) is tall, N and K are 64..512.
+//
+//   gemm_nt : C = A . B^T   nn.Linear / Conv1d(k=1) forward   (GATLayer.py:38,110,146)
+//   gemm_nn : C = A . B     input gradients
+//   gemm_tn : C = A^T . B   weight gradients, split over the node dimension with a
+//                           fixed-order second stage (bitwise reproducible)
+#include "hsg_common.cuh"
+
+namespace hsg {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int TM = 8, TN = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr int APAD = 4;
+
+// ---------------------------------------------------------------------------
+// C[M,N] = A[M,K] * op(B);  B_NT: B is [N,K] (K contiguous), else B is [K,N].
+// VEC: all of K%4, lda%4, ldb%4 (and N%4 for !B_NT) hold and pointers are 16B aligned.
+// ---------------------------------------------------------------------------
+template <bool B_NT, bool VEC>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+            float* __restrict__ C, int ldc, const float* __restrict__ bias, const float* __restrict__ R, int ldr,
+            int epi) {
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + APAD];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // staging registers
+  float4 ra[2], rb;
+  const int a_row = tid / 4, a_kq = (tid % 4) * 4;  // A tile: rows a_row and a_row+64, k = a_kq..a_kq+3
+  const int bnt_row = tid / 4, bnt_kq = (tid % 4) * 4;  // B_NT tile: BN rows x BK
+  const int bnn_k = tid / 16, bnn_n = (tid % 16) * 4;   // B_NN tile: BK rows x BN
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int m = m0 + a_row + 64 * h;
+      int k = k0 + a_kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) {
+        const float* p = A + (size_t)m * lda + k;
+        if (VEC) {
+          if (k < K) v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (k + 0 < K) v.x = p[0];
+          if (k + 1 < K) v.y = p[1];
+          if (k + 2 < K) v.z = p[2];
+          if (k + 3 < K) v.w = p[3];
+        }
+      }
+      ra[h] = v;
+    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (B_NT) {
+      int n = n0 + bnt_row, k = k0 + bnt_kq;
+      if (n < N) {
+        const float* p = B + (size_t)n * ldb + k;
+        if (VEC) {
+          if (k < K) v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (k + 0 < K) v.x = p[0];
+          if (k + 1 < K) v.y = p[1];
+          if (k + 2 < K) v.z = p[2];
+          if (k + 3 < K) v.w = p[3];
+        }
+      }
+    } else {
+      int k = k0 + bnn_k, n = n0 + bnn_n;
+      if (k < K) {
+        const float* p = B + (size_t)k * ldb + n;
+        if (VEC) {
+          if (n < N) v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (n + 0 < N) v.x = p[0];
+          if (n + 1 < N) v.y = p[1];
+          if (n + 2 < N) v.z = p[2];
+          if (n + 3 < N) v.w = p[3];
+        }
+      }
+    }
+    rb = v;
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int r = a_row + 64 * h;
+      As[buf][a_kq + 0][r] = ra[h].x;
+      As[buf][a_kq + 1][r] = ra[h].y;
+      As[buf][a_kq + 2][r] = ra[h].z;
+      As[buf][a_kq + 3][r] = ra[h].w;
+    }
+    if (B_NT) {
+      Bs[buf][bnt_kq + 0][bnt_row] = rb.x;
+      Bs[buf][bnt_kq + 1][bnt_row] = rb.y;
+      Bs[buf][bnt_kq + 2][bnt_row] = rb.z;
+      Bs[buf][bnt_kq + 3][bnt_row] = rb.w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][bnn_k][bnn_n]) = rb;
+    }
+  };
+
+  const int nk = ceil_div(K, BK);
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+      float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+  const int n = n0 + tx * TN;
+  const bool vec_out = VEC && (ldc % 4 == 0) && (n + 3 < N) && (R == nullptr || ldr % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    float v[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      float c = acc[i][j];
+      int nn = n + j;
+      if (nn < N) {
+        if (epi & HSG_EPI_BIAS) c += bias[nn];
+        if (epi & HSG_EPI_RELU) c = fmaxf(c, 0.f);
+        if (epi & HSG_EPI_ADD) c += R[(size_t)m * ldr + nn];
+        if (epi & HSG_EPI_RELU_MASK) c = R[(size_t)m * ldr + nn] > 0.f ? c : 0.f;
+      }
+      v[j] = c;
+    }
+    if (vec_out) {
+      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (n + j < N) C[(size_t)m * ldc + n + j] = v[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Weight gradient: part[z][n1][n2] = sum_{m in chunk z} A[m,n1] B[m,n2]
+// ---------------------------------------------------------------------------
+constexpr int TB = 64;      // output tile TB x TB
+constexpr int TBK = 16;     // rows of the reduction dimension per stage
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gemm_tn_kernel(int M, int N1, int N2, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+               float* __restrict__ part, float* __restrict__ part_col, int rows_per_split) {
+  __shared__ __align__(16) float As[2][TBK][TB + 4];
+  __shared__ __align__(16) float Bs[2][TBK][TB + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int n1_0 = blockIdx.x * TB, n2_0 = blockIdx.y * TB;
+  const int z = blockIdx.z;
+  const int m_beg = z * rows_per_split;
+  const int m_end = min(M, m_beg + rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;  // column sum of A for thread tid < TB (only blockIdx.y == 0)
+  const bool do_col = (part_col != nullptr) && (blockIdx.y == 0);
+
+  const int lr = tid / 16, lc = (tid % 16) * 4;
+  float4 ra, rb;
+  auto load = [&](int mrow) {
+    int m = mrow + lr;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (m < m_end) {
+      const float* pa = A + (size_t)m * lda + n1_0 + lc;
+      const float* pb = B + (size_t)m * ldb + n2_0 + lc;
+      if (VEC) {
+        if (n1_0 + lc < N1) ra = *reinterpret_cast<const float4*>(pa);
+        if (n2_0 + lc < N2) rb = *reinterpret_cast<const float4*>(pb);
+      } else {
+        if (n1_0 + lc + 0 < N1) ra.x = pa[0];
+        if (n1_0 + lc + 1 < N1) ra.y = pa[1];
+        if (n1_0 + lc + 2 < N1) ra.z = pa[2];
+        if (n1_0 + lc + 3 < N1) ra.w = pa[3];
+        if (n2_0 + lc + 0 < N2) rb.x = pb[0];
+        if (n2_0 + lc + 1 < N2) rb.y = pb[1];
+        if (n2_0 + lc + 2 < N2) rb.z = pb[2];
+        if (n2_0 + lc + 3 < N2) rb.w = pb[3];
+      }
+    }
+  };
+  auto store = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lr][lc]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = rb;
+  };
+  const int nst = ceil_div(max(m_end - m_beg, 0), TBK);
+  if (nst > 0) {
+    load(m_beg);
+    store(0);
+  }
+  __syncthreads();
+  for (int st = 0; st < nst; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nst) load(m_beg + (st + 1) * TBK);
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (do_col && tid < TB) {
+#pragma unroll
+      for (int k = 0; k < TBK; ++k) csum += As[buf][k][tid];
+    }
+    if (st + 1 < nst) {
+      store(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  float* out = part + (size_t)z * N1 * N2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int n1 = n1_0 + ty * 4 + i;
+    if (n1 >= N1) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n2 = n2_0 + tx * 4 + j;
+      if (n2 < N2) out[(size_t)n1 * N2 + n2] = acc[i][j];
+    }
+  }
+  if (do_col && tid < TB && n1_0 + tid < N1) part_col[(size_t)z * N1 + n1_0 + tid] = csum;
+}
+
+__global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* __restrict__ part,
+                                      const float* __restrict__ part_col, float* __restrict__ C, int ldc,
+                                      float* __restrict__ colsum) {
+  const int total = N1 * N2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + N1; i += gridDim.x * blockDim.x) {
+    if (i < total) {
+      float s = 0.f;
+      for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * total + i];
+      C[(size_t)(i / N2) * ldc + (i % N2)] = s;
+    } else if (colsum != nullptr) {
+      int c = i - total;
+      float s = 0.f;
+      for (int z = 0; z < nsplit; ++z) s += part_col[(size_t)z * N1 + c];
+      colsum[c] = s;
+    }
+  }
+}
+
+static int tn_splits(int M, int N1, int N2) {
+  int tiles = ceil_div(N1, TB) * ceil_div(N2, TB);
+  int want = ceil_div(2 * 148, tiles);
+  int maxs = ceil_div(M, 256);
+  int s = want < maxs ? want : maxs;
+  if (s < 1) s = 1;
+  if (s > 128) s = 128;
+  return s;
+}
+
+}  // namespace hsg
+
+using namespace hsg;
+
+extern "C" {
+
+int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* bias, const float* R, int ldr, int epi, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if ((epi & HSG_EPI_BIAS) && !bias) return HSG_ERR_ARG;
+  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
+  bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(C) &&
+             (R == nullptr || aligned16(R));
+  LaunchScope ls(SLOT_GEMM_NT, s);
+  if (vec)
+    gemm_kernel<true, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+  else
+    gemm_kernel<true, false><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+  return check_launch();
+}
+
+int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* R, int ldr, int epi, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if (epi & (HSG_EPI_BIAS | HSG_EPI_RELU)) return HSG_ERR_ARG;
+  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
+  bool vec = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) &&
+             aligned16(C) && (R == nullptr || aligned16(R));
+  LaunchScope ls(SLOT_GEMM_NN, s);
+  if (vec)
+    gemm_kernel<false, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi);
+  else
+    gemm_kernel<false, false><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi);
+  return check_launch();
+}
+
+size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
+  if (M <= 0 || N1 <= 0 || N2 <= 0) return 16;
+  size_t s = (size_t)tn_splits(M, N1, N2);
+  return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
+}
+
+int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                float* colsum, void* ws, size_t ws_bytes, void* stream) {
+  if (M < 0 || N1 <= 0 || N2 <= 0 || !A || !B || !C || !ws) return HSG_ERR_ARG;
+  if (ws_bytes < hsg_gemm_tn_workspace_bytes(M, N1, N2)) return HSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  int nsplit = M > 0 ? tn_splits(M, N1, N2) : 0;
+  float* part = reinterpret_cast<float*>(ws);
+  float* part_col = part + (size_t)nsplit * N1 * N2;
+  if (M > 0) {
+    int rows = ceil_div(M, nsplit);
+    rows = ceil_div(rows, TBK) * TBK;
+    nsplit = ceil_div(M, rows);
+    dim3 grid(ceil_div(N1, TB), ceil_div(N2, TB), nsplit);
+    bool vec = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
+    LaunchScope ls(SLOT_GEMM_TN, s);
+    if (vec)
+      gemm_tn_kernel<true><<<grid, 256, 0, s>>>(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
+    else
+      gemm_tn_kernel<false><<<grid, 256, 0, s>>>(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
+    int rc = check_launch();
+    if (rc) return rc;
+  }
+  {
+    LaunchScope ls(SLOT_GEMM_TN_REDUCE, s);
+    int total = N1 * N2 + N1;
+    int blocks = ceil_div(total, 256);
+    if (blocks > 1184) blocks = 1184;
+    gemm_tn_reduce_kernel<<<blocks, 256, 0, s>>>(nsplit, N1, N2, part, part_col, C, ldc, colsum);
+  }
+  return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+"""Autograd functions of the WSWGAT path; every stage is a call into libhsg_b200.so.
+
+Forward / backward data flow of one WSWGAT application (module/GAT.py:45-59):
+
+  prep      W_aug, q           <- hsg_attn_prep_fwd       (attn_fc folded into fc / the TF-IDF table)
+  proj      zp = h_src W_aug^T <- hsg_gemm_nt             (all heads' fc + p = a_src.z in one product)
+  edge      sh, x, stat        <- hsg_edge_fwd            (logits, edge_softmax, aggregation, ELU, +origin)
+  ffn       hdn, r, out        <- hsg_gemm_nt x2, hsg_layernorm_fwd
+  backward  mirrors it with hsg_layernorm_bwd, hsg_gemm_nn / hsg_gemm_tn, hsg_edge_bwd_prep, hsg_edge_bwd,
+            hsg_attn_prep_bwd; attention is recomputed from (p, q, m, den), no per-edge tensor is stored.
+
+There is no eager/PyTorch fallback: without the CUDA library or a B200 these raise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import EPI_ADD, EPI_BIAS, EPI_RELU, EPI_RELU_MASK
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("hsg_b200 expects float32 tensors, got %s" % t.dtype)
+    if not t.is_cuda:
+        raise RuntimeError("hsg_b200: tensor is not on a CUDA device (no CPU fallback)")
+    return t.contiguous()
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Workspace:
+    """Per-device scratch reused across calls (stream-ordered use only)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes, device, tag):
+        key = (device, tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def gemm_nt(A, B, bias=None, R=None, epi=0, N=None, out=None):
+    """C = A @ B[:N].T (+bias, relu, +R / relu-mask R)."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[0] if N is None else N
+    Cm = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.check(lib.hsg_gemm_nt(M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(Cm), Cm.stride(0), _p(bias), _p(R),
+                               R.stride(0) if R is not None else 0, epi, _st()))
+    return Cm
+
+
+def gemm_nn(A, B, R=None, epi=0):
+    """C = A @ B (+R / relu-mask R)."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[1]
+    Cm = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.check(lib.hsg_gemm_nn(M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(Cm), Cm.stride(0), _p(R),
+                               R.stride(0) if R is not None else 0, epi, _st()))
+    return Cm
+
+
+def gemm_tn(A, B, want_colsum=False):
+    """C = A.T @ B  (and column sums of A), deterministic."""
+    lib = _lib.load()
+    M, N1 = A.shape
+    N2 = B.shape[1]
+    Cm = torch.empty(N1, N2, dtype=torch.float32, device=A.device)
+    cs = torch.empty(N1, dtype=torch.float32, device=A.device) if want_colsum else None
+    nbytes = lib.hsg_gemm_tn_workspace_bytes(M, N1, N2)
+    ws = _Workspace.get(nbytes, A.device, "tn")
+    _lib.check(lib.hsg_gemm_tn(M, N1, N2, _p(A), A.stride(0), _p(B), B.stride(0), _p(Cm), Cm.stride(0), _p(cs), _p(ws),
+                               ws.numel(), _st()))
+    return Cm, cs
+
+
+# --------------------------------------------------------------------------------------------
+# multi-head attention layer: proj + edge kernel
+# --------------------------------------------------------------------------------------------
+def _mh_forward(csc, H, d, h_src, origin, W, Wf, bf, a, T):
+    lib = _lib.load()
+    F = H * d
+    ldz = round_up(F + H, 8)
+    in_dim = h_src.shape[1]
+    dev = h_src.device
+    n_dst = csc.n_dst
+    W_aug = torch.empty(ldz, in_dim, dtype=torch.float32, device=dev)
+    q = torch.empty(_N_BINS, H, dtype=torch.float32, device=dev)
+    _lib.check(lib.hsg_attn_prep_fwd(H, d, in_dim, Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a), _p(T), _p(W_aug),
+                                     _p(q), _st()))
+    zp = gemm_nt(h_src, W_aug)
+    sh = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    x = torch.empty(n_dst, F, dtype=torch.float32, device=dev) if origin is not None else None
+    stat = torch.empty(n_dst, 3 * H, dtype=torch.float32, device=dev)
+    _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, _p(zp), ldz, _p(q), _p(origin), _p(sh), _p(x), _p(stat), _st()))
+    return W_aug, q, zp, sh, x, stat
+
+
+def _mh_backward(csc_t, H, d, h_src, W, Wf, bf, a, T, W_aug, q, zp, sh, stat, dx=None, dsh=None):
+    """Returns (dh_src, dW, dWf, dbf, da, dT)."""
+    lib = _lib.load()
+    F = H * d
+    ldz = zp.shape[1]
+    dev = zp.device
+    n_dst, n_src = sh.shape[0], zp.shape[0]
+    g = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    _lib.check(lib.hsg_edge_bwd_prep(n_dst, H, d, _p(dx), _p(dsh), _p(sh), _p(g), _p(stat), _st()))
+    dzp = torch.empty(n_src, ldz, dtype=torch.float32, device=dev)
+    dq = torch.empty(_N_BINS, H, dtype=torch.float32, device=dev)
+    ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
+    _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, _p(zp), ldz, _p(q), _p(g), _p(stat), _p(dzp), _p(dq), _p(ws),
+                                ws.numel(), _st()))
+    dh_src = gemm_nn(dzp, W_aug)
+    dW_aug, _ = gemm_tn(dzp, h_src)
+    dW = torch.empty_like(W)
+    dWf = torch.empty_like(Wf)
+    dbf = torch.empty_like(bf) if bf is not None else None
+    da = torch.empty_like(a)
+    dT = torch.empty_like(T)
+    _lib.check(lib.hsg_attn_prep_bwd(H, d, W.shape[1], Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a), _p(T),
+                                     _p(dW_aug), _p(dq), _p(dW), _p(dWf), _p(dbf), _p(da), _p(dT), _st()))
+    return dh_src, dW, dWf, dbf, da, dT
+
+
+_N_BINS = 10
+
+
+class MultiHeadFn(torch.autograd.Function):
+    """MultiHeadLayer.forward(g, h) -> cat_k head_k(g, h)   (GATStackLayer.py:55-59)."""
+
+    @staticmethod
+    def forward(ctx, batch, kind, H, d, h_src, W, Wf, bf, a, T):
+        _lib.require_device()
+        csc, csc_t = batch.csc(kind)
+        h_src, W, Wf, a, T = (_f32c(t) for t in (h_src, W, Wf, a, T))
+        bf = _f32c(bf) if bf is not None else None
+        if h_src.shape[0] != csc.n_src:
+            raise ValueError("%s: input has %d rows, graph has %d source nodes" % (kind, h_src.shape[0], csc.n_src))
+        W_aug, q, zp, sh, _, stat = _mh_forward(csc, H, d, h_src, None, W, Wf, bf, a, T)
+        ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.has_bf = batch, kind, H, d, bf is not None
+        ctx.save_for_backward(h_src, W, Wf, bf if bf is not None else W.new_empty(0), a, T, W_aug, q, zp, sh, stat)
+        return sh
+
+    @staticmethod
+    def backward(ctx, dsh):
+        h_src, W, Wf, bf, a, T, W_aug, q, zp, sh, stat = ctx.saved_tensors
+        bf = bf if ctx.has_bf else None
+        _, csc_t = ctx.batch.csc(ctx.kind)
+        dh, dW, dWf, dbf, da, dT = _mh_backward(csc_t, ctx.H, ctx.d, h_src, W, Wf, bf, a, T, W_aug, q, zp, sh,
+                                                stat.clone(), dsh=_f32c(dsh))
+        return None, None, None, None, dh, dW, dWf, dbf, da, dT
+
+
+# --------------------------------------------------------------------------------------------
+# position-wise FFN
+# --------------------------------------------------------------------------------------------
+def _ffn_forward(x, w1, b1, w2, b2, gamma, beta):
+    lib = _lib.load()
+    N, D = x.shape
+    hdn = gemm_nt(x, w1, bias=b1, epi=EPI_BIAS | EPI_RELU)
+    r = gemm_nt(hdn, w2, bias=b2, R=x, epi=EPI_BIAS | EPI_ADD)
+    out = torch.empty_like(r)
+    stats = torch.empty(N, 2, dtype=torch.float32, device=x.device)
+    _lib.check(lib.hsg_layernorm_fwd(N, D, _p(r), _p(gamma), _p(beta), _p(out), _p(stats), _st()))
+    return hdn, r, stats, out
+
+
+def _ffn_backward(dout, x, w1, w2, gamma, hdn, r, stats):
+    """Returns (dx, dw1, db1, dw2, db2, dgamma, dbeta)."""
+    lib = _lib.load()
+    N, D = x.shape
+    dev = x.device
+    dr = torch.empty_like(r)
+    dgamma = torch.empty_like(gamma)
+    dbeta = torch.empty_like(gamma)
+    ws = _Workspace.get(lib.hsg_layernorm_bwd_workspace_bytes(N, D), dev, "ln")
+    _lib.check(lib.hsg_layernorm_bwd(N, D, _p(dout), _p(r), _p(stats), _p(gamma), _p(dr), _p(dgamma), _p(dbeta),
+                                     _p(ws), ws.numel(), _st()))
+    dhp = gemm_nn(dr, w2, R=hdn, epi=EPI_RELU_MASK)
+    dw2, db2 = gemm_tn(dr, hdn, want_colsum=True)
+    dw1, db1 = gemm_tn(dhp, x, want_colsum=True)
+    dx = gemm_nn(dhp, w1, R=dr, epi=EPI_ADD)
+    return dx, dw1, db1, dw2, db2, dgamma, dbeta
+
+
+class FFNFn(torch.autograd.Function):
+    """PositionwiseFeedForward.forward (GATLayer.py:35-44) on x [N, d_in] (dropout p = 0)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta):
+        _lib.require_device()
+        x, w1, b1, w2, b2, gamma, beta = (_f32c(t) for t in (x, w1, b1, w2, b2, gamma, beta))
+        hdn, r, stats, out = _ffn_forward(x, w1, b1, w2, b2, gamma, beta)
+        ctx.save_for_backward(x, w1, w2, gamma, hdn, r, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1, w2, gamma, hdn, r, stats = ctx.saved_tensors
+        return _ffn_backward(_f32c(dout), x, w1, w2, gamma, hdn, r, stats)
+
+
+# --------------------------------------------------------------------------------------------
+# whole WSWGAT application (the fused path used by the update loop)
+# --------------------------------------------------------------------------------------------
+class WSWGATFn(torch.autograd.Function):
+    """h = FFN(elu(multi_head(g, neighbor)) + origin)   (GAT.py:56-58)."""
+
+    @staticmethod
+    def forward(ctx, batch, kind, H, d, neighbor, origin, W, Wf, bf, a, T, w1, b1, w2, b2, gamma, beta):
+        _lib.require_device()
+        csc, _ = batch.csc(kind)
+        neighbor, origin, W, Wf, a, T, w1, b1, w2, b2, gamma, beta = (
+            _f32c(t) for t in (neighbor, origin, W, Wf, a, T, w1, b1, w2, b2, gamma, beta))
+        bf = _f32c(bf) if bf is not None else None
+        if neighbor.shape[0] != csc.n_src or origin.shape[0] != csc.n_dst:
+            raise ValueError("%s: got %d neighbor / %d origin rows, graph has %d / %d" %
+                             (kind, neighbor.shape[0], origin.shape[0], csc.n_src, csc.n_dst))
+        if origin.shape[1] != H * d:
+            raise ValueError("origin width %d != heads*head_dim %d" % (origin.shape[1], H * d))
+        W_aug, q, zp, sh, x, stat = _mh_forward(csc, H, d, neighbor, origin, W, Wf, bf, a, T)
+        hdn, r, stats, out = _ffn_forward(x, w1, b1, w2, b2, gamma, beta)
+        ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.has_bf = batch, kind, H, d, bf is not None
+        ctx.save_for_backward(neighbor, W, Wf, bf if bf is not None else W.new_empty(0), a, T, W_aug, q, zp, sh,
+                              stat, x, w1, w2, gamma, hdn, r, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (neighbor, W, Wf, bf, a, T, W_aug, q, zp, sh, stat, x, w1, w2, gamma, hdn, r, stats) = ctx.saved_tensors
+        bf = bf if ctx.has_bf else None
+        _, csc_t = ctx.batch.csc(ctx.kind)
+        dx, dw1, db1, dw2, db2, dgamma, dbeta = _ffn_backward(_f32c(dout), x, w1, w2, gamma, hdn, r, stats)
+        dh, dW, dWf, dbf, da, dT = _mh_backward(csc_t, ctx.H, ctx.d, neighbor, W, Wf, bf, a, T, W_aug, q, zp, sh,
+                                                stat, dx=dx)
+        # d origin = dx (residual, GAT.py:57)
+        return (None, None, None, None, dh, dx, dW, dWf, dbf, da, dT, dw1, db1, dw2, db2, dgamma, dbeta)

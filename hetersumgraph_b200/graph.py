@@ -1,0 +1,273 @@
+"""HeteroBatch: the device-resident replacement of the reference's BatchedDGLGraph.
+
+The reference hands a DGL-0.4 batched graph `g` to WSWGAT.forward (module/GAT.py:45)
+and every head re-derives the node / edge id sets with three filter UDFs
+(module/GATLayer.py:105-107, 143-145).  HeteroBatch carries those id sets once per
+batch, built on the GPU by hsg_build_count / hsg_build_fill from the same inputs
+ExampleSet.CreateGraph consumes (module/dataloader.py:222-268, 328-406):
+
+  word rows      = ascending DGL node id over unit == 0   (row order of `w`)
+  supernode rows = ascending DGL node id over unit == 1   (row order of `s`: sentences, then docs, per graph)
+  csc_super      = in-edges of supernodes from words  (w->s / w->d), ascending DGL edge id
+  csc_word       = in-edges of words from supernodes  (s->w / d->w), ascending DGL edge id
+  super_extra    = number of other in-edges of a supernode (sent<->sent dtype 1, sent->doc dtype 2):
+                   they carry e = 0 and z_src = 0 into the reference's softmax
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synthetic import TokenBatch
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceTokenBatch:
+    """The builder's inputs resident on the device (see synthetic.TokenBatch for the fields)."""
+
+    def __init__(self):
+        self.c_struct = None
+
+    @staticmethod
+    def host_buffers(tb: TokenBatch, pin=True):
+        """Contiguous (pinned) host tensors of everything that is copied per step, and their byte count."""
+        def h(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.pin_memory() if (pin and t.numel() > 0 and torch.cuda.is_available()) else t
+        bufs = dict(tokens=h(tb.tokens), sent_bin=h(tb.sent_bin), graph_sent_ptr=h(tb.graph_sent_ptr),
+                    labels=h(tb.labels))
+        if tb.hdsg:
+            bufs.update(graph_doc_ptr=h(tb.graph_doc_ptr), sent_doc=h(tb.sent_doc), doc_tok_ptr=h(tb.doc_tok_ptr),
+                        doc_tokens=h(tb.doc_tokens), doc_bin=h(tb.doc_bin))
+        nbytes = sum(t.numel() * t.element_size() for t in bufs.values())
+        return bufs, nbytes
+
+    @staticmethod
+    def upload(tb: TokenBatch, device="cuda", vocab_size: Optional[int] = None, host=None,
+               filter_bitmap_dev: Optional[torch.Tensor] = None) -> "DeviceTokenBatch":
+        dev = torch.device(device)
+        if host is None:
+            host, _ = DeviceTokenBatch.host_buffers(tb)
+        d = DeviceTokenBatch()
+        d.device, d.hdsg, d.n_graphs = dev, bool(tb.hdsg), tb.n_graphs
+
+        def up(t):
+            if t.numel() == 0:
+                return torch.zeros(1, dtype=t.dtype, device=dev)
+            return t.to(dev, non_blocking=True)
+
+        d.tokens, d.sent_bin, d.graph_sent_ptr = up(host["tokens"]), up(host["sent_bin"]), up(host["graph_sent_ptr"])
+        d.labels = up(host["labels"]) if host["labels"].numel() else None
+        if filter_bitmap_dev is None:   # constant per dataset: upload once and pass it back in for later batches
+            filter_bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
+        d.filter_bitmap = filter_bitmap_dev
+        if vocab_size is None:
+            vocab_size = int(tb.filter_bitmap.shape[0]) * 32
+        d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = None
+        n_doc = n_doc_tok = 0
+        if tb.hdsg:
+            d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = up(host["graph_doc_ptr"]), up(host["sent_doc"]), up(host["doc_tok_ptr"])
+            d.doc_tokens, d.doc_bin = up(host["doc_tokens"]), up(host["doc_bin"])
+            n_doc, n_doc_tok = int(tb.graph_doc_ptr[-1]), int(tb.doc_tok_ptr[-1])
+        S, L = tb.tokens.shape
+        per_graph = np.diff(tb.graph_sent_ptr)
+        max_sent = int(per_graph.max()) if tb.n_graphs > 0 else 0
+        d.c_struct = _lib.TokenBatchC(tb.n_graphs, S, L, int(tb.hdsg), int(vocab_size), n_doc, n_doc_tok, max_sent,
+                                      _ptr(d.tokens), _ptr(d.sent_bin), _ptr(d.graph_sent_ptr), _ptr(d.filter_bitmap),
+                                      _ptr(d.graph_doc_ptr), _ptr(d.sent_doc), _ptr(d.doc_tok_ptr), _ptr(d.doc_tokens),
+                                      _ptr(d.doc_bin))
+        return d
+
+
+@dataclass
+class HeteroBatch:
+    n_graphs: int
+    n_word: int
+    n_super: int
+    n_pair: int
+    # [B+1] offsets
+    word_ptr: torch.Tensor
+    super_ptr: torch.Tensor
+    node_ptr: torch.Tensor
+    edge_ptr: torch.Tensor
+    pair_ptr: torch.Tensor
+    # node maps
+    word_wid: torch.Tensor
+    word_nid: torch.Tensor
+    super_nid: torch.Tensor
+    super_type: torch.Tensor
+    super_graph: torch.Tensor
+    super_extra: torch.Tensor
+    # CSCs
+    super_indptr: torch.Tensor
+    super_src: torch.Tensor
+    super_bin: torch.Tensor
+    super_eid: torch.Tensor
+    word_indptr: torch.Tensor
+    word_src: torch.Tensor
+    word_bin: torch.Tensor
+    word_eid: torch.Tensor
+    word_extra: Optional[torch.Tensor] = None
+    tfidfembed_weight: Optional[torch.Tensor] = None     # set by set_tfidf_embedding (HiGraph.py:150-151)
+    labels: Optional[torch.Tensor] = None                # [n sentence rows] int64
+    sent_doc_row: Optional[torch.Tensor] = None          # HDSG: supernode row of each sentence's document
+    n_total_nodes: int = 0
+    n_total_edges: int = 0
+
+    def __post_init__(self):
+        self._csc_super = _lib.CscC(self.n_super, self.n_word, self.n_pair, 0, _ptr(self.super_indptr),
+                                    _ptr(self.super_src), _ptr(self.super_bin), _ptr(self.super_extra))
+        self._csc_word = _lib.CscC(self.n_word, self.n_super, self.n_pair, 0, _ptr(self.word_indptr),
+                                   _ptr(self.word_src), _ptr(self.word_bin), _ptr(self.word_extra))
+
+    # ---- reference-facing helpers ------------------------------------------------
+    def set_tfidf_embedding(self, weight: torch.Tensor):
+        """Counterpart of HSumGraph.set_wnfeature's edata['tfidfembed'] write (HiGraph.py:150-151):
+        only the 10 x feat_embed table is needed, the per-edge gather is folded into the edge kernel."""
+        self.tfidfembed_weight = weight
+        return self
+
+    @property
+    def device(self):
+        return self.super_indptr.device
+
+    def csc(self, kind: str):
+        """(forward CSC, transposed CSC) for layer type `kind`."""
+        if kind == "W2S":
+            return self._csc_super, self._csc_word
+        if kind == "S2W":
+            return self._csc_word, self._csc_super
+        raise NotImplementedError("GAT Layer has not been implemented!")   # module/GAT.py:41
+
+    def sentence_rows(self) -> torch.Tensor:
+        """rows of `s` that are sentence nodes (dtype == 1), ascending (HiGraph.py:191)."""
+        return torch.nonzero(self.super_type == 1).reshape(-1)
+
+    def doc_rows(self) -> torch.Tensor:
+        return torch.nonzero(self.super_type == 2).reshape(-1)
+
+    # ---- construction -----------------------------------------------------------
+    @staticmethod
+    def from_token_batch(tb: TokenBatch, device="cuda", vocab_size: Optional[int] = None) -> "HeteroBatch":
+        """Host arrays -> device (pinned H2D) -> device-side build (K0)."""
+        return HeteroBatch.build(DeviceTokenBatch.upload(tb, device, vocab_size))
+
+    @staticmethod
+    def build(dtb: "DeviceTokenBatch") -> "HeteroBatch":
+        """Device-side build (K0) from device-resident token arrays.  One small D2H read of the
+        five totals (+ status) sizes the outputs of the fill phase."""
+        _lib.require_device()
+        lib = _lib.load()
+        dev = dtb.device
+        B = dtb.n_graphs
+        tbc = dtb.c_struct
+        ws_bytes = lib.hsg_build_workspace_bytes(C.byref(tbc))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        offs = torch.empty(5, B + 1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        off_c = _lib.GraphOffsetsC(*[offs[i].data_ptr() for i in range(5)])
+        st = _stream()
+        _lib.check(lib.hsg_build_count(C.byref(tbc), off_c, status.data_ptr(), ws.data_ptr(), ws_bytes, st))
+        totals = torch.cat([offs[:, B], status]).cpu().tolist()          # the one D2H of the build
+        if totals[5] != 0:
+            _lib.check(int(totals[5]))
+        n_word, n_super, n_node, n_edge, n_pair = [int(v) for v in totals[:5]]
+        i32 = dict(dtype=torch.int32, device=dev)
+        out = dict(
+            word_wid=torch.empty(max(n_word, 1), **i32), word_nid=torch.empty(max(n_word, 1), **i32),
+            super_nid=torch.empty(max(n_super, 1), **i32),
+            super_type=torch.empty(max(n_super, 1), dtype=torch.int8, device=dev),
+            super_graph=torch.empty(max(n_super, 1), **i32), super_indptr=torch.empty(n_super + 1, **i32),
+            super_src=torch.empty(max(n_pair, 1), **i32),
+            super_bin=torch.empty(max(n_pair, 1), dtype=torch.uint8, device=dev),
+            super_eid=torch.empty(max(n_pair, 1), **i32), super_extra=torch.empty(max(n_super, 1), **i32),
+            word_indptr=torch.empty(n_word + 1, **i32), word_src=torch.empty(max(n_pair, 1), **i32),
+            word_bin=torch.empty(max(n_pair, 1), dtype=torch.uint8, device=dev),
+            word_eid=torch.empty(max(n_pair, 1), **i32))
+        if B == 0:
+            out["super_indptr"].zero_()
+            out["word_indptr"].zero_()
+        goc = _lib.GraphOutC(n_word, n_super, n_pair, 0, off_c,
+                             *[out[k].data_ptr() for k in ("word_wid", "word_nid", "super_nid", "super_type",
+                                                            "super_graph", "super_indptr", "super_src", "super_bin",
+                                                            "super_eid", "super_extra", "word_indptr", "word_src",
+                                                            "word_bin", "word_eid")], status.data_ptr())
+        _lib.check(lib.hsg_build_fill(C.byref(tbc), C.byref(goc), ws.data_ptr(), ws_bytes, st))
+        hb = HeteroBatch(
+            n_graphs=B, n_word=n_word, n_super=n_super, n_pair=n_pair,
+            word_ptr=offs[0], super_ptr=offs[1], node_ptr=offs[2], edge_ptr=offs[3], pair_ptr=offs[4],
+            word_wid=out["word_wid"][:n_word], word_nid=out["word_nid"][:n_word],
+            super_nid=out["super_nid"][:n_super], super_type=out["super_type"][:n_super],
+            super_graph=out["super_graph"][:n_super], super_extra=out["super_extra"][:n_super],
+            super_indptr=out["super_indptr"], super_src=out["super_src"][:n_pair],
+            super_bin=out["super_bin"][:n_pair], super_eid=out["super_eid"][:n_pair],
+            word_indptr=out["word_indptr"], word_src=out["word_src"][:n_pair], word_bin=out["word_bin"][:n_pair],
+            word_eid=out["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge)
+        hb._keepalive = (dtb, ws, status)
+        hb.labels = dtb.labels
+        if dtb.hdsg:
+            n_per = (dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1]).long()
+            gi = torch.repeat_interleave(torch.arange(B, device=dev), n_per)
+            hb.sent_doc_row = (offs[1][:B].long()[gi] + n_per[gi] + dtb.sent_doc[:int(n_per.sum())].long())
+        return hb
+
+    @staticmethod
+    def from_csc_arrays(super_indptr, super_src, super_bin, super_extra, word_indptr, word_src, word_bin,
+                        n_graphs=1, super_type=None, super_graph=None, word_extra=None, super_eid=None,
+                        word_eid=None, device="cuda") -> "HeteroBatch":
+        """Wrap pre-built CSC arrays (stress graph of SURVEY.md §8-d; parity tests against the oracle's arrays)."""
+        dev = torch.device(device)
+
+        def t(a, dtype):
+            if a is None:
+                return None
+            return torch.as_tensor(np.ascontiguousarray(a)).to(dev).to(dtype).contiguous()
+
+        n_super = len(super_indptr) - 1
+        n_word = len(word_indptr) - 1
+        n_pair = int(len(super_src))
+        z32 = torch.zeros(1, dtype=torch.int32, device=dev)
+        pad = lambda x, dt: x if x is not None and x.numel() > 0 else torch.zeros(1, dtype=dt, device=dev)  # noqa: E731
+        return HeteroBatch(
+            n_graphs=n_graphs, n_word=n_word, n_super=n_super, n_pair=n_pair,
+            word_ptr=z32, super_ptr=z32, node_ptr=z32, edge_ptr=z32, pair_ptr=z32,
+            word_wid=torch.zeros(n_word, dtype=torch.int32, device=dev),
+            word_nid=torch.arange(n_word, dtype=torch.int32, device=dev),
+            super_nid=torch.arange(n_super, dtype=torch.int32, device=dev),
+            super_type=t(super_type, torch.int8) if super_type is not None else torch.ones(n_super, dtype=torch.int8, device=dev),
+            super_graph=t(super_graph, torch.int32) if super_graph is not None else torch.zeros(n_super, dtype=torch.int32, device=dev),
+            super_extra=pad(t(super_extra, torch.int32), torch.int32),
+            super_indptr=t(super_indptr, torch.int32), super_src=pad(t(super_src, torch.int32), torch.int32),
+            super_bin=pad(t(super_bin, torch.uint8), torch.uint8),
+            super_eid=pad(t(super_eid, torch.int32), torch.int32) if super_eid is not None else z32,
+            word_indptr=t(word_indptr, torch.int32), word_src=pad(t(word_src, torch.int32), torch.int32),
+            word_bin=pad(t(word_bin, torch.uint8), torch.uint8),
+            word_eid=pad(t(word_eid, torch.int32), torch.int32) if word_eid is not None else z32,
+            word_extra=t(word_extra, torch.int32))
+
+
+def csc_pair_from_edges(word_row, super_row, bins, n_word, n_super):
+    """Host helper for synthetic stress graphs: both CSCs of a list of word<->supernode pairs
+    given in DGL insertion order (pair t has edge ids 2t / 2t+1)."""
+    word_row = np.asarray(word_row, np.int64)
+    super_row = np.asarray(super_row, np.int64)
+    bins = np.asarray(bins, np.int64)
+    t = np.arange(len(word_row), dtype=np.int64)
+
+    def one(dst, src, n_dst, eid):
+        o = np.argsort(dst, kind="stable")
+        indptr = np.zeros(n_dst + 1, np.int64)
+        np.add.at(indptr, dst + 1, 1)
+        return np.cumsum(indptr), src[o], bins[o], eid[o]
+
+    return one(super_row, word_row, n_super, 2 * t), one(word_row, super_row, n_word, 2 * t + 1)

@@ -1,0 +1,196 @@
+"""Drop-in replacements for the reference's WSWGAT modules.
+
+Same constructors, forward signatures and state_dict keys as
+  module/GAT.py:30-59            WSWGAT
+  module/GATStackLayer.py:46-63  MultiHeadLayer
+  module/GATLayer.py:25-44       PositionwiseFeedForward
+  module/GATLayer.py:81-152      WSGATLayer / SWGATLayer (used as the `layer=` selector)
+but the `g` argument is a hetersumgraph_b200.graph.HeteroBatch instead of a DGL
+graph and every forward/backward runs in the sm_100a kernels of libhsg_b200.so.
+
+Parameters are stored packed over heads (W [H*d, in], Wf [H*d, fe], bf [H*d],
+a [H, 3d]); state_dict()/load_state_dict() speak the reference's per-head keys
+("layer.heads.3.fc.weight", ...), so the released checkpoints load unchanged.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .functional import FFNFn, MultiHeadFn, WSWGATFn
+
+
+class WSGATLayer:
+    """Selector for word->supernode heads (reference: module/GATLayer.py:81-116; feat_fc has NO bias)."""
+    kind = "W2S"
+    feat_bias = False
+
+
+class SWGATLayer:
+    """Selector for supernode->word heads (reference: module/GATLayer.py:120-152; feat_fc HAS a bias)."""
+    kind = "S2W"
+    feat_bias = True
+
+
+def _check_dropout(module, p, what):
+    if module.training and p > 0.0:
+        raise NotImplementedError(
+            "hetersumgraph_b200: %s dropout p=%g in training mode is not implemented in the sm_100a kernels yet; "
+            "construct the module with p=0 or call .eval() (parity with the reference is defined at p=0)" % (what, p))
+
+
+class PositionwiseFeedForward(nn.Module):
+    """A two-feed-forward-layer module (reference: module/GATLayer.py:25-44)."""
+
+    def __init__(self, d_in, d_hid, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Conv1d(d_in, d_hid, 1)   # parameter containers only; the math runs in hsg_gemm_nt
+        self.w_2 = nn.Conv1d(d_hid, d_in, 1)
+        self.layer_norm = nn.LayerNorm(d_in)
+        self.dropout = nn.Dropout(dropout)
+        self.d_in, self.d_hid = d_in, d_hid
+
+    def packed(self):
+        return (self.w_1.weight.view(self.d_hid, self.d_in), self.w_1.bias,
+                self.w_2.weight.view(self.d_in, self.d_hid), self.w_2.bias,
+                self.layer_norm.weight, self.layer_norm.bias)
+
+    def forward(self, x):
+        _check_dropout(self, self.dropout.p, "FFN")
+        squeeze = x.dim() == 3
+        x2 = x.reshape(-1, x.shape[-1])
+        out = FFNFn.apply(x2, *self.packed())
+        return out.reshape(x.shape) if squeeze else out
+
+
+class MultiHeadLayer(nn.Module):
+    """num_heads attention heads, outputs concatenated (reference: module/GATStackLayer.py:46-63)."""
+
+    def __init__(self, in_dim, out_dim, num_heads, attn_drop_out, feat_embed_size, layer, merge='cat'):
+        super().__init__()
+        if merge != 'cat':
+            raise NotImplementedError("merge != 'cat' is a scalar-mean bug in the reference (GATStackLayer.py:62) "
+                                      "and is never used")
+        self.kind = layer.kind
+        self.in_dim, self.out_dim, self.num_heads, self.feat_embed_size = in_dim, out_dim, num_heads, feat_embed_size
+        F = out_dim * num_heads
+        self.fc_weight = nn.Parameter(torch.empty(F, in_dim))
+        self.feat_fc_weight = nn.Parameter(torch.empty(F, feat_embed_size))
+        self.feat_fc_bias = nn.Parameter(torch.empty(F)) if layer.feat_bias else None
+        self.attn_fc_weight = nn.Parameter(torch.empty(num_heads, 3 * out_dim))
+        self.merge = merge
+        self.dropout = nn.Dropout(attn_drop_out)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # nn.Linear default init per head (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)))
+        for w, fan_in in ((self.fc_weight, self.in_dim), (self.feat_fc_weight, self.feat_embed_size),
+                          (self.attn_fc_weight, 3 * self.out_dim)):
+            bound = 1.0 / math.sqrt(fan_in)
+            nn.init.uniform_(w, -bound, bound)
+        if self.feat_fc_bias is not None:
+            bound = 1.0 / math.sqrt(self.feat_embed_size)
+            nn.init.uniform_(self.feat_fc_bias, -bound, bound)
+
+    # ---- reference state_dict layout: heads.{k}.fc.weight / feat_fc.weight / feat_fc.bias / attn_fc.weight
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        d = self.out_dim
+        for k in range(self.num_heads):
+            sl = slice(k * d, (k + 1) * d)
+            items = [("fc.weight", self.fc_weight[sl]), ("feat_fc.weight", self.feat_fc_weight[sl])]
+            if self.feat_fc_bias is not None:
+                items.append(("feat_fc.bias", self.feat_fc_bias[sl]))
+            items.append(("attn_fc.weight", self.attn_fc_weight[k:k + 1]))
+            for name, t in items:
+                destination["%sheads.%d.%s" % (prefix, k, name)] = t if keep_vars else t.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        d = self.out_dim
+        names = ["fc.weight", "feat_fc.weight", "attn_fc.weight"] + (["feat_fc.bias"] if self.feat_fc_bias is not None else [])
+        target = {"fc.weight": self.fc_weight, "feat_fc.weight": self.feat_fc_weight,
+                  "feat_fc.bias": self.feat_fc_bias, "attn_fc.weight": self.attn_fc_weight}
+        expected = set()
+        with torch.no_grad():
+            for k in range(self.num_heads):
+                for name in names:
+                    key = "%sheads.%d.%s" % (prefix, k, name)
+                    expected.add(key)
+                    if key not in state_dict:
+                        missing_keys.append(key)
+                        continue
+                    src = state_dict[key]
+                    dst = target[name][k:k + 1] if name == "attn_fc.weight" else target[name][k * d:(k + 1) * d]
+                    if src.shape != dst.shape:
+                        error_msgs.append("size mismatch for %s: %s vs %s" % (key, tuple(src.shape), tuple(dst.shape)))
+                        continue
+                    dst.copy_(src)
+        if strict:
+            for key in state_dict:
+                if key.startswith(prefix + "heads.") and key not in expected:
+                    unexpected_keys.append(key)
+
+    def forward(self, g, h):
+        _check_dropout(self, self.dropout.p, "attention-input")
+        if g.tfidfembed_weight is None:
+            raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight) "
+                               "(counterpart of HSumGraph.set_wnfeature, HiGraph.py:150-151)")
+        return MultiHeadFn.apply(g, self.kind, self.num_heads, self.out_dim, h, self.fc_weight, self.feat_fc_weight,
+                                 self.feat_fc_bias, self.attn_fc_weight, g.tfidfembed_weight)
+
+
+class WSWGAT(nn.Module):
+    """reference: module/GAT.py:30-59."""
+
+    def __init__(self, in_dim, out_dim, num_heads, attn_drop_out, ffn_inner_hidden_size, ffn_drop_out,
+                 feat_embed_size, layerType):
+        super().__init__()
+        self.layerType = layerType
+        if layerType == "W2S":
+            self.layer = MultiHeadLayer(in_dim, int(out_dim / num_heads), num_heads, attn_drop_out, feat_embed_size,
+                                        layer=WSGATLayer)
+        elif layerType == "S2W":
+            self.layer = MultiHeadLayer(in_dim, int(out_dim / num_heads), num_heads, attn_drop_out, feat_embed_size,
+                                        layer=SWGATLayer)
+        else:
+            # "S2S" (MultiHeadSGATLayer) is never instantiated by HSumGraph / HSumDocGraph (HiGraph.py:57-76)
+            raise NotImplementedError("GAT Layer has not been implemented!")
+        self.ffn = PositionwiseFeedForward(out_dim, ffn_inner_hidden_size, ffn_drop_out)
+
+    def forward(self, g, w, s):
+        if self.layerType == "W2S":
+            origin, neighbor = s, w
+        else:
+            origin, neighbor = w, s
+        lay = self.layer
+        _check_dropout(lay, lay.dropout.p, "attention-input")
+        _check_dropout(self.ffn, self.ffn.dropout.p, "FFN")
+        if g.tfidfembed_weight is None:
+            raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight)")
+        return WSWGATFn.apply(g, self.layerType, lay.num_heads, lay.out_dim, neighbor, origin, lay.fc_weight,
+                              lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight, g.tfidfembed_weight,
+                              *self.ffn.packed())
+
+
+class WSWGATUpdateLoop(nn.Module):
+    """The iterative word<->sentence update of HSumGraph.forward / HSumDocGraph.forward
+    (HiGraph.py:98-106, 205-214): W2S, then n_iter x (S2W, W2S), weights shared across iterations."""
+
+    def __init__(self, word_emb_dim=300, hidden_size=64, n_head=8, atten_dropout_prob=0.1,
+                 ffn_inner_hidden_size=512, ffn_dropout_prob=0.1, feat_embed_size=50, n_iter=1):
+        super().__init__()
+        self._n_iter = n_iter
+        self._TFembed = nn.Embedding(10, feat_embed_size)   # box=10 (HiGraph.py:52)
+        self.word2sent = WSWGAT(word_emb_dim, hidden_size, n_head, atten_dropout_prob, ffn_inner_hidden_size,
+                                ffn_dropout_prob, feat_embed_size, "W2S")
+        self.sent2word = WSWGAT(hidden_size, word_emb_dim, 6, atten_dropout_prob, ffn_inner_hidden_size,
+                                ffn_dropout_prob, feat_embed_size, "S2W")
+
+    def forward(self, graph, word_feature, sent_feature):
+        graph.set_tfidf_embedding(self._TFembed.weight)
+        word_state = word_feature
+        sent_state = self.word2sent(graph, word_feature, sent_feature)
+        for _ in range(self._n_iter):
+            word_state = self.sent2word(graph, word_state, sent_state)
+            sent_state = self.word2sent(graph, word_state, sent_state)
+        return word_state, sent_state

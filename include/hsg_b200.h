@@ -1,0 +1,223 @@
+/* hsg_b200.h - C ABI of the B200-native WSWGAT message-passing path.
+ *
+ * Drop-in boundary for the reference's (yellow-binary-tree/HeterSumGraph, pure
+ * Python + DGL 0.4) WSWGAT path.  The reference has no FFI of its own; what a
+ * replacement has to stand behind is the nn.Module surface
+ *     WSWGAT.forward(g, w, s)              module/GAT.py:45-59
+ *     MultiHeadLayer.forward(g, h)         module/GATStackLayer.py:55-63
+ *     WSGATLayer / SWGATLayer.forward      module/GATLayer.py:104-116, 142-152
+ *     PositionwiseFeedForward.forward      module/GATLayer.py:35-44
+ *     ExampleSet.CreateGraph / graph_collate_fn (dgl.batch)
+ *                                          module/dataloader.py:201-268, 328-406, 472-481
+ * and each entry point below names the reference lines it replaces.  The
+ * Python host side (hetersumgraph_b200/) binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns all
+ *     memory (incl. workspaces); nothing here allocates or frees.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronise, and are CUDA-graph capturable.
+ *   - return 0 on success, a negative hsg_status otherwise; never throws.
+ *   - float tensors are fp32 row-major; index tensors are int32; bins are uint8.
+ *   - feature rows are 16-byte aligned: leading dimensions are multiples of 4.
+ */
+#ifndef HSG_B200_H_
+#define HSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSG_ABI_VERSION 1
+#define HSG_N_BINS 10          /* TF-IDF boxes, HiGraph.py:52, dataloader.py:253 */
+#define HSG_LEAKY_SLOPE 0.01f  /* F.leaky_relu default, GATLayer.py:92,131 */
+#define HSG_LN_EPS 1e-5f       /* nn.LayerNorm default, GATLayer.py:32 */
+
+typedef enum {
+  HSG_OK = 0,
+  HSG_ERR_ARG = -1,        /* null pointer / negative size */
+  HSG_ERR_SHAPE = -2,      /* (heads, head_dim) or size combination not supported */
+  HSG_ERR_ALIGN = -3,      /* pointer or leading dimension not 16-byte aligned */
+  HSG_ERR_WORKSPACE = -4,  /* workspace too small */
+  HSG_ERR_CUDA = -5,       /* cudaGetLastError() != cudaSuccess after launch */
+  HSG_ERR_ARCH = -6,       /* device is not sm_100 */
+  HSG_ERR_CAPACITY = -7    /* a per-graph limit of the builder was exceeded */
+} hsg_status;
+
+int hsg_version(void);
+const char* hsg_strerror(int status);
+/* 0 when the current device can run the sm_100a kernels, HSG_ERR_ARCH otherwise. */
+int hsg_device_check(void);
+int hsg_num_sms(void);
+
+/* Per-kernel CUDA-event timing (bench.py's roofline leg).  When enabled every
+ * launch is bracketed by events on its stream; hsg_profile_read synchronises
+ * and returns, for kernel slot i, the launch count and the summed milliseconds.
+ * Not capturable: disable before CUDA-graph capture. */
+int hsg_profile_enable(int on);
+int hsg_profile_reset(void);
+int hsg_profile_num_slots(void);
+const char* hsg_profile_slot_name(int slot);
+int hsg_profile_read(int slot, int* host_count, float* host_ms);
+/* total number of kernel launches issued by this library since load (always counted) */
+long long hsg_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * K0  device-side graph builder
+ *     replaces ExampleSet.AddWordNode / CreateGraph (dataloader.py:201-268),
+ *     MultiExampleSet.CreateGraph (:328-406) and dgl.batch (:480).
+ * Input: the padded token ids of every sentence of every graph, graphs already
+ * in batch order (stable sort by #sentences descending, dataloader.py:479), the
+ * TF-IDF box of every token (-1: the word is not a TF-IDF key of that
+ * sentence, dataloader.py:251) and the filter-id bitmap (dataloader.py:167-182).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_graphs;
+  int32_t n_sent;          /* total sentences S */
+  int32_t sent_len;        /* L (sent_max_len) */
+  int32_t hdsg;            /* 0: HSG (sent<->sent extras), 1: HDSG (doc nodes) */
+  int32_t vocab_size;
+  int32_t n_doc;           /* HDSG: total documents D, else 0 */
+  int32_t n_doc_tok;       /* HDSG: total document tokens T, else 0 */
+  int32_t max_sent_per_graph; /* max over graphs of the sentence count (sizes the per-CTA tables) */
+  const int32_t* tokens;          /* [S, L] */
+  const int8_t* sent_bin;         /* [S, L] */
+  const int32_t* graph_sent_ptr;  /* [B+1] */
+  const uint32_t* filter_bitmap;  /* [ceil(V/32)] bit set = filtered id */
+  const int32_t* graph_doc_ptr;   /* [B+1]  HDSG */
+  const int32_t* sent_doc;        /* [S]    HDSG: local doc index of each sentence */
+  const int32_t* doc_tok_ptr;     /* [D+1]  HDSG */
+  const int32_t* doc_tokens;      /* [T]    HDSG: unpadded doc token ids (Example2.enc_doc_input) */
+  const int8_t* doc_bin;          /* [T]    HDSG */
+} hsg_token_batch;
+
+/* Per-graph counts and offsets, [B+1] exclusive prefix sums (entry B = total). */
+typedef struct {
+  int32_t* word_ptr;    /* word rows   */
+  int32_t* super_ptr;   /* supernode rows (sentences then docs per graph) */
+  int32_t* node_ptr;    /* DGL node ids */
+  int32_t* edge_ptr;    /* DGL edge ids (all edges incl. sent<->sent / sent->doc) */
+  int32_t* pair_ptr;    /* word<->supernode pairs = CSC entries per direction */
+} hsg_graph_offsets;
+
+/* CSC of one direction: in-edges of every destination row, ascending DGL edge id. */
+typedef struct {
+  int32_t n_dst;
+  int32_t n_src;
+  int32_t n_edges;
+  int32_t reserved;
+  const int32_t* indptr;  /* [n_dst+1] */
+  const int32_t* nbr;     /* [E] source ROW (rank among unit==0 resp. unit==1 nodes) */
+  const uint8_t* bin;     /* [E] tffrac */
+  const int32_t* extra;   /* [n_dst] in-edges that are not word<->supernode edges (e=0, z_src=0); may be NULL */
+} hsg_csc;
+
+typedef struct {
+  /* capacities of the output arrays (checked) */
+  int32_t cap_word, cap_super, cap_pair, reserved;
+  hsg_graph_offsets off;
+  int32_t* word_wid;      /* [Nw] ndata["id"] of every word row */
+  int32_t* word_nid;      /* [Nw] DGL node id of every word row  (== filter_nodes(unit==0)) */
+  int32_t* super_nid;     /* [Ns] DGL node id of every supernode row (== filter_nodes(unit==1)) */
+  int8_t* super_type;     /* [Ns] ndata["dtype"]: 1 sentence, 2 document */
+  int32_t* super_graph;   /* [Ns] graph index */
+  int32_t* super_indptr;  /* [Ns+1]  word->supernode CSC */
+  int32_t* super_src;     /* [E] word row */
+  uint8_t* super_bin;     /* [E] */
+  int32_t* super_eid;     /* [E] DGL edge id of the w->s edge */
+  int32_t* super_extra;   /* [Ns] */
+  int32_t* word_indptr;   /* [Nw+1]  supernode->word CSC */
+  int32_t* word_src;      /* [E] supernode row */
+  uint8_t* word_bin;      /* [E] */
+  int32_t* word_eid;      /* [E] DGL edge id of the s->w edge */
+  int32_t* status;        /* [1] device-side error flag (0 ok, HSG_ERR_CAPACITY ...) */
+} hsg_graph_out;
+
+size_t hsg_build_workspace_bytes(const hsg_token_batch* tb);
+/* Phase 1: per-graph counts and the [B+1] offsets (off.*[B] = totals).  The host
+ * reads the totals (one small D2H) to size the arrays of phase 2. */
+int hsg_build_count(const hsg_token_batch* tb, hsg_graph_offsets off, int32_t* status,
+                    void* ws, size_t ws_bytes, void* stream);
+/* Phase 2: fill node maps and both CSCs. */
+int hsg_build_fill(const hsg_token_batch* tb, const hsg_graph_out* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K2  attention prep: folds attn_fc into the projection and the TF-IDF table.
+ *     W_aug[0:F]   = W                      (fc.weight of all heads, GATLayer.py:84,123)
+ *     W_aug[F+k]   = sum_j a_k[j] W[k d + j]   so that  p = h W_aug[F:F+H]^T = a_src . z
+ *     q[b,k]       = a_k[2d:3d] . (Wf_k T[b] + bf_k)      (GATLayer.py:90-92,129-131; HiGraph.py:150-151)
+ *     rows F+H .. ld_rows-1 of W_aug are zero.
+ * ------------------------------------------------------------------------ */
+int hsg_attn_prep_fwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
+                      const float* W, const float* Wf, const float* bf /* may be NULL */,
+                      const float* a /* [H,3d] */, const float* T /* [10,feat] */,
+                      float* W_aug /* [ld_rows, in_dim] */, float* q /* [10,H] */, void* stream);
+/* Backward of the above: given dW_aug and dq produce dW, dWf, dbf, da, dT (all overwritten). */
+int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
+                      const float* W, const float* Wf, const float* bf, const float* a, const float* T,
+                      const float* dW_aug, const float* dq,
+                      float* dW, float* dWf, float* dbf /* may be NULL */, float* da, float* dT, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Dense tall-skinny products (K1/K6 projections, K4 FFN pieces).
+ *   epilogue flags (combine with |):
+ * ------------------------------------------------------------------------ */
+#define HSG_EPI_BIAS 1      /* C += bias[n]            */
+#define HSG_EPI_RELU 2      /* C = max(C, 0)           */
+#define HSG_EPI_ADD 4       /* C += R[m,n]             */
+#define HSG_EPI_RELU_MASK 8 /* C = R[m,n] > 0 ? C : 0  */
+/* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward) */
+int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* bias, const float* R, int ldr, int epi, void* stream);
+/* C[M,N] = A[M,K] . B[K,N]    (input gradient) */
+int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* R, int ldr, int epi, void* stream);
+/* C[N1,N2] = sum_m A[m,N1] B[m,N2]  (weight gradient), deterministic split over m.
+ * colsum (may be NULL): [N1] = sum_m A[m,:] (bias gradient), same pass. */
+size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2);
+int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                float* colsum, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K3  fused edge kernel (forward): for every destination row v
+ *        e_uv  = leaky_relu(p_u + q[bin_uv])                         GATLayer.py:88-92 / 127-131
+ *        sh_v  = sum_act softmax(e)_uv z_u   over ALL in-edges       GATLayer.py:98-102 via pull :113/:149
+ *                (extra[v] never-written edges contribute exp(0) to the denominator, z = 0)
+ *        x_v   = elu(sh_v) + origin_v                                GAT.py:56-57   (optional)
+ *     zp row u = [ z_u (F) | p_u (H) | pad ],  leading dimension ldz.
+ *     stat row v = [ m (H) | den (H) | s (H, written by hsg_edge_bwd_prep) ].
+ * ------------------------------------------------------------------------ */
+int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
+                 const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F] */,
+                 float* x /* [n_dst,F] or NULL */, float* stat /* [n_dst,3H] */, void* stream);
+/* K5a: g = dx * elu'(sh) (or g = dsh when dx == NULL), s[v,k] = g_v[k] . sh_v[k]. */
+int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx /* or NULL */, const float* dsh /* or NULL */,
+                      const float* sh, float* g /* [n_dst,F] */, float* stat, void* stream);
+/* K5b: source-centric backward over the TRANSPOSED structure (csc_t: rows = forward
+ * sources, nbr = forward destinations; in HSG/HDSG graphs this is the other
+ * direction's CSC because every w->s edge has an s->w twin, dataloader.py:254-257):
+ *     dzp_u = [ sum_e alpha_e g_v | sum_e dpre_e | 0 ],   dq[b,k] = sum_{e: bin=b} dpre_e
+ * dq is reduced deterministically through ws. */
+size_t hsg_edge_bwd_workspace_bytes(int H);
+int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,
+                 const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K4  position-wise FFN pieces (GATLayer.py:35-44); the two products use hsg_gemm_*.
+ *   hsg_layernorm_fwd: y = LN(r) * gamma + beta, stats[row] = (mean, rstd)
+ *   hsg_layernorm_bwd: dr from dy; dgamma/dbeta reduced deterministically through ws.
+ * ------------------------------------------------------------------------ */
+int hsg_layernorm_fwd(int N, int D, const float* r, const float* gamma, const float* beta, float* y,
+                      float* stats, void* stream);
+size_t hsg_layernorm_bwd_workspace_bytes(int N, int D);
+int hsg_layernorm_bwd(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma,
+                      float* dr, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSG_B200_H_ */

@@ -1,0 +1,292 @@
+"""GPU parity tests (-m gpu): the sm_100a path, called through the C ABI, against the oracle
+and the golden vectors generated from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): integer outputs (node/edge ids, CSR/CSC, top-m) bit-exact;
+fp32 node outputs and every gradient: max|a-b| / max|b| <= 1e-5.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hetersumgraph_b200 as hb
+from hetersumgraph_b200 import synthetic as syn
+from hetersumgraph_b200.functional import FFNFn, gemm_nn, gemm_nt, gemm_tn
+from oracle import closed_form as cf
+from oracle import fixtures as fx
+from oracle import graph_builder_ref as gb
+from oracle import wswgat_ref as wr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-5
+
+
+def nerr(a, b):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def oracle_batch(exs, hdsg):
+    filt = set(syn.filter_ids().tolist())
+    if hdsg:
+        graphs = [gb.create_graph_hdsg(e.doc_len, e.sents.tolist(), e.doc_tokens, e.w2s, e.w2d, filt) for e in exs]
+    else:
+        graphs = [gb.create_graph_hsg(e.sents.tolist(), e.w2s, filt) for e in exs]
+    bg, order = gb.collate(graphs)
+    return bg, order
+
+
+def assert_batch_equals_oracle(batch, bg):
+    csc = gb.derive_csc(bg)
+    cpu = lambda t: t.cpu().numpy().astype(np.int64)  # noqa: E731
+    assert batch.n_word == len(csc["wnode_id"]) and batch.n_super == len(csc["snode_id"])
+    assert batch.n_total_nodes == bg.n_nodes and batch.n_total_edges == bg.n_edges
+    assert np.array_equal(cpu(batch.word_nid), csc["wnode_id"])
+    assert np.array_equal(cpu(batch.super_nid), csc["snode_id"])
+    assert np.array_equal(cpu(batch.word_wid), bg.wid[csc["wnode_id"]])
+    assert np.array_equal(cpu(batch.super_type), bg.ndtype[csc["snode_id"]])
+    assert np.array_equal(cpu(batch.super_extra), csc["extra_cnt"])
+    for name in ("super", "word"):
+        assert np.array_equal(cpu(getattr(batch, name + "_indptr")), csc[name + "_indptr"]), name
+        assert np.array_equal(cpu(getattr(batch, name + "_src")), csc[name + "_src"]), name
+        assert np.array_equal(cpu(getattr(batch, name + "_bin")), csc[name + "_bin"]), name
+        assert np.array_equal(cpu(getattr(batch, name + "_eid")), csc[name + "_eid"]), name
+    assert np.array_equal(np.diff(cpu(batch.node_ptr)), np.asarray(bg.batch_num_nodes))
+    assert np.array_equal(np.diff(cpu(batch.edge_ptr)), np.asarray(bg.batch_num_edges))
+    g_of_node = np.repeat(np.arange(len(bg.batch_num_nodes)), bg.batch_num_nodes)
+    assert np.array_equal(cpu(batch.super_graph), g_of_node[csc["snode_id"]])
+
+
+# ----------------------------------------------------------------------------- builder (K0)
+@pytest.mark.parametrize("prefix,hdsg", [("hsg", False), ("hdsg", True)])
+def test_builder_bit_exact_vs_reference_golden(prefix, hdsg):
+    z = dict(np.load(os.path.join(GOLD, "builder.npz")))
+    exs = fx.examples_from_arrays(z, prefix)
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    assert tb.order == z[prefix + "_order"].tolist()
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    assert_batch_equals_oracle(batch, fx.graph_from_arrays(z, prefix + "_g_"))
+
+
+@pytest.mark.parametrize("shape,hdsg,n,seed", [("cnndm", False, 32, 0), ("nyt50", False, 32, 1),
+                                               ("multinews", True, 32, 2), ("tiny", False, 7, 3),
+                                               ("tiny", True, 5, 4)])
+def test_builder_bit_exact_vs_oracle_configs(shape, hdsg, n, seed):
+    exs = syn.make_examples(n, shape, seed=seed, hdsg=hdsg)
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    bg, order = oracle_batch(exs, hdsg)
+    assert tb.order == order
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    assert_batch_equals_oracle(batch, bg)
+
+
+def test_builder_edge_cases():
+    L = 100
+    # a graph whose sentences hold only filtered / PAD tokens, a single-sentence graph, an empty batch
+    e0 = syn.DocExample(sents=np.zeros((2, L), np.int32), w2s=[{}, {}], labels=np.zeros(2, np.int64))
+    e0.sents[0, :3] = [5, 6, 7]
+    e1 = syn.DocExample(sents=np.zeros((1, L), np.int32), w2s=[{1000: 0.5, 1001: 0.25}], labels=np.ones(1, np.int64))
+    e1.sents[0, :4] = [1000, 1001, 1000, 1]
+    tb = syn.pack_token_batch([e0, e1])
+    bg, _ = oracle_batch([e0, e1], False)
+    assert_batch_equals_oracle(hb.HeteroBatch.from_token_batch(tb), bg)
+    # maximum sizes: 50 sentences x 100 distinct tokens
+    big = np.arange(5000, dtype=np.int32).reshape(50, 100) + 1000
+    w2s = [{int(w): 0.3 for w in row if w % 3} for row in big]
+    e2 = syn.DocExample(sents=big, w2s=w2s, labels=np.zeros(50, np.int64))
+    tb = syn.pack_token_batch([e2])
+    bg, _ = oracle_batch([e2], False)
+    assert_batch_equals_oracle(hb.HeteroBatch.from_token_batch(tb), bg)
+
+
+# ----------------------------------------------------------------------------- dense pieces
+@pytest.mark.parametrize("M,N,K", [(1000, 72, 300), (257, 312, 64), (129, 512, 64), (1, 64, 512), (333, 50, 30)])
+def test_gemm_variants(M, N, K):
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    R = torch.randn(M, N, device="cuda")
+    ref = (A.double() @ B.double().t())
+    assert nerr(gemm_nt(A, B), ref) <= 2e-6
+    assert nerr(gemm_nt(A, B, bias=bias, epi=3), torch.relu(ref + bias.double())) <= 2e-6
+    assert nerr(gemm_nt(A, B, bias=bias, R=R, epi=5), ref + bias.double() + R.double()) <= 2e-6
+    Bn = torch.randn(K, N, device="cuda")
+    refn = A.double() @ Bn.double()
+    assert nerr(gemm_nn(A, Bn), refn) <= 2e-6
+    assert nerr(gemm_nn(A, Bn, R=R, epi=8), torch.where(R > 0, refn, torch.zeros_like(refn))) <= 2e-6
+    A2 = torch.randn(M, N, device="cuda")
+    Ct, cs = gemm_tn(A2, A, want_colsum=True)
+    assert nerr(Ct, A2.double().t() @ A.double()) <= 2e-6
+    assert nerr(cs, A2.double().sum(0)) <= 2e-6
+
+
+@pytest.mark.parametrize("N,D,Dh", [(777, 64, 512), (300, 300, 512), (5, 16, 32), (1, 48, 32)])
+def test_ffn_matches_torch(N, D, Dh):
+    torch.manual_seed(1)
+    ps = [torch.randn(Dh, D) * 0.1, torch.randn(Dh) * 0.1, torch.randn(D, Dh) * 0.1, torch.randn(D) * 0.1,
+          torch.rand(D) + 0.5, torch.randn(D) * 0.1]
+    x = torch.randn(N, D)
+    c = torch.randn(N, D)
+
+    def run(dev, fn):
+        xs = x.to(dev).requires_grad_(True)
+        pp = [p.to(dev).requires_grad_(True) for p in ps]
+        out = fn(xs, *pp)
+        (out * c.to(dev)).sum().backward()
+        return [out, xs.grad] + [p.grad for p in pp]
+
+    ref = run("cpu", lambda xs, w1, b1, w2, b2, g, b: cf.ffn_cf(xs, w1, b1, w2, b2, g, b))
+    got = run("cuda", lambda xs, *pp: FFNFn.apply(xs, *pp))
+    for a, b in zip(got, ref):
+        assert nerr(a, b) <= TOL
+
+
+# ----------------------------------------------------------------------------- whole path vs golden
+def _load_fixture(name):
+    z = dict(np.load(os.path.join(GOLD, name)))
+    params = {k[2:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("p:")}
+    grads = {k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("gp:")}
+    return z, params, grads
+
+
+def _model_from_fixture(z, params):
+    emb, hid, nh, ffn_h, fe, n_iter, hdsg = [int(v) for v in z["dims"]]
+    m = hb.WSWGATUpdateLoop(emb, hid, nh, 0.0, ffn_h, 0.0, fe, n_iter).cuda()
+    m.load_state_dict(params, strict=True)
+    return m, bool(hdsg)
+
+
+@pytest.mark.parametrize("name", ["wswgat_hsg_default.npz", "wswgat_hdsg_small.npz", "wswgat_hsg_small.npz"])
+def test_update_loop_matches_reference_golden(name):
+    z, params, gold_grads = _load_fixture(name)
+    m, hdsg = _model_from_fixture(z, params)
+    exs = fx.examples_from_arrays(z, "ex")
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    assert tb.order == z["order"].tolist()
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    assert_batch_equals_oracle(batch, fx.graph_from_arrays(z, "g_"))
+    w = torch.from_numpy(z["in_w"]).cuda().requires_grad_(True)
+    s = torch.from_numpy(z["in_s"]).cuda().requires_grad_(True)
+    ws, ss = m(batch, w, s)
+    assert nerr(ws, z["out_w"]) <= TOL, nerr(ws, z["out_w"])
+    assert nerr(ss, z["out_s"]) <= TOL, nerr(ss, z["out_s"])
+    loss = (ws * torch.from_numpy(z["cw"]).cuda()).sum() + (ss * torch.from_numpy(z["cs"]).cuda()).sum()
+    loss.backward()
+    assert nerr(w.grad, z["grad_in_w"]) <= TOL
+    assert nerr(s.grad, z["grad_in_s"]) <= TOL
+    sd = m.state_dict(keep_vars=True)
+    packed_grads = {}
+    for pre in ("word2sent.", "sent2word."):
+        lay = getattr(m, pre[:-1]).layer
+        d = lay.out_dim
+        for k in range(lay.num_heads):
+            packed_grads[pre + "layer.heads.%d.fc.weight" % k] = lay.fc_weight.grad[k * d:(k + 1) * d]
+            packed_grads[pre + "layer.heads.%d.feat_fc.weight" % k] = lay.feat_fc_weight.grad[k * d:(k + 1) * d]
+            if lay.feat_fc_bias is not None:
+                packed_grads[pre + "layer.heads.%d.feat_fc.bias" % k] = lay.feat_fc_bias.grad[k * d:(k + 1) * d]
+            packed_grads[pre + "layer.heads.%d.attn_fc.weight" % k] = lay.attn_fc_weight.grad[k:k + 1]
+    for k, gref in gold_grads.items():
+        got = packed_grads[k] if k in packed_grads else sd[k].grad
+        assert got is not None, k
+        if float(gref.abs().max()) == 0.0:
+            assert float(got.abs().max()) == 0.0, k
+        else:
+            assert nerr(got, gref) <= TOL, (k, nerr(got, gref))
+        if k.endswith("attn_fc.weight"):            # dead a_dst third: exactly zero
+            d = gref.shape[1] // 3
+            assert float(got[:, d:2 * d].abs().max()) == 0.0
+
+
+def test_bitwise_determinism():
+    z, params, _ = _load_fixture("wswgat_hsg_default.npz")
+    m, hdsg = _model_from_fixture(z, params)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(fx.examples_from_arrays(z, "ex"), hdsg=hdsg))
+    outs = []
+    for _ in range(2):
+        m.zero_grad()
+        w = torch.from_numpy(z["in_w"]).cuda().requires_grad_(True)
+        s = torch.from_numpy(z["in_s"]).cuda().requires_grad_(True)
+        ws, ss = m(batch, w, s)
+        (ws.sum() + (ss * ss).sum()).backward()
+        outs.append([ws, ss, w.grad, s.grad] + [p.grad.clone() for p in m.parameters()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------- configs vs closed-form oracle
+@pytest.mark.parametrize("shape,hdsg,n_iter,n,seed", [("cnndm", False, 1, 8, 0), ("nyt50", False, 3, 4, 1),
+                                                      ("multinews", True, 1, 4, 2)])
+def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed):
+    exs = syn.make_examples(n, shape, seed=seed, hdsg=hdsg)
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    bg, _ = oracle_batch(exs, hdsg)
+    csc = gb.derive_csc(bg)
+    torch.manual_seed(1234)
+    m = hb.WSWGATUpdateLoop(n_iter=n_iter, atten_dropout_prob=0.0, ffn_dropout_prob=0.0)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    w = torch.randn(batch.n_word, 300)
+    s = torch.randn(batch.n_super, 64)
+    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter)
+    (ow.sum() + (os_ * os_).sum()).backward()
+    wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    gw, gs = m(batch, wg, sg)
+    (gw.sum() + (gs * gs).sum()).backward()
+    assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
+    assert nerr(wg.grad, wc.grad) <= TOL and nerr(sg.grad, sc.grad) <= TOL
+    assert nerr(m._TFembed.weight.grad, params["_TFembed.weight"].grad) <= TOL
+    assert nerr(m.word2sent.ffn.w_1.weight.grad, params["word2sent.ffn.w_1.weight"].grad) <= TOL
+    assert nerr(m.sent2word.ffn.w_2.weight.grad, params["sent2word.ffn.w_2.weight"].grad) <= TOL
+    W2S_W = torch.cat([params["word2sent.layer.heads.%d.fc.weight" % k].grad for k in range(8)], 0)
+    assert nerr(m.word2sent.layer.fc_weight.grad, W2S_W) <= TOL
+    A_S2W = torch.cat([params["sent2word.layer.heads.%d.attn_fc.weight" % k].grad for k in range(6)], 0)
+    assert nerr(m.sent2word.layer.attn_fc_weight.grad, A_S2W) <= TOL
+
+
+def test_bucketed_reference_port_on_device_batch():
+    """The per-head, degree-bucketed restatement (what DGL executes) agrees too - small batch."""
+    exs = syn.make_examples(3, "tiny", seed=8)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    bg, _ = oracle_batch(exs, False)
+    torch.manual_seed(3)
+    m = hb.WSWGATUpdateLoop(n_iter=1, atten_dropout_prob=0.0, ffn_dropout_prob=0.0)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    w, s = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+    ow, os_ = wr.update_loop(bg, w, s, params, 1)
+    with torch.no_grad():
+        gw, gs = m(batch, w.cuda(), s.cuda())
+    assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
+
+
+# ----------------------------------------------------------------------------- properties at large size
+def test_stress_graph_properties():
+    """Size-independent properties on a large bipartite graph (no oracle at this size):
+    all-zero attention => sh = mean of source z scaled by deg/(deg+extra); rows sum check; determinism."""
+    n_word, n_super, n_edges = 65536, 8192, 262144
+    word, sup, bins, extra = syn.stress_edges(n_word, n_super, n_edges, seed=4, extra=64)
+    (sip, ssrc, sbin, seid), (wip, wsrc, wbin, weid) = hb.csc_pair_from_edges(word, sup, bins, n_word, n_super)
+    batch = hb.HeteroBatch.from_csc_arrays(sip, ssrc, sbin, extra, wip, wsrc, wbin)
+    torch.manual_seed(0)
+    lay = hb.MultiHeadLayer(300, 8, 8, 0.0, 50, layer=hb.WSGATLayer).cuda()
+    with torch.no_grad():
+        lay.attn_fc_weight.zero_()
+    T = torch.randn(10, 50, device="cuda")
+    batch.set_tfidf_embedding(T)
+    h = torch.randn(n_word, 300, device="cuda")
+    with torch.no_grad():
+        sh = lay(batch, h)
+        sh2 = lay(batch, h)
+    assert torch.equal(sh, sh2)
+    z = h @ lay.fc_weight.t()
+    deg = torch.from_numpy(np.diff(sip)).cuda().float()
+    dst = torch.repeat_interleave(torch.arange(n_super, device="cuda"), torch.from_numpy(np.diff(sip)).cuda())
+    agg = torch.zeros(n_super, 64, device="cuda").index_add_(0, dst, z[torch.from_numpy(ssrc).cuda()])
+    want = agg / (deg + 64.0).unsqueeze(1)
+    assert nerr(sh, want) <= TOL

@@ -1,0 +1,121 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol,
+state_dict compatibility with the reference's per-head keys, error behaviour without a GPU,
+synthetic generator / packer invariants."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hetersumgraph_b200 as hb
+from hetersumgraph_b200 import _lib
+from hetersumgraph_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hsg_b200.h")).read()
+    declared = set(re.findall(r"\b(hsg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hsg_status"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libhsg_b200.so does not export %s" % name
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.hsg_version() == 1
+    assert lib.hsg_strerror(0) == b"ok"
+    assert b"workspace" in lib.hsg_strerror(-4)
+    assert lib.hsg_profile_num_slots() > 0
+    # struct layouts agree with the header (pointer-size sanity)
+    assert ctypes.sizeof(_lib.CscC) == 16 + 4 * 8
+    assert ctypes.sizeof(_lib.TokenBatchC) == 32 + 9 * 8
+    assert ctypes.sizeof(_lib.GraphOutC) == 16 + 5 * 8 + 15 * 8
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.hsg_gemm_nt(4, 4, 4, None, 4, None, 4, None, 4, None, None, 0, 0, None) == -1
+    assert lib.hsg_layernorm_fwd(4, 6, 1, 1, 1, 1, 1, None) == -2          # D % 4 != 0
+    csc = _lib.CscC(4, 4, 0, 0, 16, 16, 16, None)
+    assert lib.hsg_edge_fwd(ctypes.byref(csc), 7, 9, 16, 72, 16, None, 16, None, 16, None) == -2   # (7,9) not instantiated
+    assert lib.hsg_edge_bwd_workspace_bytes(8) > 0 and lib.hsg_gemm_tn_workspace_bytes(1000, 64, 64) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda():
+    m = hb.WSWGAT(300, 64, 8, 0.0, 512, 0.0, 50, "W2S")
+    batch = hb.HeteroBatch.from_csc_arrays(np.array([0, 1]), np.array([0]), np.array([3]), np.array([0]),
+                                           np.array([0, 1]), np.array([0]), np.array([3]), device="cpu")
+    batch.set_tfidf_embedding(torch.randn(10, 50))
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        m(batch, torch.randn(1, 300), torch.randn(1, 64))
+
+
+def test_state_dict_matches_reference_keys_and_round_trips():
+    z = dict(np.load(os.path.join(GOLD, "wswgat_hsg_default.npz")))
+    ref_sd = {k[2:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("p:")}
+    m = hb.WSWGATUpdateLoop()
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(ref_sd.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref_sd[k].shape), k
+    res = m.load_state_dict(ref_sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    # packed layout: head k occupies rows [k*d, (k+1)*d)
+    assert torch.equal(m.word2sent.layer.fc_weight[8:16], ref_sd["word2sent.layer.heads.1.fc.weight"])
+    assert torch.equal(m.sent2word.layer.attn_fc_weight[5:6], ref_sd["sent2word.layer.heads.5.attn_fc.weight"])
+    assert sum(p.numel() for p in m.word2sent.parameters()) == 88832
+    assert sum(p.numel() for p in m.sent2word.parameters()) == 344012
+    bad = dict(ref_sd)
+    bad.pop("word2sent.layer.heads.0.fc.weight")
+    with pytest.raises(RuntimeError):
+        hb.WSWGATUpdateLoop().load_state_dict(bad, strict=True)
+
+
+def test_reference_error_behaviour():
+    with pytest.raises(NotImplementedError, match="has not been implemented"):   # module/GAT.py:41
+        hb.WSWGAT(64, 64, 8, 0.1, 512, 0.1, 50, "X2Y")
+    m = hb.WSWGAT(300, 64, 8, 0.1, 512, 0.1, 50, "W2S").train()
+    batch = hb.HeteroBatch.from_csc_arrays(np.array([0, 1]), np.array([0]), np.array([3]), np.array([0]),
+                                           np.array([0, 1]), np.array([0]), np.array([3]), device="cpu")
+    batch.set_tfidf_embedding(torch.randn(10, 50))
+    with pytest.raises(NotImplementedError, match="dropout"):
+        m(batch, torch.randn(1, 300), torch.randn(1, 64))
+
+
+def test_generator_shapes_and_determinism():
+    a = syn.make_examples(4, "cnndm", seed=0)
+    b = syn.make_examples(4, "cnndm", seed=0)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.sents, y.sents) and x.w2s == y.w2s
+        assert 3 <= x.n_sent <= 50 and x.sents.shape[1] == 100
+        assert all(0.0 < v <= 1.0 for d in x.w2s for v in d.values())
+    tb = syn.pack_token_batch(a)
+    assert tb.tokens.dtype == np.int32 and tb.sent_bin.dtype == np.int8
+    assert tb.graph_sent_ptr[-1] == tb.tokens.shape[0]
+    lens = np.diff(tb.graph_sent_ptr)
+    assert np.all(lens[:-1] >= lens[1:])                  # sorted by #sentences, descending (dataloader.py:479)
+    assert tb.sent_bin.max() <= 9 and tb.sent_bin.min() >= -1
+    bm = syn.filter_bitmap()
+    assert (bm[0] & 1) == 1 and ((bm[0] >> 1) & 1) == 0   # PAD filtered, UNK kept (dataloader.py:171)
+    h = syn.make_examples(3, "multinews", seed=2, hdsg=True)
+    tbh = syn.pack_token_batch(h, hdsg=True)
+    assert tbh.graph_doc_ptr[-1] == len(tbh.doc_tok_ptr) - 1
+    assert len(tbh.sent_doc) == tbh.tokens.shape[0]
+
+
+def test_stress_edges_and_csc_pair():
+    word, sup, bins, extra = syn.stress_edges(4096, 512, 16384, seed=4)
+    assert len(word) == 16384 and sup.max() < 512 and word.max() < 4096 and bins.max() <= 9
+    (sip, ssrc, sbin, seid), (wip, wsrc, wbin, weid) = hb.csc_pair_from_edges(word, sup, bins, 4096, 512)
+    assert sip[-1] == 16384 and wip[-1] == 16384
+    assert np.array_equal(np.sort(seid), 2 * np.arange(16384))
+    # twins: pair t = (word, sup) appears in both CSCs
+    t = seid // 2
+    assert np.array_equal(ssrc, word[t]) and np.array_equal(wsrc, sup[weid // 2])
