@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py - HSG WSWGAT-path training throughput (graphs/s, fwd+bwd) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # sm_100a path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port of the DGL path)
+
+One "step" = one pass of the hot path over one batch: device-side graph build (K0) from token arrays,
+word-embedding lookup, WSWGAT update loop forward (W2S, n_iter x (S2W, W2S)), classifier + the
+reference's loss (train.py:114-119), backward, (N>1: one NCCL all-reduce of the flat gradient), fused
+Adam step.  The sentence encoder (CNN+BiLSTM, out of the hot-path scope) is replaced by a fixed
+random `sent_feature` input.  Workload at N=1: BASELINE.json configs[1] - 32 CNN/DM-shaped graphs,
+HSG, n_iter=1, seed 0.  For N>1 every rank gets its own 32-graph shard (weak scaling, sharded by graph).
+Dropout is 0 in both arms (parity mode, the reference's semantics are defined deterministically there).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (shape, hdsg, n_iter, seed, BASELINE.json config index)
+    "cnndm": ("cnndm", False, 1, 0, 1),
+    "nyt50": ("nyt50", False, 3, 1, 2),
+    "multinews": ("multinews", True, 1, 2, 3),
+}
+UNIT = "graphs/s"
+METRIC = "HSG train graphs/sec (fwd+bwd), WSWGAT path"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cnndm", choices=list(WORKLOADS))
+    ap.add_argument("--graphs-per-gpu", type=int, default=32)
+    ap.add_argument("--no-stress", action="store_true", help="skip the stress-graph edge-kernel roofline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+def make_workload(args, rank):
+    from hetersumgraph_b200 import synthetic as syn
+    shape, hdsg, n_iter, seed, cfg_idx = WORKLOADS[args.workload]
+    exs = syn.make_examples(args.graphs_per_gpu, shape, seed=seed + 1000 * rank, hdsg=hdsg)
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    return exs, tb, hdsg, n_iter, cfg_idx
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's CPU path (per head, degree-bucketed like DGL 0.4)
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, exs, tb, hdsg, n_iter, closed_form=False):
+        from hetersumgraph_b200 import synthetic as syn
+        from hetersumgraph_b200.path_model import HSGPath
+        from oracle import graph_builder_ref as gb
+        self.closed_form = closed_form
+        filt = set(syn.filter_ids().tolist())
+        t0 = time.time()
+        if hdsg:
+            graphs = [gb.create_graph_hdsg(e.doc_len, e.sents.tolist(), e.doc_tokens, e.w2s, e.w2d, filt) for e in exs]
+        else:
+            graphs = [gb.create_graph_hsg(e.sents.tolist(), e.w2s, filt) for e in exs]
+        self.g, _ = gb.collate(graphs, order=tb.order)
+        self.builder_s = time.time() - t0
+        self.csc = gb.derive_csc(self.g)
+        torch.manual_seed(1234)
+        m = HSGPath(n_iter=n_iter, hdsg=False)
+        self.params = {k[len("loop."):]: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()
+                       if k.startswith("loop.")}
+        self.wh_w = m.wh.weight.detach().clone().requires_grad_(True)
+        self.wh_b = m.wh.bias.detach().clone().requires_grad_(True)
+        self.embed = m._embed.weight.detach().clone()
+        self.n_iter = n_iter
+        self.wid = torch.from_numpy(self.g.wid[self.csc["wnode_id"]])
+        ns = int((self.g.unit == 1).sum())
+        gen = torch.Generator().manual_seed(7)
+        self.sent_feature = torch.randn(ns, 64, generator=gen).requires_grad_(True)
+        self.sent_rows = torch.from_numpy(np.nonzero(self.g.ndtype[self.csc["snode_id"]] == 1)[0])
+        self.labels = torch.from_numpy(tb.labels)
+        self.n_graphs = tb.n_graphs
+        self.opt = torch.optim.Adam(list(self.params.values()) + [self.wh_w, self.wh_b], lr=5e-4)
+
+    def step(self):
+        from oracle import closed_form as cf
+        from oracle import wswgat_ref as wr
+        self.opt.zero_grad(set_to_none=True)
+        self.sent_feature.grad = None
+        wfeat = self.embed[self.wid]
+        if self.closed_form:
+            _, ss = cf.update_loop_cf(self.csc, wfeat, self.sent_feature, self.params, self.n_iter)
+        else:
+            _, ss = wr.update_loop(self.g, wfeat, self.sent_feature, self.params, self.n_iter)
+        logits = ss[self.sent_rows] @ self.wh_w.t() + self.wh_b
+        loss = torch.nn.functional.cross_entropy(logits, self.labels, reduction="sum") / self.n_graphs
+        loss.backward()
+        self.opt.step()
+        return float(loss)
+
+
+def time_cpu(ref, steps, warmup):
+    for _ in range(warmup):
+        ref.step()
+    t0 = time.time()
+    for _ in range(steps):
+        ref.step()
+    return (time.time() - t0) / max(steps, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    exs, tb, hdsg, n_iter, cfg_idx = make_workload(args, 0)
+    ref = CpuReference(exs, tb, hdsg, n_iter)
+    sec = time_cpu(ref, args.steps, args.warmup)
+    value = tb.n_graphs / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": tb.n_graphs, "n_iter": n_iter,
+                   "dropout": 0.0},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "the whole %d-graph batch per step (graph prebuilt; reference CreateGraph restatement took %.2f s once)"
+                                   % (tb.n_graphs, ref.builder_s),
+                         "what": "oracle/wswgat_ref.py: the reference's per-head, degree-bucketed DGL-0.4 execution restated on torch CPU (real DGL not installable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args, cfg_idx):
+    return ("BASELINE.json configs[%d]: HSG WSWGAT update loop fwd+bwd, %d %s-shaped graphs per GPU, seed-0 synthetic "
+            "tokens, random-init embeddings, sentence-encoder output replaced by a fixed random sent_feature"
+            % (cfg_idx, args.graphs_per_gpu, args.workload))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import hetersumgraph_b200 as hb
+    from hetersumgraph_b200 import _lib, accounting
+    from hetersumgraph_b200.graph import DeviceTokenBatch, HeteroBatch
+    from hetersumgraph_b200.path_model import HSGPath, graph_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    lib = _lib.load()
+    pk = peaks()
+
+    exs, tb, hdsg, n_iter, cfg_idx = make_workload(args, rank)
+    n_graphs_global = tb.n_graphs * world
+    torch.manual_seed(1234)
+    model = HSGPath(n_iter=n_iter, hdsg=hdsg).to(dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)          # contiguous gradient arena
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+
+    host, h2d_tok_bytes = DeviceTokenBatch.host_buffers(tb)
+    bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
+    dtb = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
+    n_sent_rows = int(tb.tokens.shape[0])
+    gen = torch.Generator().manual_seed(7 + rank)
+    sf_host = torch.randn(n_sent_rows, 64, generator=gen).pin_memory()
+    sf_dev = sf_host.to(dev)
+
+    def compute(dtb_, sf):
+        batch = HeteroBatch.build(dtb_)
+        sf = sf.detach().requires_grad_(True)
+        logits = model(batch, sf)
+        loss = graph_loss(batch, logits, batch.labels, n_graphs_global)
+        flat.zero_()
+        loss.backward()
+        if dist is not None:
+            dist.all_reduce(flat)
+        opt.step()
+        return loss, batch
+
+    def step_resident():
+        return compute(dtb, sf_dev)
+
+    def step_e2e():
+        d = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
+        sf = sf_host.to(dev, non_blocking=True)
+        loss, batch = compute(d, sf)
+        return float(loss), batch            # D2H read of the step's result
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)           # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = lib.hsg_launch_count()
+        for a, b in evs:
+            flush.zero_()                                                    # L2 flush, outside the timed events
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        launches = lib.hsg_launch_count() - l0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, launches // steps
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
+    _, batch = step_resident()
+    torch.cuda.synchronize()
+    lib.hsg_profile_reset()
+    lib.hsg_profile_enable(1)
+    for _ in range(args.steps):
+        flush.zero_()
+        step_resident()
+    torch.cuda.synchronize()
+    lib.hsg_profile_enable(0)
+    prof = _lib.profile_snapshot()
+    acct = accounting.step_accounting(batch.n_word, batch.n_super, batch.n_pair, n_iter)
+    kernels = []
+    for name, (cnt, ms) in prof.items():
+        per_step_ms = ms / args.steps
+        fl, by, _n = acct.get(name, (0, 0, 0))
+        row = {"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_step": per_step_ms,
+               "share": None, "flops": fl, "bytes": by}
+        if fl > 0:
+            row.update(bound="tensor", achieved=fl / (per_step_ms * 1e-3) / 1e12, peak=pk["tf"], unit="TFLOP/s")
+        elif by > 0:
+            row.update(bound="hbm", achieved=by / (per_step_ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
+        if "achieved" in row:
+            row["frac"] = row["achieved"] / row["peak"]
+        kernels.append(row)
+    tot = sum(k["ms_per_step"] for k in kernels) or 1.0
+    for k in kernels:
+        k["share"] = k["ms_per_step"] / tot
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    dom = next((k for k in kernels if "achieved" in k), None)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom["kernel"])
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "peak_source": pk["src"],
+                    "share_of_kernel_time": dom["share"], "launches_per_step": dom["launches_per_step"]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    stress = None
+    if not args.no_stress and world == 1:
+        stress = stress_leg(dev, pk)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = CpuReference(exs, tb, hdsg, n_iter)
+        sec = time_cpu(ref, args.cpu_steps, 1)
+        cpu = {"value": tb.n_graphs / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "the whole %d-graph batch, %d timed steps after 1 warm-up (%.2f s/step); graph prebuilt "
+                         "(reference CreateGraph restatement: %.2f s once)" % (tb.n_graphs, args.cpu_steps, sec, ref.builder_s)}
+        refc = CpuReference(exs, tb, hdsg, n_iter, closed_form=True)
+        secc = time_cpu(refc, args.cpu_steps, 1)
+        cpu["closed_form_graphs_per_s"] = tb.n_graphs / secc
+
+    line = {
+        "metric": METRIC, "value": n_graphs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": n_graphs_global, "n_iter": n_iter,
+                   "dropout": 0.0, "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "rank0_sizes": {"word_nodes": batch.n_word, "supernodes": batch.n_super, "pairs_per_direction": batch.n_pair,
+                                   "dgl_edges": batch.n_total_edges},
+                   "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3)},
+        "e2e": {"value": n_graphs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 24},
+        "gpu_launches": int(launches),
+        "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def stress_leg(dev, pk, scale=4, iters=20):
+    """Edge kernels on the stress graph of SURVEY §8-d (x`scale`: working set > L2), timed alone with CUDA events."""
+    import ctypes as C
+
+    import hetersumgraph_b200 as hb
+    from hetersumgraph_b200 import _lib, accounting
+    from hetersumgraph_b200 import synthetic as syn
+    from hetersumgraph_b200.functional import _Workspace, round_up
+    lib = _lib.load()
+    n_word, n_super, n_edges = 262144 * scale, 32768 * scale, 1048576 * scale
+    word, sup, bins, extra = syn.stress_edges(n_word, n_super, n_edges, seed=4, extra=64)
+    (sip, ssrc, sbin, _), (wip, wsrc, wbin, _) = hb.csc_pair_from_edges(word, sup, bins, n_word, n_super)
+    batch = hb.HeteroBatch.from_csc_arrays(sip, ssrc, sbin, extra, wip, wsrc, wbin, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for kind, H, d in (("W2S", 8, 8), ("S2W", 6, 50)):
+        csc, csc_t = batch.csc(kind)
+        F = H * d
+        ldz = round_up(F + H, 8)
+        zp = torch.randn(csc.n_src, ldz, device=dev)
+        q = torch.randn(10, H, device=dev)
+        origin = torch.randn(csc.n_dst, F, device=dev)
+        sh = torch.empty(csc.n_dst, F, device=dev)
+        x = torch.empty(csc.n_dst, F, device=dev)
+        stat = torch.empty(csc.n_dst, 3 * H, device=dev)
+        g = torch.empty(csc.n_dst, F, device=dev)
+        dzp = torch.empty(csc.n_src, ldz, device=dev)
+        dq = torch.empty(10, H, device=dev)
+        ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
+
+        def fwd():
+            _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(),
+                                        sh.data_ptr(), x.data_ptr(), stat.data_ptr(), st))
+
+        def prep():
+            _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None, sh.data_ptr(), g.data_ptr(),
+                                             stat.data_ptr(), st))
+
+        def bwd():
+            _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(), g.data_ptr(),
+                                        stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+        nb = {"edge_fwd": accounting.edge_fwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d),
+              "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
+              "edge_bwd": accounting.edge_bwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d)}
+        for name, fn in (("edge_fwd", fwd), ("edge_bwd_prep", prep), ("edge_bwd", bwd)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            gbs = nb[name] / (ms * 1e-3) / 1e9
+            out.append({"kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": n_edges, "n_src": csc.n_src,
+                        "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6, "GBps": gbs,
+                        "frac_of_hbm_peak": gbs / pk["hbm"], "working_set_gt_L2": True})
+        del zp, origin, sh, x, g, dzp
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -166,13 +166,14 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
       const float mn = fmaxf(m, m2);
       const float s1 = (m == -CUDART_INF_F) ? 0.f : __expf(m - mn);
       const float s2 = (m2 == -CUDART_INF_F) ? 0.f : __expf(m2 - mn);
-      den = den * s1 + d2 * s2;
+      // only group 0 accumulates: the other groups must keep their own partial state for later reads
+      if (grp == 0) den = den * s1 + d2 * s2;
 #pragma unroll
       for (int i = 0; i < C::NE; ++i) {
         const float a2 = __shfl_sync(0xffffffffu, acc[i], src);
-        acc[i] = acc[i] * s1 + a2 * s2;
+        if (grp == 0) acc[i] = acc[i] * s1 + a2 * s2;
       }
-      m = mn;
+      if (grp == 0) m = mn;
     }
     if (grp == 0) {
       float mf, inv;
@@ -347,9 +348,13 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
 #pragma unroll
     for (int g2 = 1; g2 < C::EPS; ++g2) {
       const int src = (gl + g2 * C::GROUP) & 31;
-      acc_dp += __shfl_sync(0xffffffffu, acc_dp, src);
+      const float dp2 = __shfl_sync(0xffffffffu, acc_dp, src);
+      if (grp == 0) acc_dp += dp2;     // only group 0 accumulates (others keep their partials intact)
 #pragma unroll
-      for (int i = 0; i < C::NE; ++i) acc[i] += __shfl_sync(0xffffffffu, acc[i], src);
+      for (int i = 0; i < C::NE; ++i) {
+        const float a2 = __shfl_sync(0xffffffffu, acc[i], src);
+        if (grp == 0) acc[i] += a2;
+      }
     }
     float* drow = dzp + (size_t)u * ldz;
     if (grp == 0) {

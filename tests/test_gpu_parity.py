@@ -133,8 +133,8 @@ def test_ffn_matches_torch(N, D, Dh):
     c = torch.randn(N, D)
 
     def run(dev, fn):
-        xs = x.to(dev).requires_grad_(True)
-        pp = [p.to(dev).requires_grad_(True) for p in ps]
+        xs = x.clone().to(dev).detach().requires_grad_(True)
+        pp = [p.clone().to(dev).detach().requires_grad_(True) for p in ps]
         out = fn(xs, *pp)
         (out * c.to(dev)).sum().backward()
         return [out, xs.grad] + [p.grad for p in pp]
@@ -211,7 +211,7 @@ def test_bitwise_determinism():
         w = torch.from_numpy(z["in_w"]).cuda().requires_grad_(True)
         s = torch.from_numpy(z["in_s"]).cuda().requires_grad_(True)
         ws, ss = m(batch, w, s)
-        (ws.sum() + (ss * ss).sum()).backward()
+        ((ws * ws).sum() + (ss * ss * ss).sum()).backward()
         outs.append([ws, ss, w.grad, s.grad] + [p.grad.clone() for p in m.parameters()])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
@@ -232,12 +232,13 @@ def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed):
     m = m.cuda()
     w = torch.randn(batch.n_word, 300)
     s = torch.randn(batch.n_super, 64)
+    cw, cs = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)      # random cotangents
     wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
     ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter)
-    (ow.sum() + (os_ * os_).sum()).backward()
+    ((ow * cw).sum() + (os_ * cs).sum()).backward()
     wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
     gw, gs = m(batch, wg, sg)
-    (gw.sum() + (gs * gs).sum()).backward()
+    ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
     assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
     assert nerr(wg.grad, wc.grad) <= TOL and nerr(sg.grad, sc.grad) <= TOL
     assert nerr(m._TFembed.weight.grad, params["_TFembed.weight"].grad) <= TOL
