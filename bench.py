@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-graph edge-kernel roofline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--stress-only", action="store_true", help="run only the stress-graph edge-kernel leg (for ncu)")
+    ap.add_argument("--stress-scale", type=int, default=4)
+    ap.add_argument("--stress-iters", type=int, default=20)
     return ap.parse_args()
 
 
@@ -356,7 +359,7 @@ def run_ours(args):
 
     stress = None
     if not args.no_stress and world == 1:
-        stress = stress_leg(dev, pk)
+        stress = stress_leg(dev, pk, args.stress_scale, args.stress_iters)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -407,14 +410,14 @@ def stress_leg(dev, pk, scale=4, iters=20):
     for kind, H, d in (("W2S", 8, 8), ("S2W", 6, 50)):
         csc, csc_t = batch.csc(kind)
         F = H * d
-        ldz = round_up(F + H, 8)
+        fp, ldz = _lib.edge_layout(H, d)
         zp = torch.randn(csc.n_src, ldz, device=dev)
         q = torch.randn(10, H, device=dev)
         origin = torch.randn(csc.n_dst, F, device=dev)
         sh = torch.empty(csc.n_dst, F, device=dev)
         x = torch.empty(csc.n_dst, F, device=dev)
         stat = torch.empty(csc.n_dst, 3 * H, device=dev)
-        g = torch.empty(csc.n_dst, F, device=dev)
+        g = torch.empty(csc.n_dst, fp, device=dev)
         dzp = torch.empty(csc.n_src, ldz, device=dev)
         dq = torch.empty(10, H, device=dev)
         ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
@@ -455,7 +458,10 @@ def stress_leg(dev, pk, scale=4, iters=20):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.stress_only:
+        torch.cuda.set_device(0)
+        print(json.dumps({"edge_kernels_stress": stress_leg(torch.device("cuda", 0), peaks(), a.stress_scale, a.stress_iters)}))
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

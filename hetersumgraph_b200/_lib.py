@@ -62,10 +62,14 @@ _PROTOS = {
     "hsg_build_fill": (C.c_int, [C.POINTER(TokenBatchC), C.POINTER(GraphOutC), _P, _Z, _P]),
     "hsg_attn_prep_fwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hsg_attn_prep_bwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_set_gemm_mode": (C.c_int, [_I]),
+    "hsg_get_gemm_mode": (C.c_int, []),
     "hsg_gemm_nt": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
     "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
     "hsg_gemm_tn_workspace_bytes": (_Z, [_I, _I, _I]),
     "hsg_gemm_tn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _Z, _P]),
+    "hsg_edge_layout": (C.c_int, [_I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hsg_edge_perm": (C.c_int, [_I, _I, _I]),
     "hsg_edge_fwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd_prep": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd_workspace_bytes": (_Z, [_I]),
@@ -121,6 +125,32 @@ def require_device():
         raise RuntimeError("hsg_b200: no CUDA device - the WSWGAT path runs only on B200 (sm_100a), no CPU fallback")
     check(load().hsg_device_check())
     _DEVICE_OK = True
+
+
+GEMM_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
+
+def set_gemm_mode(mode):
+    """'fp32' (FFMA), 'tf32x3' (tcgen05, fp32-parity, default) or 'tf32' (tcgen05, single pass)."""
+    check(load().hsg_set_gemm_mode(GEMM_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+
+def get_gemm_mode():
+    inv = {v: k for k, v in GEMM_MODES.items()}
+    return inv[load().hsg_get_gemm_mode()]
+
+
+_LAYOUTS = {}
+
+
+def edge_layout(H, d):
+    """(fp, ldz) of the lane-interleaved gathered-row layout for (heads, head_dim)."""
+    key = (H, d)
+    if key not in _LAYOUTS:
+        fp, ldz = C.c_int(0), C.c_int(0)
+        check(load().hsg_edge_layout(H, d, C.byref(fp), C.byref(ldz)))
+        _LAYOUTS[key] = (fp.value, ldz.value)
+    return _LAYOUTS[key]
 
 
 def profile_snapshot():

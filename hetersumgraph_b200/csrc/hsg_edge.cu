@@ -7,18 +7,24 @@
 //     alpha = softmax over ALL in-edges of v (extra[v] never-written edges: e = 0, z = 0)
 //     sh_v  = sum alpha z_u ;   x_v = elu(sh_v) + origin_v          (GAT.py:56-57)
 //
-// Mapping (compile-time per (H, D)): one warp walks the in-edge list of one
-// destination row.  A row of F = H*D floats is spread over GROUP = H*LPH lanes so
-// that EVERY LANE OWNS ELEMENTS OF EXACTLY ONE HEAD: the attention logit, the
-// online-softmax state (m, den) and the weight alpha are per-lane scalars, there
-// is no cross-lane traffic inside the edge loop of the forward pass, and the
-// per-edge dot product of the backward pass is an LPH-lane reduction.  When a row
-// needs fewer than 32 lanes, EPS = 32/GROUP edges are processed per warp step.
-// Source rows are gathered with 128-bit (64-bit when D % 4 != 0) loads.
+// Mapping (compile-time per (H, D), see hsg_edge_layout.cuh): one warp walks the in-edge list of
+// one destination row.  A row is spread over GROUP = H*LPH lanes so that EVERY LANE OWNS ELEMENTS
+// OF EXACTLY ONE HEAD: the attention logit, the online-softmax state (m, den) and the weight alpha
+// are per-lane scalars, the forward edge loop has no cross-lane reduction, and the per-edge dot
+// product of the backward pass is an LPH-lane reduction.  EPS = 32/GROUP edge rows per warp step.
+// Memory behaviour:
+//   * gathered tensors (zp, g) are stored lane-interleaved, so each gather instruction of a warp
+//     reads one contiguous slab (128-bit per lane, 64-bit when D % 4 != 0);
+//   * the neighbour ids / bins of up to 32 edges are fetched with ONE coalesced load and
+//     broadcast by shuffle; U edge rows per group are gathered back-to-back before any of them
+//     is consumed (memory-level parallelism), and the next row's indptr is prefetched;
+//   * destination-side streams (origin, sh, x, dx) use 128-bit coalesced accesses, staged through
+//     shared memory when the lane layout is not contiguous (VPL > 1).
 // Everything is deterministic: no floating-point atomics anywhere.
 #include <math_constants.h>
 
 #include "hsg_common.cuh"
+#include "hsg_edge_layout.cuh"
 
 namespace hsg {
 
@@ -33,7 +39,11 @@ struct EdgeCfg {
   static constexpr int GROUP = H_ * LPH;                    // lanes per edge row
   static constexpr int EPS = 32 / GROUP;                    // edge rows per warp step
   static constexpr int NE = VPL * VEC;                      // elements per lane
+  static constexpr int FP = VPL * GROUP * VEC;              // permuted row width
+  static constexpr int U = NE <= 4 ? 4 : 2;                 // edge rows in flight per group
+  static constexpr bool STAGED = VPL > 1;                   // lane layout != row layout -> smem staging
   static_assert(H_ <= 32 && LPH >= 1 && EPS >= 1, "bad edge config");
+  static_assert(!STAGED || (EPS == 1 && F % 4 == 0), "staged epilogue assumes one row per warp step");
 };
 
 template <int VEC>
@@ -93,10 +103,12 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
                 float* __restrict__ x, float* __restrict__ stat) {
   using C = EdgeCfg<H, D>;
   __shared__ float q_s[HSG_N_BINS * H];
+  __shared__ __align__(16) float stage[C::STAGED ? EDGE_WARPS * C::F : 4];
   for (int i = threadIdx.x; i < HSG_N_BINS * H; i += blockDim.x) q_s[i] = q[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int grp = lane / C::GROUP;
@@ -105,56 +117,70 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
   const int l = gl % C::LPH;
   const bool lane_on = grp < C::EPS;
 
-  for (int v = warp; v < n_dst; v += nwarps) {
-    const int beg = __ldg(indptr + v), end = __ldg(indptr + v + 1);
+  int v = warp;
+  int beg = 0, end = 0;
+  if (v < n_dst) {
+    beg = __ldg(indptr + v);
+    end = __ldg(indptr + v + 1);
+  }
+  while (v < n_dst) {
+    const int vn = v + nwarps;
+    int begn = 0, endn = 0;
+    if (vn < n_dst) {                                   // prefetch the next row's extent
+      begn = __ldg(indptr + vn);
+      endn = __ldg(indptr + vn + 1);
+    }
     const float xcnt = extra ? (float)__ldg(extra + v) : 0.f;
     float m = -CUDART_INF_F, den = 0.f;
     float acc[C::NE];
 #pragma unroll
     for (int i = 0; i < C::NE; ++i) acc[i] = 0.f;
 
-    if (lane_on) {
-      int e = beg + grp;
-      int u = 0, b = 0;
-      if (e < end) {
-        u = __ldg(nbr + e);
-        b = __ldg(bin + e);
+    for (int c0 = beg; c0 < end; c0 += 32) {
+      const int cnt = min(32, end - c0);
+      int my_u = 0, my_b = 0;
+      if (lane < cnt) {                                 // one coalesced fetch of up to 32 neighbour ids / bins
+        my_u = __ldg(nbr + c0 + lane);
+        my_b = __ldg(bin + c0 + lane);
       }
-      while (e < end) {
-        const int en = e + C::EPS;
-        int un = 0, bn = 0;
-        if (en < end) {
-          un = __ldg(nbr + en);
-          bn = __ldg(bin + en);
-        }
-        const float* row = zp + (size_t)u * ldz;
-        const float pe = __ldg(row + C::F + k);
-        float zv[C::NE];
+      for (int j0 = 0; j0 < cnt; j0 += C::EPS * C::U) {  // warp-uniform trip count
+        float zv[C::U][C::NE], pe[C::U];
+        int bb[C::U];
+        bool ok[C::U];
 #pragma unroll
-        for (int i = 0; i < C::VPL; ++i) {
-          const int nv = l + C::LPH * i;
-          if (nv < C::NV) {
-            ld_vec<C::VEC>(row + k * D + C::VEC * nv, zv + i * C::VEC);
-          } else {
+        for (int uu = 0; uu < C::U; ++uu) {             // issue all gathers first
+          const int j = j0 + uu * C::EPS + grp;
+          const int u = __shfl_sync(0xffffffffu, my_u, j & 31);
+          bb[uu] = __shfl_sync(0xffffffffu, my_b, j & 31);
+          ok[uu] = lane_on && j < cnt;
+          pe[uu] = 0.f;
 #pragma unroll
-            for (int t = 0; t < C::VEC; ++t) zv[i * C::VEC + t] = 0.f;
+          for (int i = 0; i < C::NE; ++i) zv[uu][i] = 0.f;
+          if (ok[uu]) {
+            const float* row = zp + (size_t)u * ldz;
+            pe[uu] = __ldg(row + C::FP + k);
+#pragma unroll
+            for (int i = 0; i < C::VPL; ++i)
+              if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(row + (i * C::GROUP + gl) * C::VEC, zv[uu] + i * C::VEC);
           }
         }
-        const float lg = leaky(pe + q_s[b * H + k]);
-        if (lg > m) {
-          const float sc = __expf(m - lg);
-          den *= sc;
 #pragma unroll
-          for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
-          m = lg;
+        for (int uu = 0; uu < C::U; ++uu) {             // then consume them (online softmax)
+          if (ok[uu]) {
+            const float lg = leaky(pe[uu] + q_s[bb[uu] * H + k]);
+            if (lg > m) {
+              const float sc = __expf(m - lg);
+              den *= sc;
+#pragma unroll
+              for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
+              m = lg;
+            }
+            const float w = __expf(lg - m);
+            den += w;
+#pragma unroll
+            for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
+          }
         }
-        const float w = __expf(lg - m);
-        den += w;
-#pragma unroll
-        for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[i], acc[i]);
-        e = en;
-        u = un;
-        b = bn;
       }
     }
     // merge the EPS partial states into group 0 (fixed order)
@@ -175,54 +201,81 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
       }
       if (grp == 0) m = mn;
     }
-    if (grp == 0) {
-      float mf, inv;
-      if (m == -CUDART_INF_F) {  // no word<->supernode in-edge: DGL's zero fill (or softmax over z = 0 extras)
-        mf = 0.f;
-        den = xcnt > 0.f ? xcnt : 1.f;
-        inv = 0.f;
-      } else {
-        mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
-        const float sc = __expf(m - mf);
-        den = den * sc + xcnt * __expf(-mf);
-        inv = sc / den;
+    float mf = 0.f, inv = 0.f;
+    if (m == -CUDART_INF_F) {  // no word<->supernode in-edge: DGL's zero fill (or softmax over z = 0 extras)
+      den = xcnt > 0.f ? xcnt : 1.f;
+    } else {
+      mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
+      const float sc = __expf(m - mf);
+      den = den * sc + xcnt * __expf(-mf);
+      inv = sc / den;
+    }
+    if (grp == 0 && l == 0) {
+      stat[(size_t)v * 3 * H + k] = mf;
+      stat[(size_t)v * 3 * H + H + k] = den;
+    }
+    if (!C::STAGED) {
+      if (grp == 0) {                                   // lane layout == row layout: direct 128-bit stores
+        const size_t off = (size_t)v * C::F + gl * C::VEC;
+        float o[C::VEC];
+#pragma unroll
+        for (int t = 0; t < C::VEC; ++t) o[t] = acc[t] * inv;
+        st_vec<C::VEC>(sh + off, o);
+        if (x != nullptr) {
+          float og[C::VEC];
+          ld_vec<C::VEC>(origin + off, og);
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) og[t] += (o[t] > 0.f ? o[t] : expm1f(o[t]));
+          st_vec<C::VEC>(x + off, og);
+        }
       }
-      float* sh_row = sh + (size_t)v * C::F;
+    } else {
+      float* st_row = stage + wib * C::F;
+      if (lane_on) {
 #pragma unroll
-      for (int i = 0; i < C::VPL; ++i) {
-        const int nv = l + C::LPH * i;
-        if (nv < C::NV) {
-          const int col = k * D + C::VEC * nv;
-          float o[C::VEC];
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i < C::NV) {
+            float o[C::VEC];
 #pragma unroll
-          for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
-          st_vec<C::VEC>(sh_row + col, o);
-          if (x != nullptr) {
-            float og[C::VEC];
-            ld_vec<C::VEC>(origin + (size_t)v * C::F + col, og);
-#pragma unroll
-            for (int t = 0; t < C::VEC; ++t) og[t] += (o[t] > 0.f ? o[t] : expm1f(o[t]));
-            st_vec<C::VEC>(x + (size_t)v * C::F + col, og);
+            for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
+            st_vec<C::VEC>(st_row + k * D + C::VEC * (l + C::LPH * i), o);
           }
         }
       }
-      if (l == 0) {
-        stat[(size_t)v * 3 * H + k] = mf;
-        stat[(size_t)v * 3 * H + H + k] = den;
+      __syncwarp();
+      for (int c4 = lane; c4 < C::F / 4; c4 += 32) {     // coalesced 128-bit row stores
+        const float4 o = *reinterpret_cast<const float4*>(st_row + 4 * c4);
+        const size_t off = (size_t)v * C::F + 4 * c4;
+        *reinterpret_cast<float4*>(sh + off) = o;
+        if (x != nullptr) {
+          float4 og = __ldg(reinterpret_cast<const float4*>(origin + off));
+          og.x += (o.x > 0.f ? o.x : expm1f(o.x));
+          og.y += (o.y > 0.f ? o.y : expm1f(o.y));
+          og.z += (o.z > 0.f ? o.z : expm1f(o.z));
+          og.w += (o.w > 0.f ? o.w : expm1f(o.w));
+          *reinterpret_cast<float4*>(x + off) = og;
+        }
       }
+      __syncwarp();
     }
+    v = vn;
+    beg = begn;
+    end = endn;
   }
 }
 
 // ---------------------------------------------------------------------------
-// backward prep: g = dx * elu'(sh)  (or g = dsh), s[v,k] = g_v[k] . sh_v[k]
+// backward prep: g = dx * elu'(sh)  (or g = dsh) written lane-interleaved [n_dst, FP],
+//                s[v,k] = g_v[k] . sh_v[k]
 // ---------------------------------------------------------------------------
 template <int H, int D>
 __global__ void __launch_bounds__(EDGE_THREADS)
 edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __restrict__ dsh,
                      const float* __restrict__ sh, float* __restrict__ g, float* __restrict__ stat) {
   using C = EdgeCfg<H, D>;
+  __shared__ __align__(16) float stage[C::STAGED ? 2 * EDGE_WARPS * C::F : 4];
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int grp = lane / C::GROUP;
@@ -234,29 +287,69 @@ edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __res
     const int v = st * C::EPS + grp;
     const bool on = grp < C::EPS && v < n_dst;
     float part = 0.f;
-    if (on) {
+    float gv[C::NE];
 #pragma unroll
-      for (int i = 0; i < C::VPL; ++i) {
-        const int nv = l + C::LPH * i;
-        if (nv < C::NV) {
-          const size_t off = (size_t)v * C::F + k * D + C::VEC * nv;
-          float s_[C::VEC], d_[C::VEC];
-          ld_vec<C::VEC>(sh + off, s_);
+    for (int i = 0; i < C::NE; ++i) gv[i] = 0.f;
+    if (!C::STAGED) {
+      if (on) {
+        const size_t off = (size_t)v * C::F + gl * C::VEC;
+        float s_[C::VEC];
+        ld_vec<C::VEC>(sh + off, s_);
+        if (dx != nullptr) {
+          ld_vec<C::VEC>(dx + off, gv);
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) gv[t] *= (s_[t] > 0.f ? 1.f : __expf(s_[t]));
+        } else {
+          ld_vec<C::VEC>(dsh + off, gv);
+        }
+#pragma unroll
+        for (int t = 0; t < C::VEC; ++t) part = fmaf(gv[t], s_[t], part);
+      }
+    } else {
+      float* g_row = stage + (2 * wib) * C::F;
+      float* s_row = stage + (2 * wib + 1) * C::F;
+      const int vr = st;                                 // EPS == 1: the whole warp streams row `st`, 128-bit
+      if (vr < n_dst) {
+        for (int c4 = lane; c4 < C::F / 4; c4 += 32) {
+          const size_t off = (size_t)vr * C::F + 4 * c4;
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sh + off));
+          float4 g4;
           if (dx != nullptr) {
-            ld_vec<C::VEC>(dx + off, d_);
-#pragma unroll
-            for (int t = 0; t < C::VEC; ++t) d_[t] *= (s_[t] > 0.f ? 1.f : __expf(s_[t]));
+            g4 = __ldg(reinterpret_cast<const float4*>(dx + off));
+            g4.x *= (s4.x > 0.f ? 1.f : __expf(s4.x));
+            g4.y *= (s4.y > 0.f ? 1.f : __expf(s4.y));
+            g4.z *= (s4.z > 0.f ? 1.f : __expf(s4.z));
+            g4.w *= (s4.w > 0.f ? 1.f : __expf(s4.w));
           } else {
-            ld_vec<C::VEC>(dsh + off, d_);
+            g4 = __ldg(reinterpret_cast<const float4*>(dsh + off));
           }
-#pragma unroll
-          for (int t = 0; t < C::VEC; ++t) part = fmaf(d_[t], s_[t], part);
-          st_vec<C::VEC>(g + off, d_);
+          *reinterpret_cast<float4*>(g_row + 4 * c4) = g4;
+          *reinterpret_cast<float4*>(s_row + 4 * c4) = s4;
         }
       }
+      __syncwarp();
+      if (on) {
+#pragma unroll
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i < C::NV) {
+            const int col = k * D + C::VEC * (l + C::LPH * i);
+#pragma unroll
+            for (int t = 0; t < C::VEC; ++t) {
+              gv[i * C::VEC + t] = g_row[col + t];
+              part = fmaf(g_row[col + t], s_row[col + t], part);
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
     const float s = head_sum<C::LPH>(part, lane, l);
-    if (on && l == 0) stat[(size_t)v * 3 * H + 2 * H + k] = s;
+    if (on) {
+      float* out = g + (size_t)v * C::FP;
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) st_vec<C::VEC>(out + (i * C::GROUP + gl) * C::VEC, gv + i * C::VEC);
+      if (l == 0) stat[(size_t)v * 3 * H + 2 * H + k] = s;
+    }
   }
 }
 
@@ -286,10 +379,21 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
   const int k = gl / C::LPH;
   const int l = gl % C::LPH;
   const bool lane_on = grp < C::EPS;
-  float* my_dq = lane_on ? &dq_s[wib][grp][0] : nullptr;
+  float* my_dq = &dq_s[wib][lane_on ? grp : 0][0];
 
-  for (int u = warp; u < n_src; u += nwarps) {
-    const int beg = __ldg(indptr + u), end = __ldg(indptr + u + 1);
+  int u = warp;
+  int beg = 0, end = 0;
+  if (u < n_src) {
+    beg = __ldg(indptr + u);
+    end = __ldg(indptr + u + 1);
+  }
+  while (u < n_src) {
+    const int un = u + nwarps;
+    int begn = 0, endn = 0;
+    if (un < n_src) {
+      begn = __ldg(indptr + un);
+      endn = __ldg(indptr + un + 1);
+    }
     const float* zrow = zp + (size_t)u * ldz;
     float zv[C::NE], acc[C::NE];
     float pu = 0.f, acc_dp = 0.f;
@@ -299,49 +403,62 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
       acc[i] = 0.f;
     }
     if (lane_on && end > beg) {
-      pu = __ldg(zrow + C::F + k);
+      pu = __ldg(zrow + C::FP + k);
 #pragma unroll
-      for (int i = 0; i < C::VPL; ++i) {
-        const int nv = l + C::LPH * i;
-        if (nv < C::NV) ld_vec<C::VEC>(zrow + k * D + C::VEC * nv, zv + i * C::VEC);
-      }
+      for (int i = 0; i < C::VPL; ++i)
+        if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(zrow + (i * C::GROUP + gl) * C::VEC, zv + i * C::VEC);
     }
-    for (int e0 = beg; e0 < end; e0 += C::EPS) {   // warp-uniform trip count (shuffles inside)
-      const int e = e0 + grp;
-      const bool on = lane_on && e < end;
-      float gv[C::NE];
-#pragma unroll
-      for (int i = 0; i < C::NE; ++i) gv[i] = 0.f;
-      float mk = 0.f, dk = 1.f, sk = 0.f;
-      int b = 0;
-      if (on) {
-        const int v = __ldg(nbr + e);
-        b = __ldg(bin + e);
-        const float* grow = g + (size_t)v * C::F;
-        const float* st = stat + (size_t)v * 3 * H;
-        mk = __ldg(st + k);
-        dk = __ldg(st + H + k);
-        sk = __ldg(st + 2 * H + k);
-#pragma unroll
-        for (int i = 0; i < C::VPL; ++i) {
-          const int nv = l + C::LPH * i;
-          if (nv < C::NV) ld_vec<C::VEC>(grow + k * D + C::VEC * nv, gv + i * C::VEC);
-        }
+    for (int c0 = beg; c0 < end; c0 += 32) {
+      const int cnt = min(32, end - c0);
+      int my_v = 0, my_b = 0;
+      if (lane < cnt) {
+        my_v = __ldg(nbr + c0 + lane);
+        my_b = __ldg(bin + c0 + lane);
       }
-      float part = 0.f;
+      for (int j0 = 0; j0 < cnt; j0 += C::EPS * C::U) {   // warp-uniform (shuffles inside)
+        float gv[C::U][C::NE], mk[C::U], dk[C::U], sk[C::U];
+        int bb[C::U];
+        bool ok[C::U];
 #pragma unroll
-      for (int i = 0; i < C::NE; ++i) part = fmaf(gv[i], zv[i], part);
-      const float t = head_sum<C::LPH>(part, lane, l);
-      if (on) {
-        const float pre = pu + q_s[b * H + k];
-        const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-        const float alpha = __expf(lg - mk) / dk;
-        const float de = alpha * (t - sk);
-        const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
+        for (int uu = 0; uu < C::U; ++uu) {
+          const int j = j0 + uu * C::EPS + grp;
+          const int v = __shfl_sync(0xffffffffu, my_v, j & 31);
+          bb[uu] = __shfl_sync(0xffffffffu, my_b, j & 31);
+          ok[uu] = lane_on && j < cnt;
+          mk[uu] = 0.f;
+          dk[uu] = 1.f;
+          sk[uu] = 0.f;
 #pragma unroll
-        for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(alpha, gv[i], acc[i]);
-        acc_dp += dpre;
-        if (l == 0) my_dq[b * H + k] += dpre;
+          for (int i = 0; i < C::NE; ++i) gv[uu][i] = 0.f;
+          if (ok[uu]) {
+            const float* grow = g + (size_t)v * C::FP;
+            const float* st = stat + (size_t)v * 3 * H;
+            mk[uu] = __ldg(st + k);
+            dk[uu] = __ldg(st + H + k);
+            sk[uu] = __ldg(st + 2 * H + k);
+#pragma unroll
+            for (int i = 0; i < C::VPL; ++i)
+              if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(grow + (i * C::GROUP + gl) * C::VEC, gv[uu] + i * C::VEC);
+          }
+        }
+#pragma unroll
+        for (int uu = 0; uu < C::U; ++uu) {
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < C::NE; ++i) part = fmaf(gv[uu][i], zv[i], part);
+          const float t = head_sum<C::LPH>(part, lane, l);
+          if (ok[uu]) {
+            const float pre = pu + q_s[bb[uu] * H + k];
+            const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
+            const float alpha = __expf(lg - mk[uu]) / dk[uu];
+            const float de = alpha * (t - sk[uu]);
+            const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
+#pragma unroll
+            for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(alpha, gv[uu][i], acc[i]);
+            acc_dp += dpre;
+            if (l == 0) my_dq[bb[uu] * H + k] += dpre;
+          }
+        }
       }
     }
     // merge groups (fixed order) and write [dz | dp | 0]
@@ -360,12 +477,18 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
     if (grp == 0) {
 #pragma unroll
       for (int i = 0; i < C::VPL; ++i) {
-        const int nv = l + C::LPH * i;
-        if (nv < C::NV) st_vec<C::VEC>(drow + k * D + C::VEC * nv, acc + i * C::VEC);
+        if (l + C::LPH * i >= C::NV) {
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) acc[i * C::VEC + t] = 0.f;   // layout holes must be finite zeros
+        }
+        st_vec<C::VEC>(drow + (i * C::GROUP + gl) * C::VEC, acc + i * C::VEC);
       }
-      if (l == 0) drow[C::F + k] = acc_dp;
+      if (l == 0) drow[C::FP + k] = acc_dp;
     }
-    for (int c = C::F + H + lane; c < ldz; c += 32) drow[c] = 0.f;
+    for (int c = C::FP + H + lane; c < ldz; c += 32) drow[c] = 0.f;
+    u = un;
+    beg = begn;
+    end = endn;
   }
   __syncthreads();
   // per-block partial of dq, fixed summation order over (warp, group)
@@ -379,12 +502,21 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
   }
 }
 
-__global__ void edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part, float* __restrict__ dq) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
+// dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
+__global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
+                                                          float* __restrict__ dq) {
+  __shared__ float red[128];
+  const int i = blockIdx.x;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += dq_part[(size_t)b * nq + i];
-  dq[i] = s;
+  for (int b = threadIdx.x; b < nblocks; b += 128) s += dq_part[(size_t)b * nq + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+#pragma unroll
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dq[i] = red[0];
 }
 
 constexpr int EDGE_MAX_BLOCKS = 148 * 8;
@@ -431,8 +563,14 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   }
   LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
   const int nq = HSG_N_BINS * H;
-  edge_bwd_dq_kernel<<<ceil_div(nq, 128), 128, 0, s>>>(blocks, nq, ws, dq);
+  edge_bwd_dq_kernel<<<nq, 128, 0, s>>>(blocks, nq, ws, dq);
   return check_launch();
+}
+
+static bool layout_ok(int H, int d, int ldz) {
+  if (H <= 0 || d <= 0 || H > 32) return false;
+  const EdgeLayout L = make_edge_layout(H, d);
+  return ldz % 4 == 0 && ldz >= L.fp + H;
 }
 
 }  // namespace hsg
@@ -441,13 +579,33 @@ using namespace hsg;
 
 extern "C" {
 
+int hsg_edge_layout(int H, int d, int* fp, int* ldz) {
+  if (H <= 0 || d <= 0 || H > 32 || !fp || !ldz) return HSG_ERR_ARG;
+  bool found = false;
+#define X(HH, DD) \
+  if (H == HH && d == DD) found = true;
+  HSG_EDGE_CONFIGS(X)
+#undef X
+  if (!found) return HSG_ERR_SHAPE;
+  const EdgeLayout L = make_edge_layout(H, d);
+  *fp = L.fp;
+  *ldz = L.ldz;
+  return HSG_OK;
+}
+
+int hsg_edge_perm(int H, int d, int col) {
+  if (H <= 0 || d <= 0 || H > 32 || col < 0 || col >= H * d) return HSG_ERR_ARG;
+  const EdgeLayout L = make_edge_layout(H, d);
+  return edge_perm(L, col);
+}
+
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q, const float* origin,
                  float* sh, float* x, float* stat, void* stream) {
   if (!csc || !zp || !q || !sh || !stat || csc->n_dst < 0) return HSG_ERR_ARG;
   if (x != nullptr && origin == nullptr) return HSG_ERR_ARG;
   if (csc->n_dst == 0) return HSG_OK;
   if (!csc->indptr || (csc->n_edges > 0 && (!csc->nbr || !csc->bin))) return HSG_ERR_ARG;
-  if (ldz % 4 != 0 || ldz < H * d + H || !aligned16(zp) || !aligned16(sh) || (x && (!aligned16(x) || !aligned16(origin))))
+  if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(sh) || (x && (!aligned16(x) || !aligned16(origin))))
     return HSG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
 #define X(HH, DD) \
@@ -476,7 +634,7 @@ int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, c
                  const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, void* stream) {
   if (!csc_t || !zp || !q || !g || !stat || !dzp || !dq || !ws || csc_t->n_dst < 0) return HSG_ERR_ARG;
   if (ws_bytes < hsg_edge_bwd_workspace_bytes(H)) return HSG_ERR_WORKSPACE;
-  if (ldz % 4 != 0 || ldz < H * d + H || !aligned16(zp) || !aligned16(g) || !aligned16(dzp)) return HSG_ERR_ALIGN;
+  if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(g) || !aligned16(dzp)) return HSG_ERR_ALIGN;
   if (csc_t->n_dst > 0 && (!csc_t->indptr || (csc_t->n_edges > 0 && (!csc_t->nbr || !csc_t->bin)))) return HSG_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
 #define X(HH, DD) \

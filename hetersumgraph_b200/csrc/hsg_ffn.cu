@@ -151,13 +151,24 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
   }
 }
 
-__global__ void layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
-                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * D) return;
+// dgamma / dbeta = column sums of the per-block partials; 32 columns x 8 row groups per CTA, fixed order
+__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
+                                                                   float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * 2 * D + i];
-  if (i < D) dgamma[i] = s; else dbeta[i - D] = s;
+  if (i < 2 * D)
+    for (int b = ty; b < nblocks; b += 8) s += part[(size_t)b * 2 * D + i];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][tx];
+    if (i < D) dgamma[i] = t; else dbeta[i - D] = t;
+  }
 }
 
 static int ln_grid(int N) {
@@ -220,7 +231,7 @@ int hsg_layernorm_bwd(int N, int D, const float* dy, const float* r, const float
     if (rc) return rc;
   }
   LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(grid, D, part, dgamma, dbeta);
+  layernorm_bwd_reduce_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(grid, D, part, dgamma, dbeta);
   return check_launch();
 }
 

@@ -6,9 +6,24 @@
 //   gemm_nn : C = A . B     input gradients
 //   gemm_tn : C = A^T . B   weight gradients, split over the node dimension with a
 //                           fixed-order second stage (bitwise reproducible)
+#include <atomic>
+
 #include "hsg_common.cuh"
 
 namespace hsg {
+
+// tcgen05 path (hsg_gemm_tc.cu)
+namespace tc {
+int gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const float* bias, const float* R, int ldr, int epi, int precise, cudaStream_t s);
+int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* R,
+            int ldr, int epi, int precise, cudaStream_t s);
+int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* part, float* part_col,
+            int splits, int rows_per_split, int precise, cudaStream_t s);
+}  // namespace tc
+
+// 0: FFMA exact fp32, 1: tcgen05 3xTF32 (fp32-parity, default), 2: tcgen05 single-pass TF32
+static std::atomic<int> g_gemm_mode{1};
 
 constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int TM = 8, TN = 4;
@@ -280,6 +295,16 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
   }
 }
 
+// split of the node dimension for the tcgen05 weight-gradient kernel: 128 x 256 output tiles
+static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows) {
+  const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 256);
+  int want = ceil_div(148, tiles);
+  int r = ceil_div(ceil_div(M, want), 32) * 32;
+  if (r < 256) r = 256;
+  *rows = r;
+  *splits = ceil_div(M, r);
+}
+
 static int tn_splits(int M, int N1, int N2) {
   int tiles = ceil_div(N1, TB) * ceil_div(N2, TB);
   int want = ceil_div(2 * 148, tiles);
@@ -307,6 +332,8 @@ int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, in
   bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(C) &&
              (R == nullptr || aligned16(R));
   LaunchScope ls(SLOT_GEMM_NT, s);
+  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
+  if (mode != 0 && vec && (ldc % 4 == 0)) return tc::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, mode == 1, s);
   if (vec)
     gemm_kernel<true, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
   else
@@ -325,6 +352,8 @@ int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, in
   bool vec = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) &&
              aligned16(C) && (R == nullptr || aligned16(R));
   LaunchScope ls(SLOT_GEMM_NN, s);
+  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
+  if (mode != 0 && vec && (ldc % 4 == 0)) return tc::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, mode == 1, s);
   if (vec)
     gemm_kernel<false, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi);
   else
@@ -332,9 +361,20 @@ int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, in
   return check_launch();
 }
 
+int hsg_set_gemm_mode(int mode) {
+  if (mode < 0 || mode > 2) return HSG_ERR_ARG;
+  g_gemm_mode.store(mode);
+  return HSG_OK;
+}
+
+int hsg_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
 size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
   if (M <= 0 || N1 <= 0 || N2 <= 0) return 16;
   size_t s = (size_t)tn_splits(M, N1, N2);
+  int s_tc = 0, rows_tc = 0;
+  tn_plan_tc(M, N1, N2, true, &s_tc, &rows_tc);
+  if ((size_t)s_tc > s) s = (size_t)s_tc;
   return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
 }
 
@@ -346,7 +386,16 @@ int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, 
   int nsplit = M > 0 ? tn_splits(M, N1, N2) : 0;
   float* part = reinterpret_cast<float*>(ws);
   float* part_col = part + (size_t)nsplit * N1 * N2;
-  if (M > 0) {
+  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
+  const bool vec_tc = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
+  if (M > 0 && mode != 0 && vec_tc) {
+    int rows = 0;
+    tn_plan_tc(M, N1, N2, colsum != nullptr, &nsplit, &rows);
+    part_col = part + (size_t)nsplit * N1 * N2;
+    LaunchScope ls(SLOT_GEMM_TN, s);
+    int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, nsplit, rows, mode == 1, s);
+    if (rc) return rc;
+  } else if (M > 0) {
     int rows = ceil_div(M, nsplit);
     rows = ceil_div(rows, TBK) * TBK;
     nsplit = ceil_div(M, rows);

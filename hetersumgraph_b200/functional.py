@@ -95,7 +95,7 @@ def gemm_tn(A, B, want_colsum=False):
 def _mh_forward(csc, H, d, h_src, origin, W, Wf, bf, a, T):
     lib = _lib.load()
     F = H * d
-    ldz = round_up(F + H, 8)
+    fp, ldz = _lib.edge_layout(H, d)
     in_dim = h_src.shape[1]
     dev = h_src.device
     n_dst = csc.n_dst
@@ -118,7 +118,8 @@ def _mh_backward(csc_t, H, d, h_src, W, Wf, bf, a, T, W_aug, q, zp, sh, stat, dx
     ldz = zp.shape[1]
     dev = zp.device
     n_dst, n_src = sh.shape[0], zp.shape[0]
-    g = torch.empty(n_dst, F, dtype=torch.float32, device=dev)
+    fp, _ = _lib.edge_layout(H, d)
+    g = torch.empty(n_dst, fp, dtype=torch.float32, device=dev)
     _lib.check(lib.hsg_edge_bwd_prep(n_dst, H, d, _p(dx), _p(dsh), _p(sh), _p(g), _p(stat), _st()))
     dzp = torch.empty(n_src, ldz, dtype=torch.float32, device=dev)
     dq = torch.empty(_N_BINS, H, dtype=torch.float32, device=dev)
@@ -169,10 +170,17 @@ class MultiHeadFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # position-wise FFN
 # --------------------------------------------------------------------------------------------
+# test hook: when set to a list, every FFN forward appends its ReLU active set (hdn > 0) - used by the parity
+# tests to evaluate the oracle on the same active set (ReLU is the one discontinuous function on the path)
+RELU_MASK_CAPTURE = None
+
+
 def _ffn_forward(x, w1, b1, w2, b2, gamma, beta):
     lib = _lib.load()
     N, D = x.shape
     hdn = gemm_nt(x, w1, bias=b1, epi=EPI_BIAS | EPI_RELU)
+    if RELU_MASK_CAPTURE is not None:
+        RELU_MASK_CAPTURE.append((hdn > 0).cpu())
     r = gemm_nt(hdn, w2, bias=b2, R=x, epi=EPI_BIAS | EPI_ADD)
     out = torch.empty_like(r)
     stats = torch.empty(N, 2, dtype=torch.float32, device=x.device)

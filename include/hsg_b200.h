@@ -146,10 +146,10 @@ int hsg_build_fill(const hsg_token_batch* tb, const hsg_graph_out* out, void* ws
 
 /* ------------------------------------------------------------------------
  * K2  attention prep: folds attn_fc into the projection and the TF-IDF table.
- *     W_aug[0:F]   = W                      (fc.weight of all heads, GATLayer.py:84,123)
- *     W_aug[F+k]   = sum_j a_k[j] W[k d + j]   so that  p = h W_aug[F:F+H]^T = a_src . z
+ *     W_aug[perm(c)] = W[c]                 (fc.weight of all heads, GATLayer.py:84,123; rows lane-interleaved)
+ *     W_aug[fp+k]  = sum_j a_k[j] W[k d + j]   so that  p = h W_aug[fp:fp+H]^T = a_src . z
  *     q[b,k]       = a_k[2d:3d] . (Wf_k T[b] + bf_k)      (GATLayer.py:90-92,129-131; HiGraph.py:150-151)
- *     rows F+H .. ld_rows-1 of W_aug are zero.
+ *     layout holes and rows fp+H .. ld_rows-1 of W_aug are zero (ld_rows = ldz of hsg_edge_layout).
  * ------------------------------------------------------------------------ */
 int hsg_attn_prep_fwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
                       const float* W, const float* Wf, const float* bf /* may be NULL */,
@@ -169,6 +169,14 @@ int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
 #define HSG_EPI_RELU 2      /* C = max(C, 0)           */
 #define HSG_EPI_ADD 4       /* C += R[m,n]             */
 #define HSG_EPI_RELU_MASK 8 /* C = R[m,n] > 0 ? C : 0  */
+/* Arithmetic of the three products (process-wide setting):
+ *   0  FFMA, exact fp32
+ *   1  tcgen05.mma kind::tf32 with a 3-product hi/lo split ("3xTF32", ~2^-21 relative) - default; this is the
+ *      fp32-parity mode (BASELINE.json bound 1e-5)
+ *   2  tcgen05.mma kind::tf32, single product (bound 2e-2, the "bf16 projections" class of BASELINE.json)
+ * Shapes the tensor-core path cannot take (K or a leading dimension not a multiple of 4) fall back to mode 0. */
+int hsg_set_gemm_mode(int mode);
+int hsg_get_gemm_mode(void);
 /* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward) */
 int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const float* bias, const float* R, int ldr, int epi, void* stream);
@@ -187,19 +195,25 @@ int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, 
  *        sh_v  = sum_act softmax(e)_uv z_u   over ALL in-edges       GATLayer.py:98-102 via pull :113/:149
  *                (extra[v] never-written edges contribute exp(0) to the denominator, z = 0)
  *        x_v   = elu(sh_v) + origin_v                                GAT.py:56-57   (optional)
- *     zp row u = [ z_u (F) | p_u (H) | pad ],  leading dimension ldz.
+ *     zp row u = [ perm(z_u) (fp) | p_u (H) | pad ],  leading dimension ldz (hsg_edge_layout).
  *     stat row v = [ m (H) | den (H) | s (H, written by hsg_edge_bwd_prep) ].
  * ------------------------------------------------------------------------ */
+/* Lane-interleaved row layout of the gathered tensors (zp, g, dzp), see csrc/hsg_edge_layout.cuh:
+ * fp = permuted width of the F = H*d feature block (>= F), ldz = round_up(fp + H, 8) = leading dimension
+ * of zp / dzp / rows of W_aug.  hsg_edge_perm maps an original column (head-major, the order of
+ * torch.cat(head_outs), GATStackLayer.py:59) to its position inside a gathered row. */
+int hsg_edge_layout(int H, int d, int* host_fp, int* host_ldz);
+int hsg_edge_perm(int H, int d, int col);
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
                  const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F] */,
                  float* x /* [n_dst,F] or NULL */, float* stat /* [n_dst,3H] */, void* stream);
-/* K5a: g = dx * elu'(sh) (or g = dsh when dx == NULL), s[v,k] = g_v[k] . sh_v[k]. */
+/* K5a: g = dx * elu'(sh) (or g = dsh when dx == NULL) written lane-interleaved [n_dst, fp]; s[v,k] = g_v[k] . sh_v[k]. */
 int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx /* or NULL */, const float* dsh /* or NULL */,
-                      const float* sh, float* g /* [n_dst,F] */, float* stat, void* stream);
+                      const float* sh, float* g /* [n_dst,fp] */, float* stat, void* stream);
 /* K5b: source-centric backward over the TRANSPOSED structure (csc_t: rows = forward
  * sources, nbr = forward destinations; in HSG/HDSG graphs this is the other
  * direction's CSC because every w->s edge has an s->w twin, dataloader.py:254-257):
- *     dzp_u = [ sum_e alpha_e g_v | sum_e dpre_e | 0 ],   dq[b,k] = sum_{e: bin=b} dpre_e
+ *     dzp_u = [ perm(sum_e alpha_e g_v) | sum_e dpre_e | 0 ],   dq[b,k] = sum_{e: bin=b} dpre_e
  * dq is reduced deterministically through ws. */
 size_t hsg_edge_bwd_workspace_bytes(int H);
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,

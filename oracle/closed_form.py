@@ -66,12 +66,24 @@ def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T):
     return sh.reshape(n_dst, H * d)
 
 
-def ffn_cf(x, w1, b1, w2, b2, gamma, beta):
-    y = F.relu(x @ w1.reshape(w1.shape[0], -1).t() + b1) @ w2.reshape(w2.shape[0], -1).t() + b2
+def ffn_cf(x, w1, b1, w2, b2, gamma, beta, mask=None, flips=None):
+    """mask: optional bool [N, d_hid] - the ReLU active set to use instead of (pre > 0).  ReLU is the one
+    discontinuous function on the path: a unit whose pre-activation is within rounding distance of 0 may take
+    either branch depending on the arithmetic; injecting the device path's own active set lets the tests compare
+    everything else at full tolerance.  flips (list) receives (#units whose branch differs, #units, max |pre| there)."""
+    pre = x @ w1.reshape(w1.shape[0], -1).t() + b1
+    if mask is None:
+        h = F.relu(pre)
+    else:
+        if flips is not None:
+            diff = (pre.detach() > 0) != mask
+            flips.append((int(diff.sum()), diff.numel(), float(pre.detach().abs()[diff].max()) if diff.any() else 0.0))
+        h = pre * mask.to(pre.dtype)
+    y = h @ w2.reshape(w2.shape[0], -1).t() + b2
     return F.layer_norm(y + x, (x.shape[-1],), gamma, beta, 1e-5)
 
 
-def wswgat_cf(csc, w, s, params, prefix, kind, T):
+def wswgat_cf(csc, w, s, params, prefix, kind, T, mask=None, flips=None):
     H = n_heads_of(params, prefix + "layer.")
     W, Wf, bf, a = pack_layer(params, prefix + "layer.", H)
     if kind == "W2S":
@@ -85,14 +97,17 @@ def wswgat_cf(csc, w, s, params, prefix, kind, T):
     h = F.elu(sh) + origin
     return ffn_cf(h, params[prefix + "ffn.w_1.weight"], params[prefix + "ffn.w_1.bias"],
                   params[prefix + "ffn.w_2.weight"], params[prefix + "ffn.w_2.bias"],
-                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"])
+                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"], mask, flips)
 
 
-def update_loop_cf(csc, word_feature, super_feature, params, n_iter):
+def update_loop_cf(csc, word_feature, super_feature, params, n_iter, masks=None, flips=None):
+    """masks: optional list of ReLU active sets, one per WSWGAT application in execution order."""
     T = params["_TFembed.weight"]
+    it = iter(masks) if masks is not None else None
+    nxt = (lambda: next(it)) if it is not None else (lambda: None)
     word_state = word_feature
-    sent_state = wswgat_cf(csc, word_feature, super_feature, params, "word2sent.", "W2S", T)
+    sent_state = wswgat_cf(csc, word_feature, super_feature, params, "word2sent.", "W2S", T, nxt(), flips)
     for _ in range(n_iter):
-        word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T)
-        sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T)
+        word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T, nxt(), flips)
+        sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T, nxt(), flips)
     return word_state, sent_state

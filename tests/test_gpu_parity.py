@@ -103,25 +103,41 @@ def test_builder_edge_cases():
 
 
 # ----------------------------------------------------------------------------- dense pieces
-@pytest.mark.parametrize("M,N,K", [(1000, 72, 300), (257, 312, 64), (129, 512, 64), (1, 64, 512), (333, 50, 30)])
-def test_gemm_variants(M, N, K):
+GEMM_TOL = {"fp32": 2e-6, "tf32x3": 3e-6, "tf32": 2e-2}
+
+
+@pytest.fixture(params=["fp32", "tf32x3", "tf32"])
+def gemm_mode(request):
+    prev = hb.get_gemm_mode()
+    hb.set_gemm_mode(request.param)
+    yield request.param
+    hb.set_gemm_mode(prev)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 72, 300), (257, 312, 64), (129, 512, 64), (1, 64, 512), (333, 50, 30),
+                                   (4099, 300, 512), (2000, 512, 300), (77, 16, 48)])
+def test_gemm_variants(M, N, K, gemm_mode):
+    tol = GEMM_TOL[gemm_mode]
     torch.manual_seed(0)
     A = torch.randn(M, K, device="cuda")
     B = torch.randn(N, K, device="cuda")
     bias = torch.randn(N, device="cuda")
     R = torch.randn(M, N, device="cuda")
     ref = (A.double() @ B.double().t())
-    assert nerr(gemm_nt(A, B), ref) <= 2e-6
-    assert nerr(gemm_nt(A, B, bias=bias, epi=3), torch.relu(ref + bias.double())) <= 2e-6
-    assert nerr(gemm_nt(A, B, bias=bias, R=R, epi=5), ref + bias.double() + R.double()) <= 2e-6
+    assert nerr(gemm_nt(A, B), ref) <= tol
+    assert nerr(gemm_nt(A, B, bias=bias, epi=3), torch.relu(ref + bias.double())) <= tol
+    assert nerr(gemm_nt(A, B, bias=bias, R=R, epi=5), ref + bias.double() + R.double()) <= tol
     Bn = torch.randn(K, N, device="cuda")
     refn = A.double() @ Bn.double()
-    assert nerr(gemm_nn(A, Bn), refn) <= 2e-6
-    assert nerr(gemm_nn(A, Bn, R=R, epi=8), torch.where(R > 0, refn, torch.zeros_like(refn))) <= 2e-6
+    assert nerr(gemm_nn(A, Bn), refn) <= tol
+    assert nerr(gemm_nn(A, Bn, R=R, epi=8), torch.where(R > 0, refn, torch.zeros_like(refn))) <= tol
+    assert nerr(gemm_nn(A, Bn, R=R, epi=4), refn + R.double()) <= tol
     A2 = torch.randn(M, N, device="cuda")
     Ct, cs = gemm_tn(A2, A, want_colsum=True)
-    assert nerr(Ct, A2.double().t() @ A.double()) <= 2e-6
-    assert nerr(cs, A2.double().sum(0)) <= 2e-6
+    assert nerr(Ct, A2.double().t() @ A.double()) <= tol
+    assert nerr(cs, A2.double().sum(0)) <= tol
+    Ct2, none = gemm_tn(A2, A, want_colsum=False)
+    assert none is None and torch.equal(Ct, Ct2)
 
 
 @pytest.mark.parametrize("N,D,Dh", [(777, 64, 512), (300, 300, 512), (5, 16, 32), (1, 48, 32)])
@@ -218,9 +234,21 @@ def test_bitwise_determinism():
 
 
 # ----------------------------------------------------------------------------- configs vs closed-form oracle
+GRAD_TOL = {"fp32": TOL, "tf32x3": TOL, "tf32": 5e-2}
+FWD_TOL = {"fp32": TOL, "tf32x3": TOL, "tf32": 2e-2}
+
+
 @pytest.mark.parametrize("shape,hdsg,n_iter,n,seed", [("cnndm", False, 1, 8, 0), ("nyt50", False, 3, 4, 1),
                                                       ("multinews", True, 1, 4, 2)])
-def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed):
+def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed, gemm_mode):
+    """Whole update loop, forward and every gradient, in all three arithmetic modes.
+
+    ReLU is the one discontinuous function on the path: an FFN unit whose pre-activation lies within rounding
+    distance of 0 may take either branch depending on the arithmetic (true of the reference on two BLAS
+    libraries as well).  The oracle is therefore evaluated on the device path's own ReLU active set (captured
+    through functional.RELU_MASK_CAPTURE); the test also bounds how many units differ from the oracle's own
+    branch choice and how close to 0 those units are."""
+    import hetersumgraph_b200.functional as fn
     exs = syn.make_examples(n, shape, seed=seed, hdsg=hdsg)
     tb = syn.pack_token_batch(exs, hdsg=hdsg)
     batch = hb.HeteroBatch.from_token_batch(tb)
@@ -233,21 +261,42 @@ def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed):
     w = torch.randn(batch.n_word, 300)
     s = torch.randn(batch.n_super, 64)
     cw, cs = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)      # random cotangents
-    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
-    ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter)
-    ((ow * cw).sum() + (os_ * cs).sum()).backward()
     wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
-    gw, gs = m(batch, wg, sg)
+    fn.RELU_MASK_CAPTURE = []
+    try:
+        gw, gs = m(batch, wg, sg)
+        masks = fn.RELU_MASK_CAPTURE
+    finally:
+        fn.RELU_MASK_CAPTURE = None
     ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
-    assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
-    assert nerr(wg.grad, wc.grad) <= TOL and nerr(sg.grad, sc.grad) <= TOL
-    assert nerr(m._TFembed.weight.grad, params["_TFembed.weight"].grad) <= TOL
-    assert nerr(m.word2sent.ffn.w_1.weight.grad, params["word2sent.ffn.w_1.weight"].grad) <= TOL
-    assert nerr(m.sent2word.ffn.w_2.weight.grad, params["sent2word.ffn.w_2.weight"].grad) <= TOL
-    W2S_W = torch.cat([params["word2sent.layer.heads.%d.fc.weight" % k].grad for k in range(8)], 0)
-    assert nerr(m.word2sent.layer.fc_weight.grad, W2S_W) <= TOL
-    A_S2W = torch.cat([params["sent2word.layer.heads.%d.attn_fc.weight" % k].grad for k in range(6)], 0)
-    assert nerr(m.sent2word.layer.attn_fc_weight.grad, A_S2W) <= TOL
+    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    flips = []
+    ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter, masks=masks, flips=flips)
+    ((ow * cw).sum() + (os_ * cs).sum()).backward()
+    n_flip, n_unit = sum(f[0] for f in flips), sum(f[1] for f in flips)
+    pre_at_flip = max(f[2] for f in flips)
+    limit = {"fp32": (2e-5, 1e-5), "tf32x3": (2e-5, 1e-5), "tf32": (5e-3, 2e-2)}[gemm_mode]
+    assert n_flip <= limit[0] * n_unit + 1 and pre_at_flip <= limit[1], (n_flip, n_unit, pre_at_flip)
+    ftol, gtol = FWD_TOL[gemm_mode], GRAD_TOL[gemm_mode]
+    assert nerr(gw, ow) <= ftol and nerr(gs, os_) <= ftol
+    checks = [("d word", wg.grad, wc.grad), ("d sent", sg.grad, sc.grad),
+              ("TFembed", m._TFembed.weight.grad, params["_TFembed.weight"].grad)]
+    for pre in ("word2sent", "sent2word"):
+        mod = getattr(m, pre)
+        for k in ("w_1.weight", "w_1.bias", "w_2.weight", "w_2.bias", "layer_norm.weight", "layer_norm.bias"):
+            obj = mod.ffn
+            for part in k.split("."):
+                obj = getattr(obj, part)
+            checks.append((pre + ".ffn." + k, obj.grad, params["%s.ffn.%s" % (pre, k)].grad))
+        H = mod.layer.num_heads
+        cat = lambda name: torch.cat([params["%s.layer.heads.%d.%s" % (pre, k, name)].grad for k in range(H)], 0)  # noqa: E731
+        checks.append((pre + ".fc", mod.layer.fc_weight.grad, cat("fc.weight")))
+        checks.append((pre + ".feat_fc", mod.layer.feat_fc_weight.grad, cat("feat_fc.weight")))
+        checks.append((pre + ".attn_fc", mod.layer.attn_fc_weight.grad, cat("attn_fc.weight")))
+        if mod.layer.feat_fc_bias is not None:
+            checks.append((pre + ".feat_fc_bias", mod.layer.feat_fc_bias.grad, cat("feat_fc.bias")))
+    for name, got, ref in checks:
+        assert nerr(got, ref) <= gtol, (name, nerr(got, ref), gemm_mode)
 
 
 def test_bucketed_reference_port_on_device_batch():

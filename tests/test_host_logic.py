@@ -41,7 +41,11 @@ def test_argument_validation_without_gpu():
     assert lib.hsg_gemm_nt(4, 4, 4, None, 4, None, 4, None, 4, None, None, 0, 0, None) == -1
     assert lib.hsg_layernorm_fwd(4, 6, 1, 1, 1, 1, 1, None) == -2          # D % 4 != 0
     csc = _lib.CscC(4, 4, 0, 0, 16, 16, 16, None)
-    assert lib.hsg_edge_fwd(ctypes.byref(csc), 7, 9, 16, 72, 16, None, 16, None, 16, None) == -2   # (7,9) not instantiated
+    assert lib.hsg_edge_fwd(ctypes.byref(csc), 7, 8, 16, 72, 16, None, 16, None, 16, None) == -2   # (7,8) not instantiated
+    fp, ldz = _lib.edge_layout(6, 50)
+    assert (fp, ldz) == (300, 312) and _lib.edge_layout(8, 8) == (64, 72)
+    perm = sorted(lib.hsg_edge_perm(6, 50, c) for c in range(300))
+    assert perm == list(range(300))                     # a bijection onto [0, fp) for the default S2W shape
     assert lib.hsg_edge_bwd_workspace_bytes(8) > 0 and lib.hsg_gemm_tn_workspace_bytes(1000, 64, 64) > 0
 
 
