@@ -295,9 +295,9 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
   }
 }
 
-// split of the node dimension for the tcgen05 weight-gradient kernel: 128 x 256 output tiles
+// split of the node dimension for the tcgen05 weight-gradient kernel: 128 x 128 output tiles
 static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows) {
-  const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 256);
+  const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 128);
   int want = ceil_div(148, tiles);
   int r = ceil_div(ceil_div(M, want), 32) * 32;
   if (r < 256) r = 256;

@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM) version of the tall-skinny products of the WSWGAT path.
+// Tensor-core (tcgen05 / TMEM / TMA) version of the tall-skinny products of the WSWGAT path.
 //
 //   D[Md, Nd] = sum_k A(md, k) * B(nd, k)        accumulators in TMEM (fp32), 128 x BN tile per CTA
 //
@@ -7,17 +7,22 @@
 //   NN  (A_MN=0, B_MN=1)  C = A . B   : B [K,N] is MN-major
 //   TN  (A_MN=1, B_MN=1)  C = A^T . B : both operands MN-major, K = node dimension, split over gridDim.z
 //
-// Operands are fp32 in HBM.  A CTA stages 32-deep k-blocks through registers into shared memory in
-// the canonical UMMA layouts (K-major: SWIZZLE_128B, 8-row x 128 B atoms; MN-major: SWIZZLE_128B_BASE32B,
-// 4-k x 128 B atoms - the only MN-major layout the hardware accepts for 32-bit operands),
-// splitting every value on the way into hi = x rounded to the nearest TF32 value and lo = x - hi.  One elected thread issues
-//      D += A_hi B_hi ;  D += A_hi B_lo ;  D += A_lo B_hi          (precise mode, "3xTF32")
-// with tcgen05.mma.kind::tf32 - error ~2^-21 relative, inside BASELINE.json's fp32 bound of 1e-5 -
-// or only the first product in fast mode (TF32, bound 2e-2).  Two smem stages; tcgen05.commit
-// -> mbarrier releases a stage while the next k-block is being staged.  The epilogue reads the
-// accumulators with tcgen05.ld (each warp its own 32 TMEM lanes) and applies bias / ReLU /
-// residual / ReLU-mask before the global store.  Weight-gradient column sums come for free from
-// an extra all-ones B column.
+// Operands are fp32 in HBM.  Warp-specialised pipeline, STAGES shared-memory stages:
+//   * one thread issues TMA (cp.async.bulk.tensor) loads of raw 32-deep k-blocks straight into the canonical
+//     UMMA layouts - K-major operands with SWIZZLE_128B (8-row x 128 B atoms), MN-major operands with
+//     SWIZZLE_128B_ATOM_32B (4-k x 128 B atoms: the only MN-major layout the tensor core takes for 32-bit
+//     data); tile edges are zero-filled by the TMA unit;
+//   * six converter warps sweep the landed tile linearly and split every value into hi = x rounded to the
+//     nearest TF32 value (in place) and lo = x - hi (second tile);
+//   * one thread issues   D += A_hi B_hi ;  D' += A_hi B_lo ;  D' += A_lo B_hi     (precise mode, "3xTF32")
+//     with tcgen05.mma.kind::tf32 - error ~2^-22 relative, inside BASELINE.json's fp32 bound of 1e-5 - or
+//     only the first product on the raw tile in fast mode (TF32, the tensor core truncates itself);
+//   * tcgen05.commit -> mbarrier hands the stage back to the TMA thread.
+// The epilogue reads the accumulators with tcgen05.ld (each warp its own 32 TMEM lanes) and applies bias /
+// ReLU / residual / ReLU-mask before the global store.  Weight-gradient column sums come for free from an
+// extra all-ones B column.
+#include <cuda.h>
+
 #include "hsg_common.cuh"
 
 namespace hsg {
@@ -25,12 +30,13 @@ namespace tc {
 
 constexpr int TM = 128;          // MMA M (TMEM lanes)
 constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int BN_MAX = 256;      // MMA N per CTA (TMEM columns)
-constexpr int THREADS = 256;
-constexpr int A_BYTES = TM * 128;          // one hi or lo A tile
-constexpr int B_BYTES = BN_MAX * 128;      // one hi or lo B tile
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 64;  // + alignment slack + barriers
+constexpr int BN_MAX = 128;      // MMA N per CTA (TMEM columns per accumulator)
+constexpr int THREADS = 256;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-7: hi/lo converters
+constexpr int NCONV = 192;
+constexpr int TILE_BYTES = TM * 128;             // one hi or lo tile (A: 128 rows, B: up to 128 rows/cols) = 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi | A_lo | B_hi | B_lo = 64 KB
+constexpr int STAGES = 3;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 128;  // + alignment slack + barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,105 +105,25 @@ __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
 // hi = x rounded to nearest TF32 (10 explicit mantissa bits), lo = x - hi (exact in fp32, <= 12 significant
 // bits, so the tensor core's own TF32 truncation of lo costs at most one bit: ~2^-23 relative overall).
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-
-__device__ __forceinline__ void split_store(float4 v, char* hi, char* lo, uint32_t off, bool want_lo) {
-  float4 h;
-  if (want_lo) {
-    h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-    *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-  } else {
-    h = v;   // single-pass mode: the tensor core truncates to TF32 itself
-  }
-  *reinterpret_cast<float4*>(hi + off) = h;
-}
-
-struct Operand {
-  const float* p;
-  int ld;
-  int ext_mn;   // valid extent along the MMA M / N dimension
-  int ext_k;    // valid extent along K
-};
-
-// ---- staging: global fp32 -> (hi, lo) SWIZZLE_128B tiles -------------------------------------
-// K-major tile: `rows` rows (M or N index) x 32 k.  smem: row r -> (r/8)*1024 + (r%8)*128, 16B chunk c at c ^ (r%8)
-constexpr int A_CHUNKS = TM * 8 / THREADS;        // float4 per thread for a 128-row tile  (4)
-constexpr int B_CHUNKS = BN_MAX * 8 / THREADS;    // float4 per thread for a 256-row tile  (8)
-
-template <int NCH>
-__device__ __forceinline__ void load_kmajor(const Operand& op, int mn0, int k0, int rows, float4* regs) {
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int id = threadIdx.x + i * THREADS;
-    const int r = id >> 3, c = id & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int gm = mn0 + r, gk = k0 + 4 * c;
-    if (r < rows && gm < op.ext_mn && gk < op.ext_k)
-      v = __ldg(reinterpret_cast<const float4*>(op.p + (size_t)gm * op.ld + gk));
-    regs[i] = v;
-  }
-}
-
-template <int NCH>
-__device__ __forceinline__ void store_kmajor(char* hi, char* lo, int rows, const float4* regs, bool want_lo) {
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int id = threadIdx.x + i * THREADS;
-    const int r = id >> 3, c = id & 7;
-    if (r < rows) {
-      const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-      split_store(regs[i], hi, lo, off, want_lo);
-    }
-  }
-}
-
-// MN-major tile: 32 k x `width` (M or N index, multiple of 32), SWIZZLE_128B_BASE32B:
-// atoms of 4 k-rows x 128 B (32 fp32 along MN); k -> (k/4)*sbo + (k%4)*128, mn -> (mn/32)*512,
-// inside a row the 32-byte unit j = (mn%32)/8 sits at j ^ (k%4); sbo = (width/32)*512
-template <int NCH>
-__device__ __forceinline__ void load_mnmajor(const Operand& op, int mn0, int k0, int width, int ones_col,
-                                             float4* regs) {
-  const int w4 = width >> 2;
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int id = threadIdx.x + i * THREADS;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (id < 32 * w4) {
-      const int k = id / w4, n4 = id - k * w4;
-      const int gk = k0 + k, gn = mn0 + 4 * n4;
-      if (gk < op.ext_k) {
-        if (gn < op.ext_mn) v = __ldg(reinterpret_cast<const float4*>(op.p + (size_t)gk * op.ld + gn));
-        if (ones_col >= gn && ones_col < gn + 4) {       // all-ones column -> column sums of the other operand
-          if (ones_col == gn) v.x = 1.f;
-          else if (ones_col == gn + 1) v.y = 1.f;
-          else if (ones_col == gn + 2) v.z = 1.f;
-          else v.w = 1.f;
-        }
-      }
-    }
-    regs[i] = v;
-  }
-}
-
-template <int NCH>
-__device__ __forceinline__ void store_mnmajor(char* hi, char* lo, int width, const float4* regs, bool want_lo) {
-  const int w4 = width >> 2;
-  const uint32_t sbo = (uint32_t)(width >> 5) * 512u;
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int id = threadIdx.x + i * THREADS;
-    if (id < 32 * w4) {
-      const int k = id / w4, n4 = id - k * w4;
-      const uint32_t c16 = (uint32_t)(n4 & 7), kr = (uint32_t)(k & 3);
-      const uint32_t off = (uint32_t)(k >> 2) * sbo + (uint32_t)(n4 >> 3) * 512u + kr * 128u +
-                           (((c16 >> 1) ^ kr) << 5) + ((c16 & 1) << 4);
-      split_store(regs[i], hi, lo, off, want_lo);
-    }
-  }
 }
 
 struct Epilogue {
@@ -212,106 +138,145 @@ struct Epilogue {
   int ones_col;        // D column that holds the column sums, -1 if none
 };
 
+// Shared-memory tile layouts produced by the TMA boxes (all offsets relative to a 1024-byte aligned tile):
+//   K-major  operand: one box {32 k, rows}: row r at r*128, 16-byte chunk c at c ^ (r%8)          (SWIZZLE_128B)
+//   MN-major operand: one box {32 mn, 32 k} per 32-wide MN atom, atoms 4096 B apart; k row at k*128, 32-byte
+//                     unit j at j ^ (k%4)                                                   (SWIZZLE_128B_ATOM_32B)
 // grid: (ceil(Md/128), ceil(Nd_total/bn), splits).  k range of split z: [z*k_per_split, min(K, (z+1)*k_per_split))
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(Operand A, Operand B, int Md, int Nd, int K, int bn, int k_per_split, int precise, Epilogue ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Md, int Nd,
+               int K, int bn, int nb_box, int k_per_split, int precise, Epilogue ep) {
   extern __shared__ char smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);   // [0,1]: stage free, [2]: unused
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S] | ready[S] | empty[S] | acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TM;
   const int n0 = blockIdx.y * bn;
   const int n_valid = min(bn, Nd - n0);                 // valid D columns of this tile (incl. a ones column)
-  const int n_mma = (n_valid + 15) & ~15;               // MMA N (multiple of 16, <= 256)
-  const int n_stage = B_MN ? ((n_mma + 31) & ~31) : n_mma;   // staged B extent
+  const int n_mma = (n_valid + 15) & ~15;               // MMA N (multiple of 16, <= 128)
   const int k_beg = blockIdx.z * k_per_split;
   const int k_end = min(K, k_beg + k_per_split);
   const int nkb = (k_end - k_beg + BK - 1) / BK;
+  const bool want_lo = precise != 0;
+  const bool use_conv = want_lo || ep.ones_col >= 0;     // converter warps touch the stage before the MMAs
+  // precise mode keeps the small correction products in a second accumulator (columns 128..255): the tensor
+  // core's fp32 accumulation truncates, so the error grows with the number of updates of one accumulator;
+  // splitting leaves K/8 updates on the main one and adds the two in the epilogue.
+  const uint32_t tmem_cols = want_lo ? 2u * BN_MAX : (uint32_t)BN_MAX;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_ready = smem_u32(&bars[STAGES]),
+                 bar_empty = smem_u32(&bars[2 * STAGES]), bar_acc = smem_u32(&bars[3 * STAGES]);
 
-  // precise mode keeps the small correction products in a second accumulator (columns 256..511): the
-  // tensor core's fp32 accumulation truncates, so the error grows with the number of updates of one
-  // accumulator; splitting leaves K/8 updates on the main one and adds the two in the epilogue.
-  const uint32_t tmem_cols = precise ? 2u * BN_MAX : (uint32_t)BN_MAX;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (tid == 32) {
-    mbar_init(smem_u32(&bars[0]), 1);
-    mbar_init(smem_u32(&bars[1]), 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);                  // TMA: one arrive.expect_tx + the transaction bytes
+      mbar_init(bar_ready + 8 * i, NCONV);             // converters done with the stage
+      mbar_init(bar_empty + 8 * i, 1);                 // tcgen05.commit
+    }
+    mbar_init(bar_acc, 1);                             // accumulators complete
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  const uint32_t idesc = make_idesc(A_MN, B_MN, n_mma);
-  const bool want_lo = precise != 0;
+  const uint32_t stage_tx = (uint32_t)(TM * 128 + nb_box * 128);
 
-  Operand Ak = A, Bk = B;
-  Ak.ext_k = min(A.ext_k, k_end);
-  Bk.ext_k = min(B.ext_k, k_end);
-
-  float4 ra[A_CHUNKS], rb[B_CHUNKS];
-  auto load_block = [&](int kb) {
-    const int k0 = k_beg + kb * BK;
-    if (A_MN) load_mnmajor<A_CHUNKS>(Ak, m0, k0, TM, -1, ra);
-    else load_kmajor<A_CHUNKS>(Ak, m0, k0, TM, ra);
-    if (B_MN) load_mnmajor<B_CHUNKS>(Bk, n0, k0, n_stage, ep.ones_col, rb);
-    else load_kmajor<B_CHUNKS>(Bk, n0, k0, n_stage, rb);
-  };
-  auto store_block = [&](int s) {
-    char* st = smem + s * STAGE_BYTES;
-    if (A_MN) store_mnmajor<A_CHUNKS>(st, st + A_BYTES, TM, ra, want_lo);
-    else store_kmajor<A_CHUNKS>(st, st + A_BYTES, TM, ra, want_lo);
-    char* sb = st + 2 * A_BYTES;
-    if (B_MN) store_mnmajor<B_CHUNKS>(sb, sb + B_BYTES, n_stage, rb, want_lo);
-    else store_kmajor<B_CHUNKS>(sb, sb + B_BYTES, n_stage, rb, want_lo);
-  };
-
-  if (nkb > 0) load_block(0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) mbar_wait(smem_u32(&bars[s]), ((kb >> 1) - 1) & 1);   // MMAs of k-block kb-2 have drained stage s
-    store_block(s);
-    if (kb + 1 < nkb) load_block(kb + 1);                                // prefetch next k-block into registers
-    fence_async_smem();                                                  // generic-proxy writes -> async proxy
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-      // K-major: 8-row groups 1024 B apart, a k-step of 8 fp32 = 32 B inside the swizzled row.
-      // MN-major: MN atoms 512 B apart (LBO), 4-k groups sbo apart, a k-step of 8 = two 4-k groups.
-      const uint32_t a_sbo = A_MN ? (TM / 32) * 512u : 1024u, a_lbo = A_MN ? 512u : 16u, a_lay = A_MN ? 1u : 2u;
-      const uint32_t b_sbo = B_MN ? (uint32_t)(n_stage >> 5) * 512u : 1024u, b_lbo = B_MN ? 512u : 16u,
-                     b_lay = B_MN ? 1u : 2u;
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(bar_empty + 8 * slot, ((kb / STAGES) - 1) & 1);   // MMAs drained the slot
+        const uint32_t st = smem_u32(smem + slot * STAGE_BYTES);
+        const int k0 = k_beg + kb * BK;
+        const uint32_t full = bar_full + 8 * slot;
+        mbar_expect_tx(full, stage_tx);
+        if (A_MN) {
 #pragma unroll
-      for (int ks = 0; ks < BK / 8; ++ks) {
-        const uint32_t a_off = A_MN ? ks * 2u * a_sbo : ks * 32u;
-        const uint32_t b_off = B_MN ? ks * 2u * b_sbo : ks * 32u;
-        const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lay),
-                       dbh = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lay);
-        tc_mma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-        if (want_lo) {
-          const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay),
-                         dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lay);
-          tc_mma_tf32(tmem_d + BN_MAX, dah, dbl, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_d + BN_MAX, dal, dbh, idesc, 1u);
+          for (int a = 0; a < TM / 32; ++a) tma_load_2d(st + a * 4096, &tmA, m0 + 32 * a, k0, full);
+        } else {
+          tma_load_2d(st, &tmA, k0, m0, full);
+        }
+        if (B_MN) {
+          for (int a = 0; a < nb_box / 32; ++a) tma_load_2d(st + 2 * TILE_BYTES + a * 4096, &tmB, n0 + 32 * a, k0, full);
+        } else {
+          tma_load_2d(st + 2 * TILE_BYTES, &tmB, k0, n0, full);
         }
       }
-      tc_commit(smem_u32(&bars[s]));
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(A_MN, B_MN, n_mma);
+      // K-major: 8-row groups 1024 B apart, a k-step of 8 fp32 = 32 B inside the swizzled row.
+      // MN-major: MN atoms 4096 B apart (LBO), 4-k groups 512 B apart (SBO), a k-step of 8 = two groups = 1024 B.
+      const uint32_t a_sbo = A_MN ? 512u : 1024u, a_lbo = A_MN ? 4096u : 16u, a_lay = A_MN ? 1u : 2u;
+      const uint32_t b_sbo = B_MN ? 512u : 1024u, b_lbo = B_MN ? 4096u : 16u, b_lay = B_MN ? 1u : 2u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = kb % STAGES;
+        mbar_wait((use_conv ? bar_ready : bar_full) + 8 * slot, (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + slot * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t a_off = A_MN ? ks * 1024u : ks * 32u;
+          const uint32_t b_off = B_MN ? ks * 1024u : ks * 32u;
+          const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lay),
+                         dbh = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lay);
+          tc_mma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          if (want_lo) {
+            const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay),
+                           dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lay);
+            tc_mma_tf32(tmem_d + BN_MAX, dah, dbl, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            tc_mma_tf32(tmem_d + BN_MAX, dal, dbh, idesc, 1u);
+          }
+        }
+        tc_commit(bar_empty + 8 * slot);                                  // frees the slot when the MMAs retire
+        if (kb == nkb - 1) tc_commit(bar_acc);                            // ... and signals the epilogue
+      }
+    }
+  } else if (use_conv) {
+    // ===== converters (warps 2-7): linear hi/lo sweep over the landed stage =====
+    const int ct = tid - 64;
+    const bool ones_here = B_MN && ep.ones_col >= n0 && ep.ones_col < n0 + nb_box;
+    const int b_chunks = nb_box * 8;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int slot = kb % STAGES;
+      mbar_wait(bar_full + 8 * slot, (kb / STAGES) & 1);                   // this k-block has landed
+      char* st = smem + slot * STAGE_BYTES;
+      if (ones_here) {                                                     // all-ones column (TMA zero-filled it)
+        if (ct < 32 && k_beg + kb * BK + ct < k_end) {
+          const int nl = ep.ones_col - n0, k = ct;
+          const uint32_t off = (uint32_t)(nl >> 5) * 4096u + (uint32_t)k * 128u +
+                               (uint32_t)((((nl & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)(nl & 7) * 4u;
+          *reinterpret_cast<float*>(st + 2 * TILE_BYTES + off) = 1.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NCONV) : "memory");
+      }
+      if (want_lo) {
+        for (int id = ct; id < TM * 8 + b_chunks; id += NCONV) {
+          char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+          const float4 v = *reinterpret_cast<const float4*>(hi);
+          const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+          *reinterpret_cast<float4*>(hi) = h;
+          *reinterpret_cast<float4*>(hi + TILE_BYTES) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+      }
+      fence_async_smem();                                                  // generic-proxy writes -> async proxy
+      mbar_arrive(bar_ready + 8 * slot);
     }
   }
-  // wait for the last commit (it tracks all earlier MMAs of this thread)
-  if (nkb > 0) {
-    const int last = nkb - 1;
-    mbar_wait(smem_u32(&bars[last & 1]), (last >> 1) & 1);
-  }
+  if (nkb > 0) mbar_wait(bar_acc, 0);
   tc_fence_after();
 
   // ---- epilogue: TMEM -> registers -> global ----
@@ -370,6 +335,44 @@ gemm_tc_kernel(Operand A, Operand B, int Md, int Nd, int K, int bn, int k_per_sp
   }
 }
 
+// ---- host side: tensor maps + launch -----------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [outer, inner] with row pitch ld (elements); box = {32 inner, box_outer}; elements outside
+// [inner, outer] are zero-filled by the TMA unit.
+static bool make_map(CUtensorMap* m, const float* ptr, int inner, int outer, int ld, int box_outer, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Operand {
+  const float* p;
+  int ld;
+  int ext_mn;   // valid extent along the MMA M / N dimension
+  int ext_k;    // valid extent along K
+};
+
 static bool g_attr_done[3] = {false, false, false};
 
 template <bool A_MN, bool B_MN>
@@ -381,12 +384,19 @@ static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, in
       return HSG_ERR_CUDA;
     g_attr_done[which] = true;
   }
-  gemm_tc_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(A, B, Md, Nd, K, bn, k_per_split, precise, ep);
+  const int nb_box = B_MN ? ((bn + 31) & ~31) : ((bn + 15) & ~15);      // staged B rows / columns per stage
+  CUtensorMap tmA, tmB;
+  const bool okA = A_MN ? make_map(&tmA, A.p, A.ext_mn, A.ext_k, A.ld, 32, true)
+                        : make_map(&tmA, A.p, A.ext_k, A.ext_mn, A.ld, TM, false);
+  const bool okB = B_MN ? make_map(&tmB, B.p, B.ext_mn, B.ext_k, B.ld, 32, true)
+                        : make_map(&tmB, B.p, B.ext_k, B.ext_mn, B.ld, nb_box, false);
+  if (!okA || !okB) return HSG_ERR_CUDA;
+  gemm_tc_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, precise, ep);
   return check_launch();
 }
 
 static int pick_bn(int n_total) {
-  // D column tile: a multiple of 16 up to 256, tiles as even as possible
+  // D column tile: a multiple of 16 up to BN_MAX, tiles as even as possible
   const int tiles = ceil_div(n_total, BN_MAX);
   int bn = ceil_div(ceil_div(n_total, tiles), 16) * 16;
   return bn > BN_MAX ? BN_MAX : bn;

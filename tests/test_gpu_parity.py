@@ -137,7 +137,7 @@ def test_gemm_variants(M, N, K, gemm_mode):
     assert nerr(Ct, A2.double().t() @ A.double()) <= tol
     assert nerr(cs, A2.double().sum(0)) <= tol
     Ct2, none = gemm_tn(A2, A, want_colsum=False)
-    assert none is None and torch.equal(Ct, Ct2)
+    assert none is None and nerr(Ct2, Ct) <= tol          # different tiling -> different summation order
 
 
 @pytest.mark.parametrize("N,D,Dh", [(777, 64, 512), (300, 300, 512), (5, 16, 32), (1, 48, 32)])
