@@ -264,12 +264,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("bar.sync 1, %0;" ::"r"(NCONV) : "memory");
       }
       if (want_lo) {
-        for (int id = ct; id < TM * 8 + b_chunks; id += NCONV) {
-          char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
-          const float4 v = *reinterpret_cast<const float4*>(hi);
-          const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-          *reinterpret_cast<float4*>(hi) = h;
-          *reinterpret_cast<float4*>(hi + TILE_BYTES) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        // (128 + nb_box) * 8 <= 2048 chunks of 16 B over 192 threads: up to 11 per thread, all loads issued first
+        constexpr int CPT = (TM * 8 + BN_MAX * 8 + NCONV - 1) / NCONV;
+        const int total = TM * 8 + b_chunks;
+        float4 v[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int id = ct + i * NCONV;
+          const char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+          v[i] = id < total ? *reinterpret_cast<const float4*>(hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int id = ct + i * NCONV;
+          if (id < total) {
+            char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+            const float4 h = make_float4(tf32_rn(v[i].x), tf32_rn(v[i].y), tf32_rn(v[i].z), tf32_rn(v[i].w));
+            *reinterpret_cast<float4*>(hi) = h;
+            *reinterpret_cast<float4*>(hi + TILE_BYTES) =
+                make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+          }
         }
       }
       fence_async_smem();                                                  // generic-proxy writes -> async proxy

@@ -56,17 +56,17 @@ attn_prep_fwd_kernel(EdgeLayout L, int in_dim, int feat_dim, int ld_rows, const 
 
 constexpr int PREP_CCH = 32;   // feature columns per block in the feat-path backward
 
-// grid = F + ceil(F/PREP_CCH) + 1 blocks:
+// grid = F + ceil(F/PREP_CCH) + 10 blocks:
 //   block r < F                   : dW row r and da[k, j] (a_src part), da[k, d + j] = 0
 //   block F + cb                  : columns [cb*32, cb*32+32): da[k, 2d+j], dbf, dWf rows
-//   last block                    : dT
+//   last 10 blocks                : dT[b, :], one block per TF-IDF box
 __global__ void __launch_bounds__(256)
 attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __restrict__ W,
                      const float* __restrict__ Wf, const float* __restrict__ bf, const float* __restrict__ a,
                      const float* __restrict__ T, const float* __restrict__ dW_aug, const float* __restrict__ dq,
                      float* __restrict__ dW, float* __restrict__ dWf, float* __restrict__ dbf,
                      float* __restrict__ da, float* __restrict__ dT) {
-  __shared__ float sm[2 * PREP_CCH * HSG_N_BINS + 32];
+  __shared__ float sm[2 * PREP_CCH * HSG_N_BINS + 32];   // 672 floats (>= 512 for the dT blocks)
   const int H = L.H, d = L.D, F = H * d;
   const int r = blockIdx.x;
   const int ncb = ceil_div(F, PREP_CCH);
@@ -132,15 +132,33 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
     }
     return;
   }
-  // dT[b, f] = sum_c ddfeat[b, c] Wf[c, f]
-  for (int o = threadIdx.x; o < HSG_N_BINS * feat_dim; o += blockDim.x) {
-    const int b = o / feat_dim, f = o % feat_dim;
-    float s = 0.f;
+  // dT[b, :] = sum_c ddfeat[b, c] Wf[c, :]   one block per TF-IDF box b, 4 column chunks x 64 features
+  const int b = r - (F + ncb);
+  float* dd_s = sm;                                      // [F] ddfeat[b, :]  (F <= 512 fits: 2*320+32 floats? no -> loop)
+  __shared__ float part_s[4][64];
+  const int f = threadIdx.x & 63, ch = threadIdx.x >> 6;   // 256 threads
+  float acc = 0.f;
+  for (int c0 = 0; c0 < F; c0 += 512) {
+    const int cn = min(512, F - c0);
+    __syncthreads();
+    for (int c = threadIdx.x; c < cn; c += blockDim.x) {
+      const int cc = c0 + c, k = cc / d, j = cc % d;
+      dd_s[c] = dq[b * H + k] * a[k * 3 * d + 2 * d + j];
+    }
+    __syncthreads();
+    if (f < feat_dim)
+      for (int c = ch; c < cn; c += 4) acc = fmaf(dd_s[c], Wf[(size_t)(c0 + c) * feat_dim + f], acc);
+  }
+  part_s[ch][f] = acc;
+  __syncthreads();
+  if (ch == 0 && f < feat_dim) dT[b * feat_dim + f] = (part_s[0][f] + part_s[1][f]) + (part_s[2][f] + part_s[3][f]);
+  for (int f2 = 64 + threadIdx.x; f2 < feat_dim; f2 += blockDim.x) {   // feat_dim > 64: plain loop
+    float s2 = 0.f;
     for (int c = 0; c < F; ++c) {
       const int k = c / d, j = c % d;
-      s = fmaf(dq[b * H + k] * a[k * 3 * d + 2 * d + j], Wf[(size_t)c * feat_dim + f], s);
+      s2 = fmaf(dq[b * H + k] * a[k * 3 * d + 2 * d + j], Wf[(size_t)c * feat_dim + f2], s2);
     }
-    dT[o] = s;
+    dT[b * feat_dim + f2] = s2;
   }
 }
 
@@ -174,7 +192,7 @@ int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows, const
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_PREP_BWD, s);
   const int F = H * d;
-  attn_prep_bwd_kernel<<<F + ceil_div(F, PREP_CCH) + 1, 256, 0, s>>>(L, in_dim, feat_dim, W, Wf, bf, a, T, dW_aug, dq,
+  attn_prep_bwd_kernel<<<F + ceil_div(F, PREP_CCH) + HSG_N_BINS, 256, 0, s>>>(L, in_dim, feat_dim, W, Wf, bf, a, T, dW_aug, dq,
                                                                     dW, dWf, dbf, da, dT);
   return check_launch();
 }
