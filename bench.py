@@ -241,12 +241,9 @@ def run_ours(args):
     n_graphs_global = tb.n_graphs * world
     torch.manual_seed(1234)
     model = HSGPath(n_iter=n_iter, hdsg=hdsg).to(dev)
-    params = [p for p in model.parameters() if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)          # contiguous gradient arena
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    from hetersumgraph_b200.dist import FlatGradArena
+    arena = FlatGradArena(model.parameters())                               # contiguous gradient arena
+    params, flat = arena.params, arena.flat
     opt = torch.optim.Adam(params, lr=5e-4, fused=True)
 
     host, h2d_tok_bytes = DeviceTokenBatch.host_buffers(tb)

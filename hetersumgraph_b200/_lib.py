@@ -44,6 +44,22 @@ class GraphOutC(C.Structure):
                 ("word_bin", C.c_void_p), ("word_eid", C.c_void_p), ("status", C.c_void_p)]
 
 
+class WswgatFwdArgsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("H", "d", "in_dim", "d_hid", "n_src", "n_dst", "ldz", "reserved")] + \
+               [("csc", C.POINTER(CscC))] + \
+               [(n, C.c_void_p) for n in ("neighbor", "origin", "W_aug", "q", "w1", "b1", "w2", "b2", "gamma", "beta",
+                                          "zp", "sh", "x", "stat", "hdn", "r", "ln_stats", "out")]
+
+
+class WswgatBwdArgsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("H", "d", "in_dim", "d_hid", "n_src", "n_dst", "ldz", "reserved")] + \
+               [("csc_t", C.POINTER(CscC))] + \
+               [(n, C.c_void_p) for n in ("dout", "neighbor", "W_aug", "q", "w1", "w2", "gamma", "zp", "sh", "x", "hdn",
+                                          "r", "ln_stats", "stat", "dr", "dhp", "g", "dzp", "dx", "d_neighbor",
+                                          "dW_aug", "dq", "dw1", "db1", "dw2", "db2", "dgamma", "dbeta", "ws")] + \
+               [("ws_bytes", C.c_size_t)]
+
+
 _I, _P, _Z = C.c_int, C.c_void_p, C.c_size_t
 
 _PROTOS = {
@@ -74,6 +90,9 @@ _PROTOS = {
     "hsg_edge_bwd_prep": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd_workspace_bytes": (_Z, [_I]),
     "hsg_edge_bwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "hsg_wswgat_fwd": (C.c_int, [C.POINTER(WswgatFwdArgsC), _P]),
+    "hsg_wswgat_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "hsg_wswgat_bwd": (C.c_int, [C.POINTER(WswgatBwdArgsC), _P]),
     "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),
     "hsg_layernorm_bwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

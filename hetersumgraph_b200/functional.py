@@ -224,37 +224,113 @@ class FFNFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
-# whole WSWGAT application (the fused path used by the update loop)
+# whole WSWGAT application: attention prep (once per layer) + one coarse-grained C call per direction
 # --------------------------------------------------------------------------------------------
-class WSWGATFn(torch.autograd.Function):
-    """h = FFN(elu(multi_head(g, neighbor)) + origin)   (GAT.py:56-58)."""
+class AttnPrepFn(torch.autograd.Function):
+    """(W, Wf, bf, a, T) -> (W_aug, q): attn_fc folded into the projection weight and the TF-IDF table.
+    Depends on parameters only, so the update loop runs it once per layer and step; autograd sums the
+    dW_aug / dq of every application before the single backward call."""
 
     @staticmethod
-    def forward(ctx, batch, kind, H, d, neighbor, origin, W, Wf, bf, a, T, w1, b1, w2, b2, gamma, beta):
+    def forward(ctx, H, d, W, Wf, bf, a, T):
         _lib.require_device()
-        csc, _ = batch.csc(kind)
-        neighbor, origin, W, Wf, a, T, w1, b1, w2, b2, gamma, beta = (
-            _f32c(t) for t in (neighbor, origin, W, Wf, a, T, w1, b1, w2, b2, gamma, beta))
+        lib = _lib.load()
+        W, Wf, a, T = (_f32c(t) for t in (W, Wf, a, T))
         bf = _f32c(bf) if bf is not None else None
-        if neighbor.shape[0] != csc.n_src or origin.shape[0] != csc.n_dst:
+        _, ldz = _lib.edge_layout(H, d)
+        W_aug = torch.empty(ldz, W.shape[1], dtype=torch.float32, device=W.device)
+        q = torch.empty(_N_BINS, H, dtype=torch.float32, device=W.device)
+        _lib.check(lib.hsg_attn_prep_fwd(H, d, W.shape[1], Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a), _p(T),
+                                         _p(W_aug), _p(q), _st()))
+        ctx.H, ctx.d, ctx.has_bf = H, d, bf is not None
+        ctx.save_for_backward(W, Wf, bf if bf is not None else W.new_empty(0), a, T)
+        return W_aug, q
+
+    @staticmethod
+    def backward(ctx, dW_aug, dq):
+        lib = _lib.load()
+        W, Wf, bf, a, T = ctx.saved_tensors
+        bf = bf if ctx.has_bf else None
+        _, ldz = _lib.edge_layout(ctx.H, ctx.d)
+        dW_aug, dq = _f32c(dW_aug), _f32c(dq)
+        dW, dWf, da, dT = torch.empty_like(W), torch.empty_like(Wf), torch.empty_like(a), torch.empty_like(T)
+        dbf = torch.empty_like(bf) if bf is not None else None
+        _lib.check(lib.hsg_attn_prep_bwd(ctx.H, ctx.d, W.shape[1], Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a),
+                                         _p(T), _p(dW_aug), _p(dq), _p(dW), _p(dWf), _p(dbf), _p(da), _p(dT), _st()))
+        return None, None, dW, dWf, dbf, da, dT
+
+
+def _carve(sizes, device):
+    """One allocation, 16-byte aligned sub-buffers: returns (arena, {name: (offset, numel)})."""
+    off, table = 0, {}
+    for name, n in sizes:
+        table[name] = (off, n)
+        off += (n + 3) & ~3
+    return torch.empty(max(off, 4), dtype=torch.float32, device=device), table
+
+
+class WSWGATCoreFn(torch.autograd.Function):
+    """out = FFN(elu(multi_head(g, neighbor)) + origin)   (GAT.py:56-58) given the prepared (W_aug, q)."""
+
+    @staticmethod
+    def forward(ctx, batch, kind, H, d, neighbor, origin, W_aug, q, w1, b1, w2, b2, gamma, beta):
+        _lib.require_device()
+        lib = _lib.load()
+        csc, csc_t = batch.csc(kind)
+        neighbor, origin, W_aug, q, w1, b1, w2, b2, gamma, beta = (
+            _f32c(t) for t in (neighbor, origin, W_aug, q, w1, b1, w2, b2, gamma, beta))
+        n_src, n_dst, F, in_dim, d_hid = csc.n_src, csc.n_dst, H * d, neighbor.shape[1], w1.shape[0]
+        if neighbor.shape[0] != n_src or origin.shape[0] != n_dst:
             raise ValueError("%s: got %d neighbor / %d origin rows, graph has %d / %d" %
-                             (kind, neighbor.shape[0], origin.shape[0], csc.n_src, csc.n_dst))
-        if origin.shape[1] != H * d:
-            raise ValueError("origin width %d != heads*head_dim %d" % (origin.shape[1], H * d))
-        W_aug, q, zp, sh, x, stat = _mh_forward(csc, H, d, neighbor, origin, W, Wf, bf, a, T)
-        hdn, r, stats, out = _ffn_forward(x, w1, b1, w2, b2, gamma, beta)
-        ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.has_bf = batch, kind, H, d, bf is not None
-        ctx.save_for_backward(neighbor, W, Wf, bf if bf is not None else W.new_empty(0), a, T, W_aug, q, zp, sh,
-                              stat, x, w1, w2, gamma, hdn, r, stats)
-        return out
+                             (kind, neighbor.shape[0], origin.shape[0], n_src, n_dst))
+        if origin.shape[1] != F:
+            raise ValueError("origin width %d != heads*head_dim %d" % (origin.shape[1], F))
+        fp, ldz = _lib.edge_layout(H, d)
+        arena, tb = _carve([("out", n_dst * F), ("zp", n_src * ldz), ("sh", n_dst * F), ("x", n_dst * F),
+                            ("stat", n_dst * 3 * H), ("hdn", n_dst * d_hid), ("r", n_dst * F), ("ln", n_dst * 2)],
+                           neighbor.device)
+        base = arena.data_ptr()
+        ptr = {k: base + 4 * v[0] for k, v in tb.items()}
+        args = _lib.WswgatFwdArgsC(H, d, in_dim, d_hid, n_src, n_dst, ldz, 0, C.pointer(csc), _p(neighbor), _p(origin),
+                                   _p(W_aug), _p(q), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(beta), ptr["zp"],
+                                   ptr["sh"], ptr["x"], ptr["stat"], ptr["hdn"], ptr["r"], ptr["ln"], ptr["out"])
+        _lib.check(lib.hsg_wswgat_fwd(C.byref(args), _st()))
+        if RELU_MASK_CAPTURE is not None:
+            o, n = tb["hdn"]
+            RELU_MASK_CAPTURE.append((arena[o:o + n].view(n_dst, d_hid) > 0).cpu())
+        ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.dims = batch, kind, H, d, (n_src, n_dst, F, in_dim, d_hid, fp, ldz)
+        ctx.ptr = ptr
+        ctx.save_for_backward(neighbor, W_aug, q, w1, w2, gamma, arena)
+        return arena[:n_dst * F].view(n_dst, F)
 
     @staticmethod
     def backward(ctx, dout):
-        (neighbor, W, Wf, bf, a, T, W_aug, q, zp, sh, stat, x, w1, w2, gamma, hdn, r, stats) = ctx.saved_tensors
-        bf = bf if ctx.has_bf else None
+        lib = _lib.load()
+        neighbor, W_aug, q, w1, w2, gamma, arena = ctx.saved_tensors
+        n_src, n_dst, F, in_dim, d_hid, fp, ldz = ctx.dims
+        H, d, ptr = ctx.H, ctx.d, ctx.ptr
         _, csc_t = ctx.batch.csc(ctx.kind)
-        dx, dw1, db1, dw2, db2, dgamma, dbeta = _ffn_backward(_f32c(dout), x, w1, w2, gamma, hdn, r, stats)
-        dh, dW, dWf, dbf, da, dT = _mh_backward(csc_t, ctx.H, ctx.d, neighbor, W, Wf, bf, a, T, W_aug, q, zp, sh,
-                                                stat, dx=dx)
-        # d origin = dx (residual, GAT.py:57)
-        return (None, None, None, None, dh, dx, dW, dWf, dbf, da, dT, dw1, db1, dw2, db2, dgamma, dbeta)
+        dout = _f32c(dout)
+        dev = dout.device
+        garena, tb = _carve([("dx", n_dst * F), ("d_neighbor", n_src * in_dim), ("dW_aug", ldz * in_dim),
+                             ("dq", _N_BINS * H), ("dw1", d_hid * F), ("db1", d_hid), ("dw2", F * d_hid), ("db2", F),
+                             ("dgamma", F), ("dbeta", F), ("dr", n_dst * F), ("dhp", n_dst * d_hid), ("g", n_dst * fp),
+                             ("dzp", n_src * ldz)], dev)
+        gbase = garena.data_ptr()
+        gp = {k: gbase + 4 * v[0] for k, v in tb.items()}
+        ws_bytes = lib.hsg_wswgat_bwd_workspace_bytes(H, d, in_dim, d_hid, n_src, n_dst)
+        ws = _Workspace.get(ws_bytes, dev, "wswgat")
+        args = _lib.WswgatBwdArgsC(H, d, in_dim, d_hid, n_src, n_dst, ldz, 0, C.pointer(csc_t), _p(dout), _p(neighbor),
+                                   _p(W_aug), _p(q), _p(w1), _p(w2), _p(gamma), ptr["zp"], ptr["sh"], ptr["x"],
+                                   ptr["hdn"], ptr["r"], ptr["ln"], ptr["stat"], gp["dr"], gp["dhp"], gp["g"],
+                                   gp["dzp"], gp["dx"], gp["d_neighbor"], gp["dW_aug"], gp["dq"], gp["dw1"], gp["db1"],
+                                   gp["dw2"], gp["db2"], gp["dgamma"], gp["dbeta"], _p(ws), ws.numel())
+        _lib.check(lib.hsg_wswgat_bwd(C.byref(args), _st()))
+
+        def view(name, *shape):
+            o, n = tb[name]
+            return garena[o:o + n].view(*shape)
+
+        return (None, None, None, None, view("d_neighbor", n_src, in_dim), view("dx", n_dst, F),
+                view("dW_aug", ldz, in_dim), view("dq", _N_BINS, H), view("dw1", d_hid, F), view("db1", d_hid),
+                view("dw2", F, d_hid), view("db2", F), view("dgamma", F), view("dbeta", F))

@@ -17,7 +17,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .functional import FFNFn, MultiHeadFn, WSWGATFn
+from .functional import AttnPrepFn, FFNFn, MultiHeadFn, WSWGATCoreFn
 
 
 class WSGATLayer:
@@ -157,7 +157,16 @@ class WSWGAT(nn.Module):
             raise NotImplementedError("GAT Layer has not been implemented!")
         self.ffn = PositionwiseFeedForward(out_dim, ffn_inner_hidden_size, ffn_drop_out)
 
-    def forward(self, g, w, s):
+    def prepare(self, g):
+        """(W_aug, q) of this layer for the TF-IDF table carried by `g`: parameters only, reusable across the
+        applications of one step (the update loop of HiGraph.py:98-106 re-applies the same modules)."""
+        lay = self.layer
+        if g.tfidfembed_weight is None:
+            raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight)")
+        return AttnPrepFn.apply(lay.num_heads, lay.out_dim, lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias,
+                                lay.attn_fc_weight, g.tfidfembed_weight)
+
+    def forward(self, g, w, s, prepared=None):
         if self.layerType == "W2S":
             origin, neighbor = s, w
         else:
@@ -165,11 +174,9 @@ class WSWGAT(nn.Module):
         lay = self.layer
         _check_dropout(lay, lay.dropout.p, "attention-input")
         _check_dropout(self.ffn, self.ffn.dropout.p, "FFN")
-        if g.tfidfembed_weight is None:
-            raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight)")
-        return WSWGATFn.apply(g, self.layerType, lay.num_heads, lay.out_dim, neighbor, origin, lay.fc_weight,
-                              lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight, g.tfidfembed_weight,
-                              *self.ffn.packed())
+        W_aug, q = prepared if prepared is not None else self.prepare(g)
+        return WSWGATCoreFn.apply(g, self.layerType, lay.num_heads, lay.out_dim, neighbor, origin, W_aug, q,
+                                  *self.ffn.packed())
 
 
 class WSWGATUpdateLoop(nn.Module):
@@ -188,9 +195,11 @@ class WSWGATUpdateLoop(nn.Module):
 
     def forward(self, graph, word_feature, sent_feature):
         graph.set_tfidf_embedding(self._TFembed.weight)
+        p_w2s = self.word2sent.prepare(graph)                 # once per layer and step (shared weights)
+        p_s2w = self.sent2word.prepare(graph) if self._n_iter > 0 else None
         word_state = word_feature
-        sent_state = self.word2sent(graph, word_feature, sent_feature)
+        sent_state = self.word2sent(graph, word_feature, sent_feature, prepared=p_w2s)
         for _ in range(self._n_iter):
-            word_state = self.sent2word(graph, word_state, sent_state)
-            sent_state = self.word2sent(graph, word_state, sent_state)
+            word_state = self.sent2word(graph, word_state, sent_state, prepared=p_s2w)
+            sent_state = self.word2sent(graph, word_state, sent_state, prepared=p_w2s)
         return word_state, sent_state

@@ -231,6 +231,41 @@ size_t hsg_layernorm_bwd_workspace_bytes(int N, int D);
 int hsg_layernorm_bwd(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma,
                       float* dr, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Coarse-grained entry points: every kernel of ONE WSWGAT application (module/GAT.py:45-59), forward or
+ * backward, from one call.  W_aug / q come from hsg_attn_prep_fwd (once per layer and step: the update loop
+ * of HiGraph.py:98-106 re-applies the same two weight sets); dW_aug / dq are summed over the applications by
+ * the caller and go through hsg_attn_prep_bwd once.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t H, d, in_dim, d_hid, n_src, n_dst, ldz, reserved;
+  const hsg_csc* csc;                  /* in-edges of the destination rows */
+  const float *neighbor, *origin;      /* [n_src,in_dim], [n_dst,H*d] */
+  const float *W_aug, *q;              /* [ldz,in_dim], [10,H] */
+  const float *w1, *b1, *w2, *b2, *gamma, *beta;   /* FFN: [d_hid,F] [d_hid] [F,d_hid] [F] [F] [F] */
+  float *zp, *sh, *x, *stat, *hdn, *r, *ln_stats;  /* saved for backward */
+  float* out;                          /* [n_dst,F] */
+} hsg_wswgat_fwd_args;
+int hsg_wswgat_fwd(const hsg_wswgat_fwd_args* args, void* stream);
+
+typedef struct {
+  int32_t H, d, in_dim, d_hid, n_src, n_dst, ldz, reserved;
+  const hsg_csc* csc_t;                /* transposed structure (rows = forward sources) */
+  const float* dout;                   /* [n_dst,F] */
+  const float *neighbor, *W_aug, *q, *w1, *w2, *gamma;
+  const float *zp, *sh, *x, *hdn, *r, *ln_stats;
+  float* stat;                         /* (m, den) from forward; s is written here */
+  float *dr, *dhp, *g, *dzp;           /* scratch: [n_dst,F] [n_dst,d_hid] [n_dst,fp] [n_src,ldz] */
+  float *dx;                           /* [n_dst,F]  = d origin */
+  float *d_neighbor;                   /* [n_src,in_dim] */
+  float *dW_aug, *dq;                  /* [ldz,in_dim], [10,H] */
+  float *dw1, *db1, *dw2, *db2, *dgamma, *dbeta;
+  void* ws;
+  size_t ws_bytes;
+} hsg_wswgat_bwd_args;
+size_t hsg_wswgat_bwd_workspace_bytes(int H, int d, int in_dim, int d_hid, int n_src, int n_dst);
+int hsg_wswgat_bwd(const hsg_wswgat_bwd_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
