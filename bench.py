@@ -242,9 +242,9 @@ def run_ours(args):
     torch.manual_seed(1234)
     model = HSGPath(n_iter=n_iter, hdsg=hdsg).to(dev)
     from hetersumgraph_b200.dist import FlatGradArena
-    arena = FlatGradArena(model.parameters())                               # contiguous gradient arena
-    params, flat = arena.params, arena.flat
-    opt = torch.optim.Adam(params, lr=5e-4, fused=True)
+    arena = FlatGradArena(model.parameters(), flatten_params=True)         # contiguous gradient + parameter arenas
+    flat = arena.flat
+    opt = torch.optim.Adam([arena.flat_param], lr=5e-4, fused=True)       # one fused kernel over the flat arena
 
     host, h2d_tok_bytes = DeviceTokenBatch.host_buffers(tb)
     bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)

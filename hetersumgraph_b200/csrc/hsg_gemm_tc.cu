@@ -23,6 +23,9 @@
 // extra all-ones B column.
 #include <cuda.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "hsg_common.cuh"
 
 namespace hsg {
@@ -366,18 +369,69 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+typedef CUresult (*ReplaceAddrFn)(CUtensorMap*, void*);
+
+static ReplaceAddrFn replace_fn() {
+  static ReplaceAddrFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapReplaceAddress", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<ReplaceAddrFn>(p);
+  }
+  return fn;
+}
+
 // 2-D fp32 tensor [outer, inner] with row pitch ld (elements); box = {32 inner, box_outer}; elements outside
-// [inner, outer] are zero-filled by the TMA unit.
+// [inner, outer] are zero-filled by the TMA unit.  Encoded maps are cached by geometry (the same few shapes recur
+// every step); only the base address is patched per call.
+struct MapKey {
+  int inner, outer, ld, box_outer, mn;
+  bool operator==(const MapKey& o) const {
+    return inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer && mn == o.mn;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.inner * 1000003u;
+    h = (h ^ (size_t)k.outer) * 1000003u;
+    h = (h ^ (size_t)k.ld) * 1000003u;
+    h = (h ^ (size_t)k.box_outer) * 1000003u;
+    return h ^ (size_t)k.mn;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
 static bool make_map(CUtensorMap* m, const float* ptr, int inner, int outer, int ld, int box_outer, bool mn_major) {
+  ReplaceAddrFn rep = replace_fn();
+  const MapKey key{inner, outer, ld, box_outer, mn_major ? 1 : 0};
+  if (rep) {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *m = it->second;
+      return rep(m, const_cast<float*>(ptr)) == CUDA_SUCCESS;
+    }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const bool ok =
+      fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (ok && rep) {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() < 4096) g_maps.emplace(key, *m);
+  }
+  return ok;
 }
 
 struct Operand {

@@ -32,7 +32,7 @@ class FlatGradArena:
     """All trainable gradients of a module as views into ONE contiguous fp32 buffer, so the data-parallel
     exchange is a single in-place all-reduce (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests)."""
 
-    def __init__(self, params):
+    def __init__(self, params, flatten_params=False):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
@@ -41,6 +41,19 @@ class FlatGradArena:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self.flat_param = None
+        if flatten_params:
+            # parameters become views of one buffer as well: the optimizer then updates ONE tensor with ONE fused
+            # kernel (Adam is element-wise, so this is the same arithmetic as per-tensor Adam)
+            with torch.no_grad():
+                buf = torch.empty(n, dtype=torch.float32, device=dev)
+                off = 0
+                for p in self.params:
+                    buf[off:off + p.numel()].copy_(p.reshape(-1))
+                    p.data = buf[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+            self.flat_param = torch.nn.Parameter(buf)
+            self.flat_param.grad = self.flat
 
     def zero(self):
         self.flat.zero_()

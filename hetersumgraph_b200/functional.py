@@ -260,13 +260,35 @@ class AttnPrepFn(torch.autograd.Function):
         return None, None, dW, dWf, dbf, da, dT
 
 
-def _carve(sizes, device):
-    """One allocation, 16-byte aligned sub-buffers: returns (arena, {name: (offset, numel)})."""
-    off, table = 0, {}
-    for name, n in sizes:
-        table[name] = (off, n)
-        off += (n + 3) & ~3
-    return torch.empty(max(off, 4), dtype=torch.float32, device=device), table
+_LAYOUT_CACHE = {}
+
+
+def _layout(key, sizes):
+    """cached (names, sizes, offsets, total) of an arena; every size is padded to a multiple of 4 floats."""
+    lay = _LAYOUT_CACHE.get(key)
+    if lay is None:
+        names = [n for n, _ in sizes]
+        padded = [(n + 3) & ~3 for _, n in sizes]
+        offs, off = [], 0
+        for n in padded:
+            offs.append(off)
+            off += n
+        lay = (names, [n for _, n in sizes], padded, offs, max(off, 4))
+        _LAYOUT_CACHE[key] = lay
+    return lay
+
+
+def _fill(struct, ints, ptrs):
+    """bulk-fill a ctypes argument block: 8 leading int32 + pointer-sized fields (much cheaper than 30+ keyword
+    conversions per call)."""
+    n = len(ptrs)
+    arr = (C.c_uint64 * (4 + n)).from_buffer(struct)
+    arr[0] = (ints[0] & 0xFFFFFFFF) | (ints[1] << 32)
+    arr[1] = (ints[2] & 0xFFFFFFFF) | (ints[3] << 32)
+    arr[2] = (ints[4] & 0xFFFFFFFF) | (ints[5] << 32)
+    arr[3] = (ints[6] & 0xFFFFFFFF) | (ints[7] << 32)
+    arr[4:4 + n] = ptrs
+    return struct
 
 
 class WSWGATCoreFn(torch.autograd.Function):
@@ -286,20 +308,21 @@ class WSWGATCoreFn(torch.autograd.Function):
         if origin.shape[1] != F:
             raise ValueError("origin width %d != heads*head_dim %d" % (origin.shape[1], F))
         fp, ldz = _lib.edge_layout(H, d)
-        arena, tb = _carve([("out", n_dst * F), ("zp", n_src * ldz), ("sh", n_dst * F), ("x", n_dst * F),
-                            ("stat", n_dst * 3 * H), ("hdn", n_dst * d_hid), ("r", n_dst * F), ("ln", n_dst * 2)],
-                           neighbor.device)
+        _, _, _, offs, total = _layout(("f", H, d, n_src, n_dst, in_dim, d_hid), (
+            ("out", n_dst * F), ("zp", n_src * ldz), ("sh", n_dst * F), ("x", n_dst * F), ("stat", n_dst * 3 * H),
+            ("hdn", n_dst * d_hid), ("r", n_dst * F), ("ln", n_dst * 2)))
+        arena = torch.empty(total, dtype=torch.float32, device=neighbor.device)
         base = arena.data_ptr()
-        ptr = {k: base + 4 * v[0] for k, v in tb.items()}
-        args = _lib.WswgatFwdArgsC(H, d, in_dim, d_hid, n_src, n_dst, ldz, 0, C.pointer(csc), _p(neighbor), _p(origin),
-                                   _p(W_aug), _p(q), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(beta), ptr["zp"],
-                                   ptr["sh"], ptr["x"], ptr["stat"], ptr["hdn"], ptr["r"], ptr["ln"], ptr["out"])
+        o_out, o_zp, o_sh, o_x, o_stat, o_hdn, o_r, o_ln = (base + 4 * o for o in offs)
+        args = _fill(_lib.WswgatFwdArgsC(), (H, d, in_dim, d_hid, n_src, n_dst, ldz, 0),
+                     [C.addressof(csc), neighbor.data_ptr(), origin.data_ptr(), W_aug.data_ptr(), q.data_ptr(),
+                      w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                      o_zp, o_sh, o_x, o_stat, o_hdn, o_r, o_ln, o_out])
         _lib.check(lib.hsg_wswgat_fwd(C.byref(args), _st()))
         if RELU_MASK_CAPTURE is not None:
-            o, n = tb["hdn"]
-            RELU_MASK_CAPTURE.append((arena[o:o + n].view(n_dst, d_hid) > 0).cpu())
+            RELU_MASK_CAPTURE.append((arena[offs[5]:offs[5] + n_dst * d_hid].view(n_dst, d_hid) > 0).cpu())
         ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.dims = batch, kind, H, d, (n_src, n_dst, F, in_dim, d_hid, fp, ldz)
-        ctx.ptr = ptr
+        ctx.ptr = (o_zp, o_sh, o_x, o_stat, o_hdn, o_r, o_ln)
         ctx.save_for_backward(neighbor, W_aug, q, w1, w2, gamma, arena)
         return arena[:n_dst * F].view(n_dst, F)
 
@@ -308,29 +331,33 @@ class WSWGATCoreFn(torch.autograd.Function):
         lib = _lib.load()
         neighbor, W_aug, q, w1, w2, gamma, arena = ctx.saved_tensors
         n_src, n_dst, F, in_dim, d_hid, fp, ldz = ctx.dims
-        H, d, ptr = ctx.H, ctx.d, ctx.ptr
+        H, d = ctx.H, ctx.d
+        o_zp, o_sh, o_x, o_stat, o_hdn, o_r, o_ln = ctx.ptr
         _, csc_t = ctx.batch.csc(ctx.kind)
         dout = _f32c(dout)
         dev = dout.device
-        garena, tb = _carve([("dx", n_dst * F), ("d_neighbor", n_src * in_dim), ("dW_aug", ldz * in_dim),
-                             ("dq", _N_BINS * H), ("dw1", d_hid * F), ("db1", d_hid), ("dw2", F * d_hid), ("db2", F),
-                             ("dgamma", F), ("dbeta", F), ("dr", n_dst * F), ("dhp", n_dst * d_hid), ("g", n_dst * fp),
-                             ("dzp", n_src * ldz)], dev)
-        gbase = garena.data_ptr()
-        gp = {k: gbase + 4 * v[0] for k, v in tb.items()}
+        # returned gradients first (sizes are multiples of 4 floats: one split_with_sizes gives all views), scratch after
+        names, sizes, padded, offs, total = _layout(("b", H, d, n_src, n_dst, in_dim, d_hid), (
+            ("d_neighbor", n_src * in_dim), ("dx", n_dst * F), ("dW_aug", ldz * in_dim), ("dq", _N_BINS * H),
+            ("dw1", d_hid * F), ("db1", d_hid), ("dw2", F * d_hid), ("db2", F), ("dgamma", F), ("dbeta", F),
+            ("dr", n_dst * F), ("dhp", n_dst * d_hid), ("g", n_dst * fp), ("dzp", n_src * ldz)))
+        garena = torch.empty(total, dtype=torch.float32, device=dev)
+        gb_ = garena.data_ptr()
+        (p_dn, p_dx, p_dWa, p_dq, p_dw1, p_db1, p_dw2, p_db2, p_dg, p_db, p_dr, p_dhp, p_g, p_dzp) = (
+            gb_ + 4 * o for o in offs)
         ws_bytes = lib.hsg_wswgat_bwd_workspace_bytes(H, d, in_dim, d_hid, n_src, n_dst)
         ws = _Workspace.get(ws_bytes, dev, "wswgat")
-        args = _lib.WswgatBwdArgsC(H, d, in_dim, d_hid, n_src, n_dst, ldz, 0, C.pointer(csc_t), _p(dout), _p(neighbor),
-                                   _p(W_aug), _p(q), _p(w1), _p(w2), _p(gamma), ptr["zp"], ptr["sh"], ptr["x"],
-                                   ptr["hdn"], ptr["r"], ptr["ln"], ptr["stat"], gp["dr"], gp["dhp"], gp["g"],
-                                   gp["dzp"], gp["dx"], gp["d_neighbor"], gp["dW_aug"], gp["dq"], gp["dw1"], gp["db1"],
-                                   gp["dw2"], gp["db2"], gp["dgamma"], gp["dbeta"], _p(ws), ws.numel())
+        args = _fill(_lib.WswgatBwdArgsC(), (H, d, in_dim, d_hid, n_src, n_dst, ldz, 0),
+                     [C.addressof(csc_t), dout.data_ptr(), neighbor.data_ptr(), W_aug.data_ptr(), q.data_ptr(),
+                      w1.data_ptr(), w2.data_ptr(), gamma.data_ptr(), o_zp, o_sh, o_x, o_hdn, o_r, o_ln, o_stat, p_dr,
+                      p_dhp, p_g, p_dzp, p_dx, p_dn, p_dWa, p_dq, p_dw1, p_db1, p_dw2, p_db2, p_dg, p_db,
+                      ws.data_ptr(), ws.numel()])
         _lib.check(lib.hsg_wswgat_bwd(C.byref(args), _st()))
-
-        def view(name, *shape):
-            o, n = tb[name]
-            return garena[o:o + n].view(*shape)
-
-        return (None, None, None, None, view("d_neighbor", n_src, in_dim), view("dx", n_dst, F),
-                view("dW_aug", ldz, in_dim), view("dq", _N_BINS, H), view("dw1", d_hid, F), view("db1", d_hid),
-                view("dw2", F, d_hid), view("db2", F), view("dgamma", F), view("dbeta", F))
+        n_ret = 10
+        if padded[:n_ret] == sizes[:n_ret]:
+            parts = garena[:offs[n_ret]].split_with_sizes(sizes[:n_ret])
+        else:
+            parts = [garena[offs[i]:offs[i] + sizes[i]] for i in range(n_ret)]
+        dn, dx, dWa, dq, dw1, db1, dw2, db2, dg, db = parts
+        return (None, None, None, None, dn.view(n_src, in_dim), dx.view(n_dst, F), dWa.view(ldz, in_dim),
+                dq.view(_N_BINS, H), dw1.view(d_hid, F), db1, dw2.view(F, d_hid), db2, dg, db)
