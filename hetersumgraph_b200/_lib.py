@@ -80,6 +80,7 @@ _PROTOS = {
     "hsg_attn_prep_bwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hsg_set_gemm_mode": (C.c_int, [_I]),
     "hsg_get_gemm_mode": (C.c_int, []),
+    "hsg_gemm_trace": (C.c_int, [_I, C.POINTER(C.c_ulonglong), _I]),
     "hsg_gemm_nt": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
     "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
     "hsg_gemm_tn_workspace_bytes": (_Z, [_I, _I, _I]),

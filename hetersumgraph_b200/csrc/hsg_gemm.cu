@@ -20,6 +20,7 @@ int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ld
             int ldr, int epi, int precise, cudaStream_t s);
 int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* part, float* part_col,
             int splits, int rows_per_split, int precise, cudaStream_t s);
+int trace_ctl(int on, unsigned long long* host_out, int max_events);
 }  // namespace tc
 
 // 0: FFMA exact fp32, 1: tcgen05 3xTF32 (fp32-parity, default), 2: tcgen05 single-pass TF32
@@ -368,6 +369,8 @@ int hsg_set_gemm_mode(int mode) {
 }
 
 int hsg_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
+int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events) { return tc::trace_ctl(on, host_out, max_events); }
 
 size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
   if (M <= 0 || N1 <= 0 || N2 <= 0) return 16;

@@ -34,12 +34,13 @@ namespace tc {
 constexpr int TM = 128;          // MMA M (TMEM lanes)
 constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int BN_MAX = 128;      // MMA N per CTA (TMEM columns per accumulator)
-constexpr int THREADS = 256;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-7: hi/lo converters
+constexpr int THREADS = 384;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-7: converters, warps 8-11: epilogue
 constexpr int NCONV = 192;
+constexpr int NEPI_WARPS = 4;
 constexpr int TILE_BYTES = TM * 128;             // one hi or lo tile (A: 128 rows, B: up to 128 rows/cols) = 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr int STAGES = 3;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 128;  // + alignment slack + barriers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NEPI_WARPS * 32 * 33 * 4;  // + alignment slack + barriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -145,31 +146,64 @@ struct Epilogue {
 //   K-major  operand: one box {32 k, rows}: row r at r*128, 16-byte chunk c at c ^ (r%8)          (SWIZZLE_128B)
 //   MN-major operand: one box {32 mn, 32 k} per 32-wide MN atom, atoms 4096 B apart; k row at k*128, 32-byte
 //                     unit j at j ^ (k%4)                                                   (SWIZZLE_128B_ATOM_32B)
-// grid: (ceil(Md/128), ceil(Nd_total/bn), splits).  k range of split z: [z*k_per_split, min(K, (z+1)*k_per_split))
+//
+// Persistent kernel: grid = min(#tiles, #SMs); CTA b processes tiles b, b+grid, ... (N fastest, so the CTAs that
+// run together share the A tile through L2).  Two TMEM accumulator sets: the epilogue warps drain set a while the
+// MMA warp already accumulates the next tile into set a^1.
+// optional pipeline trace of CTA 0 (debug / profiling aid): (event id, k-block counter, clock) triples
+__device__ unsigned long long g_trace[3 * 2048];
+__device__ unsigned int g_trace_n;
+__device__ int g_trace_on;
+__device__ __forceinline__ void trace(int ev, uint32_t it) {   // fire-and-forget stores: slot = ev * 256 + it
+  if (g_trace_on && blockIdx.x == 0 && it < 256) {
+    const unsigned int i = (unsigned int)ev * 256u + it;
+    g_trace[3 * i] = (unsigned long long)ev;
+    g_trace[3 * i + 1] = it;
+    g_trace[3 * i + 2] = clock64();
+  }
+}
+
+struct TileInfo {
+  int m0, n0, n_valid, n_mma, k_beg, nkb, z;
+};
+
+__device__ __forceinline__ TileInfo tile_info(int t, int m_tiles, int n_tiles, int Nd, int bn, int K, int k_per_split) {
+  TileInfo ti;
+  const int nt = t % n_tiles;
+  const int r = t / n_tiles;
+  const int mt = r % m_tiles;
+  ti.z = r / m_tiles;
+  ti.m0 = mt * TM;
+  ti.n0 = nt * bn;
+  ti.n_valid = min(bn, Nd - ti.n0);
+  ti.n_mma = (ti.n_valid + 15) & ~15;
+  ti.k_beg = ti.z * k_per_split;
+  const int k_end = min(K, ti.k_beg + k_per_split);
+  ti.nkb = (k_end - ti.k_beg + BK - 1) / BK;
+  return ti;
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Md, int Nd,
-               int K, int bn, int nb_box, int k_per_split, int precise, Epilogue ep) {
+               int K, int bn, int nb_box, int k_per_split, int m_tiles, int n_tiles, int total_tiles, int precise,
+               Epilogue ep) {
   extern __shared__ char smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S] | ready[S] | empty[S] | acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 warps x 32 x 33 floats
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TM;
-  const int n0 = blockIdx.y * bn;
-  const int n_valid = min(bn, Nd - n0);                 // valid D columns of this tile (incl. a ones column)
-  const int n_mma = (n_valid + 15) & ~15;               // MMA N (multiple of 16, <= 128)
-  const int k_beg = blockIdx.z * k_per_split;
-  const int k_end = min(K, k_beg + k_per_split);
-  const int nkb = (k_end - k_beg + BK - 1) / BK;
   const bool want_lo = precise != 0;
   const bool use_conv = want_lo || ep.ones_col >= 0;     // converter warps touch the stage before the MMAs
-  // precise mode keeps the small correction products in a second accumulator (columns 128..255): the tensor
-  // core's fp32 accumulation truncates, so the error grows with the number of updates of one accumulator;
-  // splitting leaves K/8 updates on the main one and adds the two in the epilogue.
-  const uint32_t tmem_cols = want_lo ? 2u * BN_MAX : (uint32_t)BN_MAX;
+  // accumulator set a: main columns [a*acc_cols, +128), precise mode adds correction columns [.. +128, +256):
+  // the tensor core's fp32 accumulation truncates, so the small hi*lo / lo*hi products get their own accumulator
+  // (K/8 updates on the main one instead of 3K/8) and are added in the epilogue.
+  const uint32_t acc_cols = want_lo ? 2u * BN_MAX : (uint32_t)BN_MAX;
+  const uint32_t tmem_cols = 2u * acc_cols;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_ready = smem_u32(&bars[STAGES]),
-                 bar_empty = smem_u32(&bars[2 * STAGES]), bar_acc = smem_u32(&bars[3 * STAGES]);
+                 bar_empty = smem_u32(&bars[2 * STAGES]), bar_tfull = smem_u32(&bars[3 * STAGES]),
+                 bar_tempty = smem_u32(&bars[3 * STAGES + 2]);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -180,9 +214,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);                  // TMA: one arrive.expect_tx + the transaction bytes
       mbar_init(bar_ready + 8 * i, NCONV);             // converters done with the stage
-      mbar_init(bar_empty + 8 * i, 1);                 // tcgen05.commit
+      mbar_init(bar_empty + 8 * i, 1);                 // tcgen05.commit: MMAs drained the stage
     }
-    mbar_init(bar_acc, 1);                             // accumulators complete
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);                 // tcgen05.commit: accumulator set complete
+      mbar_init(bar_tempty + 8 * i, NEPI_WARPS);       // epilogue warps drained the accumulator set
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -196,153 +233,216 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(bar_empty + 8 * slot, ((kb / STAGES) - 1) & 1);   // MMAs drained the slot
-        const uint32_t st = smem_u32(smem + slot * STAGE_BYTES);
-        const int k0 = k_beg + kb * BK;
-        const uint32_t full = bar_full + 8 * slot;
-        mbar_expect_tx(full, stage_tx);
-        if (A_MN) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + 8 * slot, ph ^ 1);                          // MMAs drained the slot
+          trace(1, it);
+          const uint32_t st = smem_u32(smem + slot * STAGE_BYTES);
+          const int k0 = ti.k_beg + kb * BK;
+          const uint32_t full = bar_full + 8 * slot;
+          mbar_expect_tx(full, stage_tx);
+          if (A_MN) {
 #pragma unroll
-          for (int a = 0; a < TM / 32; ++a) tma_load_2d(st + a * 4096, &tmA, m0 + 32 * a, k0, full);
-        } else {
-          tma_load_2d(st, &tmA, k0, m0, full);
-        }
-        if (B_MN) {
-          for (int a = 0; a < nb_box / 32; ++a) tma_load_2d(st + 2 * TILE_BYTES + a * 4096, &tmB, n0 + 32 * a, k0, full);
-        } else {
-          tma_load_2d(st + 2 * TILE_BYTES, &tmB, k0, n0, full);
+            for (int a = 0; a < TM / 32; ++a) tma_load_2d(st + a * 4096, &tmA, ti.m0 + 32 * a, k0, full);
+          } else {
+            tma_load_2d(st, &tmA, k0, ti.m0, full);
+          }
+          if (B_MN) {
+            for (int a = 0; a < nb_box / 32; ++a)
+              tma_load_2d(st + 2 * TILE_BYTES + a * 4096, &tmB, ti.n0 + 32 * a, k0, full);
+          } else {
+            tma_load_2d(st + 2 * TILE_BYTES, &tmB, k0, ti.n0, full);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(A_MN, B_MN, n_mma);
       // K-major: 8-row groups 1024 B apart, a k-step of 8 fp32 = 32 B inside the swizzled row.
       // MN-major: MN atoms 4096 B apart (LBO), 4-k groups 512 B apart (SBO), a k-step of 8 = two groups = 1024 B.
       const uint32_t a_sbo = A_MN ? 512u : 1024u, a_lbo = A_MN ? 4096u : 16u, a_lay = A_MN ? 1u : 2u;
       const uint32_t b_sbo = B_MN ? 512u : 1024u, b_lbo = B_MN ? 4096u : 16u, b_lay = B_MN ? 1u : 2u;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int slot = kb % STAGES;
-        mbar_wait((use_conv ? bar_ready : bar_full) + 8 * slot, (kb / STAGES) & 1);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);                           // epilogue drained this accumulator set
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + slot * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
-        const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+        const uint32_t d_main = tmem_d + acc * acc_cols, d_corr = d_main + BN_MAX;
+        const uint32_t idesc = make_idesc(A_MN, B_MN, ti.n_mma);
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait((use_conv ? bar_ready : bar_full) + 8 * slot, ph);
+          trace(2, it);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + slot * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint32_t a_off = A_MN ? ks * 1024u : ks * 32u;
-          const uint32_t b_off = B_MN ? ks * 1024u : ks * 32u;
-          const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lay),
-                         dbh = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lay);
-          tc_mma_tf32(tmem_d, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          if (want_lo) {
-            const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay),
-                           dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lay);
-            tc_mma_tf32(tmem_d + BN_MAX, dah, dbl, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            tc_mma_tf32(tmem_d + BN_MAX, dal, dbh, idesc, 1u);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t a_off = A_MN ? ks * 1024u : ks * 32u;
+            const uint32_t b_off = B_MN ? ks * 1024u : ks * 32u;
+            const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lay),
+                           dbh = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lay);
+            tc_mma_tf32(d_main, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            if (want_lo) {
+              const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay),
+                             dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lay);
+              tc_mma_tf32(d_corr, dah, dbl, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              tc_mma_tf32(d_corr, dal, dbh, idesc, 1u);
+            }
           }
+          tc_commit(bar_empty + 8 * slot);                                  // frees the slot when the MMAs retire
+          trace(3, it);
         }
-        tc_commit(bar_empty + 8 * slot);                                  // frees the slot when the MMAs retire
-        if (kb == nkb - 1) tc_commit(bar_acc);                            // ... and signals the epilogue
+        tc_commit(bar_tfull + 8 * acc);                                     // accumulators of this tile complete
       }
     }
-  } else if (use_conv) {
+  } else if (warp < 8) {
     // ===== converters (warps 2-7): linear hi/lo sweep over the landed stage =====
-    const int ct = tid - 64;
-    const bool ones_here = B_MN && ep.ones_col >= n0 && ep.ones_col < n0 + nb_box;
-    const int b_chunks = nb_box * 8;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int slot = kb % STAGES;
-      mbar_wait(bar_full + 8 * slot, (kb / STAGES) & 1);                   // this k-block has landed
-      char* st = smem + slot * STAGE_BYTES;
-      if (ones_here) {                                                     // all-ones column (TMA zero-filled it)
-        if (ct < 32 && k_beg + kb * BK + ct < k_end) {
-          const int nl = ep.ones_col - n0, k = ct;
-          const uint32_t off = (uint32_t)(nl >> 5) * 4096u + (uint32_t)k * 128u +
-                               (uint32_t)((((nl & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)(nl & 7) * 4u;
-          *reinterpret_cast<float*>(st + 2 * TILE_BYTES + off) = 1.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(NCONV) : "memory");
-      }
-      if (want_lo) {
-        // (128 + nb_box) * 8 <= 2048 chunks of 16 B over 192 threads: up to 11 per thread, all loads issued first
-        constexpr int CPT = (TM * 8 + BN_MAX * 8 + NCONV - 1) / NCONV;
-        const int total = TM * 8 + b_chunks;
-        float4 v[CPT];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const int id = ct + i * NCONV;
-          const char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
-          v[i] = id < total ? *reinterpret_cast<const float4*>(hi) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const int id = ct + i * NCONV;
-          if (id < total) {
-            char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
-            const float4 h = make_float4(tf32_rn(v[i].x), tf32_rn(v[i].y), tf32_rn(v[i].z), tf32_rn(v[i].w));
-            *reinterpret_cast<float4*>(hi) = h;
-            *reinterpret_cast<float4*>(hi + TILE_BYTES) =
-                make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+    if (use_conv) {
+      const int ct = tid - 64;
+      const int b_chunks = nb_box * 8;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        const bool ones_here = B_MN && ep.ones_col >= ti.n0 && ep.ones_col < ti.n0 + nb_box;
+        const int k_end = min(K, ti.k_beg + k_per_split);
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + 8 * slot, ph);                                // this k-block has landed
+          if (ct == 0) trace(4, it);
+          char* st = smem + slot * STAGE_BYTES;
+          if (ones_here) {                                                   // all-ones column (TMA zero-filled it)
+            if (ct < 32 && ti.k_beg + kb * BK + ct < k_end) {
+              const int nl = ep.ones_col - ti.n0, k = ct;
+              const uint32_t off = (uint32_t)(nl >> 5) * 4096u + (uint32_t)k * 128u +
+                                   (uint32_t)((((nl & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)(nl & 7) * 4u;
+              *reinterpret_cast<float*>(st + 2 * TILE_BYTES + off) = 1.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NCONV) : "memory");
           }
-        }
-      }
-      fence_async_smem();                                                  // generic-proxy writes -> async proxy
-      mbar_arrive(bar_ready + 8 * slot);
-    }
-  }
-  if (nkb > 0) mbar_wait(bar_acc, 0);
-  tc_fence_after();
-
-  // ---- epilogue: TMEM -> registers -> global ----
-  const int lg = warp & 3;                     // TMEM lane group of this warp
-  const int row = m0 + lg * 32 + lane;
-  float* Dz = ep.D + (size_t)blockIdx.z * ep.split_stride;
-  for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
-    float v[32];
-    if (nkb > 0) {
-      tc_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-      if (want_lo) {
-        float w[32];
-        tc_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN_MAX + c0), w);
+          if (want_lo) {
+            // (128 + nb_box) * 8 <= 2048 chunks of 16 B over 192 threads: up to 11 per thread, loads issued first
+            constexpr int CPT = (TM * 8 + BN_MAX * 8 + NCONV - 1) / NCONV;
+            const int total = TM * 8 + b_chunks;
+            float4 v[CPT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += w[i];
-      }
-    } else {
+            for (int i = 0; i < CPT; ++i) {
+              const int id = ct + i * NCONV;
+              const char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+              v[i] = id < total ? *reinterpret_cast<const float4*>(hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    }
-    if (row < Md) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = n0 + c0 + j;
-        float o[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float c = v[j + t];
-          const int cc = col + t;
-          if (cc < n0 + n_valid && cc != ep.ones_col) {
-            if (ep.epi & HSG_EPI_BIAS) c += __ldg(ep.bias + cc);
-            if (ep.epi & HSG_EPI_RELU) c = fmaxf(c, 0.f);
-            if (ep.epi & HSG_EPI_ADD) c += __ldg(ep.R + (size_t)row * ep.ldr + cc);
-            if (ep.epi & HSG_EPI_RELU_MASK) c = __ldg(ep.R + (size_t)row * ep.ldr + cc) > 0.f ? c : 0.f;
+            for (int i = 0; i < CPT; ++i) {
+              const int id = ct + i * NCONV;
+              if (id < total) {
+                char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+                const float4 h = make_float4(tf32_rn(v[i].x), tf32_rn(v[i].y), tf32_rn(v[i].z), tf32_rn(v[i].w));
+                *reinterpret_cast<float4*>(hi) = h;
+                *reinterpret_cast<float4*>(hi + TILE_BYTES) =
+                    make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+              }
+            }
           }
-          o[t] = c;
+          fence_async_smem();                                                // generic-proxy writes -> async proxy
+          if (ct == 0) trace(5, it);
+          mbar_arrive(bar_ready + 8 * slot);
         }
-        // real output columns of THIS tile (never touch the neighbouring tile's columns)
-        const int n_out = min(ep.ones_col >= 0 ? ep.ones_col : Nd, n0 + n_valid);
-        if (col + 3 < n_out && (ep.ldd & 3) == 0) {
-          *reinterpret_cast<float4*>(Dz + (size_t)row * ep.ldd + col) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 8-11): TMEM -> registers -> global, overlapped with the next tile's main loop =====
+    const int lg = warp & 3;                     // TMEM lane group of this warp (warp 8 -> lanes 0..31, ...)
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      if (tid == 256) trace(6, tl);
+      tc_fence_after();
+      const uint32_t d_main = tmem_d + acc * acc_cols + ((uint32_t)(lg * 32) << 16);
+      float* Dz = ep.D + (size_t)ti.z * ep.split_stride;
+      const int n_lim = ti.n0 + ti.n_valid;
+      const int n_out = min(ep.ones_col >= 0 ? ep.ones_col : Nd, n_lim);   // real output columns of THIS tile
+      // Each thread holds one accumulator ROW (32 columns per TMEM load).  Writing rows from registers would make
+      // every store instruction touch 32 different lines with 16 B each (partial sectors: ~6x slower than the whole
+      // main loop, measured).  So each 32x32 chunk is transposed through a padded shared-memory tile and leaves the
+      // SM as full 128-byte lines: 8 lanes x 16 B per row, 4 rows per store instruction.
+      float* tile = epi_stage + (warp - 8) * (32 * 33);
+      const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
+      for (int c0 = 0; c0 < ti.n_mma; c0 += 32) {
+        float v[32];
+        if (ti.nkb > 0) {
+          tc_ld32(d_main + (uint32_t)c0, v);
+          if (want_lo) {
+            float w[32];
+            tc_ld32(d_main + (uint32_t)(BN_MAX + c0), w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+          }
         } else {
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (col + t < n_out) Dz[(size_t)row * ep.ldd + col + t] = o[t];
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (ep.colsum_part != nullptr && ep.ones_col >= col && ep.ones_col < col + 4)
-          ep.colsum_part[(size_t)blockIdx.z * Md + row] = o[ep.ones_col - col];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];           // bank (lane + i) % 32: conflict-free
+        __syncwarp();
+        const int col = ti.n0 + c0 + c_sub;
+#pragma unroll
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const int rl = p8 * 4 + r_sub;
+          const int row = ti.m0 + lg * 32 + rl;
+          float o[4];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) o[tt] = tile[rl * 33 + c_sub + tt];
+          if (row < Md) {
+            const bool vec = col + 3 < n_out && (ep.ldd & 3) == 0;
+            if (ep.epi != 0) {
+              float rv[4] = {0.f, 0.f, 0.f, 0.f};
+              if (ep.epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) {
+                if (vec && (ep.ldr & 3) == 0) {
+                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.R + (size_t)row * ep.ldr + col));
+                  rv[0] = r4.x; rv[1] = r4.y; rv[2] = r4.z; rv[3] = r4.w;
+                } else {
+#pragma unroll
+                  for (int tt = 0; tt < 4; ++tt)
+                    if (col + tt < n_out) rv[tt] = __ldg(ep.R + (size_t)row * ep.ldr + col + tt);
+                }
+              }
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt) {
+                const int cc = col + tt;
+                if (cc < n_out) {
+                  float c = o[tt];
+                  if (ep.epi & HSG_EPI_BIAS) c += __ldg(ep.bias + cc);
+                  if (ep.epi & HSG_EPI_RELU) c = fmaxf(c, 0.f);
+                  if (ep.epi & HSG_EPI_ADD) c += rv[tt];
+                  if (ep.epi & HSG_EPI_RELU_MASK) c = rv[tt] > 0.f ? c : 0.f;
+                  o[tt] = c;
+                }
+              }
+            }
+            if (vec) {
+              *reinterpret_cast<float4*>(Dz + (size_t)row * ep.ldd + col) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int tt = 0; tt < 4; ++tt)
+                if (col + tt < n_out) Dz[(size_t)row * ep.ldd + col + tt] = o[tt];
+            }
+            if (ep.colsum_part != nullptr && ep.ones_col >= col && ep.ones_col < col + 4)
+              ep.colsum_part[(size_t)ti.z * Md + row] = o[ep.ones_col - col];
+          }
+        }
+        __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (tid == 256) trace(7, tl);
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);                     // hand the accumulator set back
     }
   }
   tc_fence_before();
@@ -459,7 +559,10 @@ static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, in
   const bool okB = B_MN ? make_map(&tmB, B.p, B.ext_mn, B.ext_k, B.ld, 32, true)
                         : make_map(&tmB, B.p, B.ext_k, B.ext_mn, B.ld, nb_box, false);
   if (!okA || !okB) return HSG_ERR_CUDA;
-  gemm_tc_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, precise, ep);
+  const int m_tiles = (int)grid.x, n_tiles = (int)grid.y, total = m_tiles * n_tiles * (int)grid.z;
+  const int ctas = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<A_MN, B_MN><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, m_tiles,
+                                                               n_tiles, total, precise, ep);
   return check_launch();
 }
 
@@ -497,6 +600,19 @@ int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int 
   Epilogue ep{part, N2, (size_t)N1 * N2, nullptr, nullptr, 0, 0, part_col, part_col ? N2 : -1};
   dim3 grid(ceil_div(N1, TM), ceil_div(n_total, bn), splits);
   return launch<true, true>(2, grid, a, b, N1, n_total, M, bn, rows_per_split, precise, ep, s);
+}
+
+int trace_ctl(int on, unsigned long long* host_out, int max_events) {
+  if (on >= 0) {
+    static unsigned long long zeros[3 * 2048];
+    cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+    cudaMemcpyToSymbol(g_trace_on, &on, sizeof(on));
+    return 0;
+  }
+  unsigned int n = 2048;
+  if ((int)n > max_events) n = max_events;
+  if (host_out && n) cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * 3 * sizeof(unsigned long long));
+  return (int)n;
 }
 
 }  // namespace tc

@@ -177,6 +177,9 @@ int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
  * Shapes the tensor-core path cannot take (K or a leading dimension not a multiple of 4) fall back to mode 0. */
 int hsg_set_gemm_mode(int mode);
 int hsg_get_gemm_mode(void);
+/* Profiling aid for the tensor-core pipeline: on = 1/0 arms/disarms a trace of CTA 0 (synchronous call); on < 0 reads
+ * up to max_events (event id, k-block counter, SM clock) triples into host_out and returns their number. */
+int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events);
 /* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward) */
 int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const float* bias, const float* R, int ldr, int epi, void* stream);
