@@ -357,6 +357,9 @@ def run_ours(args):
     stress = None
     if not args.no_stress and world == 1:
         stress = stress_leg(dev, pk, args.stress_scale, args.stress_iters)
+    large = None
+    if not args.no_stress and world == 1:
+        large = large_shard_leg(dev, pk)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -375,6 +378,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": n_graphs_global, "n_iter": n_iter,
                    "dropout": 0.0, "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "gemm_mode": "tf32x3 (tcgen05 kind::tf32, hi/lo split: fp32-parity mode)",
                    "rank0_sizes": {"word_nodes": batch.n_word, "supernodes": batch.n_super, "pairs_per_direction": batch.n_pair,
                                    "dgl_edges": batch.n_total_edges},
                    "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3)},
@@ -382,11 +386,109 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 24},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,
+        "large_shard": large,
     }
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _time_edge_kernels(batch, label, dev, pk, flush, iters):
+    """the three edge kernels of both layer types on `batch`, each timed alone with CUDA events (L2 flushed)."""
+    import ctypes as C
+
+    from hetersumgraph_b200 import _lib, accounting
+    from hetersumgraph_b200.functional import _Workspace
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for kind, H, d in (("W2S", 8, 8), ("S2W", 6, 50)):
+        csc, csc_t = batch.csc(kind)
+        F = H * d
+        fp, ldz = _lib.edge_layout(H, d)
+        E = csc.n_edges
+        zp = torch.randn(csc.n_src, ldz, device=dev)
+        q = torch.randn(10, H, device=dev)
+        origin = torch.randn(csc.n_dst, F, device=dev)
+        sh = torch.empty(csc.n_dst, F, device=dev)
+        x = torch.empty(csc.n_dst, F, device=dev)
+        stat = torch.empty(csc.n_dst, 3 * H, device=dev)
+        g = torch.empty(csc.n_dst, fp, device=dev)
+        dzp = torch.empty(csc.n_src, ldz, device=dev)
+        dq = torch.empty(10, H, device=dev)
+        ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
+        fns = {
+            "edge_fwd": lambda: _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(),
+                                                            origin.data_ptr(), sh.data_ptr(), x.data_ptr(),
+                                                            stat.data_ptr(), st)),
+            "edge_bwd_prep": lambda: _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None,
+                                                                      sh.data_ptr(), g.data_ptr(), stat.data_ptr(), st)),
+            "edge_bwd": lambda: _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(),
+                                                            g.data_ptr(), stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(),
+                                                            ws.data_ptr(), ws.numel(), st))}
+        nb = {"edge_fwd": accounting.edge_fwd_bytes(E, csc.n_src, csc.n_dst, H, d),
+              "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
+              "edge_bwd": accounting.edge_bwd_bytes(E, csc.n_src, csc.n_dst, H, d)}
+        for name, fn in fns.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(iters):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            ms = tot / iters
+            gbs = nb[name] / (ms * 1e-3) / 1e9
+            out.append({"input": label, "kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": E,
+                        "n_src": csc.n_src, "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6,
+                        "GBps": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "l2": "flushed before every launch"})
+        del zp, origin, sh, x, g, dzp
+    return out
+
+
+def large_shard_leg(dev, pk, n_graphs=2048, iters=10):
+    """What a data-parallel shard looks like (config 5): n_graphs CNN/DM-shaped graphs on one GPU.  Edge kernels
+    alone (HBM roofline) and the whole fwd+bwd step (graphs/s when the GPU, not the host, is the limit)."""
+    import hetersumgraph_b200 as hb
+    from hetersumgraph_b200 import synthetic as syn
+    from hetersumgraph_b200.graph import DeviceTokenBatch, HeteroBatch
+    from hetersumgraph_b200.path_model import HSGPath, graph_loss
+    exs = syn.make_examples(n_graphs, "cnndm", seed=3)
+    tb = syn.pack_token_batch(exs)
+    dtb = DeviceTokenBatch.upload(tb, dev)
+    batch = HeteroBatch.build(dtb)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    edges = _time_edge_kernels(batch, "%d cnndm graphs" % n_graphs, dev, pk, flush, iters)
+    torch.manual_seed(1234)
+    model = HSGPath(n_iter=1).to(dev)
+    sf = torch.randn(tb.tokens.shape[0], 64, device=dev)
+
+    def step():
+        b = HeteroBatch.build(dtb)
+        loss = graph_loss(b, model(b, sf.detach().requires_grad_(True)), b.labels)
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    return {"n_graphs": n_graphs, "word_nodes": batch.n_word, "supernodes": batch.n_super, "pairs": batch.n_pair,
+            "step_ms": ms, "graphs_per_s": n_graphs / (ms * 1e-3), "edge_kernels": edges,
+            "what": "device build + update loop fwd+bwd + loss (no optimizer), inputs resident"}
 
 
 def stress_leg(dev, pk, scale=4, iters=20):
