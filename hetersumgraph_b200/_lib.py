@@ -60,6 +60,42 @@ class WswgatBwdArgsC(C.Structure):
                [("ws_bytes", C.c_size_t)]
 
 
+class LayerParamsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("H", "d", "in_dim", "feat_dim", "d_hid", "reserved")] + \
+               [(n, C.c_void_p) for n in ("W", "Wf", "bf", "a", "w1", "b1", "w2", "b2", "gamma", "beta")]
+
+
+class LayerGradsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dW", "dWf", "dbf", "da", "dw1", "db1", "dw2", "db2", "dgamma", "dbeta")]
+
+
+class LoopArgsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_iter", "n_word", "n_super", "reserved")] + \
+               [("csc_super", C.POINTER(CscC)), ("csc_word", C.POINTER(CscC)),
+                ("w2s", LayerParamsC), ("s2w", LayerParamsC),
+                ("T", C.c_void_p), ("word_feature", C.c_void_p), ("super_feature", C.c_void_p),
+                ("state", C.c_void_p), ("state_floats", C.c_size_t)]
+
+
+class LoopPlanC(C.Structure):
+    _fields_ = [("state_floats", C.c_size_t), ("scratch_floats", C.c_size_t), ("ws_bytes", C.c_size_t),
+                ("word_state_off", C.c_size_t), ("super_state_off", C.c_size_t), ("hdn_off", C.c_size_t * 2),
+                ("pair_stride", C.c_size_t)]
+
+
+class LoopBwdArgsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_word_state", "d_super_state", "d_word_feature", "d_super_feature")] + \
+               [("w2s", LayerGradsC), ("s2w", LayerGradsC), ("dT", C.c_void_p),
+                ("accumulate", C.c_int32), ("reserved", C.c_int32),
+                ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+class HeadArgsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_sent", "n_super", "hidden", "two_part", "n_graphs", "reserved")] + \
+               [(n, C.c_void_p) for n in ("state", "sent_row", "doc_row", "graph_sent_ptr", "wh_w", "wh_b", "labels")] + \
+               [("inv_graphs", C.c_float), ("reserved2", C.c_float)]
+
+
 _I, _P, _Z = C.c_int, C.c_void_p, C.c_size_t
 
 _PROTOS = {
@@ -80,6 +116,7 @@ _PROTOS = {
     "hsg_attn_prep_bwd": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hsg_set_gemm_mode": (C.c_int, [_I]),
     "hsg_get_gemm_mode": (C.c_int, []),
+    "hsg_set_gemm_small_flops": (C.c_int, [C.c_double]),
     "hsg_gemm_trace": (C.c_int, [_I, C.POINTER(C.c_ulonglong), _I]),
     "hsg_gemm_nt": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
     "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
@@ -94,6 +131,16 @@ _PROTOS = {
     "hsg_wswgat_fwd": (C.c_int, [C.POINTER(WswgatFwdArgsC), _P]),
     "hsg_wswgat_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "hsg_wswgat_bwd": (C.c_int, [C.POINTER(WswgatBwdArgsC), _P]),
+    "hsg_update_loop_plan": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopPlanC)]),
+    "hsg_update_loop_fwd": (C.c_int, [C.POINTER(LoopArgsC), _P]),
+    "hsg_update_loop_bwd": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopBwdArgsC), _P]),
+    "hsg_head_workspace_bytes": (_Z, [_I, _I]),
+    "hsg_head_fwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _Z, _P]),
+    "hsg_head_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "hsg_topm": (C.c_int, [_P, _P, _I, _I, _P, _P]),
+    "hsg_adam_workspace_bytes": (_Z, []),
+    "hsg_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P, _Z,
+                                _P]),
     "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),
     "hsg_layernorm_bwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -25,6 +25,8 @@ enum Slot {
   SLOT_LN_FWD,
   SLOT_LN_BWD,
   SLOT_LN_BWD_REDUCE,
+  SLOT_HEAD,
+  SLOT_ADAM,
   SLOT_COUNT
 };
 

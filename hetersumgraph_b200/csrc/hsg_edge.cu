@@ -24,6 +24,7 @@
 #include <math_constants.h>
 
 #include "hsg_common.cuh"
+#include "hsg_internal.cuh"
 #include "hsg_edge_layout.cuh"
 
 namespace hsg {
@@ -567,7 +568,7 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
 
 // dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
 __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
-                                                          float* __restrict__ dq) {
+                                                          float* __restrict__ dq, int accumulate) {
   __shared__ float red[128];
   const int i = blockIdx.x;
   float s = 0.f;
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, c
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) dq[i] = red[0];
+  if (threadIdx.x == 0) dq[i] = accumulate ? dq[i] + red[0] : red[0];
 }
 
 constexpr int EDGE_MAX_BLOCKS = 148 * 8;
@@ -623,7 +624,7 @@ static int launch_prep(int n_dst, const float* dx, const float* dsh, const float
 
 template <int H, int D>
 static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g, const float* stat,
-                      float* dzp, float* dq, float* ws, cudaStream_t s) {
+                      float* dzp, float* dq, float* ws, int accumulate_dq, cudaStream_t s) {
   using C = EdgeCfg<H, D>;
   constexpr int UHI = C::NE <= 4 ? 4 : 2, ULO = C::NE <= 4 ? 2 : 1;
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
@@ -641,7 +642,7 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   }
   LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
   const int nq = HSG_N_BINS * H;
-  edge_bwd_dq_kernel<<<nq, 128, 0, s>>>(blocks, nq, ws, dq);
+  edge_bwd_dq_kernel<<<nq, 128, 0, s>>>(blocks, nq, ws, dq, accumulate_dq);
   return check_launch();
 }
 
@@ -710,16 +711,23 @@ size_t hsg_edge_bwd_workspace_bytes(int H) { return (size_t)EDGE_MAX_BLOCKS * HS
 
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
                  const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, void* stream) {
+  return edge_bwd_ex(csc_t, H, d, zp, ldz, q, g, stat, dzp, dq, ws, ws_bytes, 0, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace hsg {
+int edge_bwd_ex(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
+                const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s) {
   if (!csc_t || !zp || !q || !g || !stat || !dzp || !dq || !ws || csc_t->n_dst < 0) return HSG_ERR_ARG;
   if (ws_bytes < hsg_edge_bwd_workspace_bytes(H)) return HSG_ERR_WORKSPACE;
   if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(g) || !aligned16(dzp)) return HSG_ERR_ALIGN;
   if (csc_t->n_dst > 0 && (!csc_t->indptr || (csc_t->n_edges > 0 && (!csc_t->nbr || !csc_t->bin)))) return HSG_ERR_ARG;
-  cudaStream_t s = (cudaStream_t)stream;
 #define X(HH, DD) \
-  if (H == HH && d == DD) return launch_bwd<HH, DD>(csc_t, zp, ldz, q, g, stat, dzp, dq, (float*)ws, s);
+  if (H == HH && d == DD) return launch_bwd<HH, DD>(csc_t, zp, ldz, q, g, stat, dzp, dq, (float*)ws, accumulate_dq, s);
   HSG_EDGE_CONFIGS(X)
 #undef X
   return HSG_ERR_SHAPE;
 }
 
-}  // extern "C"
+}  // namespace hsg

@@ -3,6 +3,7 @@
 // One warp per row, the row lives in registers (D <= 512, D % 4 == 0), 128-bit accesses.
 // dgamma / dbeta are reduced in a fixed order (per-warp registers -> per-block -> second stage).
 #include "hsg_common.cuh"
+#include "hsg_internal.cuh"
 
 namespace hsg {
 
@@ -154,7 +155,7 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
 // dgamma / dbeta = column sums of the per-block partials; 32 columns x 8 row groups per CTA, fixed order
 __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
                                                                    float* __restrict__ dgamma,
-                                                                   float* __restrict__ dbeta) {
+                                                                   float* __restrict__ dbeta, int accumulate) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int nblocks, 
     float t = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; ++r) t += red[r][tx];
-    if (i < D) dgamma[i] = t; else dbeta[i - D] = t;
+    float* o = i < D ? dgamma + i : dbeta + (i - D);
+    *o = accumulate ? *o + t : t;
   }
 }
 
@@ -181,6 +183,35 @@ static int ln_grid(int N) {
 }  // namespace hsg
 
 using namespace hsg;
+
+namespace hsg {
+int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,
+                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+  if (N < 0 || D <= 0 || !dy || !r || !stats || !gamma || !dr || !dgamma || !dbeta || !ws) return HSG_ERR_ARG;
+  if (D % 4 != 0 || D > 512) return HSG_ERR_SHAPE;
+  if (ws_bytes < hsg_layernorm_bwd_workspace_bytes(N, D)) return HSG_ERR_WORKSPACE;
+  if (!aligned16(dy) || !aligned16(r) || !aligned16(dr) || !aligned16(gamma)) return HSG_ERR_ALIGN;
+  const int grid = ln_grid(N);
+  const int nv4 = ceil_div(D, 128);
+  const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
+  float* part = reinterpret_cast<float*>(ws);
+  {
+    LaunchScope ls(SLOT_LN_BWD, s);
+    switch (nv4) {
+      case 1: layernorm_bwd_kernel<1><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
+      case 2: layernorm_bwd_kernel<2><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
+      case 3: layernorm_bwd_kernel<3><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
+      default: layernorm_bwd_kernel<4><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
+    }
+    int rc = check_launch();
+    if (rc) return rc;
+  }
+  LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
+  layernorm_bwd_reduce_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(grid, D, part, dgamma, dbeta, accumulate);
+  return check_launch();
+}
+
+}  // namespace hsg
 
 extern "C" {
 
@@ -210,29 +241,7 @@ size_t hsg_layernorm_bwd_workspace_bytes(int N, int D) {
 
 int hsg_layernorm_bwd(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma,
                       float* dr, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
-  if (N < 0 || D <= 0 || !dy || !r || !stats || !gamma || !dr || !dgamma || !dbeta || !ws) return HSG_ERR_ARG;
-  if (D % 4 != 0 || D > 512) return HSG_ERR_SHAPE;
-  if (ws_bytes < hsg_layernorm_bwd_workspace_bytes(N, D)) return HSG_ERR_WORKSPACE;
-  if (!aligned16(dy) || !aligned16(r) || !aligned16(dr) || !aligned16(gamma)) return HSG_ERR_ALIGN;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int grid = ln_grid(N);
-  const int nv4 = ceil_div(D, 128);
-  const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
-  float* part = reinterpret_cast<float*>(ws);
-  {
-    LaunchScope ls(SLOT_LN_BWD, s);
-    switch (nv4) {
-      case 1: layernorm_bwd_kernel<1><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      case 2: layernorm_bwd_kernel<2><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      case 3: layernorm_bwd_kernel<3><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      default: layernorm_bwd_kernel<4><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-    }
-    int rc = check_launch();
-    if (rc) return rc;
-  }
-  LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(grid, D, part, dgamma, dbeta);
-  return check_launch();
+  return layernorm_bwd_ex(N, D, dy, r, stats, gamma, dr, dgamma, dbeta, ws, ws_bytes, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

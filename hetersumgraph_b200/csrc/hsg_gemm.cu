@@ -9,6 +9,7 @@
 #include <atomic>
 
 #include "hsg_common.cuh"
+#include "hsg_internal.cuh"
 
 namespace hsg {
 
@@ -26,20 +27,27 @@ int trace_ctl(int on, unsigned long long* host_out, int max_events);
 // 0: FFMA exact fp32, 1: tcgen05 3xTF32 (fp32-parity, default), 2: tcgen05 single-pass TF32
 static std::atomic<int> g_gemm_mode{1};
 
-constexpr int BM = 128, BN = 64, BK = 16;
-constexpr int TM = 8, TN = 4;
+
+constexpr int BN = 64, BK = 16;
+constexpr int TN = 4;
 constexpr int GEMM_THREADS = 256;
 constexpr int APAD = 4;
+// Products below this many flops run on the FFMA tiles even in the tensor-core modes: a 128x128 tcgen05 tile
+// pipeline has ~15-20 us of fill/drain latency and leaves most SMs idle on the sentence-side shapes (M ~ 1 k),
+// where 64x64 FFMA tiles finish in a few microseconds (and are exact fp32).
+static std::atomic<double> g_small_flops{3.0e8};
 
 // ---------------------------------------------------------------------------
 // C[M,N] = A[M,K] * op(B);  B_NT: B is [N,K] (K contiguous), else B is [K,N].
 // VEC: all of K%4, lda%4, ldb%4 (and N%4 for !B_NT) hold and pointers are 16B aligned.
 // ---------------------------------------------------------------------------
-template <bool B_NT, bool VEC>
+// BM = 128 (8x4 micro-tile) for tall products, BM = 64 (4x4) for small ones (more CTAs).
+template <bool B_NT, bool VEC, int BM>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
             float* __restrict__ C, int ldc, const float* __restrict__ bias, const float* __restrict__ R, int ldr,
             int epi) {
+  constexpr int TM = BM / 16, AH = BM / 64;
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + APAD];
   const int tid = threadIdx.x;
@@ -53,14 +61,14 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   // staging registers
-  float4 ra[2], rb;
+  float4 ra[AH], rb;
   const int a_row = tid / 4, a_kq = (tid % 4) * 4;  // A tile: rows a_row and a_row+64, k = a_kq..a_kq+3
   const int bnt_row = tid / 4, bnt_kq = (tid % 4) * 4;  // B_NT tile: BN rows x BK
   const int bnn_k = tid / 16, bnn_n = (tid % 16) * 4;   // B_NN tile: BK rows x BN
 
   auto load_tiles = [&](int k0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < AH; ++h) {
       int m = m0 + a_row + 64 * h;
       int k = k0 + a_kq;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -109,7 +117,7 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
   };
   auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < AH; ++h) {
       int r = a_row + 64 * h;
       As[buf][a_kq + 0][r] = ra[h].x;
       As[buf][a_kq + 1][r] = ra[h].y;
@@ -135,10 +143,13 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const flo
     if (kt + 1 < nk) load_tiles((kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4]);
+      float a[TM];
+#pragma unroll
+      for (int h = 0; h < TM / 4; ++h) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4 * h]);
+        a[4 * h] = av.x; a[4 * h + 1] = av.y; a[4 * h + 2] = av.z; a[4 * h + 3] = av.w;
+      }
       float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
-      float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float b[TN] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
       for (int i = 0; i < TM; ++i)
@@ -280,18 +291,19 @@ gemm_tn_kernel(int M, int N1, int N2, const float* __restrict__ A, int lda, cons
 
 __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* __restrict__ part,
                                       const float* __restrict__ part_col, float* __restrict__ C, int ldc,
-                                      float* __restrict__ colsum) {
+                                      float* __restrict__ colsum, int accumulate) {
   const int total = N1 * N2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + N1; i += gridDim.x * blockDim.x) {
     if (i < total) {
       float s = 0.f;
       for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * total + i];
-      C[(size_t)(i / N2) * ldc + (i % N2)] = s;
+      float* o = C + (size_t)(i / N2) * ldc + (i % N2);
+      *o = accumulate ? *o + s : s;
     } else if (colsum != nullptr) {
       int c = i - total;
       float s = 0.f;
       for (int z = 0; z < nsplit; ++z) s += part_col[(size_t)z * N1 + c];
-      colsum[c] = s;
+      colsum[c] = accumulate ? colsum[c] + s : s;
     }
   }
 }
@@ -299,7 +311,8 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
 // split of the node dimension for the tcgen05 weight-gradient kernel: 128 x 128 output tiles
 static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows) {
   const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 128);
-  int want = ceil_div(148, tiles);
+  int want = 148 / tiles;   // floor: tiles * splits <= #SMs, ONE wave of the persistent kernel (ceil made 150 > 148)
+  if (want < 1) want = 1;
   int r = ceil_div(ceil_div(M, want), 32) * 32;
   if (r < 256) r = 256;
   *rows = r;
@@ -316,76 +329,32 @@ static int tn_splits(int M, int N1, int N2) {
   return s;
 }
 
-}  // namespace hsg
+static bool is_small(int M, int N, int K) {
+  return 2.0 * (double)M * (double)N * (double)K < g_small_flops.load(std::memory_order_relaxed);
+}
 
-using namespace hsg;
-
-extern "C" {
-
-int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                const float* bias, const float* R, int ldr, int epi, void* stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
-  if ((epi & HSG_EPI_BIAS) && !bias) return HSG_ERR_ARG;
-  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
-  if (M == 0) return HSG_OK;
-  cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
-  bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(C) &&
-             (R == nullptr || aligned16(R));
-  LaunchScope ls(SLOT_GEMM_NT, s);
-  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
-  if (mode != 0 && vec && (ldc % 4 == 0)) return tc::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, mode == 1, s);
+template <bool B_NT>
+static int launch_ffma(bool small, bool vec, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, const float* bias, const float* R, int ldr, int epi, cudaStream_t s) {
+  if (small)
+    return B_NT ? gemm_small_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, s)
+                : gemm_small_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, s);
+  dim3 grid(ceil_div(M, 128), ceil_div(N, BN));
   if (vec)
-    gemm_kernel<true, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+    gemm_kernel<B_NT, true, 128><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
   else
-    gemm_kernel<true, false><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+    gemm_kernel<B_NT, false, 128><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
   return check_launch();
 }
 
-int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                const float* R, int ldr, int epi, void* stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
-  if (epi & (HSG_EPI_BIAS | HSG_EPI_RELU)) return HSG_ERR_ARG;
-  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
-  if (M == 0) return HSG_OK;
-  cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
-  bool vec = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) &&
-             aligned16(C) && (R == nullptr || aligned16(R));
-  LaunchScope ls(SLOT_GEMM_NN, s);
-  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
-  if (mode != 0 && vec && (ldc % 4 == 0)) return tc::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, mode == 1, s);
-  if (vec)
-    gemm_kernel<false, true><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi);
-  else
-    gemm_kernel<false, false><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi);
-  return check_launch();
-}
-
-int hsg_set_gemm_mode(int mode) {
-  if (mode < 0 || mode > 2) return HSG_ERR_ARG;
-  g_gemm_mode.store(mode);
-  return HSG_OK;
-}
-
-int hsg_get_gemm_mode(void) { return g_gemm_mode.load(); }
-
-int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events) { return tc::trace_ctl(on, host_out, max_events); }
-
-size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
-  if (M <= 0 || N1 <= 0 || N2 <= 0) return 16;
-  size_t s = (size_t)tn_splits(M, N1, N2);
-  int s_tc = 0, rows_tc = 0;
-  tn_plan_tc(M, N1, N2, true, &s_tc, &rows_tc);
-  if ((size_t)s_tc > s) s = (size_t)s_tc;
-  return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
-}
-
-int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                float* colsum, void* ws, size_t ws_bytes, void* stream) {
+int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+               float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
   if (M < 0 || N1 <= 0 || N2 <= 0 || !A || !B || !C || !ws) return HSG_ERR_ARG;
   if (ws_bytes < hsg_gemm_tn_workspace_bytes(M, N1, N2)) return HSG_ERR_WORKSPACE;
-  cudaStream_t s = (cudaStream_t)stream;
+  if (M > 0 && is_small(M, N1, N2)) {   // cluster split over the node rows: no partials, no reduce launch
+    LaunchScope ls(SLOT_GEMM_TN, s);
+    return gemm_small_tn(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, accumulate, s);
+  }
   int nsplit = M > 0 ? tn_splits(M, N1, N2) : 0;
   float* part = reinterpret_cast<float*>(ws);
   float* part_col = part + (size_t)nsplit * N1 * N2;
@@ -402,6 +371,7 @@ int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, 
     int rows = ceil_div(M, nsplit);
     rows = ceil_div(rows, TBK) * TBK;
     nsplit = ceil_div(M, rows);
+    part_col = part + (size_t)nsplit * N1 * N2;
     dim3 grid(ceil_div(N1, TB), ceil_div(N2, TB), nsplit);
     bool vec = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
     LaunchScope ls(SLOT_GEMM_TN, s);
@@ -417,9 +387,79 @@ int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, 
     int total = N1 * N2 + N1;
     int blocks = ceil_div(total, 256);
     if (blocks > 1184) blocks = 1184;
-    gemm_tn_reduce_kernel<<<blocks, 256, 0, s>>>(nsplit, N1, N2, part, part_col, C, ldc, colsum);
+    gemm_tn_reduce_kernel<<<blocks, 256, 0, s>>>(nsplit, N1, N2, part, part_col, C, ldc, colsum, accumulate);
   }
   return check_launch();
+}
+
+}  // namespace hsg
+
+using namespace hsg;
+
+extern "C" {
+
+int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* bias, const float* R, int ldr, int epi, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if ((epi & HSG_EPI_BIAS) && !bias) return HSG_ERR_ARG;
+  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(C) &&
+             (R == nullptr || aligned16(R));
+  LaunchScope ls(SLOT_GEMM_NT, s);
+  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
+  const bool small = is_small(M, N, K);
+  if (mode != 0 && !small && vec && (ldc % 4 == 0))
+    return tc::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, mode == 1, s);
+  return launch_ffma<true>(small, vec, M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, s);
+}
+
+int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* R, int ldr, int epi, void* stream) {
+  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if (epi & (HSG_EPI_BIAS | HSG_EPI_RELU)) return HSG_ERR_ARG;
+  if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) &&
+             aligned16(C) && (R == nullptr || aligned16(R));
+  LaunchScope ls(SLOT_GEMM_NN, s);
+  const int mode = g_gemm_mode.load(std::memory_order_relaxed);
+  const bool small = is_small(M, N, K);
+  if (mode != 0 && !small && vec && (ldc % 4 == 0))
+    return tc::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, mode == 1, s);
+  return launch_ffma<false>(small, vec, M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi, s);
+}
+
+int hsg_set_gemm_mode(int mode) {
+  if (mode < 0 || mode > 2) return HSG_ERR_ARG;
+  g_gemm_mode.store(mode);
+  return HSG_OK;
+}
+
+int hsg_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
+int hsg_set_gemm_small_flops(double flops) {
+  if (!(flops >= 0.0)) return HSG_ERR_ARG;
+  g_small_flops.store(flops);
+  return HSG_OK;
+}
+
+int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events) { return tc::trace_ctl(on, host_out, max_events); }
+
+size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
+  if (M <= 0 || N1 <= 0 || N2 <= 0) return 16;
+  size_t s = (size_t)tn_splits(M, N1, N2);
+  int s_tc = 0, rows_tc = 0;
+  tn_plan_tc(M, N1, N2, true, &s_tc, &rows_tc);
+  if ((size_t)s_tc > s) s = (size_t)s_tc;
+  return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
+}
+
+int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                float* colsum, void* ws, size_t ws_bytes, void* stream) {
+  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -374,7 +374,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // SM as full 128-byte lines: 8 lanes x 16 B per row, 4 rows per store instruction.
       float* tile = epi_stage + (warp - 8) * (32 * 33);
       const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
+      const bool has_r = (ep.epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) != 0;
+      const bool ld_vec = (ep.ldd & 3) == 0, lr_vec = (ep.ldr & 3) == 0;
       for (int c0 = 0; c0 < ti.n_mma; c0 += 32) {
+        const int col = ti.n0 + c0 + c_sub;
+        // residual / ReLU-mask operand of the whole 32x32 chunk first: eight independent 16-byte loads per lane in
+        // flight while the accumulators come out of TMEM (one exposed L2/HBM latency per chunk instead of eight)
+        float4 rv4[8];
+        if (has_r) {
+#pragma unroll
+          for (int p8 = 0; p8 < 8; ++p8) {
+            const int row = ti.m0 + lg * 32 + p8 * 4 + r_sub;
+            rv4[p8] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < Md) {
+              const float* rp = ep.R + (size_t)row * ep.ldr + col;
+              if (lr_vec && col + 3 < n_out) {
+                rv4[p8] = __ldg(reinterpret_cast<const float4*>(rp));
+              } else {
+                if (col + 0 < n_out) rv4[p8].x = __ldg(rp + 0);
+                if (col + 1 < n_out) rv4[p8].y = __ldg(rp + 1);
+                if (col + 2 < n_out) rv4[p8].z = __ldg(rp + 2);
+                if (col + 3 < n_out) rv4[p8].w = __ldg(rp + 3);
+              }
+            }
+          }
+        }
         float v[32];
         if (ti.nkb > 0) {
           tc_ld32(d_main + (uint32_t)c0, v);
@@ -391,7 +415,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];           // bank (lane + i) % 32: conflict-free
         __syncwarp();
-        const int col = ti.n0 + c0 + c_sub;
 #pragma unroll
         for (int p8 = 0; p8 < 8; ++p8) {
           const int rl = p8 * 4 + r_sub;
@@ -400,19 +423,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int tt = 0; tt < 4; ++tt) o[tt] = tile[rl * 33 + c_sub + tt];
           if (row < Md) {
-            const bool vec = col + 3 < n_out && (ep.ldd & 3) == 0;
+            const bool vec = col + 3 < n_out && ld_vec;
             if (ep.epi != 0) {
-              float rv[4] = {0.f, 0.f, 0.f, 0.f};
-              if (ep.epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) {
-                if (vec && (ep.ldr & 3) == 0) {
-                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.R + (size_t)row * ep.ldr + col));
-                  rv[0] = r4.x; rv[1] = r4.y; rv[2] = r4.z; rv[3] = r4.w;
-                } else {
-#pragma unroll
-                  for (int tt = 0; tt < 4; ++tt)
-                    if (col + tt < n_out) rv[tt] = __ldg(ep.R + (size_t)row * ep.ldr + col + tt);
-                }
-              }
+              const float rv[4] = {rv4[p8].x, rv4[p8].y, rv4[p8].z, rv4[p8].w};
 #pragma unroll
               for (int tt = 0; tt < 4; ++tt) {
                 const int cc = col + tt;

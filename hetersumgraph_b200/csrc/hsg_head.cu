@@ -1,0 +1,285 @@
+// Readout, loss and extraction on the device - the step right after the update loop:
+//   logits = wh(sentence state)                         HiGraph.py:108   (HDSG: wh(cat(sentence, its document)), :216-228)
+//   loss   = mean_graphs sum_sentences CE(logits, y)    train.py:114-119 (CrossEntropyLoss(reduction='none'),
+//                                                                          dgl.sum_nodes, .mean())
+//   top-m  = per graph torch.topk(logits[:, 1], m)      Tester.py:128
+// plus the fused Adam update over the flat parameter arena (train.py:90,135; optional clip_grad_norm_, :132-133).
+// Everything is reduced in a fixed order (bitwise reproducible); the reference does the same work with ~20 tiny
+// launches of stock kernels and a Python loop over dgl.unbatch(G).
+#include "hsg_common.cuh"
+
+namespace hsg {
+
+constexpr int HEAD_ROWS_PER_BLOCK = 32;
+
+// warp per sentence: logits, per-sentence CE, d loss / d logits (already scaled by 1/n_graphs)
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(hsg_head_args a, float* __restrict__ logits, float* __restrict__ dlogits,
+                float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= a.n_sent) return;
+  const int srow = a.sent_row ? a.sent_row[i] : i;
+  const int width = a.hidden * (a.two_part ? 2 : 1);
+  float l0 = 0.f, l1 = 0.f;
+  for (int j = lane; j < a.hidden; j += 32) {
+    const float s = a.state[(size_t)srow * a.hidden + j];
+    l0 = fmaf(s, a.wh_w[j], l0);
+    l1 = fmaf(s, a.wh_w[width + j], l1);
+  }
+  if (a.two_part) {
+    const int drow = a.doc_row[i];
+    for (int j = lane; j < a.hidden; j += 32) {
+      const float s = a.state[(size_t)drow * a.hidden + j];
+      l0 = fmaf(s, a.wh_w[a.hidden + j], l0);
+      l1 = fmaf(s, a.wh_w[width + a.hidden + j], l1);
+    }
+  }
+  l0 = warp_sum(l0) + a.wh_b[0];
+  l1 = warp_sum(l1) + a.wh_b[1];
+  if (lane == 0) {
+    const int y = (int)a.labels[i];
+    const float mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+    const float lse = mx + logf(e0 + e1);
+    const float inv = 1.f / (e0 + e1);
+    logits[2 * i] = l0;
+    logits[2 * i + 1] = l1;
+    row_loss[i] = lse - (y ? l1 : l0);
+    dlogits[2 * i] = a.inv_graphs * (e0 * inv - (y == 0 ? 1.f : 0.f));
+    dlogits[2 * i + 1] = a.inv_graphs * (e1 * inv - (y == 1 ? 1.f : 0.f));
+  }
+}
+
+// loss = scale * sum(row_loss) in a fixed order (one block)
+__global__ void __launch_bounds__(1024) head_loss_reduce_kernel(int n, const float* __restrict__ row_loss, float scale,
+                                                                float* __restrict__ loss) {
+  __shared__ float red[1024];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) s += row_loss[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] * scale;
+}
+
+// block = `width` threads (<= 256), HEAD_ROWS_PER_BLOCK sentences: thread j owns column j of the wh input.
+// Writes the sentence rows of d_state and the per-block partials of d wh.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(hsg_head_args a, const float* __restrict__ dlogits, const float* __restrict__ gout,
+                float* __restrict__ d_state, float* __restrict__ part /* [blocks][2*width + 2] */) {
+  const int width = a.hidden * (a.two_part ? 2 : 1);
+  const int j = threadIdx.x;
+  const float g = gout ? gout[0] : 1.f;
+  const int i0 = blockIdx.x * HEAD_ROWS_PER_BLOCK, i1 = min(a.n_sent, i0 + HEAD_ROWS_PER_BLOCK);
+  float w0 = 0.f, w1 = 0.f, b0 = 0.f, b1 = 0.f;
+  const float wc0 = j < width ? a.wh_w[j] : 0.f, wc1 = j < width ? a.wh_w[width + j] : 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float d0 = dlogits[2 * i] * g, d1 = dlogits[2 * i + 1] * g;
+    if (j < width) {
+      const int srow = a.sent_row ? a.sent_row[i] : i;
+      const int row = j < a.hidden ? srow : a.doc_row[i];
+      const int jj = j < a.hidden ? j : j - a.hidden;
+      const float f = a.state[(size_t)row * a.hidden + jj];
+      w0 = fmaf(d0, f, w0);
+      w1 = fmaf(d1, f, w1);
+      if (j < a.hidden) d_state[(size_t)srow * a.hidden + j] = d0 * wc0 + d1 * wc1;   // sentence rows are unique
+    }
+    b0 += d0;
+    b1 += d1;
+  }
+  float* p = part + (size_t)blockIdx.x * (2 * width + 2);
+  if (j < width) {
+    p[j] = w0;
+    p[width + j] = w1;
+  }
+  if (j == 0) {
+    p[2 * width] = b0;
+    p[2 * width + 1] = b1;
+  }
+}
+
+// HDSG: document rows collect the second half of wh's input gradient from their sentences.  One block per graph,
+// thread j owns column j and walks the graph's sentences in order (deterministic; rows were zero-filled).
+__global__ void __launch_bounds__(256)
+head_bwd_doc_kernel(hsg_head_args a, const float* __restrict__ dlogits, const float* __restrict__ gout,
+                    float* __restrict__ d_state) {
+  const int gph = blockIdx.x, j = threadIdx.x;
+  if (j >= a.hidden) return;
+  const int width = 2 * a.hidden;
+  const float g = gout ? gout[0] : 1.f;
+  const float wc0 = a.wh_w[a.hidden + j], wc1 = a.wh_w[width + a.hidden + j];
+  for (int i = a.graph_sent_ptr[gph]; i < a.graph_sent_ptr[gph + 1]; ++i) {
+    float* o = d_state + (size_t)a.doc_row[i] * a.hidden + j;
+    *o += (dlogits[2 * i] * wc0 + dlogits[2 * i + 1] * wc1) * g;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_bwd_reduce_kernel(int nblocks, int n_out, const float* __restrict__ part, float* __restrict__ d_w,
+                       float* __restrict__ d_b, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n_out + i];   // fixed order
+  float* o = i < n_out - 2 ? d_w + i : d_b + (i - (n_out - 2));
+  *o = accumulate ? *o + s : s;
+}
+
+// one warp per graph: out[g, rank] = local sentence index with the rank-th largest class-1 logit (ties: lower index
+// first), -1 padded.  n is at most a few hundred, so rank counting is cheaper than a sort.
+__global__ void __launch_bounds__(256)
+topm_kernel(const float* __restrict__ logits, const int* __restrict__ graph_sent_ptr, int n_graphs, int m,
+            int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int gph = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gph >= n_graphs) return;
+  const int s0 = graph_sent_ptr[gph], n = graph_sent_ptr[gph + 1] - s0;
+  for (int r = lane; r < m; r += 32) out[(size_t)gph * m + r] = -1;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float pi = logits[2 * (s0 + i) + 1];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const float pk = logits[2 * (s0 + k) + 1];
+      rank += (pk > pi || (pk == pi && k < i)) ? 1 : 0;
+    }
+    if (rank < m) out[(size_t)gph * m + rank] = i;
+  }
+}
+
+// ---- optimizer -----------------------------------------------------------------------------------------------
+constexpr int SUMSQ_BLOCKS = 296;
+
+__global__ void __launch_bounds__(256) sumsq_part_kernel(size_t n, const float* __restrict__ g, float* __restrict__ part) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s = fmaf(g[i], g[i], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(512) sumsq_final_kernel(int nparts, const float* __restrict__ part, float* __restrict__ out) {
+  __shared__ float red[512];
+  red[threadIdx.x] = threadIdx.x < nparts ? part[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int o = 256; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// torch.optim.Adam (no amsgrad, no weight decay) on flat arrays; optional clip_grad_norm_ coefficient from sumsq.
+__global__ void __launch_bounds__(256)
+adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            float beta1, float beta2, float step_size, float inv_sqrt_bc2, float eps, const float* __restrict__ sumsq,
+            float max_norm) {
+  float coef = 1.f;
+  if (sumsq) coef = fminf(1.f, max_norm / (sqrtf(sumsq[0]) + 1e-6f));
+  for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
+}  // namespace hsg
+
+using namespace hsg;
+
+extern "C" {
+
+size_t hsg_head_workspace_bytes(int n_sent, int width) {
+  const int blocks = ceil_div(n_sent > 0 ? n_sent : 1, HEAD_ROWS_PER_BLOCK);
+  return ((size_t)(n_sent > 0 ? n_sent : 1) + (size_t)blocks * (2 * (size_t)width + 2)) * sizeof(float) + 16;
+}
+
+static bool head_args_ok(const hsg_head_args* a) {
+  if (!a || a->n_sent < 0 || a->n_super < 0 || a->hidden <= 0 || !a->state || !a->wh_w || !a->wh_b || !a->labels)
+    return false;
+  if (a->two_part && (!a->doc_row || !a->graph_sent_ptr || a->n_graphs < 0)) return false;
+  return a->hidden * (a->two_part ? 2 : 1) <= 256;
+}
+
+int hsg_head_fwd(const hsg_head_args* a, float* logits, float* dlogits, float* loss, void* ws, size_t ws_bytes,
+                 void* stream) {
+  if (!head_args_ok(a) || !logits || !dlogits || !loss || !ws) return HSG_ERR_ARG;
+  const int width = a->hidden * (a->two_part ? 2 : 1);
+  if (ws_bytes < hsg_head_workspace_bytes(a->n_sent, width)) return HSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* row_loss = reinterpret_cast<float*>(ws);
+  LaunchScope ls(SLOT_HEAD, s);
+  if (a->n_sent > 0) head_fwd_kernel<<<ceil_div(a->n_sent, 8), 256, 0, s>>>(*a, logits, dlogits, row_loss);
+  head_loss_reduce_kernel<<<1, 1024, 0, s>>>(a->n_sent, row_loss, a->inv_graphs, loss);
+  return check_launch();
+}
+
+int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout, float* d_state, float* d_wh_w,
+                 float* d_wh_b, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  if (!head_args_ok(a) || !dlogits || !d_state || !d_wh_w || !d_wh_b || !ws) return HSG_ERR_ARG;
+  const int width = a->hidden * (a->two_part ? 2 : 1);
+  if (ws_bytes < hsg_head_workspace_bytes(a->n_sent, width)) return HSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(ws) + (a->n_sent > 0 ? a->n_sent : 1);
+  const int blocks = ceil_div(a->n_sent, HEAD_ROWS_PER_BLOCK);
+  LaunchScope ls(SLOT_HEAD, s);
+  // rows that are not sentences (documents) and sentences without ... every row starts at zero
+  if (a->sent_row || a->two_part) {
+    if (cudaMemsetAsync(d_state, 0, (size_t)a->n_super * a->hidden * sizeof(float), s) != cudaSuccess) return HSG_ERR_CUDA;
+  }
+  if (blocks > 0) {
+    head_bwd_kernel<<<blocks, 256, 0, s>>>(*a, dlogits, gout, d_state, part);
+    if (a->two_part && a->n_graphs > 0) head_bwd_doc_kernel<<<a->n_graphs, 256, 0, s>>>(*a, dlogits, gout, d_state);
+  }
+  const int n_out = 2 * width + 2;
+  head_bwd_reduce_kernel<<<ceil_div(n_out, 256), 256, 0, s>>>(blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
+  return check_launch();
+}
+
+int hsg_topm(const float* logits, const int32_t* graph_sent_ptr, int n_graphs, int m, int32_t* out_idx, void* stream) {
+  if (!logits || !graph_sent_ptr || n_graphs < 0 || m <= 0 || !out_idx) return HSG_ERR_ARG;
+  if (n_graphs == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(SLOT_HEAD, s);
+  topm_kernel<<<ceil_div(n_graphs, 8), 256, 0, s>>>(logits, graph_sent_ptr, n_graphs, m, out_idx);
+  return check_launch();
+}
+
+size_t hsg_adam_workspace_bytes(void) { return (size_t)(SUMSQ_BLOCKS + 4) * sizeof(float); }
+
+int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, int step, float max_grad_norm, void* ws, size_t ws_bytes, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return HSG_ERR_ARG;
+  if (n == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* sumsq = nullptr;
+  LaunchScope ls(SLOT_ADAM, s);
+  if (max_grad_norm > 0.f) {
+    if (!ws || ws_bytes < hsg_adam_workspace_bytes()) return HSG_ERR_WORKSPACE;
+    float* part = reinterpret_cast<float*>(ws);
+    sumsq_part_kernel<<<SUMSQ_BLOCKS, 256, 0, s>>>(n, grad, part);
+    sumsq_final_kernel<<<1, 512, 0, s>>>(SUMSQ_BLOCKS, part, part + SUMSQ_BLOCKS);
+    sumsq = part + SUMSQ_BLOCKS;
+  }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, param, grad, exp_avg, exp_avg_sq, beta1, beta2, step_size,
+                                              inv_sqrt_bc2, eps, sumsq, max_grad_norm);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@
 // projection product writes z rows directly in the layout the edge kernels gather:
 //     W_aug[perm(c)] = W[c]   (c < F),   W_aug[FP + k] = sum_j a_k[j] W[k d + j],   other rows 0.
 #include "hsg_common.cuh"
+#include "hsg_internal.cuh"
 #include "hsg_edge_layout.cuh"
 
 namespace hsg {
@@ -54,6 +55,8 @@ attn_prep_fwd_kernel(EdgeLayout L, int in_dim, int feat_dim, int ld_rows, const 
   }
 }
 
+__device__ __forceinline__ void put(float* p, float v, int accumulate) { *p = accumulate ? *p + v : v; }
+
 constexpr int PREP_CCH = 32;   // feature columns per block in the feat-path backward
 
 // grid = F + ceil(F/PREP_CCH) + 10 blocks:
@@ -65,7 +68,7 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
                      const float* __restrict__ Wf, const float* __restrict__ bf, const float* __restrict__ a,
                      const float* __restrict__ T, const float* __restrict__ dW_aug, const float* __restrict__ dq,
                      float* __restrict__ dW, float* __restrict__ dWf, float* __restrict__ dbf,
-                     float* __restrict__ da, float* __restrict__ dT) {
+                     float* __restrict__ da, float* __restrict__ dT, int acc_p, int acc_T) {
   __shared__ float sm[2 * PREP_CCH * HSG_N_BINS + 32];   // 672 floats (>= 512 for the dT blocks)
   const int H = L.H, d = L.D, F = H * d;
   const int r = blockIdx.x;
@@ -78,7 +81,7 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
     float part = 0.f;
     for (int i = threadIdx.x; i < in_dim; i += blockDim.x) {
       const float g = dwp[i];
-      dW[(size_t)r * in_dim + i] = fmaf(aj, g, dwr[i]);
+      put(dW + (size_t)r * in_dim + i, fmaf(aj, g, dwr[i]), acc_p);
       part = fmaf(g, W[(size_t)r * in_dim + i], part);
     }
     part = warp_sum(part);
@@ -87,8 +90,8 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];   // fixed order
-      da[k * 3 * d + j] = s;
-      da[k * 3 * d + d + j] = 0.f;   // a_dst multiplies DGL's zero-filled destination z
+      put(da + k * 3 * d + j, s, acc_p);
+      put(da + k * 3 * d + d + j, 0.f, acc_p);   // a_dst multiplies DGL's zero-filled destination z
     }
     return;
   }
@@ -120,15 +123,15 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
         sa += prod_s[cl * HSG_N_BINS + b];
         sb += ddfeat_s[cl * HSG_N_BINS + b];
       }
-      da[k * 3 * d + 2 * d + j] = sa;
-      if (dbf) dbf[c] = sb;
+      put(da + k * 3 * d + 2 * d + j, sa, acc_p);
+      if (dbf) put(dbf + c, sb, acc_p);
     }
     for (int o = threadIdx.x; o < PREP_CCH * feat_dim; o += blockDim.x) {
       const int cl = o / feat_dim, f = o % feat_dim, c = c0 + cl;
       if (c >= F) continue;
       float s = 0.f;
       for (int b = 0; b < HSG_N_BINS; ++b) s = fmaf(ddfeat_s[cl * HSG_N_BINS + b], T[b * feat_dim + f], s);
-      dWf[(size_t)c * feat_dim + f] = s;
+      put(dWf + (size_t)c * feat_dim + f, s, acc_p);
     }
     return;
   }
@@ -151,14 +154,15 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
   }
   part_s[ch][f] = acc;
   __syncthreads();
-  if (ch == 0 && f < feat_dim) dT[b * feat_dim + f] = (part_s[0][f] + part_s[1][f]) + (part_s[2][f] + part_s[3][f]);
+  if (ch == 0 && f < feat_dim)
+    put(dT + b * feat_dim + f, (part_s[0][f] + part_s[1][f]) + (part_s[2][f] + part_s[3][f]), acc_T);
   for (int f2 = 64 + threadIdx.x; f2 < feat_dim; f2 += blockDim.x) {   // feat_dim > 64: plain loop
     float s2 = 0.f;
     for (int c = 0; c < F; ++c) {
       const int k = c / d, j = c % d;
       s2 = fmaf(dq[b * H + k] * a[k * 3 * d + 2 * d + j], Wf[(size_t)c * feat_dim + f2], s2);
     }
-    dT[b * feat_dim + f2] = s2;
+    put(dT + b * feat_dim + f2, s2, acc_T);
   }
 }
 
@@ -184,17 +188,26 @@ int hsg_attn_prep_fwd(int H, int d, int in_dim, int feat_dim, int ld_rows, const
 int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows, const float* W, const float* Wf,
                       const float* bf, const float* a, const float* T, const float* dW_aug, const float* dq,
                       float* dW, float* dWf, float* dbf, float* da, float* dT, void* stream) {
+  return attn_prep_bwd_ex(H, d, in_dim, feat_dim, ld_rows, W, Wf, bf, a, T, dW_aug, dq, dW, dWf, dbf, da, dT, 0, 0,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace hsg {
+int attn_prep_bwd_ex(int H, int d, int in_dim, int feat_dim, int ld_rows, const float* W, const float* Wf,
+                     const float* bf, const float* a, const float* T, const float* dW_aug, const float* dq, float* dW,
+                     float* dWf, float* dbf, float* da, float* dT, int acc_params, int acc_T, cudaStream_t s) {
   if (H <= 0 || d <= 0 || H > 32 || in_dim <= 0 || feat_dim <= 0 || !W || !Wf || !a || !T || !dW_aug || !dq || !dW ||
       !dWf || !da || !dT)
     return HSG_ERR_ARG;
   const EdgeLayout L = make_edge_layout(H, d);
   if (ld_rows < L.fp + H) return HSG_ERR_SHAPE;
-  cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_PREP_BWD, s);
   const int F = H * d;
   attn_prep_bwd_kernel<<<F + ceil_div(F, PREP_CCH) + HSG_N_BINS, 256, 0, s>>>(L, in_dim, feat_dim, W, Wf, bf, a, T, dW_aug, dq,
-                                                                    dW, dWf, dbf, da, dT);
+                                                                    dW, dWf, dbf, da, dT, acc_params, acc_T);
   return check_launch();
 }
 
-}  // extern "C"
+}  // namespace hsg

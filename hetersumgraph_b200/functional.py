@@ -361,3 +361,193 @@ class WSWGATCoreFn(torch.autograd.Function):
         dn, dx, dWa, dq, dw1, db1, dw2, db2, dg, db = parts
         return (None, None, None, None, dn.view(n_src, in_dim), dx.view(n_dst, F), dWa.view(ldz, in_dim),
                 dq.view(_N_BINS, H), dw1.view(d_hid, F), db1, dw2.view(F, d_hid), db2, dg, db)
+
+
+# --------------------------------------------------------------------------------------------
+# whole update loop: ONE C call forward, ONE backward (hsg_update_loop_fwd / _bwd)
+# --------------------------------------------------------------------------------------------
+_PARAM_ORDER = ("W", "Wf", "bf", "a", "w1", "b1", "w2", "b2", "gamma", "beta")
+
+
+def _layer_params_c(H, d, in_dim, feat_dim, d_hid, tensors):
+    return _lib.LayerParamsC(H, d, in_dim, feat_dim, d_hid, 0, *[_p(t) for t in tensors])
+
+
+class UpdateLoopFn(torch.autograd.Function):
+    """(word_state, super_state) = update loop of HSumGraph.forward / HSumDocGraph.forward (HiGraph.py:98-106,
+    205-214) on a HeteroBatch.  Tensor arguments after `cfg`: word_feature, super_feature, T, then the ten packed
+    parameters of word2sent and of sent2word (W, Wf, bf, a, w1, b1, w2, b2, gamma, beta; word2sent's bf is None).
+
+    cfg = (n_iter, (H, d, d_hid) of W2S, (H, d, d_hid) of S2W, grad_targets) - grad_targets is None (gradients are
+    returned to autograd) or a list of 21 tensors [dT, 10 x W2S, 10 x S2W] that the backward ADDS the parameter
+    gradients into (fused accumulation into .grad; None is returned for those inputs)."""
+
+    @staticmethod
+    def forward(ctx, batch, cfg, word_feature, super_feature, T, *params):
+        _lib.require_device()
+        lib = _lib.load()
+        n_iter, (H1, d1, hid1), (H2, d2, hid2), grad_targets = cfg
+        word_feature, super_feature, T = _f32c(word_feature), _f32c(super_feature), _f32c(T)
+        params = tuple(_f32c(t) if t is not None else None for t in params)
+        pw, ps = params[:10], params[10:]
+        n_word, n_super = batch.n_word, batch.n_super
+        if word_feature.shape[0] != n_word or super_feature.shape[0] != n_super:
+            raise ValueError("update loop: got %d word / %d supernode rows, graph has %d / %d" %
+                             (word_feature.shape[0], super_feature.shape[0], n_word, n_super))
+        Dw, Ds, fe = word_feature.shape[1], super_feature.shape[1], T.shape[1]
+        if Ds != H1 * d1 or (n_iter > 0 and Dw != H2 * d2):
+            raise ValueError("update loop: feature widths (%d, %d) do not match heads*head_dim" % (Dw, Ds))
+        csc_s, csc_w = batch.csc("W2S")
+        args = _lib.LoopArgsC(n_iter, n_word, n_super, 0, C.pointer(csc_s), C.pointer(csc_w),
+                              _layer_params_c(H1, d1, Dw, fe, hid1, pw), _layer_params_c(H2, d2, Ds, fe, hid2, ps),
+                              _p(T), _p(word_feature), _p(super_feature), None, 0)
+        plan = _lib.LoopPlanC()
+        _lib.check(lib.hsg_update_loop_plan(C.byref(args), C.byref(plan)))
+        state = torch.empty(plan.state_floats, dtype=torch.float32, device=word_feature.device)
+        args.state, args.state_floats = state.data_ptr(), plan.state_floats
+        _lib.check(lib.hsg_update_loop_fwd(C.byref(args), _st()))
+        if RELU_MASK_CAPTURE is not None:
+            for i in range(1 + 2 * n_iter):
+                n_rows, hid = (n_super, hid1) if i % 2 == 0 else (n_word, hid2)
+                off = plan.hdn_off[i % 2] + (i // 2) * plan.pair_stride
+                RELU_MASK_CAPTURE.append((state[off:off + n_rows * hid].view(n_rows, hid) > 0).cpu())
+        so = plan.super_state_off
+        super_state = state[so:so + n_super * Ds].view(n_super, Ds)
+        if n_iter > 0:
+            wo = plan.word_state_off
+            word_state = state[wo:wo + n_word * Dw].view(n_word, Dw)
+        else:
+            word_state = word_feature.clone()
+        ctx.batch, ctx.cfg, ctx.plan, ctx.args = batch, cfg, plan, args
+        ctx.set_materialize_grads(False)          # an unused result's gradient arrives as None, not as a zero tensor
+        ctx.save_for_backward(word_feature, super_feature, T, state, *[t for t in params if t is not None])
+        ctx.param_present = [t is not None for t in params]
+        return word_state, super_state
+
+    @staticmethod
+    def backward(ctx, d_word, d_super):
+        lib = _lib.load()
+        n_iter, _, _, grad_targets = ctx.cfg
+        saved = ctx.saved_tensors
+        word_feature, super_feature, T, state = saved[:4]
+        it = iter(saved[4:])
+        params = [next(it) if present else None for present in ctx.param_present]
+        dev = state.device
+        plan, args = ctx.plan, ctx.args
+        if d_word is None and d_super is None:
+            return (None,) * (5 + len(params))
+        d_word = _f32c(d_word) if d_word is not None else None
+        d_super = _f32c(d_super) if d_super is not None else None
+        need_dw = ctx.needs_input_grad[2]
+        d_wf = torch.empty_like(word_feature) if need_dw else None
+        d_sf = torch.empty_like(super_feature)
+        if grad_targets is not None:
+            targets = list(grad_targets)
+            acc = 1
+        else:
+            targets = [torch.empty_like(T)] + [torch.empty_like(p) if p is not None else None for p in params]
+            if n_iter == 0:                                  # sent2word unused: its gradients are zero
+                for i in range(11, 21):
+                    if targets[i] is not None:
+                        targets[i].zero_()
+            acc = 0
+        scratch = torch.empty(plan.scratch_floats, dtype=torch.float32, device=dev)
+        ws = _Workspace.get(plan.ws_bytes, dev, "loop")
+        b = _lib.LoopBwdArgsC(_p(d_word), _p(d_super), _p(d_wf), _p(d_sf),
+                              _lib.LayerGradsC(*[_p(t) for t in targets[1:11]]),
+                              _lib.LayerGradsC(*[_p(t) for t in targets[11:21]]),
+                              _p(targets[0]), acc, 0, scratch.data_ptr(), plan.scratch_floats, ws.data_ptr(),
+                              ws.numel())
+        _lib.check(lib.hsg_update_loop_bwd(C.byref(args), C.byref(b), _st()))
+        if grad_targets is not None:
+            return (None, None, d_wf, d_sf) + (None,) * (1 + len(params))
+        return (None, None, d_wf, d_sf, targets[0]) + tuple(targets[1:])
+
+
+# --------------------------------------------------------------------------------------------
+# readout + loss (hsg_head_fwd / _bwd), top-m extraction, fused Adam
+# --------------------------------------------------------------------------------------------
+class SentenceLossFn(torch.autograd.Function):
+    """(loss, logits) = mean over graphs of the per-graph sum of sentence cross-entropies of wh(state)
+    (HiGraph.py:108 / :216-228 + train.py:114-119).  `logits` is returned for extraction (not differentiable here:
+    the reference only back-propagates the loss)."""
+
+    @staticmethod
+    def forward(ctx, batch, n_graphs_global, grad_targets, state, wh_w, wh_b, labels):
+        _lib.require_device()
+        lib = _lib.load()
+        state, wh_w, wh_b = _f32c(state), _f32c(wh_w), _f32c(wh_b)
+        n_super, hidden = state.shape
+        two_part = 1 if wh_w.shape[1] == 2 * hidden else 0
+        if wh_w.shape[0] != 2 or wh_w.shape[1] != hidden * (1 + two_part):
+            raise ValueError("wh weight must be [2, hidden] (HSG) or [2, 2*hidden] (HDSG)")
+        n_sent = labels.shape[0]
+        labels = labels.contiguous()
+        if labels.dtype != torch.int64:
+            raise TypeError("labels must be int64")
+        sent_row = batch.sent_row
+        if sent_row is None and n_sent != n_super:
+            raise ValueError("HSG batch: %d labels for %d sentence nodes" % (n_sent, n_super))
+        doc_row = batch.sent_doc_row.int() if two_part else None
+        gptr = batch.graph_sent_ptr
+        args = _lib.HeadArgsC(n_sent, n_super, hidden, two_part, batch.n_graphs, 0, _p(state), _p(sent_row), _p(doc_row),
+                              _p(gptr), _p(wh_w), _p(wh_b), _p(labels), 1.0 / float(n_graphs_global), 0.0)
+        dev = state.device
+        out = torch.empty(4 * n_sent + 4, dtype=torch.float32, device=dev)
+        logits, dlogits, loss = out[:2 * n_sent].view(n_sent, 2), out[2 * n_sent:4 * n_sent], out[4 * n_sent:4 * n_sent + 1]
+        ws_bytes = lib.hsg_head_workspace_bytes(n_sent, hidden * (1 + two_part))
+        ws = _Workspace.get(ws_bytes, dev, "head")
+        _lib.check(lib.hsg_head_fwd(C.byref(args), _p(logits), _p(dlogits), _p(loss), ws.data_ptr(), ws.numel(), _st()))
+        ctx.args, ctx.keep, ctx.grad_targets = args, (sent_row, doc_row, gptr, labels), grad_targets
+        ctx.save_for_backward(state, wh_w, wh_b, dlogits)
+        ctx.mark_non_differentiable(logits)
+        return loss.view(()), logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        lib = _lib.load()
+        state, wh_w, wh_b, dlogits = ctx.saved_tensors
+        dev = state.device
+        d_state = torch.empty_like(state)
+        if ctx.grad_targets is not None:
+            d_w, d_b = ctx.grad_targets
+            acc = 1
+        else:
+            d_w, d_b = torch.empty_like(wh_w), torch.empty_like(wh_b)
+            acc = 0
+        gout = _f32c(dloss) if dloss is not None else None
+        ws = _Workspace.get(lib.hsg_head_workspace_bytes(ctx.args.n_sent, wh_w.shape[1]), dev, "head")
+        _lib.check(lib.hsg_head_bwd(C.byref(ctx.args), _p(dlogits), _p(gout), _p(d_state), _p(d_w), _p(d_b), acc,
+                                    ws.data_ptr(), ws.numel(), _st()))
+        if ctx.grad_targets is not None:
+            return None, None, None, d_state, None, None, None
+        return None, None, None, d_state, d_w, d_b, None
+
+
+def topm(logits, graph_sent_ptr, m):
+    """[n_graphs, m] int32: per graph the local indices of the m sentences with the largest class-1 logit, in
+    descending order, -1 padded (Tester.py:128 torch.topk(p_sent[:, 1], min(m, N)))."""
+    _lib.require_device()
+    lib = _lib.load()
+    logits = _f32c(logits)
+    n_graphs = graph_sent_ptr.shape[0] - 1
+    out = torch.empty(n_graphs, m, dtype=torch.int32, device=logits.device)
+    _lib.check(lib.hsg_topm(_p(logits), _p(graph_sent_ptr), n_graphs, m, _p(out), _st()))
+    return out
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps) (train.py:90) over ONE flat fp32 parameter arena and its flat gradient
+    (dist.FlatGradArena), one kernel per step; max_grad_norm > 0 folds clip_grad_norm_ (train.py:132-133) in."""
+
+    def __init__(self, flat_param, flat_grad, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0):
+        self.p, self.g = flat_param, flat_grad
+        self.m, self.v = torch.zeros_like(flat_param), torch.zeros_like(flat_param)
+        self.lr, self.betas, self.eps, self.max_grad_norm, self.t = lr, betas, eps, float(max_grad_norm), 0
+        self.ws = torch.empty(_lib.load().hsg_adam_workspace_bytes(), dtype=torch.uint8, device=flat_param.device)
+
+    def step(self):
+        self.t += 1
+        _lib.check(_lib.load().hsg_adam_step(self.p.numel(), _p(self.p), _p(self.g), _p(self.m), _p(self.v), self.lr,
+                                             self.betas[0], self.betas[1], self.eps, self.t, self.max_grad_norm,
+                                             self.ws.data_ptr(), self.ws.numel(), _st()))

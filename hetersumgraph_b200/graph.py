@@ -47,8 +47,12 @@ class DeviceTokenBatch:
         bufs = dict(tokens=h(tb.tokens), sent_bin=h(tb.sent_bin), graph_sent_ptr=h(tb.graph_sent_ptr),
                     labels=h(tb.labels))
         if tb.hdsg:
+            per = np.diff(tb.graph_sent_ptr)
+            sent_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int32), per)
+            sent_local = (np.arange(int(per.sum()), dtype=np.int32) - np.repeat(tb.graph_sent_ptr[:-1], per)).astype(np.int32)
             bufs.update(graph_doc_ptr=h(tb.graph_doc_ptr), sent_doc=h(tb.sent_doc), doc_tok_ptr=h(tb.doc_tok_ptr),
-                        doc_tokens=h(tb.doc_tokens), doc_bin=h(tb.doc_bin))
+                        doc_tokens=h(tb.doc_tokens), doc_bin=h(tb.doc_bin), sent_graph=h(sent_graph),
+                        sent_local=h(sent_local))
         nbytes = sum(t.numel() * t.element_size() for t in bufs.values())
         return bufs, nbytes
 
@@ -73,11 +77,13 @@ class DeviceTokenBatch:
         d.filter_bitmap = filter_bitmap_dev
         if vocab_size is None:
             vocab_size = int(tb.filter_bitmap.shape[0]) * 32
-        d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = None
+        d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = d.sent_graph = d.sent_local = None
+        d.n_sent = int(tb.tokens.shape[0])
         n_doc = n_doc_tok = 0
         if tb.hdsg:
             d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = up(host["graph_doc_ptr"]), up(host["sent_doc"]), up(host["doc_tok_ptr"])
             d.doc_tokens, d.doc_bin = up(host["doc_tokens"]), up(host["doc_bin"])
+            d.sent_graph, d.sent_local = up(host["sent_graph"]).long(), up(host["sent_local"])
             n_doc, n_doc_tok = int(tb.graph_doc_ptr[-1]), int(tb.doc_tok_ptr[-1])
         S, L = tb.tokens.shape
         per_graph = np.diff(tb.graph_sent_ptr)
@@ -121,6 +127,8 @@ class HeteroBatch:
     tfidfembed_weight: Optional[torch.Tensor] = None     # set by set_tfidf_embedding (HiGraph.py:150-151)
     labels: Optional[torch.Tensor] = None                # [n sentence rows] int64
     sent_doc_row: Optional[torch.Tensor] = None          # HDSG: supernode row of each sentence's document
+    sent_row: Optional[torch.Tensor] = None              # HDSG: supernode row of each sentence (None: identity)
+    graph_sent_ptr: Optional[torch.Tensor] = None        # [B+1] sentence offsets per graph
     n_total_nodes: int = 0
     n_total_edges: int = 0
 
@@ -166,6 +174,12 @@ class HeteroBatch:
     def build(dtb: "DeviceTokenBatch") -> "HeteroBatch":
         """Device-side build (K0) from device-resident token arrays.  One small D2H read of the
         five totals (+ status) sizes the outputs of the fill phase."""
+        return HeteroBatch._build_fill(HeteroBatch._build_count(dtb))
+
+    @staticmethod
+    def _build_count(dtb: "DeviceTokenBatch"):
+        """Phase 1 on the current stream: per-graph counts + offsets; the totals start their way to pinned host
+        memory.  Returns the state _build_fill needs."""
         _lib.require_device()
         lib = _lib.load()
         dev = dtb.device
@@ -178,22 +192,48 @@ class HeteroBatch:
         off_c = _lib.GraphOffsetsC(*[offs[i].data_ptr() for i in range(5)])
         st = _stream()
         _lib.check(lib.hsg_build_count(C.byref(tbc), off_c, status.data_ptr(), ws.data_ptr(), ws_bytes, st))
-        totals = torch.cat([offs[:, B], status]).cpu().tolist()          # the one D2H of the build
+        totals_dev = torch.cat([offs[:, B], status])
+        totals_host = torch.empty(6, dtype=torch.int32, pin_memory=True)
+        totals_host.copy_(totals_dev, non_blocking=True)                 # the one D2H of the build
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(dtb=dtb, ws=ws, ws_bytes=ws_bytes, offs=offs, status=status, off_c=off_c,
+                    totals_dev=totals_dev, totals_host=totals_host, event=ev)
+
+    @staticmethod
+    def _build_fill(c) -> "HeteroBatch":
+        """Phase 2 on the current stream (the same one phase 1 ran on): waits for the totals, sizes and fills
+        the node maps and both CSCs."""
+        lib = _lib.load()
+        dtb, ws, ws_bytes, offs, status, off_c = c["dtb"], c["ws"], c["ws_bytes"], c["offs"], c["status"], c["off_c"]
+        dev, B, tbc = dtb.device, dtb.n_graphs, dtb.c_struct
+        c["event"].synchronize()
+        totals = c["totals_host"].tolist()
         if totals[5] != 0:
             _lib.check(int(totals[5]))
         n_word, n_super, n_node, n_edge, n_pair = [int(v) for v in totals[:5]]
+        st = _stream()
         i32 = dict(dtype=torch.int32, device=dev)
-        out = dict(
-            word_wid=torch.empty(max(n_word, 1), **i32), word_nid=torch.empty(max(n_word, 1), **i32),
-            super_nid=torch.empty(max(n_super, 1), **i32),
-            super_type=torch.empty(max(n_super, 1), dtype=torch.int8, device=dev),
-            super_graph=torch.empty(max(n_super, 1), **i32), super_indptr=torch.empty(n_super + 1, **i32),
-            super_src=torch.empty(max(n_pair, 1), **i32),
-            super_bin=torch.empty(max(n_pair, 1), dtype=torch.uint8, device=dev),
-            super_eid=torch.empty(max(n_pair, 1), **i32), super_extra=torch.empty(max(n_super, 1), **i32),
-            word_indptr=torch.empty(n_word + 1, **i32), word_src=torch.empty(max(n_pair, 1), **i32),
-            word_bin=torch.empty(max(n_pair, 1), dtype=torch.uint8, device=dev),
-            word_eid=torch.empty(max(n_pair, 1), **i32))
+        # one int32 arena for every 4-byte array, one byte arena for the rest: 2 allocations instead of 14
+        sizes32 = [("word_wid", max(n_word, 1)), ("word_nid", max(n_word, 1)), ("super_nid", max(n_super, 1)),
+                   ("super_graph", max(n_super, 1)), ("super_indptr", n_super + 1), ("super_src", max(n_pair, 1)),
+                   ("super_eid", max(n_pair, 1)), ("super_extra", max(n_super, 1)), ("word_indptr", n_word + 1),
+                   ("word_src", max(n_pair, 1)), ("word_eid", max(n_pair, 1))]
+        sizes8 = [("super_type", max(n_super, 1)), ("super_bin", max(n_pair, 1)), ("word_bin", max(n_pair, 1))]
+        out = {}
+        tot = sum((n + 3) & ~3 for _, n in sizes32)
+        a32 = torch.empty(tot, **i32)
+        off = 0
+        for name, n in sizes32:
+            out[name] = a32[off:off + n]
+            off += (n + 3) & ~3
+        tot = sum((n + 15) & ~15 for _, n in sizes8)
+        a8 = torch.empty(tot, dtype=torch.uint8, device=dev)
+        off = 0
+        for name, n in sizes8:
+            out[name] = a8[off:off + n]
+            off += (n + 15) & ~15
+        out["super_type"] = out["super_type"].view(torch.int8)
         if B == 0:
             out["super_indptr"].zero_()
             out["word_indptr"].zero_()
@@ -213,12 +253,15 @@ class HeteroBatch:
             super_bin=out["super_bin"][:n_pair], super_eid=out["super_eid"][:n_pair],
             word_indptr=out["word_indptr"], word_src=out["word_src"][:n_pair], word_bin=out["word_bin"][:n_pair],
             word_eid=out["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge)
-        hb._keepalive = (dtb, ws, status)
+        hb._keepalive = (dtb, ws, status, a32, a8, c["totals_dev"])
         hb.labels = dtb.labels
-        if dtb.hdsg:
-            n_per = (dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1]).long()
-            gi = torch.repeat_interleave(torch.arange(B, device=dev), n_per)
-            hb.sent_doc_row = (offs[1][:B].long()[gi] + n_per[gi] + dtb.sent_doc[:int(n_per.sum())].long())
+        hb.graph_sent_ptr = dtb.graph_sent_ptr
+        if dtb.hdsg and dtb.n_sent > 0:
+            # supernode rows of a graph: its sentences, then its documents (dataloader.py:348-363) - no host sync
+            base = offs[1][:B][dtb.sent_graph]                                       # first supernode row of the graph
+            n_per = (dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1])[dtb.sent_graph]
+            hb.sent_row = (base + dtb.sent_local[:dtb.n_sent]).int()
+            hb.sent_doc_row = (base + n_per + dtb.sent_doc[:dtb.n_sent]).long()
         return hb
 
     @staticmethod
@@ -271,3 +314,62 @@ def csc_pair_from_edges(word_row, super_row, bins, n_word, n_super):
         return np.cumsum(indptr), src[o], bins[o], eid[o]
 
     return one(super_row, word_row, n_super, 2 * t), one(word_row, super_row, n_word, 2 * t + 1)
+
+
+class BuildPipeline:
+    """Double-buffered device-side graph builds on a side stream.
+
+    The reference builds its DGL graphs in DataLoader worker processes while the previous batch trains
+    (module/dataloader.py:222-268 under torch.utils.data.DataLoader, train.py).  Here the build of batch i+1
+    (hsg_build_count, the 24-byte D2H of the totals, hsg_build_fill) runs on its own CUDA stream while the
+    kernels of batch i run on the compute stream, so neither the two latency-bound builder kernels (one CTA per
+    graph) nor the host read of the totals sit on the critical path:
+
+        pipe.submit(tokens_0); pipe.finish()           # prime
+        for i in ...:
+            batch = pipe.take()                        # compute stream waits for the fill of batch i (done long ago)
+            pipe.submit(tokens_{i+1})                  # phase 1 of the next build, side stream
+            ... enqueue forward / backward / optimizer on the compute stream ...
+            pipe.finish()                              # totals have arrived: size + phase 2, side stream
+    """
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._pending = None
+        self._ready = None
+
+    def submit(self, source):
+        """`source`: a DeviceTokenBatch, or a callable returning one (e.g. the pinned-host -> device upload), run
+        on the side stream."""
+        if self._pending is not None or self._ready is not None:
+            raise RuntimeError("BuildPipeline: previous batch not taken yet")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            dtb = source() if callable(source) else source
+            self._pending = HeteroBatch._build_count(dtb)
+
+    def finish(self):
+        if self._pending is None:
+            return
+        with torch.cuda.stream(self.stream):
+            hb = HeteroBatch._build_fill(self._pending)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pending = None
+        self._ready = (hb, ev)
+
+    def take(self) -> "HeteroBatch":
+        if self._ready is None:
+            self.finish()
+        if self._ready is None:
+            raise RuntimeError("BuildPipeline: nothing submitted")
+        hb, ev = self._ready
+        self._ready = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        # allocated on the side stream, consumed on the compute stream: tell the caching allocator
+        for t in list(hb._keepalive) + list(vars(hb).values()):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(cur)
+        return hb

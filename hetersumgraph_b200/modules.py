@@ -17,7 +17,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .functional import AttnPrepFn, FFNFn, MultiHeadFn, WSWGATCoreFn
+from .functional import AttnPrepFn, FFNFn, MultiHeadFn, UpdateLoopFn, WSWGATCoreFn
 
 
 class WSGATLayer:
@@ -193,7 +193,51 @@ class WSWGATUpdateLoop(nn.Module):
         self.sent2word = WSWGAT(hidden_size, word_emb_dim, 6, atten_dropout_prob, ffn_inner_hidden_size,
                                 ffn_dropout_prob, feat_embed_size, "S2W")
 
+    # When True, backward ADDS the parameter gradients straight into the existing `.grad` buffers (e.g. the views
+    # of a dist.FlatGradArena) from inside the kernels' last stages instead of returning them to autograd, which
+    # would launch one add per parameter.  Same arithmetic; requires every parameter to have a `.grad` tensor.
+    fuse_grad_accumulation = False
+
+    def _packed(self, mod):
+        lay = mod.layer
+        return (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight) + mod.ffn.packed()
+
+    def _grad_buffers(self, mod):
+        """.grad of the ten packed parameters, viewed in the packed shapes (Conv1d weights are [out, in, 1])."""
+        lay, ffn = mod.layer, mod.ffn
+        leaves = (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight, ffn.w_1.weight, ffn.w_1.bias,
+                  ffn.w_2.weight, ffn.w_2.bias, ffn.layer_norm.weight, ffn.layer_norm.bias)
+        out = []
+        for p in leaves:
+            if p is None:
+                out.append(None)
+                continue
+            if p.grad is None or not p.grad.is_contiguous():
+                raise RuntimeError("fuse_grad_accumulation needs a contiguous .grad buffer on every parameter "
+                                   "(see hetersumgraph_b200.dist.FlatGradArena)")
+            out.append(p.grad.view(p.shape[0], -1) if p.dim() == 3 else p.grad)
+        return out
+
     def forward(self, graph, word_feature, sent_feature):
+        graph.set_tfidf_embedding(self._TFembed.weight)
+        for mod in (self.word2sent, self.sent2word):
+            _check_dropout(mod.layer, mod.layer.dropout.p, "attention-input")
+            _check_dropout(mod.ffn, mod.ffn.dropout.p, "FFN")
+        pw, ps = self._packed(self.word2sent), self._packed(self.sent2word)
+        targets = None
+        if self.fuse_grad_accumulation and torch.is_grad_enabled():
+            if self._TFembed.weight.grad is None:
+                raise RuntimeError("fuse_grad_accumulation needs a .grad buffer on every parameter")
+            targets = [self._TFembed.weight.grad] + self._grad_buffers(self.word2sent) + \
+                self._grad_buffers(self.sent2word)
+        lw, ls = self.word2sent.layer, self.sent2word.layer
+        cfg = (self._n_iter, (lw.num_heads, lw.out_dim, self.word2sent.ffn.d_hid),
+               (ls.num_heads, ls.out_dim, self.sent2word.ffn.d_hid), targets)
+        return UpdateLoopFn.apply(graph, cfg, word_feature, sent_feature, self._TFembed.weight, *pw, *ps)
+
+    def forward_per_application(self, graph, word_feature, sent_feature):
+        """Same loop through one autograd node per WSWGAT application (the path a caller gets by invoking the
+        WSWGAT modules directly, as HiGraph.py:100-106 does); kept for the parity tests."""
         graph.set_tfidf_embedding(self._TFembed.weight)
         p_w2s = self.word2sent.prepare(graph)                 # once per layer and step (shared weights)
         p_s2w = self.sent2word.prepare(graph) if self._n_iter > 0 else None

@@ -37,8 +37,8 @@ class HSGPath(nn.Module):
         """supernode row of the document of every sentence row (HDSG), from the builder's sent->doc map."""
         return g.sent_doc_row
 
-    def forward(self, g: HeteroBatch, sent_feature: torch.Tensor):
-        """sent_feature: [n sentence rows, hidden] (HSG) - the encoder output in batched-graph sentence order."""
+    def states(self, g: HeteroBatch, sent_feature: torch.Tensor):
+        """(word_state, supernode_state) after the update loop."""
         word_feature = self._embed(g.word_wid.long())
         if not self.hdsg:
             super_feature = sent_feature
@@ -54,11 +54,28 @@ class HSGPath(nn.Module):
             doc_feature = self.dn_feature_proj(sums / cnt.unsqueeze(1))
             super_feature = torch.zeros(g.n_super, sent_feature.shape[1], device=sent_feature.device)
             super_feature = super_feature.index_copy(0, srows, sent_feature).index_copy(0, drows, doc_feature)
-        word_state, sent_state = self.loop(g, word_feature, super_feature)
+        return self.loop(g, word_feature, super_feature)
+
+    def forward(self, g: HeteroBatch, sent_feature: torch.Tensor):
+        """sent_feature: [n sentence rows, hidden] (HSG) - the encoder output in batched-graph sentence order."""
+        _, sent_state = self.states(g, sent_feature)
         if not self.hdsg:
             return self.wh(sent_state)
-        s_state = torch.cat([sent_state[srows], sent_state[d_of_s]], dim=-1)          # HiGraph.py:216-228
+        s_state = torch.cat([sent_state[g.sentence_rows()], sent_state[g.sent_doc_row]], dim=-1)   # HiGraph.py:216-228
         return self.wh(s_state)
+
+
+def fused_loss(model: "HSGPath", g: HeteroBatch, sent_feature: torch.Tensor, n_graphs_global=None,
+               fuse_grad_accumulation=False):
+    """(loss, logits) with the classifier, the per-graph cross-entropy sums and their mean in one device kernel pair
+    (hsg_head_fwd/bwd) instead of ~20 stock launches.  Same value as graph_loss(g, model(g, sf), g.labels, ...)."""
+    from .functional import SentenceLossFn
+    state = model.states(g, sent_feature)[1]
+    targets = None
+    if fuse_grad_accumulation and torch.is_grad_enabled():
+        targets = (model.wh.weight.grad, model.wh.bias.grad)
+    n = n_graphs_global if n_graphs_global is not None else g.n_graphs
+    return SentenceLossFn.apply(g, n, targets, state, model.wh.weight, model.wh.bias, g.labels)
 
 
 def graph_loss(g: HeteroBatch, logits: torch.Tensor, labels: torch.Tensor, n_graphs_global=None):

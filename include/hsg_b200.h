@@ -177,6 +177,10 @@ int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
  * Shapes the tensor-core path cannot take (K or a leading dimension not a multiple of 4) fall back to mode 0. */
 int hsg_set_gemm_mode(int mode);
 int hsg_get_gemm_mode(void);
+/* Products of fewer than `flops` (2 M N K) run on 64x64 FFMA tiles in every mode: the 128x128 tcgen05 tile pipeline
+ * has ~15 us of fill/drain latency and idles most SMs on the sentence-side shapes (M ~ 1 k).  Default 3e8; 0 sends
+ * everything the TMA path can take to the tensor cores. */
+int hsg_set_gemm_small_flops(double flops);
 /* Profiling aid for the tensor-core pipeline: on = 1/0 arms/disarms a trace of CTA 0 (synchronous call); on < 0 reads
  * up to max_events (event id, k-block counter, SM clock) triples into host_out and returns their number. */
 int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events);
@@ -268,6 +272,101 @@ typedef struct {
 } hsg_wswgat_bwd_args;
 size_t hsg_wswgat_bwd_workspace_bytes(int H, int d, int in_dim, int d_hid, int n_src, int n_dst);
 int hsg_wswgat_bwd(const hsg_wswgat_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Whole update loop from one call each way: HSumGraph.forward's
+ *     sent = W2S(word, sent);  n_iter x { word = S2W(word, sent);  sent = W2S(word, sent) }
+ * (HiGraph.py:98-106, HSumDocGraph :205-214), attention prep included.  The two weight sets are shared by
+ * the 1 + 2 n_iter applications: their gradients are accumulated inside the producing kernels' last stage,
+ * and the state gradients that meet at a node set (origin path of the later application + neighbor path of
+ * the earlier one, GAT.py:47-57) are summed in the projection-backward epilogue - no separate add launches.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t H, d, in_dim, feat_dim, d_hid, reserved;
+  const float *W, *Wf, *bf, *a;  /* heads packed: fc [H*d,in_dim], feat_fc [H*d,feat_dim], its bias [H*d] or NULL, attn_fc [H,3d] */
+  const float *w1, *b1, *w2, *b2, *gamma, *beta; /* FFN + LayerNorm (GATLayer.py:25-44) */
+} hsg_layer_params;
+
+typedef struct {
+  float *dW, *dWf, *dbf, *da, *dw1, *db1, *dw2, *db2, *dgamma, *dbeta;
+} hsg_layer_grads;
+
+typedef struct {
+  int32_t n_iter, n_word, n_super, reserved;
+  const hsg_csc *csc_super, *csc_word;  /* in-edges of supernodes from words / of words from supernodes */
+  hsg_layer_params w2s, s2w;            /* s2w is ignored when n_iter == 0 */
+  const float* T;                       /* _TFembed.weight [10, feat_dim]  (HiGraph.py:52) */
+  const float *word_feature;            /* [n_word,  w2s.in_dim]        */
+  const float *super_feature;           /* [n_super, w2s.H * w2s.d]     */
+  float* state;                         /* forward arena: everything backward needs + the two results */
+  size_t state_floats;
+} hsg_loop_args;
+
+typedef struct {
+  size_t state_floats;    /* size of hsg_loop_args.state                                 */
+  size_t scratch_floats;  /* size of hsg_loop_bwd_args.scratch                           */
+  size_t ws_bytes;        /* size of hsg_loop_bwd_args.ws                                */
+  size_t word_state_off;  /* float offset of the final word state in `state` ((size_t)-1 when n_iter == 0: it is word_feature) */
+  size_t super_state_off; /* float offset of the final supernode state in `state`        */
+  size_t hdn_off[2];      /* float offset of the FFN hidden activation of application 0 (W2S) / 1 (S2W) - test hook */
+  size_t pair_stride;     /* floats between application i and i+2 (same layer type) in `state` */
+} hsg_loop_plan;
+
+typedef struct {
+  const float *d_word_state, *d_super_state; /* upstream gradients; either may be NULL (= 0) */
+  float* d_word_feature;                     /* [n_word, w2s.in_dim] or NULL (skips that product) */
+  float* d_super_feature;                    /* [n_super, w2s.H*w2s.d] */
+  hsg_layer_grads w2s, s2w;
+  float* dT;                                 /* [10, feat_dim] */
+  int32_t accumulate;                        /* 1: parameter gradients are ADDED to the given buffers (fused
+                                                accumulation into .grad), 0: overwritten */
+  int32_t reserved;
+  float* scratch;
+  size_t scratch_floats;
+  void* ws;
+  size_t ws_bytes;
+} hsg_loop_bwd_args;
+
+/* Sizes/offsets for the given dimensions (pointers inside `a` are not read). */
+int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan);
+int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream);
+int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Readout, loss, extraction and optimizer on the device (the step right after the update loop):
+ *   logits = wh(sentence state)                       HiGraph.py:108; HDSG: wh(cat(sentence, its document)), :216-228
+ *   loss   = mean_graphs sum_sentences CE(logits, y)  train.py:114-119
+ *   top-m  = per graph torch.topk(logits[:, 1], m)    Tester.py:128
+ *   Adam (+ optional clip_grad_norm_)                 train.py:90,132-135
+ * All reductions run in a fixed order.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_sent, n_super, hidden, two_part; /* two_part = 1 (HDSG): wh input is [sentence | document], 2*hidden wide */
+  int32_t n_graphs, reserved;
+  const float* state;            /* [n_super, hidden] final supernode state */
+  const int32_t* sent_row;       /* [n_sent] supernode row of every sentence; NULL = identity (HSG: every supernode is a sentence) */
+  const int32_t* doc_row;        /* [n_sent] supernode row of the sentence's document (two_part only) */
+  const int32_t* graph_sent_ptr; /* [n_graphs+1] sentence offsets per graph (two_part only) */
+  const float* wh_w;             /* [2, hidden * (1 + two_part)] */
+  const float* wh_b;             /* [2] */
+  const int64_t* labels;         /* [n_sent] in {0, 1} */
+  float inv_graphs;              /* 1 / (global number of graphs) */
+  float reserved2;
+} hsg_head_args;
+size_t hsg_head_workspace_bytes(int n_sent, int width);
+/* logits [n_sent,2]; dlogits [n_sent,2] = d loss / d logits (saved for hsg_head_bwd); loss [1] */
+int hsg_head_fwd(const hsg_head_args* a, float* logits, float* dlogits, float* loss, void* ws, size_t ws_bytes,
+                 void* stream);
+/* gout: device scalar d L / d loss, or NULL (= 1).  d_state [n_super, hidden] is fully written. */
+int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout, float* d_state, float* d_wh_w,
+                 float* d_wh_b, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* out_idx [n_graphs, m]: local sentence indices by descending class-1 logit (ties: lower index first), -1 padded */
+int hsg_topm(const float* logits, const int32_t* graph_sent_ptr, int n_graphs, int m, int32_t* out_idx, void* stream);
+/* torch.optim.Adam semantics (no amsgrad / weight decay) on flat fp32 arrays, `step` counts from 1.
+ * max_grad_norm > 0 applies clip_grad_norm_'s coefficient min(1, max_norm / (||g|| + 1e-6)) on the fly (needs ws). */
+size_t hsg_adam_workspace_bytes(void);
+int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, int step, float max_grad_norm, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

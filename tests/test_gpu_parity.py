@@ -340,3 +340,139 @@ def test_stress_graph_properties():
     agg = torch.zeros(n_super, 64, device="cuda").index_add_(0, dst, z[torch.from_numpy(ssrc).cuda()])
     want = agg / (deg + 64.0).unsqueeze(1)
     assert nerr(sh, want) <= TOL
+
+
+# ----------------------------------------------------------------------------- whole-loop C entry points
+def _loop_inputs(n_iter, hdsg=False, n=6, seed=11):
+    exs = syn.make_examples(n, "tiny", seed=seed, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
+    torch.manual_seed(5)
+    m = hb.WSWGATUpdateLoop(n_iter=n_iter, atten_dropout_prob=0.0, ffn_dropout_prob=0.0).cuda()
+    w = torch.randn(batch.n_word, 300, device="cuda")
+    s = torch.randn(batch.n_super, 64, device="cuda")
+    cw, cs = torch.randn_like(w), torch.randn_like(s)
+    return batch, m, w, s, cw, cs
+
+
+def _run_loop(m, fwd, batch, w, s, cw, cs, use_w=True, use_s=True):
+    m.zero_grad(set_to_none=True)
+    wg, sg = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    ow, os_ = fwd(batch, wg, sg)
+    loss = 0.0
+    if use_w:
+        loss = loss + (ow * cw).sum()
+    if use_s:
+        loss = loss + (os_ * cs).sum()
+    loss.backward()
+    return [ow.detach(), os_.detach(), wg.grad, sg.grad] + [p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+                                                            for p in m.parameters()]
+
+
+@pytest.mark.parametrize("n_iter,hdsg", [(0, False), (1, False), (2, True), (3, False)])
+def test_whole_loop_call_equals_per_application_path(n_iter, hdsg):
+    """hsg_update_loop_fwd/bwd (one C call each way, in-kernel gradient accumulation) against the per-application
+    autograd path (hsg_wswgat_fwd/bwd + autograd's own accumulation): same kernels, so only the order of the
+    accumulating adds may differ."""
+    batch, m, w, s, cw, cs = _loop_inputs(n_iter, hdsg)
+    a = _run_loop(m, m.forward, batch, w, s, cw, cs)
+    b = _run_loop(m, m.forward_per_application, batch, w, s, cw, cs)
+    for x, y in zip(a, b):
+        if float(y.abs().max()) == 0.0:
+            assert float(x.abs().max()) == 0.0
+        else:
+            assert nerr(x, y) <= 2e-6, nerr(x, y)
+
+
+@pytest.mark.parametrize("use_w,use_s", [(True, False), (False, True)])
+def test_whole_loop_call_single_cotangent(use_w, use_s):
+    batch, m, w, s, cw, cs = _loop_inputs(1)
+    a = _run_loop(m, m.forward, batch, w, s, cw, cs, use_w, use_s)
+    b = _run_loop(m, m.forward_per_application, batch, w, s, cw, cs, use_w, use_s)
+    for x, y in zip(a, b):
+        if float(y.abs().max()) == 0.0:
+            assert float(x.abs().max()) == 0.0
+        else:
+            assert nerr(x, y) <= 2e-6, nerr(x, y)
+
+
+def test_fused_grad_accumulation_adds_into_existing_grads():
+    """fuse_grad_accumulation: the kernels ADD into .grad (flat arena views) - equals autograd's result, and a
+    second backward doubles it."""
+    from hetersumgraph_b200.dist import FlatGradArena
+    batch, m, w, s, cw, cs = _loop_inputs(1)
+    ref = _run_loop(m, m.forward, batch, w, s, cw, cs)[4:]
+    arena = FlatGradArena(m.parameters())
+    m.fuse_grad_accumulation = True
+    for rep in (1, 2):
+        wg, sg = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+        ow, os_ = m(batch, wg, sg)
+        ((ow * cw).sum() + (os_ * cs).sum()).backward()
+        for p, r in zip(m.parameters(), ref):
+            assert p.grad.data_ptr() >= arena.flat.data_ptr()
+            if float(r.abs().max()) == 0.0:
+                assert float(p.grad.abs().max()) == 0.0
+            else:
+                assert nerr(p.grad, rep * r) <= 2e-6
+
+
+# ----------------------------------------------------------------------------- readout / loss / top-m / Adam
+@pytest.mark.parametrize("hdsg", [False, True])
+def test_fused_loss_matches_reference_loss(hdsg):
+    """hsg_head_fwd/bwd against wh + CrossEntropyLoss + per-graph sum + mean (train.py:114-119) in stock PyTorch."""
+    from hetersumgraph_b200.path_model import HSGPath, fused_loss, graph_loss
+    exs = syn.make_examples(6, "tiny", seed=21, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
+    torch.manual_seed(2)
+    model = HSGPath(n_iter=1, hdsg=hdsg).cuda()
+    n_sent = batch.labels.shape[0]
+    sf = torch.randn(n_sent, 64, device="cuda")
+    res = []
+    for fused in (False, True):
+        model.zero_grad(set_to_none=True)
+        s = sf.clone().requires_grad_(True)
+        if fused:
+            loss, logits = fused_loss(model, batch, s, n_graphs_global=7)
+        else:
+            logits = model(batch, s)
+            loss = graph_loss(batch, logits, batch.labels, 7)
+        (loss * 1.7).backward()
+        res.append([loss.detach(), logits.detach(), s.grad] + [p.grad.clone() for p in model.parameters() if p.grad is not None])
+    assert len(res[0]) == len(res[1])
+    for a, b in zip(res[1], res[0]):
+        assert nerr(a, b) <= TOL, nerr(a, b)
+
+
+def test_topm_bit_exact_vs_torch_topk():
+    from hetersumgraph_b200.functional import topm
+    rng = np.random.default_rng(0)
+    counts = [1, 7, 50, 3, 100, 2]
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    logits = torch.randn(int(ptr[-1]), 2)
+    for m in (1, 3, 5):
+        got = topm(logits.cuda(), torch.from_numpy(ptr).cuda(), m).cpu()
+        for g, c in enumerate(counts):
+            want = torch.topk(logits[ptr[g]:ptr[g + 1], 1], min(m, c))[1].tolist()      # Tester.py:128
+            assert got[g, :len(want)].tolist() == want
+            assert (got[g, len(want):] == -1).all()
+
+
+@pytest.mark.parametrize("clip", [0.0, 0.5])
+def test_fused_adam_matches_torch(clip):
+    from hetersumgraph_b200.functional import FusedAdam
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n)
+    ref = torch.nn.Parameter(p0.clone().cuda())
+    opt = torch.optim.Adam([ref], lr=5e-4)
+    mine = p0.clone().cuda()
+    g = torch.zeros(n, device="cuda")
+    fa = FusedAdam(mine, g, lr=5e-4, max_grad_norm=clip)
+    for step in range(5):
+        grad = torch.randn(n, device="cuda") * (0.1 + step)
+        ref.grad = grad.clone()
+        if clip > 0:
+            torch.nn.utils.clip_grad_norm_([ref], clip)
+        opt.step()
+        g.copy_(grad)
+        fa.step()
+        assert nerr(mine, ref) <= 1e-6
