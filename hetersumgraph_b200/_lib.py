@@ -103,6 +103,7 @@ _PROTOS = {
     "hsg_strerror": (C.c_char_p, [_I]),
     "hsg_device_check": (C.c_int, []),
     "hsg_num_sms": (C.c_int, []),
+    "hsg_set_pdl": (C.c_int, [_I]),
     "hsg_profile_enable": (C.c_int, [_I]),
     "hsg_profile_reset": (C.c_int, []),
     "hsg_profile_num_slots": (C.c_int, []),

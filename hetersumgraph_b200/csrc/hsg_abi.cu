@@ -1,5 +1,6 @@
 // C-ABI bookkeeping: version, error strings, device check, per-kernel profiling.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -74,6 +75,18 @@ static void drain() {
   g_pending.clear();
 }
 
+static std::atomic<int> g_pdl{-1};
+
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HSG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v);
+  }
+  return v != 0;
+}
+
 int num_sms() {
   if (g_sms == 0) {
     int dev = 0;
@@ -115,6 +128,11 @@ int hsg_device_check(void) {
 }
 
 int hsg_num_sms(void) { return num_sms(); }
+
+int hsg_set_pdl(int on) {
+  g_pdl.store(on ? 1 : 0);
+  return HSG_OK;
+}
 
 int hsg_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_mu);

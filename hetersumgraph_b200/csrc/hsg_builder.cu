@@ -114,6 +114,7 @@ __device__ __forceinline__ int table_find(const int32_t* keys, uint32_t mask, in
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLD_THREADS)
 build_count_kernel(hsg_token_batch tb, BuildWs ws, int ht_size, int cap_tok, int32_t* status) {
+  pdl_prologue();
   extern __shared__ int32_t smem[];
   __shared__ int warp_buf[BLD_WARPS + 1];
   __shared__ int s_pairs;
@@ -265,6 +266,7 @@ build_count_kernel(hsg_token_batch tb, BuildWs ws, int ht_size, int cap_tok, int
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLD_THREADS)
 build_scan_kernel(int B, BuildWs ws, hsg_graph_offsets off) {
+  pdl_prologue();
   __shared__ int warp_buf[BLD_WARPS + 1];
   const int32_t* in[5] = {ws.cnt_word, ws.cnt_super, ws.cnt_node, ws.cnt_edge, ws.cnt_pair};
   int32_t* out[5] = {off.word_ptr, off.super_ptr, off.node_ptr, off.edge_ptr, off.pair_ptr};
@@ -288,6 +290,7 @@ build_scan_kernel(int B, BuildWs ws, hsg_graph_offsets off) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLD_THREADS)
 build_fill_kernel(hsg_token_batch tb, BuildWs ws, hsg_graph_out out, int cap_tok, int cap_sup) {
+  pdl_prologue();
   extern __shared__ int32_t smem[];
   __shared__ int warp_buf[BLD_WARPS + 1];
   int32_t* wscan = smem;
@@ -469,12 +472,12 @@ int hsg_build_count(const hsg_token_batch* tb, hsg_graph_offsets off, int32_t* s
       configured = smem;
     }
     LaunchScope ls(SLOT_BUILD_COUNT, s);
-    build_count_kernel<<<tb->n_graphs, BLD_THREADS, smem, s>>>(*tb, w, ht, cap_tok, status);
+    launch_k(build_count_kernel, dim3(tb->n_graphs), dim3(BLD_THREADS), smem, s, *tb, w, ht, cap_tok, status);
     rc = check_launch();
     if (rc) return rc;
   }
   LaunchScope ls(SLOT_BUILD_SCAN, s);
-  build_scan_kernel<<<1, BLD_THREADS, 0, s>>>(tb->n_graphs, w, off);
+  launch_k(build_scan_kernel, dim3(1), dim3(BLD_THREADS), 0, s, tb->n_graphs, w, off);
   return check_launch();
 }
 
@@ -498,7 +501,7 @@ int hsg_build_fill(const hsg_token_batch* tb, const hsg_graph_out* out, void* ws
     configured = smem;
   }
   LaunchScope ls(SLOT_BUILD_FILL, s);
-  build_fill_kernel<<<tb->n_graphs, BLD_THREADS, smem, s>>>(*tb, w, *out, cap_tok, cap_sup);
+  launch_k(build_fill_kernel, dim3(tb->n_graphs), dim3(BLD_THREADS), smem, s, *tb, w, *out, cap_tok, cap_sup);
   return check_launch();
 }
 

@@ -42,6 +42,37 @@ struct LaunchScope {
   ~LaunchScope() { prof_end(slot, s); }
 };
 
+// Programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and starts with pdl_prologue(): it lets ITS dependents be scheduled at once
+// (griddepcontrol.launch_dependents) and then waits until everything before it in the stream has completed and
+// flushed (griddepcontrol.wait) before touching global memory.  The ~45 short kernels of a step are a dependent
+// chain; this overlaps each kernel's launch latency and prologue (barrier init, TMEM allocation, tensor-map
+// prefetch, index loads of parameters) with its predecessor's execution.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+bool pdl_enabled();   // hsg_abi.cu (HSG_PDL=0 in the environment or hsg_set_pdl(0) turns it off)
+
+template <typename... P, typename... A>
+inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? HSG_OK : HSG_ERR_CUDA; }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

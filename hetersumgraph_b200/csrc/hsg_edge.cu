@@ -107,6 +107,7 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
                 const uint8_t* __restrict__ bin, const int32_t* __restrict__ extra, const float* __restrict__ zp,
                 int ldz, const float* __restrict__ q, const float* __restrict__ origin, float* __restrict__ sh,
                 float* __restrict__ x, float* __restrict__ stat) {
+  pdl_prologue();
   using C = EdgeCfg<H, D>;
   constexpr int OV = C::STAGED ? (C::F / 4 + 31) / 32 : 1;   // origin float4 per lane (staged epilogue)
   __shared__ float q_s[HSG_N_BINS * H];
@@ -315,6 +316,7 @@ template <int H, int D>
 __global__ void __launch_bounds__(EDGE_THREADS)
 edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __restrict__ dsh,
                      const float* __restrict__ sh, float* __restrict__ g, float* __restrict__ stat) {
+  pdl_prologue();
   using C = EdgeCfg<H, D>;
   __shared__ __align__(16) float stage[C::STAGED ? 2 * EDGE_WARPS * C::F : 4];
   const int lane = threadIdx.x & 31;
@@ -405,6 +407,7 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
                 const uint8_t* __restrict__ bin, const float* __restrict__ zp, int ldz, const float* __restrict__ q,
                 const float* __restrict__ g, const float* __restrict__ stat, float* __restrict__ dzp,
                 float* __restrict__ dq_part) {
+  pdl_prologue();
   using C = EdgeCfg<H, D>;
   constexpr int NQ = HSG_N_BINS * H;
   __shared__ float q_s[NQ];
@@ -569,6 +572,7 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
 // dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
 __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
                                                           float* __restrict__ dq, int accumulate) {
+  pdl_prologue();
   __shared__ float red[128];
   const int i = blockIdx.x;
   float s = 0.f;
@@ -605,10 +609,10 @@ static int launch_fwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
   LaunchScope ls(SLOT_EDGE_FWD, s);
   if (deep)
-    edge_fwd_kernel<H, D, UHI><<<edge_grid(c->n_dst), EDGE_THREADS, 0, s>>>(c->n_dst, c->indptr, c->nbr, c->bin,
+    launch_k(edge_fwd_kernel<H, D, UHI>, dim3(edge_grid(c->n_dst)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
   else
-    edge_fwd_kernel<H, D, ULO><<<edge_grid(c->n_dst), EDGE_THREADS, 0, s>>>(c->n_dst, c->indptr, c->nbr, c->bin,
+    launch_k(edge_fwd_kernel<H, D, ULO>, dim3(edge_grid(c->n_dst)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
   return check_launch();
 }
@@ -617,7 +621,7 @@ template <int H, int D>
 static int launch_prep(int n_dst, const float* dx, const float* dsh, const float* sh, float* g, float* stat,
                        cudaStream_t s) {
   LaunchScope ls(SLOT_EDGE_BWD_PREP, s);
-  edge_bwd_prep_kernel<H, D><<<edge_grid(ceil_div(n_dst, EdgeCfg<H, D>::EPS)), EDGE_THREADS, 0, s>>>(n_dst, dx, dsh,
+  launch_k(edge_bwd_prep_kernel<H, D>, dim3(edge_grid(ceil_div(n_dst, EdgeCfg<H, D>::EPS))), dim3(EDGE_THREADS), 0, s, n_dst, dx, dsh,
                                                                                                    sh, g, stat);
   return check_launch();
 }
@@ -632,17 +636,17 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   {
     LaunchScope ls(SLOT_EDGE_BWD, s);
     if (deep)
-      edge_bwd_kernel<H, D, UHI><<<blocks, EDGE_THREADS, 0, s>>>(c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
+      launch_k(edge_bwd_kernel<H, D, UHI>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
                                                                  stat, dzp, ws);
     else
-      edge_bwd_kernel<H, D, ULO><<<blocks, EDGE_THREADS, 0, s>>>(c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
+      launch_k(edge_bwd_kernel<H, D, ULO>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
                                                                  stat, dzp, ws);
     int rc = check_launch();
     if (rc) return rc;
   }
   LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
   const int nq = HSG_N_BINS * H;
-  edge_bwd_dq_kernel<<<nq, 128, 0, s>>>(blocks, nq, ws, dq, accumulate_dq);
+  launch_k(edge_bwd_dq_kernel, dim3(nq), dim3(128), 0, s, blocks, nq, ws, dq, accumulate_dq);
   return check_launch();
 }
 

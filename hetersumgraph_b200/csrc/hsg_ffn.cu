@@ -15,6 +15,7 @@ template <int NV4>  // float4 per lane; D <= 128 * NV4
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_fwd_kernel(int N, int D, const float* __restrict__ r, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ stats) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __restrict__ r,
                      const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dr,
                      float* __restrict__ part /* [gridDim.x][2][D] */) {
+  pdl_prologue();
   extern __shared__ float red[];  // [LN_WARPS][2][D]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -156,6 +158,7 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
 __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
                                                                    float* __restrict__ dgamma,
                                                                    float* __restrict__ dbeta, int accumulate) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
@@ -198,16 +201,16 @@ int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float*
   {
     LaunchScope ls(SLOT_LN_BWD, s);
     switch (nv4) {
-      case 1: layernorm_bwd_kernel<1><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      case 2: layernorm_bwd_kernel<2><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      case 3: layernorm_bwd_kernel<3><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
-      default: layernorm_bwd_kernel<4><<<grid, LN_THREADS, smem, s>>>(N, D, dy, r, stats, gamma, dr, part); break;
+      case 1: launch_k(layernorm_bwd_kernel<1>, dim3(grid), dim3(LN_THREADS), smem, s, N, D, dy, r, stats, gamma, dr, part); break;
+      case 2: launch_k(layernorm_bwd_kernel<2>, dim3(grid), dim3(LN_THREADS), smem, s, N, D, dy, r, stats, gamma, dr, part); break;
+      case 3: launch_k(layernorm_bwd_kernel<3>, dim3(grid), dim3(LN_THREADS), smem, s, N, D, dy, r, stats, gamma, dr, part); break;
+      default: launch_k(layernorm_bwd_kernel<4>, dim3(grid), dim3(LN_THREADS), smem, s, N, D, dy, r, stats, gamma, dr, part); break;
     }
     int rc = check_launch();
     if (rc) return rc;
   }
   LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(grid, D, part, dgamma, dbeta, accumulate);
+  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * D, 32)), dim3(256), 0, s, grid, D, part, dgamma, dbeta, accumulate);
   return check_launch();
 }
 
@@ -226,10 +229,10 @@ int hsg_layernorm_fwd(int N, int D, const float* r, const float* gamma, const fl
   const int grid = ln_grid(N);
   const int nv4 = ceil_div(D, 128);
   switch (nv4) {
-    case 1: layernorm_fwd_kernel<1><<<grid, LN_THREADS, 0, s>>>(N, D, r, gamma, beta, y, stats); break;
-    case 2: layernorm_fwd_kernel<2><<<grid, LN_THREADS, 0, s>>>(N, D, r, gamma, beta, y, stats); break;
-    case 3: layernorm_fwd_kernel<3><<<grid, LN_THREADS, 0, s>>>(N, D, r, gamma, beta, y, stats); break;
-    default: layernorm_fwd_kernel<4><<<grid, LN_THREADS, 0, s>>>(N, D, r, gamma, beta, y, stats); break;
+    case 1: launch_k(layernorm_fwd_kernel<1>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
+    case 2: launch_k(layernorm_fwd_kernel<2>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
+    case 3: launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
+    default: launch_k(layernorm_fwd_kernel<4>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
   }
   return check_launch();
 }

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
             float* __restrict__ C, int ldc, const float* __restrict__ bias, const float* __restrict__ R, int ldr,
             int epi) {
+  pdl_prologue();
   constexpr int TM = BM / 16, AH = BM / 64;
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + APAD];
@@ -202,6 +203,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(int M, int N1, int N2, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                float* __restrict__ part, float* __restrict__ part_col, int rows_per_split) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][TBK][TB + 4];
   __shared__ __align__(16) float Bs[2][TBK][TB + 4];
   const int tid = threadIdx.x;
@@ -292,6 +294,7 @@ gemm_tn_kernel(int M, int N1, int N2, const float* __restrict__ A, int lda, cons
 __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* __restrict__ part,
                                       const float* __restrict__ part_col, float* __restrict__ C, int ldc,
                                       float* __restrict__ colsum, int accumulate) {
+  pdl_prologue();
   const int total = N1 * N2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + N1; i += gridDim.x * blockDim.x) {
     if (i < total) {
@@ -341,9 +344,9 @@ static int launch_ffma(bool small, bool vec, int M, int N, int K, const float* A
                 : gemm_small_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, s);
   dim3 grid(ceil_div(M, 128), ceil_div(N, BN));
   if (vec)
-    gemm_kernel<B_NT, true, 128><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+    launch_k(gemm_kernel<B_NT, true, 128>, dim3(grid), dim3(GEMM_THREADS), 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
   else
-    gemm_kernel<B_NT, false, 128><<<grid, GEMM_THREADS, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
+    launch_k(gemm_kernel<B_NT, false, 128>, dim3(grid), dim3(GEMM_THREADS), 0, s, M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi);
   return check_launch();
 }
 
@@ -376,9 +379,9 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
     bool vec = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
     LaunchScope ls(SLOT_GEMM_TN, s);
     if (vec)
-      gemm_tn_kernel<true><<<grid, 256, 0, s>>>(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
+      launch_k(gemm_tn_kernel<true>, dim3(grid), dim3(256), 0, s, M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
     else
-      gemm_tn_kernel<false><<<grid, 256, 0, s>>>(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
+      launch_k(gemm_tn_kernel<false>, dim3(grid), dim3(256), 0, s, M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, rows);
     int rc = check_launch();
     if (rc) return rc;
   }
@@ -387,7 +390,7 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
     int total = N1 * N2 + N1;
     int blocks = ceil_div(total, 256);
     if (blocks > 1184) blocks = 1184;
-    gemm_tn_reduce_kernel<<<blocks, 256, 0, s>>>(nsplit, N1, N2, part, part_col, C, ldc, colsum, accumulate);
+    launch_k(gemm_tn_reduce_kernel, dim3(blocks), dim3(256), 0, s, nsplit, N1, N2, part, part_col, C, ldc, colsum, accumulate);
   }
   return check_launch();
 }

@@ -91,6 +91,7 @@ __device__ __forceinline__ void store_stage(float (*S)[T + PAD], float4 v, int t
 
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(THREADS) gemm_small_kernel(Params p) {
+  pdl_prologue();
   constexpr bool A_KC = MODE != 2, B_KC = MODE == 0;
   __shared__ __align__(16) float As[2][KB][T + PAD];
   __shared__ __align__(16) float Bs[2][KB][T + PAD];
@@ -225,13 +226,15 @@ static int launch(Params p, bool vec, cudaStream_t s) {
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = cs;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, gemm_small_kernel<MODE, true>, p)
                       : cudaLaunchKernelEx(&cfg, gemm_small_kernel<MODE, false>, p);
   if (e != cudaSuccess) return HSG_ERR_CUDA;

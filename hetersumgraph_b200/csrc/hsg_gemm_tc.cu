@@ -227,6 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: everything above (TMEM allocation, barrier init, tensor-map prefetch) overlapped the previous kernel's tail;
+  // from here on global memory written by earlier kernels is read, so wait for them.
+  pdl_prologue();
   const uint32_t tmem_d = *tmem_slot;
   const uint32_t stage_tx = (uint32_t)(TM * 128 + nb_box * 128);
 
@@ -574,7 +577,7 @@ static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, in
   if (!okA || !okB) return HSG_ERR_CUDA;
   const int m_tiles = (int)grid.x, n_tiles = (int)grid.y, total = m_tiles * n_tiles * (int)grid.z;
   const int ctas = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<A_MN, B_MN><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, m_tiles,
+  launch_k(gemm_tc_kernel<A_MN, B_MN>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, m_tiles,
                                                                n_tiles, total, precise, ep);
   return check_launch();
 }

@@ -16,6 +16,7 @@ constexpr int HEAD_ROWS_PER_BLOCK = 32;
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(hsg_head_args a, float* __restrict__ logits, float* __restrict__ dlogits,
                 float* __restrict__ row_loss) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= a.n_sent) return;
@@ -54,6 +55,7 @@ head_fwd_kernel(hsg_head_args a, float* __restrict__ logits, float* __restrict__
 // loss = scale * sum(row_loss) in a fixed order (one block)
 __global__ void __launch_bounds__(1024) head_loss_reduce_kernel(int n, const float* __restrict__ row_loss, float scale,
                                                                 float* __restrict__ loss) {
+  pdl_prologue();
   __shared__ float red[1024];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 1024) s += row_loss[i];
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(1024) head_loss_reduce_kernel(int n, const flo
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(hsg_head_args a, const float* __restrict__ dlogits, const float* __restrict__ gout,
                 float* __restrict__ d_state, float* __restrict__ part /* [blocks][2*width + 2] */) {
+  pdl_prologue();
   const int width = a.hidden * (a.two_part ? 2 : 1);
   const int j = threadIdx.x;
   const float g = gout ? gout[0] : 1.f;
@@ -107,6 +110,7 @@ head_bwd_kernel(hsg_head_args a, const float* __restrict__ dlogits, const float*
 __global__ void __launch_bounds__(256)
 head_bwd_doc_kernel(hsg_head_args a, const float* __restrict__ dlogits, const float* __restrict__ gout,
                     float* __restrict__ d_state) {
+  pdl_prologue();
   const int gph = blockIdx.x, j = threadIdx.x;
   if (j >= a.hidden) return;
   const int width = 2 * a.hidden;
@@ -121,6 +125,7 @@ head_bwd_doc_kernel(hsg_head_args a, const float* __restrict__ dlogits, const fl
 __global__ void __launch_bounds__(256)
 head_bwd_reduce_kernel(int nblocks, int n_out, const float* __restrict__ part, float* __restrict__ d_w,
                        float* __restrict__ d_b, int accumulate) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   float s = 0.f;
@@ -134,6 +139,7 @@ head_bwd_reduce_kernel(int nblocks, int n_out, const float* __restrict__ part, f
 __global__ void __launch_bounds__(256)
 topm_kernel(const float* __restrict__ logits, const int* __restrict__ graph_sent_ptr, int n_graphs, int m,
             int* __restrict__ out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int gph = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gph >= n_graphs) return;
@@ -155,6 +161,7 @@ topm_kernel(const float* __restrict__ logits, const int* __restrict__ graph_sent
 constexpr int SUMSQ_BLOCKS = 296;
 
 __global__ void __launch_bounds__(256) sumsq_part_kernel(size_t n, const float* __restrict__ g, float* __restrict__ part) {
+  pdl_prologue();
   __shared__ float red[256];
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s = fmaf(g[i], g[i], s);
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(256) sumsq_part_kernel(size_t n, const float* 
 }
 
 __global__ void __launch_bounds__(512) sumsq_final_kernel(int nparts, const float* __restrict__ part, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[512];
   red[threadIdx.x] = threadIdx.x < nparts ? part[threadIdx.x] : 0.f;
   __syncthreads();
@@ -183,6 +191,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             float beta1, float beta2, float step_size, float inv_sqrt_bc2, float eps, const float* __restrict__ sumsq,
             float max_norm) {
+  pdl_prologue();
   float coef = 1.f;
   if (sumsq) coef = fminf(1.f, max_norm / (sqrtf(sumsq[0]) + 1e-6f));
   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
@@ -221,8 +230,8 @@ int hsg_head_fwd(const hsg_head_args* a, float* logits, float* dlogits, float* l
   cudaStream_t s = (cudaStream_t)stream;
   float* row_loss = reinterpret_cast<float*>(ws);
   LaunchScope ls(SLOT_HEAD, s);
-  if (a->n_sent > 0) head_fwd_kernel<<<ceil_div(a->n_sent, 8), 256, 0, s>>>(*a, logits, dlogits, row_loss);
-  head_loss_reduce_kernel<<<1, 1024, 0, s>>>(a->n_sent, row_loss, a->inv_graphs, loss);
+  if (a->n_sent > 0) launch_k(head_fwd_kernel, dim3(ceil_div(a->n_sent, 8)), dim3(256), 0, s, *a, logits, dlogits, row_loss);
+  launch_k(head_loss_reduce_kernel, dim3(1), dim3(1024), 0, s, a->n_sent, row_loss, a->inv_graphs, loss);
   return check_launch();
 }
 
@@ -240,11 +249,11 @@ int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout
     if (cudaMemsetAsync(d_state, 0, (size_t)a->n_super * a->hidden * sizeof(float), s) != cudaSuccess) return HSG_ERR_CUDA;
   }
   if (blocks > 0) {
-    head_bwd_kernel<<<blocks, 256, 0, s>>>(*a, dlogits, gout, d_state, part);
-    if (a->two_part && a->n_graphs > 0) head_bwd_doc_kernel<<<a->n_graphs, 256, 0, s>>>(*a, dlogits, gout, d_state);
+    launch_k(head_bwd_kernel, dim3(blocks), dim3(256), 0, s, *a, dlogits, gout, d_state, part);
+    if (a->two_part && a->n_graphs > 0) launch_k(head_bwd_doc_kernel, dim3(a->n_graphs), dim3(256), 0, s, *a, dlogits, gout, d_state);
   }
   const int n_out = 2 * width + 2;
-  head_bwd_reduce_kernel<<<ceil_div(n_out, 256), 256, 0, s>>>(blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
+  launch_k(head_bwd_reduce_kernel, dim3(ceil_div(n_out, 256)), dim3(256), 0, s, blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
   return check_launch();
 }
 
@@ -253,7 +262,7 @@ int hsg_topm(const float* logits, const int32_t* graph_sent_ptr, int n_graphs, i
   if (n_graphs == 0) return HSG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_HEAD, s);
-  topm_kernel<<<ceil_div(n_graphs, 8), 256, 0, s>>>(logits, graph_sent_ptr, n_graphs, m, out_idx);
+  launch_k(topm_kernel, dim3(ceil_div(n_graphs, 8)), dim3(256), 0, s, logits, graph_sent_ptr, n_graphs, m, out_idx);
   return check_launch();
 }
 
@@ -269,15 +278,15 @@ int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
   if (max_grad_norm > 0.f) {
     if (!ws || ws_bytes < hsg_adam_workspace_bytes()) return HSG_ERR_WORKSPACE;
     float* part = reinterpret_cast<float*>(ws);
-    sumsq_part_kernel<<<SUMSQ_BLOCKS, 256, 0, s>>>(n, grad, part);
-    sumsq_final_kernel<<<1, 512, 0, s>>>(SUMSQ_BLOCKS, part, part + SUMSQ_BLOCKS);
+    launch_k(sumsq_part_kernel, dim3(SUMSQ_BLOCKS), dim3(256), 0, s, n, grad, part);
+    launch_k(sumsq_final_kernel, dim3(1), dim3(512), 0, s, SUMSQ_BLOCKS, part, part + SUMSQ_BLOCKS);
     sumsq = part + SUMSQ_BLOCKS;
   }
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   size_t blocks = (n + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, param, grad, exp_avg, exp_avg_sq, beta1, beta2, step_size,
+  launch_k(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n, param, grad, exp_avg, exp_avg_sq, beta1, beta2, step_size,
                                               inv_sqrt_bc2, eps, sumsq, max_grad_norm);
   return check_launch();
 }

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 attn_prep_fwd_kernel(EdgeLayout L, int in_dim, int feat_dim, int ld_rows, const float* __restrict__ W,
                      const float* __restrict__ Wf, const float* __restrict__ bf, const float* __restrict__ a,
                      const float* __restrict__ T, float* __restrict__ W_aug, float* __restrict__ q) {
+  pdl_prologue();
   extern __shared__ float dfeat_s[];  // [F] (q blocks only)
   const int H = L.H, d = L.D, F = H * d;
   const int r = blockIdx.x;
@@ -69,6 +70,7 @@ attn_prep_bwd_kernel(EdgeLayout L, int in_dim, int feat_dim, const float* __rest
                      const float* __restrict__ T, const float* __restrict__ dW_aug, const float* __restrict__ dq,
                      float* __restrict__ dW, float* __restrict__ dWf, float* __restrict__ dbf,
                      float* __restrict__ da, float* __restrict__ dT, int acc_p, int acc_T) {
+  pdl_prologue();
   __shared__ float sm[2 * PREP_CCH * HSG_N_BINS + 32];   // 672 floats (>= 512 for the dT blocks)
   const int H = L.H, d = L.D, F = H * d;
   const int r = blockIdx.x;
@@ -181,7 +183,7 @@ int hsg_attn_prep_fwd(int H, int d, int in_dim, int feat_dim, int ld_rows, const
   if (smem > 48 * 1024) return HSG_ERR_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_PREP_FWD, s);
-  attn_prep_fwd_kernel<<<ld_rows + HSG_N_BINS, 256, smem, s>>>(L, in_dim, feat_dim, ld_rows, W, Wf, bf, a, T, W_aug, q);
+  launch_k(attn_prep_fwd_kernel, dim3(ld_rows + HSG_N_BINS), dim3(256), smem, s, L, in_dim, feat_dim, ld_rows, W, Wf, bf, a, T, W_aug, q);
   return check_launch();
 }
 
@@ -205,7 +207,7 @@ int attn_prep_bwd_ex(int H, int d, int in_dim, int feat_dim, int ld_rows, const 
   if (ld_rows < L.fp + H) return HSG_ERR_SHAPE;
   LaunchScope ls(SLOT_PREP_BWD, s);
   const int F = H * d;
-  attn_prep_bwd_kernel<<<F + ceil_div(F, PREP_CCH) + HSG_N_BINS, 256, 0, s>>>(L, in_dim, feat_dim, W, Wf, bf, a, T, dW_aug, dq,
+  launch_k(attn_prep_bwd_kernel, dim3(F + ceil_div(F, PREP_CCH) + HSG_N_BINS), dim3(256), 0, s, L, in_dim, feat_dim, W, Wf, bf, a, T, dW_aug, dq,
                                                                     dW, dWf, dbf, da, dT, acc_params, acc_T);
   return check_launch();
 }

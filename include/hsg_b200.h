@@ -52,6 +52,9 @@ const char* hsg_strerror(int status);
 /* 0 when the current device can run the sm_100a kernels, HSG_ERR_ARCH otherwise. */
 int hsg_device_check(void);
 int hsg_num_sms(void);
+/* Programmatic dependent launch for every kernel of the library (default on; HSG_PDL=0 in the environment or
+ * hsg_set_pdl(0) turns it off): each kernel's launch latency and prologue overlap its predecessor's tail. */
+int hsg_set_pdl(int on);
 
 /* Per-kernel CUDA-event timing (bench.py's roofline leg).  When enabled every
  * launch is bracketed by events on its stream; hsg_profile_read synchronises
