@@ -70,11 +70,12 @@ class LayerGradsC(C.Structure):
 
 
 class LoopArgsC(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("n_iter", "n_word", "n_super", "reserved")] + \
+    _fields_ = [(n, C.c_int32) for n in ("n_apps", "start_kind", "n_word", "n_super")] + \
                [("csc_super", C.POINTER(CscC)), ("csc_word", C.POINTER(CscC)),
                 ("w2s", LayerParamsC), ("s2w", LayerParamsC),
                 ("T", C.c_void_p), ("word_feature", C.c_void_p), ("super_feature", C.c_void_p),
-                ("state", C.c_void_p), ("state_floats", C.c_size_t)]
+                ("state", C.c_void_p), ("state_floats", C.c_size_t),
+                ("attn_p", C.c_float), ("ffn_p", C.c_float), ("seed", C.c_ulonglong)]
 
 
 class LoopPlanC(C.Structure):
@@ -142,6 +143,7 @@ _PROTOS = {
     "hsg_adam_workspace_bytes": (_Z, []),
     "hsg_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P, _Z,
                                 _P]),
+    "hsg_dropout_mask": (C.c_int, [_Z, C.c_float, C.c_ulonglong, C.c_uint, _P, _P]),
     "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),
     "hsg_layernorm_bwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -27,6 +27,7 @@ enum Slot {
   SLOT_LN_BWD_REDUCE,
   SLOT_HEAD,
   SLOT_ADAM,
+  SLOT_DROPOUT,
   SLOT_COUNT
 };
 

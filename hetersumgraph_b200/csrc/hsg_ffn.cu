@@ -11,10 +11,13 @@ constexpr int LN_WARPS = 8;
 constexpr int LN_THREADS = LN_WARPS * 32;
 constexpr int LN_MAX_BLOCKS = 148 * 4;
 
-template <int NV4>  // float4 per lane; D <= 128 * NV4
+// DROPRES: r holds the FFN output y = W2 relu(.) + b2; the kernel forms r = dropout(y) + resid (GATLayer.py:41-42),
+// writes it back (backward needs r) and normalises it.
+template <int NV4, bool DROPRES>  // float4 per lane; D <= 128 * NV4
 __global__ void __launch_bounds__(LN_THREADS)
-layernorm_fwd_kernel(int N, int D, const float* __restrict__ r, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ stats) {
+layernorm_fwd_kernel(int N, int D, const float* r, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ stats,
+                     float* r_out, const float* __restrict__ resid, DropCfg dc) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -35,7 +38,16 @@ layernorm_fwd_kernel(int N, int D, const float* __restrict__ r, const float* __r
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + 32 * i;
-      v[i] = c < D4 ? __ldg(rr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = c < D4 ? (DROPRES ? rr[c] : __ldg(rr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (DROPRES && c < D4) {
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(resid + (size_t)row * D) + c);
+        const unsigned long long e = (unsigned long long)row * (unsigned long long)D + 4ull * c;
+        v[i].x = (drop_keep(dc, e + 0) ? v[i].x * dc.scale : 0.f) + x4.x;
+        v[i].y = (drop_keep(dc, e + 1) ? v[i].y * dc.scale : 0.f) + x4.y;
+        v[i].z = (drop_keep(dc, e + 2) ? v[i].z * dc.scale : 0.f) + x4.z;
+        v[i].w = (drop_keep(dc, e + 3) ? v[i].w * dc.scale : 0.f) + x4.w;
+        reinterpret_cast<float4*>(r_out + (size_t)row * D)[c] = v[i];
+      }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     const float mean = warp_sum(s) * invD;
@@ -188,6 +200,23 @@ static int ln_grid(int N) {
 using namespace hsg;
 
 namespace hsg {
+int layernorm_fwd_dropres(int N, int D, float* r, const float* resid, DropCfg dc, const float* gamma, const float* beta,
+                          float* y, float* stats, cudaStream_t s) {
+  if (N < 0 || D <= 0 || !r || !resid || !gamma || !beta || !y || !stats) return HSG_ERR_ARG;
+  if (D % 4 != 0 || D > 512) return HSG_ERR_SHAPE;
+  if (!aligned16(r) || !aligned16(y) || !aligned16(resid) || !aligned16(gamma) || !aligned16(beta)) return HSG_ERR_ALIGN;
+  if (N == 0) return HSG_OK;
+  LaunchScope ls(SLOT_LN_FWD, s);
+  const int grid = ln_grid(N);
+  switch (ceil_div(D, 128)) {
+    case 1: launch_k(layernorm_fwd_kernel<1, true>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, r, resid, dc); break;
+    case 2: launch_k(layernorm_fwd_kernel<2, true>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, r, resid, dc); break;
+    case 3: launch_k(layernorm_fwd_kernel<3, true>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, r, resid, dc); break;
+    default: launch_k(layernorm_fwd_kernel<4, true>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, r, resid, dc); break;
+  }
+  return check_launch();
+}
+
 int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,
                      float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
   if (N < 0 || D <= 0 || !dy || !r || !stats || !gamma || !dr || !dgamma || !dbeta || !ws) return HSG_ERR_ARG;
@@ -229,10 +258,10 @@ int hsg_layernorm_fwd(int N, int D, const float* r, const float* gamma, const fl
   const int grid = ln_grid(N);
   const int nv4 = ceil_div(D, 128);
   switch (nv4) {
-    case 1: launch_k(layernorm_fwd_kernel<1>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
-    case 2: launch_k(layernorm_fwd_kernel<2>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
-    case 3: launch_k(layernorm_fwd_kernel<3>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
-    default: launch_k(layernorm_fwd_kernel<4>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats); break;
+    case 1: launch_k(layernorm_fwd_kernel<1, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
+    case 2: launch_k(layernorm_fwd_kernel<2, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
+    case 3: launch_k(layernorm_fwd_kernel<3, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
+    default: launch_k(layernorm_fwd_kernel<4, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
   }
   return check_launch();
 }

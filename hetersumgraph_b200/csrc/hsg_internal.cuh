@@ -7,6 +7,44 @@
 
 namespace hsg {
 
+// ---- counter-based dropout masks --------------------------------------------------------------------------------
+// keep(seed, stream, idx): splitmix64 of the element counter, top 24 bits against p * 2^24.  A pure function of
+// its arguments: forward and backward regenerate the same mask, nothing is stored.
+struct DropCfg {
+  unsigned long long key;   // seed mixed with the stream id
+  unsigned int thresh;      // drop when the 24-bit draw < thresh
+  float scale;              // 1 / (1 - p)
+};
+
+inline DropCfg make_drop(float p, unsigned long long seed, unsigned int stream_id) {
+  DropCfg c;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(stream_id + 1u);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  c.key = z ^ (z >> 31);
+  c.thresh = (unsigned int)((double)p * 16777216.0);
+  c.scale = 1.f / (1.f - p);
+  return c;
+}
+
+__device__ __forceinline__ bool drop_keep(const DropCfg& c, unsigned long long idx) {
+  unsigned long long z = c.key + 0x9E3779B97F4A7C15ull * (idx + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 40) >= c.thresh;
+}
+
+// hsg_dropout.cu
+int dropout_expand(int n, int in_dim, int H, const float* h, float* out, DropCfg dc, cudaStream_t s);
+int dropout_reduce(int n, int in_dim, int H, const float* dA, const float* add, float* out, DropCfg dc, cudaStream_t s);
+int wblk_build(int H, int d, int in_dim, int ld_rows, const float* W_aug, float* W_blk, cudaStream_t s);
+int wblk_gather(int H, int d, int in_dim, int ld_rows, const float* dW_blk, float* dW_aug, int accumulate, cudaStream_t s);
+int dropout_mul(size_t n, const float* x, float* out, DropCfg dc, cudaStream_t s);
+// hsg_ffn.cu: r <- dropout(r) + resid (in place), then LayerNorm(r)
+int layernorm_fwd_dropres(int N, int D, float* r, const float* resid, DropCfg dc, const float* gamma, const float* beta,
+                          float* y, float* stats, cudaStream_t s);
+
 // C (+)= A^T B, colsum (+)= column sums of A
 int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);

@@ -374,19 +374,23 @@ def _layer_params_c(H, d, in_dim, feat_dim, d_hid, tensors):
 
 
 class UpdateLoopFn(torch.autograd.Function):
-    """(word_state, super_state) = update loop of HSumGraph.forward / HSumDocGraph.forward (HiGraph.py:98-106,
-    205-214) on a HeteroBatch.  Tensor arguments after `cfg`: word_feature, super_feature, T, then the ten packed
-    parameters of word2sent and of sent2word (W, Wf, bf, a, w1, b1, w2, b2, gamma, beta; word2sent's bf is None).
+    """(word_state, super_state) of a chain of WSWGAT applications whose kinds alternate from `start_kind` (0 = W2S,
+    1 = S2W) on a HeteroBatch: the update loop of HSumGraph.forward / HSumDocGraph.forward (HiGraph.py:98-106,
+    205-214) is (n_apps = 1 + 2 n_iter, start 0); one stand-alone WSWGAT.forward (GAT.py:45-59) is (1, kind).
+    Tensor arguments after `cfg`: word_feature, super_feature, T, then the ten packed parameters of word2sent and of
+    sent2word (W, Wf, bf, a, w1, b1, w2, b2, gamma, beta; word2sent's bf is None).
 
-    cfg = (n_iter, (H, d, d_hid) of W2S, (H, d, d_hid) of S2W, grad_targets) - grad_targets is None (gradients are
-    returned to autograd) or a list of 21 tensors [dT, 10 x W2S, 10 x S2W] that the backward ADDS the parameter
-    gradients into (fused accumulation into .grad; None is returned for those inputs)."""
+    cfg = dict(n_apps, start_kind, w2s=(H, d, d_hid), s2w=(H, d, d_hid), grad_targets, attn_p, ffn_p, seed):
+    grad_targets is None (gradients are returned to autograd) or a list of 21 tensors [dT, 10 x W2S, 10 x S2W] that
+    the backward ADDS the parameter gradients into (fused accumulation into .grad; None is returned for those
+    inputs).  attn_p / ffn_p > 0 enable training-mode dropout with masks drawn from `seed` (hsg_dropout.cu)."""
 
     @staticmethod
     def forward(ctx, batch, cfg, word_feature, super_feature, T, *params):
         _lib.require_device()
         lib = _lib.load()
-        n_iter, (H1, d1, hid1), (H2, d2, hid2), grad_targets = cfg
+        n_apps, start = cfg["n_apps"], cfg["start_kind"]
+        (H1, d1, hid1), (H2, d2, hid2) = cfg["w2s"], cfg["s2w"]
         word_feature, super_feature, T = _f32c(word_feature), _f32c(super_feature), _f32c(T)
         params = tuple(_f32c(t) if t is not None else None for t in params)
         pw, ps = params[:10], params[10:]
@@ -395,29 +399,28 @@ class UpdateLoopFn(torch.autograd.Function):
             raise ValueError("update loop: got %d word / %d supernode rows, graph has %d / %d" %
                              (word_feature.shape[0], super_feature.shape[0], n_word, n_super))
         Dw, Ds, fe = word_feature.shape[1], super_feature.shape[1], T.shape[1]
-        if Ds != H1 * d1 or (n_iter > 0 and Dw != H2 * d2):
+        uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
+        if (uses[0] and Ds != H1 * d1) or (uses[1] and Dw != H2 * d2):
             raise ValueError("update loop: feature widths (%d, %d) do not match heads*head_dim" % (Dw, Ds))
         csc_s, csc_w = batch.csc("W2S")
-        args = _lib.LoopArgsC(n_iter, n_word, n_super, 0, C.pointer(csc_s), C.pointer(csc_w),
+        args = _lib.LoopArgsC(n_apps, start, n_word, n_super, C.pointer(csc_s), C.pointer(csc_w),
                               _layer_params_c(H1, d1, Dw, fe, hid1, pw), _layer_params_c(H2, d2, Ds, fe, hid2, ps),
-                              _p(T), _p(word_feature), _p(super_feature), None, 0)
+                              _p(T), _p(word_feature), _p(super_feature), None, 0,
+                              float(cfg.get("attn_p", 0.0)), float(cfg.get("ffn_p", 0.0)), int(cfg.get("seed", 0)))
         plan = _lib.LoopPlanC()
         _lib.check(lib.hsg_update_loop_plan(C.byref(args), C.byref(plan)))
         state = torch.empty(plan.state_floats, dtype=torch.float32, device=word_feature.device)
         args.state, args.state_floats = state.data_ptr(), plan.state_floats
         _lib.check(lib.hsg_update_loop_fwd(C.byref(args), _st()))
         if RELU_MASK_CAPTURE is not None:
-            for i in range(1 + 2 * n_iter):
-                n_rows, hid = (n_super, hid1) if i % 2 == 0 else (n_word, hid2)
+            for i in range(n_apps):
+                n_rows, hid = (n_super, hid1) if (i + start) % 2 == 0 else (n_word, hid2)
                 off = plan.hdn_off[i % 2] + (i // 2) * plan.pair_stride
                 RELU_MASK_CAPTURE.append((state[off:off + n_rows * hid].view(n_rows, hid) > 0).cpu())
-        so = plan.super_state_off
-        super_state = state[so:so + n_super * Ds].view(n_super, Ds)
-        if n_iter > 0:
-            wo = plan.word_state_off
-            word_state = state[wo:wo + n_word * Dw].view(n_word, Dw)
-        else:
-            word_state = word_feature.clone()
+        none = (1 << 64) - 1
+        so, wo = plan.super_state_off, plan.word_state_off
+        super_state = state[so:so + n_super * Ds].view(n_super, Ds) if so != none else super_feature.clone()
+        word_state = state[wo:wo + n_word * Dw].view(n_word, Dw) if wo != none else word_feature.clone()
         ctx.batch, ctx.cfg, ctx.plan, ctx.args = batch, cfg, plan, args
         ctx.set_materialize_grads(False)          # an unused result's gradient arrives as None, not as a zero tensor
         ctx.save_for_backward(word_feature, super_feature, T, state, *[t for t in params if t is not None])
@@ -427,7 +430,8 @@ class UpdateLoopFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_word, d_super):
         lib = _lib.load()
-        n_iter, _, _, grad_targets = ctx.cfg
+        cfg = ctx.cfg
+        grad_targets = cfg.get("grad_targets")
         saved = ctx.saved_tensors
         word_feature, super_feature, T, state = saved[:4]
         it = iter(saved[4:])
@@ -438,18 +442,20 @@ class UpdateLoopFn(torch.autograd.Function):
             return (None,) * (5 + len(params))
         d_word = _f32c(d_word) if d_word is not None else None
         d_super = _f32c(d_super) if d_super is not None else None
-        need_dw = ctx.needs_input_grad[2]
-        d_wf = torch.empty_like(word_feature) if need_dw else None
-        d_sf = torch.empty_like(super_feature)
+        d_wf = torch.empty_like(word_feature) if ctx.needs_input_grad[2] else None
+        d_sf = torch.empty_like(super_feature) if ctx.needs_input_grad[3] else None
+        n_apps, start = cfg["n_apps"], cfg["start_kind"]
+        uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
         if grad_targets is not None:
             targets = list(grad_targets)
             acc = 1
         else:
             targets = [torch.empty_like(T)] + [torch.empty_like(p) if p is not None else None for p in params]
-            if n_iter == 0:                                  # sent2word unused: its gradients are zero
-                for i in range(11, 21):
-                    if targets[i] is not None:
-                        targets[i].zero_()
+            for k in (0, 1):                                 # a layer no application used: zero gradients
+                if not uses[k]:
+                    for i in range(1 + 10 * k, 11 + 10 * k):
+                        if targets[i] is not None:
+                            targets[i].zero_()
             acc = 0
         scratch = torch.empty(plan.scratch_floats, dtype=torch.float32, device=dev)
         ws = _Workspace.get(plan.ws_bytes, dev, "loop")
@@ -462,6 +468,13 @@ class UpdateLoopFn(torch.autograd.Function):
         if grad_targets is not None:
             return (None, None, d_wf, d_sf) + (None,) * (1 + len(params))
         return (None, None, d_wf, d_sf, targets[0]) + tuple(targets[1:])
+
+
+def dropout_keep_mask(n, p, seed, stream_id, device="cuda"):
+    """Test hook: the keep flags (uint8) of the first n element indices of the mask (p, seed, stream_id)."""
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().hsg_dropout_mask(n, float(p), int(seed), int(stream_id), out.data_ptr(), _st()))
+    return out
 
 
 # --------------------------------------------------------------------------------------------

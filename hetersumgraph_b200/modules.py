@@ -35,8 +35,53 @@ class SWGATLayer:
 def _check_dropout(module, p, what):
     if module.training and p > 0.0:
         raise NotImplementedError(
-            "hetersumgraph_b200: %s dropout p=%g in training mode is not implemented in the sm_100a kernels yet; "
-            "construct the module with p=0 or call .eval() (parity with the reference is defined at p=0)" % (what, p))
+            "hetersumgraph_b200: %s dropout p=%g in training mode is implemented inside WSWGAT / WSWGATUpdateLoop "
+            "(hsg_update_loop_fwd), not for this sub-layer on its own; call it through WSWGAT, construct it with "
+            "p=0 or use .eval()" % (what, p))
+
+
+def _next_dropout_seed():
+    """A fresh 63-bit seed from torch's CPU generator (so torch.manual_seed makes runs reproducible); drawn on the
+    host, no device synchronisation."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# test hook: when set to a list, every dropout-enabled forward appends its (seed, n_apps, start_kind)
+DROPOUT_SEED_LOG = None
+
+
+def _packed_params(mod):
+    lay = mod.layer
+    return (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight) + mod.ffn.packed()
+
+
+def _grad_buffers(mod):
+    """.grad of the ten packed parameters, viewed in the packed shapes (Conv1d weights are [out, in, 1])."""
+    lay, ffn = mod.layer, mod.ffn
+    leaves = (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight, ffn.w_1.weight, ffn.w_1.bias,
+              ffn.w_2.weight, ffn.w_2.bias, ffn.layer_norm.weight, ffn.layer_norm.bias)
+    out = []
+    for p in leaves:
+        if p is None:
+            out.append(None)
+            continue
+        if p.grad is None or not p.grad.is_contiguous():
+            raise RuntimeError("fuse_grad_accumulation needs a contiguous .grad buffer on every parameter "
+                               "(see hetersumgraph_b200.dist.FlatGradArena)")
+        out.append(p.grad.view(p.shape[0], -1) if p.dim() == 3 else p.grad)
+    return out
+
+
+def _dropout_cfg(mods):
+    """(attn_p, ffn_p, seed) of a chain over `mods` (training mode only; the C loop takes one pair of rates)."""
+    attn = {m.layer.dropout.p if m.layer.training else 0.0 for m in mods}
+    ffn = {m.ffn.dropout.p if m.ffn.training else 0.0 for m in mods}
+    if len(attn) > 1 or len(ffn) > 1:
+        raise NotImplementedError("word2sent and sent2word must share their dropout rates (the reference builds both "
+                                  "from hps.atten_dropout_prob / hps.ffn_dropout_prob, HiGraph.py:57-76)")
+    attn_p, ffn_p = attn.pop(), ffn.pop()
+    seed = _next_dropout_seed() if (attn_p > 0.0 or ffn_p > 0.0) else 0
+    return attn_p, ffn_p, seed
 
 
 class PositionwiseFeedForward(nn.Module):
@@ -172,8 +217,22 @@ class WSWGAT(nn.Module):
         else:
             origin, neighbor = w, s
         lay = self.layer
-        _check_dropout(lay, lay.dropout.p, "attention-input")
-        _check_dropout(self.ffn, self.ffn.dropout.p, "FFN")
+        attn_p, ffn_p, seed = _dropout_cfg([self])
+        if attn_p > 0.0 or ffn_p > 0.0:
+            # training-mode dropout lives in the whole-loop entry point: one application of this kind
+            if g.tfidfembed_weight is None:
+                raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight)")
+            kind = 0 if self.layerType == "W2S" else 1
+            dims = (lay.num_heads, lay.out_dim, self.ffn.d_hid)
+            cfg = dict(n_apps=1, start_kind=kind, w2s=dims, s2w=dims, grad_targets=None, attn_p=attn_p, ffn_p=ffn_p,
+                       seed=seed)
+            if DROPOUT_SEED_LOG is not None:
+                DROPOUT_SEED_LOG.append((seed, 1, kind))
+            mine = _packed_params(self)
+            none10 = (None,) * 10
+            pw, ps = (mine, none10) if kind == 0 else (none10, mine)
+            ws_, ss_ = UpdateLoopFn.apply(g, cfg, w, s, g.tfidfembed_weight, *pw, *ps)
+            return ss_ if kind == 0 else ws_
         W_aug, q = prepared if prepared is not None else self.prepare(g)
         return WSWGATCoreFn.apply(g, self.layerType, lay.num_heads, lay.out_dim, neighbor, origin, W_aug, q,
                                   *self.ffn.packed())
@@ -198,41 +257,23 @@ class WSWGATUpdateLoop(nn.Module):
     # would launch one add per parameter.  Same arithmetic; requires every parameter to have a `.grad` tensor.
     fuse_grad_accumulation = False
 
-    def _packed(self, mod):
-        lay = mod.layer
-        return (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight) + mod.ffn.packed()
-
-    def _grad_buffers(self, mod):
-        """.grad of the ten packed parameters, viewed in the packed shapes (Conv1d weights are [out, in, 1])."""
-        lay, ffn = mod.layer, mod.ffn
-        leaves = (lay.fc_weight, lay.feat_fc_weight, lay.feat_fc_bias, lay.attn_fc_weight, ffn.w_1.weight, ffn.w_1.bias,
-                  ffn.w_2.weight, ffn.w_2.bias, ffn.layer_norm.weight, ffn.layer_norm.bias)
-        out = []
-        for p in leaves:
-            if p is None:
-                out.append(None)
-                continue
-            if p.grad is None or not p.grad.is_contiguous():
-                raise RuntimeError("fuse_grad_accumulation needs a contiguous .grad buffer on every parameter "
-                                   "(see hetersumgraph_b200.dist.FlatGradArena)")
-            out.append(p.grad.view(p.shape[0], -1) if p.dim() == 3 else p.grad)
-        return out
-
     def forward(self, graph, word_feature, sent_feature):
         graph.set_tfidf_embedding(self._TFembed.weight)
-        for mod in (self.word2sent, self.sent2word):
-            _check_dropout(mod.layer, mod.layer.dropout.p, "attention-input")
-            _check_dropout(mod.ffn, mod.ffn.dropout.p, "FFN")
-        pw, ps = self._packed(self.word2sent), self._packed(self.sent2word)
+        mods = (self.word2sent, self.sent2word) if self._n_iter > 0 else (self.word2sent,)
+        attn_p, ffn_p, seed = _dropout_cfg(mods)
+        pw, ps = _packed_params(self.word2sent), _packed_params(self.sent2word)
         targets = None
         if self.fuse_grad_accumulation and torch.is_grad_enabled():
             if self._TFembed.weight.grad is None:
                 raise RuntimeError("fuse_grad_accumulation needs a .grad buffer on every parameter")
-            targets = [self._TFembed.weight.grad] + self._grad_buffers(self.word2sent) + \
-                self._grad_buffers(self.sent2word)
+            targets = [self._TFembed.weight.grad] + _grad_buffers(self.word2sent) + _grad_buffers(self.sent2word)
         lw, ls = self.word2sent.layer, self.sent2word.layer
-        cfg = (self._n_iter, (lw.num_heads, lw.out_dim, self.word2sent.ffn.d_hid),
-               (ls.num_heads, ls.out_dim, self.sent2word.ffn.d_hid), targets)
+        n_apps = 1 + 2 * self._n_iter
+        cfg = dict(n_apps=n_apps, start_kind=0, w2s=(lw.num_heads, lw.out_dim, self.word2sent.ffn.d_hid),
+                   s2w=(ls.num_heads, ls.out_dim, self.sent2word.ffn.d_hid), grad_targets=targets, attn_p=attn_p,
+                   ffn_p=ffn_p, seed=seed)
+        if DROPOUT_SEED_LOG is not None and seed:
+            DROPOUT_SEED_LOG.append((seed, n_apps, 0))
         return UpdateLoopFn.apply(graph, cfg, word_feature, sent_feature, self._TFembed.weight, *pw, *ps)
 
     def forward_per_application(self, graph, word_feature, sent_feature):

@@ -295,30 +295,39 @@ typedef struct {
 } hsg_layer_grads;
 
 typedef struct {
-  int32_t n_iter, n_word, n_super, reserved;
+  int32_t n_apps;       /* number of WSWGAT applications, >= 1; HSG / HDSG: 1 + 2 n_iter */
+  int32_t start_kind;   /* kind of application 0: 0 = W2S (HSG / HDSG), 1 = S2W; kinds alternate from there, so
+                           (n_apps = 1, start_kind) is one stand-alone WSWGAT.forward (GAT.py:45-59) */
+  int32_t n_word, n_super;
   const hsg_csc *csc_super, *csc_word;  /* in-edges of supernodes from words / of words from supernodes */
-  hsg_layer_params w2s, s2w;            /* s2w is ignored when n_iter == 0 */
+  hsg_layer_params w2s, s2w;            /* a layer that no application uses is ignored */
   const float* T;                       /* _TFembed.weight [10, feat_dim]  (HiGraph.py:52) */
-  const float *word_feature;            /* [n_word,  w2s.in_dim]        */
-  const float *super_feature;           /* [n_super, w2s.H * w2s.d]     */
+  const float *word_feature;            /* [n_word,  word dim = s2w.H * s2w.d = w2s.in_dim]   */
+  const float *super_feature;           /* [n_super, hidden   = w2s.H * w2s.d = s2w.in_dim]   */
   float* state;                         /* forward arena: everything backward needs + the two results */
   size_t state_floats;
+  /* training-mode dropout (0 = off): attn_p on the layer input, drawn independently per head
+   * (GATStackLayer.py:56); ffn_p on the FFN output before the residual (GATLayer.py:41-42).  Masks are a pure
+   * function of (seed, application index, element), regenerated in backward. */
+  float attn_p, ffn_p;
+  unsigned long long seed;
 } hsg_loop_args;
 
 typedef struct {
   size_t state_floats;    /* size of hsg_loop_args.state                                 */
   size_t scratch_floats;  /* size of hsg_loop_bwd_args.scratch                           */
   size_t ws_bytes;        /* size of hsg_loop_bwd_args.ws                                */
-  size_t word_state_off;  /* float offset of the final word state in `state` ((size_t)-1 when n_iter == 0: it is word_feature) */
-  size_t super_state_off; /* float offset of the final supernode state in `state`        */
-  size_t hdn_off[2];      /* float offset of the FFN hidden activation of application 0 (W2S) / 1 (S2W) - test hook */
+  size_t word_state_off;  /* float offset of the final word state in `state`; (size_t)-1: no application produced one
+                             (it is word_feature) */
+  size_t super_state_off; /* same for the supernode state ((size_t)-1: it is super_feature) */
+  size_t hdn_off[2];      /* float offset of the FFN hidden activation of application 0 / 1 - test hook */
   size_t pair_stride;     /* floats between application i and i+2 (same layer type) in `state` */
 } hsg_loop_plan;
 
 typedef struct {
   const float *d_word_state, *d_super_state; /* upstream gradients; either may be NULL (= 0) */
-  float* d_word_feature;                     /* [n_word, w2s.in_dim] or NULL (skips that product) */
-  float* d_super_feature;                    /* [n_super, w2s.H*w2s.d] */
+  float* d_word_feature;                     /* [n_word, word dim] or NULL (skips that product) */
+  float* d_super_feature;                    /* [n_super, hidden] or NULL */
   hsg_layer_grads w2s, s2w;
   float* dT;                                 /* [10, feat_dim] */
   int32_t accumulate;                        /* 1: parameter gradients are ADDED to the given buffers (fused
@@ -334,6 +343,11 @@ typedef struct {
 int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan);
 int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream);
 int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void* stream);
+/* Test hook: keep flags (1/0) of the dropout mask of `n` consecutive element indices for (p, seed, stream_id).
+ * Stream ids used by the loop: 2*app for the attention-input mask (element ((head * n_src) + row) * in_dim + col),
+ * 2*app + 1 for the FFN mask (element row * F + col). */
+int hsg_dropout_mask(size_t n, float p, unsigned long long seed, unsigned int stream_id, unsigned char* out,
+                     void* stream);
 
 /* ------------------------------------------------------------------------
  * Readout, loss, extraction and optimizer on the device (the step right after the update loop):

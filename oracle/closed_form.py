@@ -39,8 +39,10 @@ def n_heads_of(params, prefix):
     return n
 
 
-def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T):
-    """All heads of one MultiHeadLayer application on a CSC (dst-major) edge list."""
+def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T, attn_mask=None):
+    """All heads of one MultiHeadLayer application on a CSC (dst-major) edge list.
+    attn_mask: optional [H, N_src, in] multiplier (0 or 1/(1-p)): head k sees its own dropped-out copy of the
+    input, `attn_head(g, self.dropout(h))` (GATStackLayer.py:56)."""
     H = a.shape[0]
     d = a.shape[1] // 3
     indptr = torch.as_tensor(indptr, dtype=torch.int64)
@@ -49,7 +51,10 @@ def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T):
     extra = torch.as_tensor(extra_cnt, dtype=h_src.dtype).reshape(-1, 1)
     deg = indptr[1:] - indptr[:-1]
     dst = torch.repeat_interleave(torch.arange(n_dst), deg)
-    z = (h_src @ W.t()).reshape(-1, H, d)
+    if attn_mask is None:
+        z = (h_src @ W.t()).reshape(-1, H, d)
+    else:
+        z = torch.stack([(h_src * attn_mask[k]) @ W[k * d:(k + 1) * d].t() for k in range(H)], 1)
     p = (z * a[:, :d].unsqueeze(0)).sum(-1)                                   # [N_src, H]
     dfeat = (T @ Wf.t() + bf).reshape(-1, H, d)                               # [10, H, d]
     q = (dfeat * a[:, 2 * d:].unsqueeze(0)).sum(-1)                           # [10, H]
@@ -66,7 +71,7 @@ def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T):
     return sh.reshape(n_dst, H * d)
 
 
-def ffn_cf(x, w1, b1, w2, b2, gamma, beta, mask=None, flips=None):
+def ffn_cf(x, w1, b1, w2, b2, gamma, beta, mask=None, flips=None, ffn_mask=None):
     """mask: optional bool [N, d_hid] - the ReLU active set to use instead of (pre > 0).  ReLU is the one
     discontinuous function on the path: a unit whose pre-activation is within rounding distance of 0 may take
     either branch depending on the arithmetic; injecting the device path's own active set lets the tests compare
@@ -80,34 +85,43 @@ def ffn_cf(x, w1, b1, w2, b2, gamma, beta, mask=None, flips=None):
             flips.append((int(diff.sum()), diff.numel(), float(pre.detach().abs()[diff].max()) if diff.any() else 0.0))
         h = pre * mask.to(pre.dtype)
     y = h @ w2.reshape(w2.shape[0], -1).t() + b2
+    if ffn_mask is not None:                       # nn.Dropout on the FFN output before the residual (GATLayer.py:41-42)
+        y = y * ffn_mask
     return F.layer_norm(y + x, (x.shape[-1],), gamma, beta, 1e-5)
 
 
-def wswgat_cf(csc, w, s, params, prefix, kind, T, mask=None, flips=None):
+def wswgat_cf(csc, w, s, params, prefix, kind, T, mask=None, flips=None, drop=None):
+    """drop: optional dict(attn=[H, N_src, in] multiplier, ffn=[N_dst, F] multiplier) - explicit dropout masks."""
+    attn_mask = drop.get("attn") if drop else None
+    ffn_mask = drop.get("ffn") if drop else None
     H = n_heads_of(params, prefix + "layer.")
     W, Wf, bf, a = pack_layer(params, prefix + "layer.", H)
     if kind == "W2S":
         origin, neighbor = s, w
         sh = multi_head_cf(neighbor, s.shape[0], csc["super_indptr"], csc["super_src"], csc["super_bin"],
-                           csc["extra_cnt"], W, Wf, bf, a, T)
+                           csc["extra_cnt"], W, Wf, bf, a, T, attn_mask)
     else:
         origin, neighbor = w, s
         sh = multi_head_cf(neighbor, w.shape[0], csc["word_indptr"], csc["word_src"], csc["word_bin"],
-                           csc["extra_cnt_word"], W, Wf, bf, a, T)
+                           csc["extra_cnt_word"], W, Wf, bf, a, T, attn_mask)
     h = F.elu(sh) + origin
     return ffn_cf(h, params[prefix + "ffn.w_1.weight"], params[prefix + "ffn.w_1.bias"],
                   params[prefix + "ffn.w_2.weight"], params[prefix + "ffn.w_2.bias"],
-                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"], mask, flips)
+                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"], mask, flips,
+                  ffn_mask)
 
 
-def update_loop_cf(csc, word_feature, super_feature, params, n_iter, masks=None, flips=None):
-    """masks: optional list of ReLU active sets, one per WSWGAT application in execution order."""
+def update_loop_cf(csc, word_feature, super_feature, params, n_iter, masks=None, flips=None, drops=None):
+    """masks: optional list of ReLU active sets, one per WSWGAT application in execution order.
+    drops: optional list of explicit dropout masks (see wswgat_cf), one per application."""
     T = params["_TFembed.weight"]
     it = iter(masks) if masks is not None else None
     nxt = (lambda: next(it)) if it is not None else (lambda: None)
+    itd = iter(drops) if drops is not None else None
+    nxd = (lambda: next(itd)) if itd is not None else (lambda: None)
     word_state = word_feature
-    sent_state = wswgat_cf(csc, word_feature, super_feature, params, "word2sent.", "W2S", T, nxt(), flips)
+    sent_state = wswgat_cf(csc, word_feature, super_feature, params, "word2sent.", "W2S", T, nxt(), flips, nxd())
     for _ in range(n_iter):
-        word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T, nxt(), flips)
-        sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T, nxt(), flips)
+        word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T, nxt(), flips, nxd())
+        sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T, nxt(), flips, nxd())
     return word_state, sent_state

@@ -476,3 +476,105 @@ def test_fused_adam_matches_torch(clip):
         g.copy_(grad)
         fa.step()
         assert nerr(mine, ref) <= 1e-6
+
+
+# ----------------------------------------------------------------------------- training-mode dropout
+def _drop_masks(seed, n_apps, start, p_attn, p_ffn, n_word, n_super):
+    """explicit multipliers of every application, read back from the device generator (hsg_dropout_mask)."""
+    from hetersumgraph_b200.functional import dropout_keep_mask
+    out = []
+    for i in range(n_apps):
+        kind = (i + start) % 2
+        H, d, in_dim, n_src, n_dst = (8, 8, 300, n_word, n_super) if kind == 0 else (6, 50, 64, n_super, n_word)
+        drop = {}
+        if p_attn > 0:
+            keep = dropout_keep_mask(H * n_src * in_dim, p_attn, seed, 2 * i).cpu().float()
+            drop["attn"] = keep.view(H, n_src, in_dim) / (1.0 - p_attn)
+        if p_ffn > 0:
+            keep = dropout_keep_mask(n_dst * H * d, p_ffn, seed, 2 * i + 1).cpu().float()
+            drop["ffn"] = keep.view(n_dst, H * d) / (1.0 - p_ffn)
+        out.append(drop)
+    return out
+
+
+@pytest.mark.parametrize("p_attn,p_ffn,n_iter", [(0.1, 0.1, 1), (0.3, 0.0, 1), (0.0, 0.2, 2)])
+def test_training_dropout_matches_oracle_with_same_masks(p_attn, p_ffn, n_iter):
+    """Training-mode dropout (per-head input dropout GATStackLayer.py:56, FFN dropout GATLayer.py:41-42): the
+    device path draws its masks from a counter-based generator; the oracle is evaluated with the very same masks
+    (read back through hsg_dropout_mask), forward and all gradients."""
+    import hetersumgraph_b200.functional as fn
+    import hetersumgraph_b200.modules as md
+    exs = syn.make_examples(5, "tiny", seed=31)
+    tb = syn.pack_token_batch(exs)
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    bg, _ = oracle_batch(exs, False)
+    csc = gb.derive_csc(bg)
+    torch.manual_seed(77)
+    m = hb.WSWGATUpdateLoop(n_iter=n_iter, atten_dropout_prob=p_attn, ffn_dropout_prob=p_ffn)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    w, s = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+    cw, cs = torch.randn_like(w), torch.randn_like(s)
+    wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG = [], []
+    try:
+        gw, gs = m(batch, wg, sg)
+        relu_masks, (seed, n_apps, start) = fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG[0]
+    finally:
+        fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG = None, None
+    ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
+    drops = _drop_masks(seed, n_apps, start, p_attn, p_ffn, batch.n_word, batch.n_super)
+    if p_attn > 0:      # the generator really drops about p of the entries, independently per head
+        frac = float((drops[0]["attn"] == 0).float().mean())
+        assert abs(frac - p_attn) < 0.02
+        assert not torch.equal(drops[0]["attn"][0], drops[0]["attn"][1])
+    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter, masks=relu_masks, drops=drops)
+    ((ow * cw).sum() + (os_ * cs).sum()).backward()
+    assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
+    assert nerr(wg.grad, wc.grad) <= TOL and nerr(sg.grad, sc.grad) <= TOL
+    assert nerr(m._TFembed.weight.grad, params["_TFembed.weight"].grad) <= TOL
+    for pre in ("word2sent", "sent2word"):
+        mod = getattr(m, pre)
+        H = mod.layer.num_heads
+        cat = lambda name: torch.cat([params["%s.layer.heads.%d.%s" % (pre, k, name)].grad for k in range(H)], 0)  # noqa: E731
+        assert nerr(mod.layer.fc_weight.grad, cat("fc.weight")) <= TOL, pre
+        assert nerr(mod.layer.attn_fc_weight.grad, cat("attn_fc.weight")) <= TOL, pre
+        assert nerr(mod.ffn.w_1.weight.grad, params[pre + ".ffn.w_1.weight"].grad) <= TOL, pre
+        assert nerr(mod.ffn.w_2.weight.grad, params[pre + ".ffn.w_2.weight"].grad) <= TOL, pre
+        assert nerr(mod.ffn.w_2.bias.grad, params[pre + ".ffn.w_2.bias"].grad) <= TOL, pre
+    # a second forward draws a different mask; eval mode is deterministic and mask-free
+    gw2, _ = m(batch, wg, sg)
+    assert not torch.equal(gw2, gw)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(batch, wg, sg), m(batch, wg, sg)
+    assert torch.equal(e1[0], e2[0]) and torch.equal(e1[1], e2[1])
+
+
+def test_standalone_wswgat_module_with_dropout():
+    """One WSWGAT module called directly (GAT.py:45-59) in training mode, both layer types."""
+    import hetersumgraph_b200.functional as fn
+    import hetersumgraph_b200.modules as md
+    exs = syn.make_examples(4, "tiny", seed=41)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    bg, _ = oracle_batch(exs, False)
+    csc = gb.derive_csc(bg)
+    T = torch.randn(10, 50)
+    batch.set_tfidf_embedding(T.cuda())
+    w, s = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+    for kind, in_dim, out_dim, H in (("W2S", 300, 64, 8), ("S2W", 64, 300, 6)):
+        torch.manual_seed(3)
+        mod = hb.WSWGAT(in_dim, out_dim, H, 0.2, 512, 0.1, 50, kind)
+        params = {"x." + k: v.detach().clone() for k, v in mod.state_dict().items()}
+        mod = mod.cuda().train()
+        fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG = [], []
+        try:
+            got = mod(batch, w.cuda(), s.cuda())
+            relu_masks, (seed, n_apps, start) = fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG[0]
+        finally:
+            fn.RELU_MASK_CAPTURE, md.DROPOUT_SEED_LOG = None, None
+        assert (n_apps, start) == (1, 0 if kind == "W2S" else 1)
+        drops = _drop_masks(seed, 1, start, 0.2, 0.1, batch.n_word, batch.n_super)
+        want = cf.wswgat_cf(csc, w, s, params, "x.", kind, T, relu_masks[0], None, drops[0])
+        assert nerr(got, want) <= TOL, kind

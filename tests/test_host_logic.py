@@ -89,8 +89,14 @@ def test_reference_error_behaviour():
     batch = hb.HeteroBatch.from_csc_arrays(np.array([0, 1]), np.array([0]), np.array([3]), np.array([0]),
                                            np.array([0, 1]), np.array([0]), np.array([3]), device="cpu")
     batch.set_tfidf_embedding(torch.randn(10, 50))
-    with pytest.raises(NotImplementedError, match="dropout"):
+    # training-mode dropout is implemented in the sm_100a kernels: without a GPU the call fails loudly (no fallback)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
         m(batch, torch.randn(1, 300), torch.randn(1, 64))
+    # the bare sub-layers do not carry dropout on their own (the reference only runs them inside WSWGAT)
+    with pytest.raises(NotImplementedError, match="dropout"):
+        m.layer(batch, torch.randn(1, 300))
+    with pytest.raises(NotImplementedError, match="dropout"):
+        m.ffn(torch.randn(1, 1, 64))
 
 
 def test_generator_shapes_and_determinism():
