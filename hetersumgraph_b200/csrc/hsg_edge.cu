@@ -23,6 +23,9 @@
 // Everything is deterministic: no floating-point atomics anywhere.
 #include <math_constants.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "hsg_common.cuh"
 #include "hsg_internal.cuh"
 #include "hsg_edge_layout.cuh"
@@ -569,6 +572,166 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
   }
 }
 
+// ---------------------------------------------------------------------------
+// backward over LOW-DEGREE rows (word rows: 1-3 in-edges): every GROUP-lane group of a warp walks ITS OWN row, so a
+// warp has EPS rows in flight, instead of the EPS groups sharing one row's (mostly single-entry) edge list.  Same
+// arithmetic and summation order per row as edge_bwd_kernel with one group; ncu on the 2 048-graph shard showed
+// the shared-row mapping issue-bound on these rows (sm throughput 67 %, DRAM 21 %).
+// ---------------------------------------------------------------------------
+template <int H, int D>
+__global__ void __launch_bounds__(EDGE_THREADS, 4)
+edge_bwd_rowpar_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                       const uint8_t* __restrict__ bin, const float* __restrict__ zp, int ldz,
+                       const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ stat,
+                       float* __restrict__ dzp, float* __restrict__ dq_part) {
+  pdl_prologue();
+  using C = EdgeCfg<H, D>;
+  constexpr int NQ = HSG_N_BINS * H;
+  constexpr int U = 2;
+  __shared__ float q_s[NQ];
+  __shared__ float dq_s[EDGE_WARPS][C::EPS][NQ];
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) q_s[i] = q[i];
+  for (int i = threadIdx.x; i < EDGE_WARPS * C::EPS * NQ; i += blockDim.x) (&dq_s[0][0][0])[i] = 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int grp = lane / C::GROUP;
+  const int gl = lane % C::GROUP;
+  const int k = gl / C::LPH;
+  const int l = gl % C::LPH;
+  const bool lane_on = grp < C::EPS;
+  float* my_dq = &dq_s[wib][lane_on ? grp : 0][0];
+  const int nsteps = ceil_div(n_src, C::EPS);
+
+  int st = warp;
+  int beg = 0, end = 0, v0 = 0, b0 = 0;
+  {
+    const int u = st * C::EPS + grp;
+    if (lane_on && st < nsteps && u < n_src) {
+      beg = __ldg(indptr + u);
+      end = __ldg(indptr + u + 1);
+      if (beg < end) {
+        v0 = __ldg(nbr + beg);
+        b0 = __ldg(bin + beg);
+      }
+    }
+  }
+  while (st < nsteps) {
+    const int u = st * C::EPS + grp;
+    const bool row_on = lane_on && u < n_src;
+    // next step's edge range: issued now, consumed at the bottom of the loop
+    int begn = 0, endn = 0;
+    {
+      const int un = (st + nwarps) * C::EPS + grp;
+      if (lane_on && st + nwarps < nsteps && un < n_src) {
+        begn = __ldg(indptr + un);
+        endn = __ldg(indptr + un + 1);
+      }
+    }
+    const int deg = row_on ? end - beg : 0;
+    int maxdeg = deg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    float zv[C::NE], acc[C::NE];
+    float pu = 0.f, acc_dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::NE; ++i) {
+      zv[i] = 0.f;
+      acc[i] = 0.f;
+    }
+    if (deg > 0) {
+      const float* zrow = zp + (size_t)u * ldz;
+      pu = __ldg(zrow + C::FP + k);
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i)
+        if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(zrow + (i * C::GROUP + gl) * C::VEC, zv + i * C::VEC);
+    }
+    for (int j0 = 0; j0 < maxdeg; j0 += U) {           // warp-uniform trip count (shuffles inside)
+      float gv[U][C::NE], mk[U], dk[U], sk[U];
+      int bb[U];
+      bool ok[U];
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        const int j = j0 + uu;
+        ok[uu] = j < deg;
+        int v = 0;
+        bb[uu] = 0;
+        if (ok[uu]) {
+          v = j == 0 ? v0 : __ldg(nbr + beg + j);
+          bb[uu] = j == 0 ? b0 : (int)__ldg(bin + beg + j);
+        }
+        mk[uu] = 0.f;
+        dk[uu] = 1.f;
+        sk[uu] = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) gv[uu][i] = 0.f;
+        if (ok[uu]) {
+          const float* grow = g + (size_t)v * C::FP;
+          const float* stp = stat + (size_t)v * 3 * H;
+          mk[uu] = __ldg(stp + k);
+          dk[uu] = __ldg(stp + H + k);
+          sk[uu] = __ldg(stp + 2 * H + k);
+#pragma unroll
+          for (int i = 0; i < C::VPL; ++i)
+            if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(grow + (i * C::GROUP + gl) * C::VEC, gv[uu] + i * C::VEC);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) part = fmaf(gv[uu][i], zv[i], part);
+        const float t = head_sum<C::LPH>(part, lane, l);
+        if (ok[uu]) {
+          const float pre = pu + q_s[bb[uu] * H + k];
+          const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
+          const float alpha = __expf(lg - mk[uu]) / dk[uu];
+          const float de = alpha * (t - sk[uu]);
+          const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
+#pragma unroll
+          for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(alpha, gv[uu][i], acc[i]);
+          acc_dp += dpre;
+          if (l == 0) my_dq[bb[uu] * H + k] += dpre;
+        }
+      }
+    }
+    if (row_on) {
+      float* drow = dzp + (size_t)u * ldz;
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) {
+        if (l + C::LPH * i >= C::NV) {
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) acc[i * C::VEC + t] = 0.f;   // layout holes must be finite zeros
+        }
+        st_vec<C::VEC>(drow + (i * C::GROUP + gl) * C::VEC, acc + i * C::VEC);
+      }
+      if (l == 0) drow[C::FP + k] = acc_dp;
+      for (int c = C::FP + H + gl; c < ldz; c += C::GROUP) drow[c] = 0.f;
+    }
+    st += nwarps;
+    beg = begn;
+    end = endn;
+    v0 = 0;
+    b0 = 0;
+    if (beg < end) {                                   // first edge of the next row
+      v0 = __ldg(nbr + beg);
+      b0 = __ldg(bin + beg);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < EDGE_WARPS; ++w)
+#pragma unroll
+      for (int g2 = 0; g2 < C::EPS; ++g2) s += dq_s[w][g2][i];
+    dq_part[(size_t)blockIdx.x * NQ + i] = s;
+  }
+}
+
 // dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
 __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
                                                           float* __restrict__ dq, int accumulate) {
@@ -587,11 +750,30 @@ __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, c
   if (threadIdx.x == 0) dq[i] = accumulate ? dq[i] + red[0] : red[0];
 }
 
-constexpr int EDGE_MAX_BLOCKS = 148 * 8;
+constexpr int EDGE_MAX_BLOCKS = 148 * 32;  // upper bound of the grid (sizes the dq partial workspace)
+constexpr int EDGE_DEFAULT_BLOCKS = 148 * 8;
 
-static int edge_grid(int n_rows_steps) {
+// Grid caps (blocks of 8 warps; a warp walks rows in a grid-stride loop with a software pipeline over rows).  Measured
+// on the 2 048-graph shard (L2 flushed): the streaming-heavy kernels (bwd_prep; forward over wide rows) gain from
+// 32 blocks per SM in flight-order (S2W prep 0.60 -> 0.67 of the HBM peak, S2W fwd 0.705 -> 0.735), the gather-heavy
+// backward kernels prefer 8 per SM.  HSG_EDGE_MAX_BLOCKS overrides all of them (tuning).
+static int edge_block_cap(int dflt) {
+  static int env = -1;
+  if (env < 0) {
+    env = 0;
+    const char* e = getenv("HSG_EDGE_MAX_BLOCKS");
+    if (e) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= EDGE_MAX_BLOCKS) env = v;
+    }
+  }
+  return env > 0 ? env : dflt;
+}
+
+static int edge_grid(int n_rows_steps, int cap = EDGE_DEFAULT_BLOCKS) {
   int blocks = ceil_div(n_rows_steps, EDGE_WARPS);
-  if (blocks > EDGE_MAX_BLOCKS) blocks = EDGE_MAX_BLOCKS;
+  cap = edge_block_cap(cap);
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return blocks;
 }
@@ -609,10 +791,10 @@ static int launch_fwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
   LaunchScope ls(SLOT_EDGE_FWD, s);
   if (deep)
-    launch_k(edge_fwd_kernel<H, D, UHI>, dim3(edge_grid(c->n_dst)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
+    launch_k(edge_fwd_kernel<H, D, UHI>, dim3(edge_grid(c->n_dst, C::STAGED ? EDGE_MAX_BLOCKS : EDGE_DEFAULT_BLOCKS)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
   else
-    launch_k(edge_fwd_kernel<H, D, ULO>, dim3(edge_grid(c->n_dst)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
+    launch_k(edge_fwd_kernel<H, D, ULO>, dim3(edge_grid(c->n_dst, C::STAGED ? EDGE_MAX_BLOCKS : EDGE_DEFAULT_BLOCKS)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
   return check_launch();
 }
@@ -621,9 +803,20 @@ template <int H, int D>
 static int launch_prep(int n_dst, const float* dx, const float* dsh, const float* sh, float* g, float* stat,
                        cudaStream_t s) {
   LaunchScope ls(SLOT_EDGE_BWD_PREP, s);
-  launch_k(edge_bwd_prep_kernel<H, D>, dim3(edge_grid(ceil_div(n_dst, EdgeCfg<H, D>::EPS))), dim3(EDGE_THREADS), 0, s, n_dst, dx, dsh,
+  launch_k(edge_bwd_prep_kernel<H, D>, dim3(edge_grid(ceil_div(n_dst, EdgeCfg<H, D>::EPS), EDGE_MAX_BLOCKS)), dim3(EDGE_THREADS), 0, s, n_dst, dx, dsh,
                                                                                                    sh, g, stat);
   return check_launch();
+}
+
+static std::atomic<int> g_rowpar{-1};   // -1 auto (low average degree), 0 never, 1 whenever the layout allows
+
+template <int H, int D>
+static void launch_rowpar(int blocks, const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g,
+                          const float* stat, float* dzp, float* ws, cudaStream_t s) {
+  if constexpr (EdgeCfg<H, D>::EPS > 1 && !EdgeCfg<H, D>::STAGED) {
+    launch_k(edge_bwd_rowpar_kernel<H, D>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
+             zp, ldz, q, g, stat, dzp, ws);
+  }
 }
 
 template <int H, int D>
@@ -632,10 +825,14 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   using C = EdgeCfg<H, D>;
   constexpr int UHI = C::NE <= 4 ? 4 : 2, ULO = C::NE <= 4 ? 2 : 1;
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
-  const int blocks = edge_grid(c->n_dst);
+  const int rp = g_rowpar.load(std::memory_order_relaxed);
+  const bool rowpar = C::EPS > 1 && !C::STAGED && (rp == 1 || (rp < 0 && !deep));
+  const int blocks = rowpar ? edge_grid(ceil_div(c->n_dst, C::EPS)) : edge_grid(c->n_dst);
   {
     LaunchScope ls(SLOT_EDGE_BWD, s);
-    if (deep)
+    if (rowpar)
+      launch_rowpar<H, D>(blocks, c, zp, ldz, q, g, stat, dzp, ws, s);
+    else if (deep)
       launch_k(edge_bwd_kernel<H, D, UHI>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
                                                                  stat, dzp, ws);
     else
@@ -709,6 +906,11 @@ int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx, const float* dsh
   HSG_EDGE_CONFIGS(X)
 #undef X
   return HSG_ERR_SHAPE;
+}
+
+int hsg_set_edge_rowpar(int mode) {
+  g_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  return HSG_OK;
 }
 
 size_t hsg_edge_bwd_workspace_bytes(int H) { return (size_t)EDGE_MAX_BLOCKS * HSG_N_BINS * H * sizeof(float) + 16; }

@@ -226,6 +226,10 @@ int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx /* or NULL */, co
  *     dzp_u = [ perm(sum_e alpha_e g_v) | sum_e dpre_e | 0 ],   dq[b,k] = sum_{e: bin=b} dpre_e
  * dq is reduced deterministically through ws. */
 size_t hsg_edge_bwd_workspace_bytes(int H);
+/* Row mapping of hsg_edge_bwd when a warp holds several GROUP-lane groups ((8,8): two): -1 auto (each group walks its
+ * own row when the average degree is low - word rows; the groups share one row's edge list otherwise), 0 never,
+ * 1 always.  Same results either way (tested); a tuning / test knob. */
+int hsg_set_edge_rowpar(int mode);
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,
                  const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
                  void* ws, size_t ws_bytes, void* stream);

@@ -578,3 +578,44 @@ def test_standalone_wswgat_module_with_dropout():
         drops = _drop_masks(seed, 1, start, 0.2, 0.1, batch.n_word, batch.n_super)
         want = cf.wswgat_cf(csc, w, s, params, "x.", kind, T, relu_masks[0], None, drops[0])
         assert nerr(got, want) <= TOL, kind
+
+
+def test_edge_bwd_row_mappings_agree():
+    """hsg_edge_bwd's two row mappings for multi-group layouts ((8,8): two groups per warp) - groups sharing one
+    row's edge list vs. each group walking its own row - give the same dzp / dq up to summation order."""
+    import ctypes as C
+    from hetersumgraph_b200 import _lib
+    from hetersumgraph_b200.functional import _Workspace
+    lib = _lib.load()
+    exs = syn.make_examples(16, "cnndm", seed=5)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    H, d = 8, 8
+    csc, csc_t = batch.csc("W2S")
+    fp, ldz = _lib.edge_layout(H, d)
+    torch.manual_seed(0)
+    dev = "cuda"
+    zp = torch.randn(csc.n_src, ldz, device=dev)
+    q = torch.randn(10, H, device=dev)
+    origin = torch.randn(csc.n_dst, H * d, device=dev)
+    sh, x = torch.empty_like(origin), torch.empty_like(origin)
+    stat = torch.empty(csc.n_dst, 3 * H, device=dev)
+    g = torch.empty(csc.n_dst, fp, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(), sh.data_ptr(),
+                                x.data_ptr(), stat.data_ptr(), st))
+    _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None, sh.data_ptr(), g.data_ptr(),
+                                     stat.data_ptr(), st))
+    ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), torch.device(dev), "edge")
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.hsg_set_edge_rowpar(mode)
+            dzp = torch.full((csc.n_src, ldz), float("nan"), device=dev)
+            dq = torch.empty(10, H, device=dev)
+            _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(), g.data_ptr(),
+                                        stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            outs.append((dzp, dq))
+    finally:
+        lib.hsg_set_edge_rowpar(-1)
+    assert torch.isfinite(outs[1][0]).all()
+    assert nerr(outs[1][0], outs[0][0]) <= 2e-6 and nerr(outs[1][1], outs[0][1]) <= 2e-6
