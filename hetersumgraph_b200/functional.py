@@ -19,7 +19,13 @@ from . import _lib
 from ._lib import EPI_ADD, EPI_BIAS, EPI_RELU, EPI_RELU_MASK
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _st():
+    """cudaStream_t of torch's current stream on the current device (the raw getter skips ~15 us of Python)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -391,24 +397,46 @@ class UpdateLoopFn(torch.autograd.Function):
         lib = _lib.load()
         n_apps, start = cfg["n_apps"], cfg["start_kind"]
         (H1, d1, hid1), (H2, d2, hid2) = cfg["w2s"], cfg["s2w"]
-        word_feature, super_feature, T = _f32c(word_feature), _f32c(super_feature), _f32c(T)
-        params = tuple(_f32c(t) if t is not None else None for t in params)
-        pw, ps = params[:10], params[10:]
+        word_feature, super_feature = _f32c(word_feature), _f32c(super_feature)
         n_word, n_super = batch.n_word, batch.n_super
         if word_feature.shape[0] != n_word or super_feature.shape[0] != n_super:
             raise ValueError("update loop: got %d word / %d supernode rows, graph has %d / %d" %
                              (word_feature.shape[0], super_feature.shape[0], n_word, n_super))
-        Dw, Ds, fe = word_feature.shape[1], super_feature.shape[1], T.shape[1]
-        uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
-        if (uses[0] and Ds != H1 * d1) or (uses[1] and Dw != H2 * d2):
-            raise ValueError("update loop: feature widths (%d, %d) do not match heads*head_dim" % (Dw, Ds))
+        Dw, Ds = word_feature.shape[1], super_feature.shape[1]
+        # the argument block of the parameters is cached on the caller (cfg["cache"]) and reused while every
+        # parameter tensor keeps its storage: ~40 ctypes field conversions per call otherwise
+        cache = cfg.get("cache")
+        sig = (T.data_ptr(), Dw, Ds) + tuple(0 if t is None else t.data_ptr() for t in params)
+        ent = cache.get("fwd") if cache is not None else None
+        if ent is not None and ent[0] == sig:
+            args = type(ent[1]).from_buffer_copy(ent[1])
+        else:
+            T = _f32c(T)
+            params = tuple(_f32c(t) if t is not None else None for t in params)
+            fe = T.shape[1]
+            uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
+            if (uses[0] and Ds != H1 * d1) or (uses[1] and Dw != H2 * d2):
+                raise ValueError("update loop: feature widths (%d, %d) do not match heads*head_dim" % (Dw, Ds))
+            args = _lib.LoopArgsC(n_apps, start, 0, 0, None, None,
+                                  _layer_params_c(H1, d1, Dw, fe, hid1, params[:10]),
+                                  _layer_params_c(H2, d2, Ds, fe, hid2, params[10:]),
+                                  _p(T), None, None, None, 0, 0.0, 0.0, 0)
+            if cache is not None and all(t is None or t.is_contiguous() for t in params) and T.is_contiguous():
+                cache["fwd"] = (sig, type(args).from_buffer_copy(args))
         csc_s, csc_w = batch.csc("W2S")
-        args = _lib.LoopArgsC(n_apps, start, n_word, n_super, C.pointer(csc_s), C.pointer(csc_w),
-                              _layer_params_c(H1, d1, Dw, fe, hid1, pw), _layer_params_c(H2, d2, Ds, fe, hid2, ps),
-                              _p(T), _p(word_feature), _p(super_feature), None, 0,
-                              float(cfg.get("attn_p", 0.0)), float(cfg.get("ffn_p", 0.0)), int(cfg.get("seed", 0)))
-        plan = _lib.LoopPlanC()
-        _lib.check(lib.hsg_update_loop_plan(C.byref(args), C.byref(plan)))
+        args.n_apps, args.start_kind, args.n_word, args.n_super = n_apps, start, n_word, n_super
+        args.csc_super, args.csc_word = C.pointer(csc_s), C.pointer(csc_w)
+        args.word_feature, args.super_feature = word_feature.data_ptr(), super_feature.data_ptr()
+        args.attn_p, args.ffn_p, args.seed = float(cfg.get("attn_p", 0.0)), float(cfg.get("ffn_p", 0.0)), int(cfg.get("seed", 0))
+        pkey = (n_apps, start, n_word, n_super, args.attn_p > 0, args.ffn_p > 0, sig[1:])
+        pent = cache.get("plan") if cache is not None else None
+        if pent is not None and pent[0] == pkey:
+            plan = pent[1]
+        else:
+            plan = _lib.LoopPlanC()
+            _lib.check(lib.hsg_update_loop_plan(C.byref(args), C.byref(plan)))
+            if cache is not None:
+                cache["plan"] = (pkey, plan)
         state = torch.empty(plan.state_floats, dtype=torch.float32, device=word_feature.device)
         args.state, args.state_floats = state.data_ptr(), plan.state_floats
         _lib.check(lib.hsg_update_loop_fwd(C.byref(args), _st()))
@@ -434,22 +462,23 @@ class UpdateLoopFn(torch.autograd.Function):
         grad_targets = cfg.get("grad_targets")
         saved = ctx.saved_tensors
         word_feature, super_feature, T, state = saved[:4]
-        it = iter(saved[4:])
-        params = [next(it) if present else None for present in ctx.param_present]
+        n_params = len(ctx.param_present)
         dev = state.device
         plan, args = ctx.plan, ctx.args
         if d_word is None and d_super is None:
-            return (None,) * (5 + len(params))
+            return (None,) * (5 + n_params)
         d_word = _f32c(d_word) if d_word is not None else None
         d_super = _f32c(d_super) if d_super is not None else None
         d_wf = torch.empty_like(word_feature) if ctx.needs_input_grad[2] else None
         d_sf = torch.empty_like(super_feature) if ctx.needs_input_grad[3] else None
         n_apps, start = cfg["n_apps"], cfg["start_kind"]
-        uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
         if grad_targets is not None:
-            targets = list(grad_targets)
+            targets = grad_targets
             acc = 1
         else:
+            it = iter(saved[4:])
+            params = [next(it) if present else None for present in ctx.param_present]
+            uses = [start == 0 or n_apps > 1, start == 1 or n_apps > 1]
             targets = [torch.empty_like(T)] + [torch.empty_like(p) if p is not None else None for p in params]
             for k in (0, 1):                                 # a layer no application used: zero gradients
                 if not uses[k]:
@@ -459,14 +488,24 @@ class UpdateLoopFn(torch.autograd.Function):
             acc = 0
         scratch = torch.empty(plan.scratch_floats, dtype=torch.float32, device=dev)
         ws = _Workspace.get(plan.ws_bytes, dev, "loop")
-        b = _lib.LoopBwdArgsC(_p(d_word), _p(d_super), _p(d_wf), _p(d_sf),
-                              _lib.LayerGradsC(*[_p(t) for t in targets[1:11]]),
-                              _lib.LayerGradsC(*[_p(t) for t in targets[11:21]]),
-                              _p(targets[0]), acc, 0, scratch.data_ptr(), plan.scratch_floats, ws.data_ptr(),
-                              ws.numel())
+        cache = cfg.get("cache") if grad_targets is not None else None
+        tsig = tuple(0 if t is None else t.data_ptr() for t in targets) if cache is not None else None
+        ent = cache.get("bwd") if cache is not None else None
+        if ent is not None and ent[0] == tsig:
+            b = type(ent[1]).from_buffer_copy(ent[1])
+        else:
+            b = _lib.LoopBwdArgsC(None, None, None, None,
+                                  _lib.LayerGradsC(*[_p(t) for t in targets[1:11]]),
+                                  _lib.LayerGradsC(*[_p(t) for t in targets[11:21]]),
+                                  _p(targets[0]), acc, 0, None, 0, None, 0)
+            if cache is not None:
+                cache["bwd"] = (tsig, type(b).from_buffer_copy(b))
+        b.d_word_state, b.d_super_state, b.d_word_feature, b.d_super_feature = _p(d_word), _p(d_super), _p(d_wf), _p(d_sf)
+        b.accumulate = acc
+        b.scratch, b.scratch_floats, b.ws, b.ws_bytes = scratch.data_ptr(), plan.scratch_floats, ws.data_ptr(), ws.numel()
         _lib.check(lib.hsg_update_loop_bwd(C.byref(args), C.byref(b), _st()))
         if grad_targets is not None:
-            return (None, None, d_wf, d_sf) + (None,) * (1 + len(params))
+            return (None, None, d_wf, d_sf) + (None,) * (1 + n_params)
         return (None, None, d_wf, d_sf, targets[0]) + tuple(targets[1:])
 
 

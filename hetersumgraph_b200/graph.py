@@ -28,7 +28,12 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -40,21 +45,36 @@ class DeviceTokenBatch:
 
     @staticmethod
     def host_buffers(tb: TokenBatch, pin=True):
-        """Contiguous (pinned) host tensors of everything that is copied per step, and their byte count."""
-        def h(a):
-            t = torch.from_numpy(np.ascontiguousarray(a))
-            return t.pin_memory() if (pin and t.numel() > 0 and torch.cuda.is_available()) else t
-        bufs = dict(tokens=h(tb.tokens), sent_bin=h(tb.sent_bin), graph_sent_ptr=h(tb.graph_sent_ptr),
-                    labels=h(tb.labels))
+        """Everything that is copied per step packed into ONE contiguous (pinned) host blob - a single H2D copy per
+        batch - with the segment layout and the host-known sizes.  Returns (host, bytes copied per step)."""
+        arrays = dict(tokens=tb.tokens, sent_bin=tb.sent_bin, graph_sent_ptr=tb.graph_sent_ptr, labels=tb.labels)
         if tb.hdsg:
             per = np.diff(tb.graph_sent_ptr)
-            sent_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int32), per)
+            sent_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int64), per)
             sent_local = (np.arange(int(per.sum()), dtype=np.int32) - np.repeat(tb.graph_sent_ptr[:-1], per)).astype(np.int32)
-            bufs.update(graph_doc_ptr=h(tb.graph_doc_ptr), sent_doc=h(tb.sent_doc), doc_tok_ptr=h(tb.doc_tok_ptr),
-                        doc_tokens=h(tb.doc_tokens), doc_bin=h(tb.doc_bin), sent_graph=h(sent_graph),
-                        sent_local=h(sent_local))
-        nbytes = sum(t.numel() * t.element_size() for t in bufs.values())
-        return bufs, nbytes
+            arrays.update(graph_doc_ptr=tb.graph_doc_ptr, sent_doc=tb.sent_doc, doc_tok_ptr=tb.doc_tok_ptr,
+                          doc_tokens=tb.doc_tokens, doc_bin=tb.doc_bin, sent_graph=sent_graph, sent_local=sent_local)
+        layout, off = {}, 0
+        for name, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            arrays[name] = a
+            layout[name] = (off, a.nbytes, torch.from_numpy(a[:0].copy()).dtype if a.size == 0 else torch.from_numpy(a.reshape(-1)[:1]).dtype,
+                            tuple(a.shape))
+            off += (a.nbytes + 15) & ~15
+        blob = np.zeros(max(off, 16), np.uint8)
+        for name, a in arrays.items():
+            o, nb, _, _ = layout[name]
+            blob[o:o + nb] = a.reshape(-1).view(np.uint8)
+        t = torch.from_numpy(blob)
+        if pin and torch.cuda.is_available():
+            t = t.pin_memory()
+        S, L = tb.tokens.shape
+        per_graph = np.diff(tb.graph_sent_ptr)
+        meta = dict(S=int(S), L=int(L), max_sent=int(per_graph.max()) if tb.n_graphs > 0 else 0,
+                    n_doc=int(tb.graph_doc_ptr[-1]) if tb.hdsg else 0, n_doc_tok=int(tb.doc_tok_ptr[-1]) if tb.hdsg else 0,
+                    vocab=int(tb.filter_bitmap.shape[0]) * 32)
+        nbytes = sum(v[1] for v in layout.values())
+        return dict(blob=t, layout=layout, meta=meta), nbytes
 
     @staticmethod
     def upload(tb: TokenBatch, device="cuda", vocab_size: Optional[int] = None, host=None,
@@ -64,31 +84,30 @@ class DeviceTokenBatch:
             host, _ = DeviceTokenBatch.host_buffers(tb)
         d = DeviceTokenBatch()
         d.device, d.hdsg, d.n_graphs = dev, bool(tb.hdsg), tb.n_graphs
+        blob = host["blob"].to(dev, non_blocking=True)                 # the ONE host -> device copy of the batch
+        d._blob = blob
+        lay, meta = host["layout"], host["meta"]
 
-        def up(t):
-            if t.numel() == 0:
-                return torch.zeros(1, dtype=t.dtype, device=dev)
-            return t.to(dev, non_blocking=True)
+        def view(name):
+            o, nb, dt, shape = lay[name]
+            if nb == 0:
+                return None
+            return blob[o:o + nb].view(dt).view(shape)
 
-        d.tokens, d.sent_bin, d.graph_sent_ptr = up(host["tokens"]), up(host["sent_bin"]), up(host["graph_sent_ptr"])
-        d.labels = up(host["labels"]) if host["labels"].numel() else None
+        d.tokens, d.sent_bin, d.graph_sent_ptr, d.labels = view("tokens"), view("sent_bin"), view("graph_sent_ptr"), view("labels")
         if filter_bitmap_dev is None:   # constant per dataset: upload once and pass it back in for later batches
             filter_bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
         d.filter_bitmap = filter_bitmap_dev
         if vocab_size is None:
-            vocab_size = int(tb.filter_bitmap.shape[0]) * 32
+            vocab_size = meta["vocab"]
         d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = d.sent_graph = d.sent_local = None
-        d.n_sent = int(tb.tokens.shape[0])
-        n_doc = n_doc_tok = 0
+        d.n_sent = meta["S"]
         if tb.hdsg:
-            d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = up(host["graph_doc_ptr"]), up(host["sent_doc"]), up(host["doc_tok_ptr"])
-            d.doc_tokens, d.doc_bin = up(host["doc_tokens"]), up(host["doc_bin"])
-            d.sent_graph, d.sent_local = up(host["sent_graph"]).long(), up(host["sent_local"])
-            n_doc, n_doc_tok = int(tb.graph_doc_ptr[-1]), int(tb.doc_tok_ptr[-1])
-        S, L = tb.tokens.shape
-        per_graph = np.diff(tb.graph_sent_ptr)
-        max_sent = int(per_graph.max()) if tb.n_graphs > 0 else 0
-        d.c_struct = _lib.TokenBatchC(tb.n_graphs, S, L, int(tb.hdsg), int(vocab_size), n_doc, n_doc_tok, max_sent,
+            d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = view("graph_doc_ptr"), view("sent_doc"), view("doc_tok_ptr")
+            d.doc_tokens, d.doc_bin = view("doc_tokens"), view("doc_bin")
+            d.sent_graph, d.sent_local = view("sent_graph"), view("sent_local")
+        d.c_struct = _lib.TokenBatchC(tb.n_graphs, meta["S"], meta["L"], int(tb.hdsg), int(vocab_size), meta["n_doc"],
+                                      meta["n_doc_tok"], meta["max_sent"],
                                       _ptr(d.tokens), _ptr(d.sent_bin), _ptr(d.graph_sent_ptr), _ptr(d.filter_bitmap),
                                       _ptr(d.graph_doc_ptr), _ptr(d.sent_doc), _ptr(d.doc_tok_ptr), _ptr(d.doc_tokens),
                                       _ptr(d.doc_bin))
@@ -187,14 +206,16 @@ class HeteroBatch:
         tbc = dtb.c_struct
         ws_bytes = lib.hsg_build_workspace_bytes(C.byref(tbc))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        offs = torch.empty(5, B + 1, dtype=torch.int32, device=dev)
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
-        off_c = _lib.GraphOffsetsC(*[offs[i].data_ptr() for i in range(5)])
+        # [5, B+1] offsets followed by the status word: one buffer, one zero fill, ONE small D2H (no gather launch)
+        meta = torch.zeros(5 * (B + 1) + 1, dtype=torch.int32, device=dev)
+        offs = meta[:5 * (B + 1)].view(5, B + 1)
+        status = meta[5 * (B + 1):]
+        off_c = _lib.GraphOffsetsC(*[offs.data_ptr() + 4 * i * (B + 1) for i in range(5)])
         st = _stream()
         _lib.check(lib.hsg_build_count(C.byref(tbc), off_c, status.data_ptr(), ws.data_ptr(), ws_bytes, st))
-        totals_dev = torch.cat([offs[:, B], status])
-        totals_host = torch.empty(6, dtype=torch.int32, pin_memory=True)
-        totals_host.copy_(totals_dev, non_blocking=True)                 # the one D2H of the build
+        totals_host = torch.empty(5 * (B + 1) + 1, dtype=torch.int32, pin_memory=True)
+        totals_host.copy_(meta, non_blocking=True)                       # the one D2H of the build
+        totals_dev = meta
         ev = torch.cuda.Event()
         ev.record()
         return dict(dtb=dtb, ws=ws, ws_bytes=ws_bytes, offs=offs, status=status, off_c=off_c,
@@ -208,10 +229,11 @@ class HeteroBatch:
         dtb, ws, ws_bytes, offs, status, off_c = c["dtb"], c["ws"], c["ws_bytes"], c["offs"], c["status"], c["off_c"]
         dev, B, tbc = dtb.device, dtb.n_graphs, dtb.c_struct
         c["event"].synchronize()
-        totals = c["totals_host"].tolist()
-        if totals[5] != 0:
-            _lib.check(int(totals[5]))
-        n_word, n_super, n_node, n_edge, n_pair = [int(v) for v in totals[:5]]
+        th = c["totals_host"]
+        status_h = int(th[5 * (B + 1)])
+        if status_h != 0:
+            _lib.check(status_h)
+        n_word, n_super, n_node, n_edge, n_pair = [int(th[i * (B + 1) + B]) for i in range(5)]
         st = _stream()
         i32 = dict(dtype=torch.int32, device=dev)
         # one int32 arena for every 4-byte array, one byte arena for the rest: 2 allocations instead of 14
@@ -368,8 +390,16 @@ class BuildPipeline:
         self._ready = None
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        # allocated on the side stream, consumed on the compute stream: tell the caching allocator
-        for t in list(hb._keepalive) + list(vars(hb).values()):
-            if isinstance(t, torch.Tensor) and t.is_cuda:
+        # allocated on the side stream, consumed on the compute stream: tell the caching allocator.  Every field of
+        # the batch is a view of one of these few storages.
+        bases = [t for t in hb._keepalive if isinstance(t, torch.Tensor)]
+        blob = getattr(hb._keepalive[0], "_blob", None)
+        if blob is not None:
+            bases.append(blob)
+        for extra in (hb.sent_row, hb.sent_doc_row):
+            if extra is not None:
+                bases.append(extra)
+        for t in bases:
+            if t.is_cuda:
                 t.record_stream(cur)
         return hb

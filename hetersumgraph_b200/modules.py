@@ -257,24 +257,42 @@ class WSWGATUpdateLoop(nn.Module):
     # would launch one add per parameter.  Same arithmetic; requires every parameter to have a `.grad` tensor.
     fuse_grad_accumulation = False
 
-    def forward(self, graph, word_feature, sent_feature):
+    def _grad_targets(self):
+        """[dT, 10 x word2sent, 10 x sent2word] .grad buffers in packed shapes; the views are rebuilt only when a
+        .grad tensor has been replaced."""
+        leaves = [self._TFembed.weight] + [p for m in (self.word2sent, self.sent2word) for p in m.parameters()]
+        sig = tuple(-1 if p.grad is None else p.grad.data_ptr() for p in leaves)
+        ent = self.__dict__.get("_gt_cache")
+        if ent is None or ent[0] != sig:
+            if self._TFembed.weight.grad is None:
+                raise RuntimeError("fuse_grad_accumulation needs a .grad buffer on every parameter")
+            targets = [self._TFembed.weight.grad] + _grad_buffers(self.word2sent) + _grad_buffers(self.sent2word)
+            ent = (sig, targets)
+            self.__dict__["_gt_cache"] = ent
+        return ent[1]
+
+    def loop_call(self, graph):
+        """(cfg, parameter tensors) of one UpdateLoopFn call on `graph` - shared by forward() and by
+        path_model.FusedTrainStep (which drives the same functions without the autograd engine)."""
         graph.set_tfidf_embedding(self._TFembed.weight)
         mods = (self.word2sent, self.sent2word) if self._n_iter > 0 else (self.word2sent,)
         attn_p, ffn_p, seed = _dropout_cfg(mods)
         pw, ps = _packed_params(self.word2sent), _packed_params(self.sent2word)
         targets = None
         if self.fuse_grad_accumulation and torch.is_grad_enabled():
-            if self._TFembed.weight.grad is None:
-                raise RuntimeError("fuse_grad_accumulation needs a .grad buffer on every parameter")
-            targets = [self._TFembed.weight.grad] + _grad_buffers(self.word2sent) + _grad_buffers(self.sent2word)
+            targets = self._grad_targets()
         lw, ls = self.word2sent.layer, self.sent2word.layer
         n_apps = 1 + 2 * self._n_iter
         cfg = dict(n_apps=n_apps, start_kind=0, w2s=(lw.num_heads, lw.out_dim, self.word2sent.ffn.d_hid),
                    s2w=(ls.num_heads, ls.out_dim, self.sent2word.ffn.d_hid), grad_targets=targets, attn_p=attn_p,
-                   ffn_p=ffn_p, seed=seed)
+                   ffn_p=ffn_p, seed=seed, cache=self.__dict__.setdefault("_arg_cache", {}))
         if DROPOUT_SEED_LOG is not None and seed:
             DROPOUT_SEED_LOG.append((seed, n_apps, 0))
-        return UpdateLoopFn.apply(graph, cfg, word_feature, sent_feature, self._TFembed.weight, *pw, *ps)
+        return cfg, (self._TFembed.weight,) + pw + ps
+
+    def forward(self, graph, word_feature, sent_feature):
+        cfg, tensors = self.loop_call(graph)
+        return UpdateLoopFn.apply(graph, cfg, word_feature, sent_feature, *tensors)
 
     def forward_per_application(self, graph, word_feature, sent_feature):
         """Same loop through one autograd node per WSWGAT application (the path a caller gets by invoking the

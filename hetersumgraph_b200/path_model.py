@@ -39,7 +39,7 @@ class HSGPath(nn.Module):
 
     def states(self, g: HeteroBatch, sent_feature: torch.Tensor):
         """(word_state, supernode_state) after the update loop."""
-        word_feature = self._embed(g.word_wid.long())
+        word_feature = self._embed(g.word_wid)              # F.embedding takes the int32 ids directly
         if not self.hdsg:
             super_feature = sent_feature
         else:
@@ -76,6 +76,67 @@ def fused_loss(model: "HSGPath", g: HeteroBatch, sent_feature: torch.Tensor, n_g
         targets = (model.wh.weight.grad, model.wh.bias.grad)
     n = n_graphs_global if n_graphs_global is not None else g.n_graphs
     return SentenceLossFn.apply(g, n, targets, state, model.wh.weight, model.wh.bias, g.labels)
+
+
+class _Ctx:
+    """Minimal stand-in for the autograd context of the Function classes (FusedTrainStep calls their static
+    forward / backward directly)."""
+
+    def __init__(self, needs_input_grad):
+        self.needs_input_grad = needs_input_grad
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+    def set_materialize_grads(self, value):
+        pass
+
+
+class FusedTrainStep:
+    """loss, logits, d_sent_feature = step(batch, sent_feature): forward AND backward of the HSG path from the
+    encoder output to the loss, with every parameter gradient accumulated straight into the existing `.grad` buffers
+    (a dist.FlatGradArena) - the same C entry points as `fused_loss(...); loss.backward()` (embedding gather,
+    hsg_update_loop_fwd, hsg_head_fwd, hsg_head_bwd, hsg_update_loop_bwd), driven without the autograd engine,
+    whose CUDA worker-thread hand-off costs about as much host time per step as all the kernel launches together
+    at batch 32.  d_sent_feature is what the sentence encoder's backward consumes (HiGraph.py:96).
+
+    HSG with a frozen embedding (the reference default, train.py:340-342); other configurations use the autograd
+    path.  Gradient parity with the autograd path is tested."""
+
+    def __init__(self, model: "HSGPath", n_graphs_global=None):
+        if model.hdsg:
+            raise NotImplementedError("FusedTrainStep covers HSG; HDSG goes through fused_loss(...).backward()")
+        if model._embed.weight.requires_grad:
+            raise NotImplementedError("FusedTrainStep assumes the frozen word embedding of the reference default")
+        self.model, self.n_graphs_global = model, n_graphs_global
+
+    def __call__(self, g: HeteroBatch, sent_feature: torch.Tensor):
+        from .functional import SentenceLossFn, UpdateLoopFn
+        m = self.model
+        loop = m.loop
+        prev = loop.fuse_grad_accumulation
+        loop.fuse_grad_accumulation = True
+        try:
+            cfg, tensors = loop.loop_call(g)                       # needs grad mode on to pick up the .grad targets
+        finally:
+            loop.fuse_grad_accumulation = prev
+        if m.wh.weight.grad is None or m.wh.bias.grad is None:
+            raise RuntimeError("FusedTrainStep needs .grad buffers on every parameter (dist.FlatGradArena)")
+        n = self.n_graphs_global if self.n_graphs_global is not None else g.n_graphs
+        with torch.no_grad():
+            word_feature = F.embedding(g.word_wid, m._embed.weight)
+            c1 = _Ctx([False, False, False, True] + [False] * len(tensors))
+            _, super_state = UpdateLoopFn.forward(c1, g, cfg, word_feature, sent_feature, *tensors)
+            c2 = _Ctx([False] * 7)
+            loss, logits = SentenceLossFn.forward(c2, g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
+                                                  m.wh.weight, m.wh.bias, g.labels)
+            d_state = SentenceLossFn.backward(c2, None, None)[3]
+            d_sent_feature = UpdateLoopFn.backward(c1, None, d_state)[3]
+        return loss, logits, d_sent_feature
 
 
 def graph_loss(g: HeteroBatch, logits: torch.Tensor, labels: torch.Tensor, n_graphs_global=None):

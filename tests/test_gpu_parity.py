@@ -619,3 +619,27 @@ def test_edge_bwd_row_mappings_agree():
         lib.hsg_set_edge_rowpar(-1)
     assert torch.isfinite(outs[1][0]).all()
     assert nerr(outs[1][0], outs[0][0]) <= 2e-6 and nerr(outs[1][1], outs[0][1]) <= 2e-6
+
+
+def test_fused_train_step_equals_autograd_path():
+    """path_model.FusedTrainStep (forward + backward driven without the autograd engine) against
+    fused_loss(...).backward(): same loss, same d_sent_feature, same gradients in the flat arena."""
+    from hetersumgraph_b200.dist import FlatGradArena
+    from hetersumgraph_b200.path_model import FusedTrainStep, HSGPath, fused_loss
+    exs = syn.make_examples(6, "tiny", seed=51)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    torch.manual_seed(9)
+    model = HSGPath(n_iter=1).cuda()
+    arena = FlatGradArena(model.parameters())
+    sf = torch.randn(batch.labels.shape[0], 64, device="cuda")
+    model.loop.fuse_grad_accumulation = True
+    s1 = sf.clone().requires_grad_(True)
+    loss1, logits1 = fused_loss(model, batch, s1, 6, fuse_grad_accumulation=True)
+    loss1.backward()
+    g1 = arena.flat.clone()
+    arena.flat.zero_()
+    loss2, logits2, d_sf = FusedTrainStep(model, 6)(batch, sf)
+    assert torch.equal(loss1.detach(), loss2) and torch.equal(logits1, logits2)
+    assert torch.equal(s1.grad, d_sf)
+    assert torch.equal(g1, arena.flat)
+    assert float(g1.abs().max()) > 0
