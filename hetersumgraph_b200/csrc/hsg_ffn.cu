@@ -166,23 +166,24 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
   }
 }
 
-// dgamma / dbeta = column sums of the per-block partials; 32 columns x 8 row groups per CTA, fixed order
-__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
-                                                                   float* __restrict__ dgamma,
-                                                                   float* __restrict__ dbeta, int accumulate) {
+// dgamma / dbeta = column sums of the per-block partials; 32 columns x 32 row groups per CTA, fixed order
+// (row group r sums blocks r, r+32, ... ; the 32 group sums are then added in order)
+__global__ void __launch_bounds__(1024) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
+                                                                    float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, int accumulate) {
   pdl_prologue();
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (i < 2 * D)
-    for (int b = ty; b < nblocks; b += 8) s += part[(size_t)b * 2 * D + i];
+    for (int b = ty; b < nblocks; b += 32) s += part[(size_t)b * 2 * D + i];
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && i < 2 * D) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += red[r][tx];
+    for (int r = 0; r < 32; ++r) t += red[r][tx];
     float* o = i < D ? dgamma + i : dbeta + (i - D);
     *o = accumulate ? *o + t : t;
   }
@@ -239,7 +240,7 @@ int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float*
     if (rc) return rc;
   }
   LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * D, 32)), dim3(256), 0, s, grid, D, part, dgamma, dbeta, accumulate);
+  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * D, 32)), dim3(1024), 0, s, grid, D, part, dgamma, dbeta, accumulate);
   return check_launch();
 }
 

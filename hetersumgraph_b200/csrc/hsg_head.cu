@@ -10,7 +10,7 @@
 
 namespace hsg {
 
-constexpr int HEAD_ROWS_PER_BLOCK = 32;
+constexpr int HEAD_ROWS_PER_BLOCK = 8;
 
 // warp per sentence: logits, per-sentence CE, d loss / d logits (already scaled by 1/n_graphs)
 __global__ void __launch_bounds__(256)
