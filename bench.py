@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cnndm", choices=list(WORKLOADS))
     ap.add_argument("--graphs-per-gpu", type=int, default=32)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE.json configs[4]): total graphs per step, split evenly over the GPUs")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-graph edge-kernel roofline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -66,6 +68,9 @@ def peaks():
 def make_workload(args, rank):
     from hetersumgraph_b200 import synthetic as syn
     shape, hdsg, n_iter, seed, cfg_idx = WORKLOADS[args.workload]
+    if args.global_batch > 0:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.graphs_per_gpu = max(1, args.global_batch // world)
     exs = syn.make_examples(args.graphs_per_gpu, shape, seed=seed + 1000 * rank, hdsg=hdsg)
     tb = syn.pack_token_batch(exs, hdsg=hdsg)
     return exs, tb, hdsg, n_iter, cfg_idx
@@ -444,7 +449,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": n_graphs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.global_batch > 0 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": n_graphs_global, "n_iter": n_iter,
                    "dropout": 0.0, "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "build": "device-side (K0), double-buffered: batch i+1 is built on a side stream while batch i computes; "

@@ -7,8 +7,8 @@ sm_100a CUDA kernels behind the C ABI of include/hsg_b200.h.  No DGL, no Triton,
 from . import _lib, synthetic  # noqa: F401
 from ._lib import get_gemm_mode, set_gemm_mode  # noqa: F401
 from .graph import BuildPipeline, DeviceTokenBatch, HeteroBatch, csc_pair_from_edges  # noqa: F401
-from .modules import (MultiHeadLayer, PositionwiseFeedForward, SWGATLayer, WSGATLayer, WSWGAT,  # noqa: F401
+from .modules import (MultiHeadLayer, MultiHeadSGATLayer, PositionwiseFeedForward, SWGATLayer, WSGATLayer, WSWGAT,  # noqa: F401
                       WSWGATUpdateLoop)
 
-__all__ = ["BuildPipeline", "DeviceTokenBatch", "HeteroBatch", "csc_pair_from_edges", "MultiHeadLayer", "PositionwiseFeedForward", "SWGATLayer",
+__all__ = ["BuildPipeline", "DeviceTokenBatch", "HeteroBatch", "csc_pair_from_edges", "MultiHeadLayer", "MultiHeadSGATLayer", "PositionwiseFeedForward", "SWGATLayer",
            "WSGATLayer", "WSWGAT", "WSWGATUpdateLoop", "synthetic"]

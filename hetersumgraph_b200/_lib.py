@@ -91,6 +91,11 @@ class LoopBwdArgsC(C.Structure):
                 ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class S2SGraphC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_graphs", "n_super", "H", "d", "mult", "reserved")] + \
+               [(n, C.c_void_p) for n in ("super_ptr", "deg_indptr", "extra", "xgrp", "xmember")]
+
+
 class HeadArgsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_sent", "n_super", "hidden", "two_part", "n_graphs", "reserved")] + \
                [(n, C.c_void_p) for n in ("state", "sent_row", "doc_row", "graph_sent_ptr", "wh_w", "wh_b", "labels")] + \
@@ -144,6 +149,9 @@ _PROTOS = {
     "hsg_adam_workspace_bytes": (_Z, []),
     "hsg_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P, _Z,
                                 _P]),
+    "hsg_s2s_fwd": (C.c_int, [C.POINTER(S2SGraphC), _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_s2s_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
+    "hsg_s2s_bwd": (C.c_int, [C.POINTER(S2SGraphC), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "hsg_dropout_mask": (C.c_int, [_Z, C.c_float, C.c_ulonglong, C.c_uint, _P, _P]),
     "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),

@@ -28,6 +28,7 @@ enum Slot {
   SLOT_HEAD,
   SLOT_ADAM,
   SLOT_DROPOUT,
+  SLOT_S2S,
   SLOT_COUNT
 };
 

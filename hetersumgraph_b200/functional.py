@@ -173,6 +173,47 @@ class MultiHeadFn(torch.autograd.Function):
         return None, None, None, None, dh, dW, dWf, dbf, da, dT
 
 
+class S2SFn(torch.autograd.Function):
+    """MultiHeadSGATLayer.forward(g, h) (GATStackLayer.py:36-44) -> cat of the heads' sh, or, with `origin`,
+    elu(.) + origin (GAT.py:56-57 for layerType "S2S")."""
+
+    @staticmethod
+    def forward(ctx, batch, H, d, h, origin, W, a):
+        _lib.require_device()
+        lib = _lib.load()
+        h, W, a = _f32c(h), _f32c(W), _f32c(a)
+        origin = _f32c(origin) if origin is not None else None
+        n, F = batch.n_super, H * d
+        if h.shape[0] != n:
+            raise ValueError("S2S: input has %d rows, graph has %d supernodes" % (h.shape[0], n))
+        xgrp, xmember, mult = batch.s2s_groups()
+        gc = _lib.S2SGraphC(batch.n_graphs, n, H, d, mult, 0, _p(batch.super_ptr), _p(batch.super_indptr),
+                            _p(batch.super_extra), _p(xgrp), _p(xmember))
+        z = gemm_nt(h, W)
+        S = torch.empty(n, F, dtype=torch.float32, device=h.device)
+        sh = torch.empty_like(S)
+        x = torch.empty_like(S) if origin is not None else None
+        _lib.check(lib.hsg_s2s_fwd(C.byref(gc), _p(z), _p(a), _p(origin), _p(S), _p(sh), _p(x), _st()))
+        ctx.gc, ctx.keep, ctx.has_origin, ctx.dims = gc, (batch, xgrp, xmember), origin is not None, (H, d)
+        ctx.save_for_backward(h, W, a, z, S)
+        return x if origin is not None else sh
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        h, W, a, z, S = ctx.saved_tensors
+        H, d = ctx.dims
+        dout = _f32c(dout)
+        dS, dz, da = torch.empty_like(S), torch.empty_like(z), torch.empty_like(a)
+        ws = _Workspace.get(lib.hsg_s2s_bwd_workspace_bytes(ctx.gc.n_graphs, H, d), z.device, "s2s")
+        _lib.check(lib.hsg_s2s_bwd(C.byref(ctx.gc), _p(z), _p(a), _p(S), _p(dout) if ctx.has_origin else None,
+                                   None if ctx.has_origin else _p(dout), _p(dS), _p(dz), _p(da), 0, ws.data_ptr(),
+                                   ws.numel(), _st()))
+        dh = gemm_nn(dz, W)
+        dW, _ = gemm_tn(dz, h)
+        return None, None, None, dh, (dout if ctx.has_origin else None), dW, da
+
+
 # --------------------------------------------------------------------------------------------
 # position-wise FFN
 # --------------------------------------------------------------------------------------------

@@ -52,8 +52,12 @@ class DeviceTokenBatch:
             per = np.diff(tb.graph_sent_ptr)
             sent_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int64), per)
             sent_local = (np.arange(int(per.sum()), dtype=np.int32) - np.repeat(tb.graph_sent_ptr[:-1], per)).astype(np.int32)
+            per_d = np.diff(tb.graph_doc_ptr)
+            doc_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int64), per_d)
+            doc_local = (np.arange(int(per_d.sum()), dtype=np.int32) - np.repeat(tb.graph_doc_ptr[:-1], per_d)).astype(np.int32)
             arrays.update(graph_doc_ptr=tb.graph_doc_ptr, sent_doc=tb.sent_doc, doc_tok_ptr=tb.doc_tok_ptr,
-                          doc_tokens=tb.doc_tokens, doc_bin=tb.doc_bin, sent_graph=sent_graph, sent_local=sent_local)
+                          doc_tokens=tb.doc_tokens, doc_bin=tb.doc_bin, sent_graph=sent_graph, sent_local=sent_local,
+                          doc_graph=doc_graph, doc_local=doc_local)
         layout, off = {}, 0
         for name, a in arrays.items():
             a = np.ascontiguousarray(a)
@@ -101,11 +105,13 @@ class DeviceTokenBatch:
         if vocab_size is None:
             vocab_size = meta["vocab"]
         d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = d.sent_graph = d.sent_local = None
+        d.doc_graph = d.doc_local = None
         d.n_sent = meta["S"]
         if tb.hdsg:
             d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = view("graph_doc_ptr"), view("sent_doc"), view("doc_tok_ptr")
             d.doc_tokens, d.doc_bin = view("doc_tokens"), view("doc_bin")
             d.sent_graph, d.sent_local = view("sent_graph"), view("sent_local")
+            d.doc_graph, d.doc_local = view("doc_graph"), view("doc_local")
         d.c_struct = _lib.TokenBatchC(tb.n_graphs, meta["S"], meta["L"], int(tb.hdsg), int(vocab_size), meta["n_doc"],
                                       meta["n_doc_tok"], meta["max_sent"],
                                       _ptr(d.tokens), _ptr(d.sent_bin), _ptr(d.graph_sent_ptr), _ptr(d.filter_bitmap),
@@ -147,6 +153,7 @@ class HeteroBatch:
     labels: Optional[torch.Tensor] = None                # [n sentence rows] int64
     sent_doc_row: Optional[torch.Tensor] = None          # HDSG: supernode row of each sentence's document
     sent_row: Optional[torch.Tensor] = None              # HDSG: supernode row of each sentence (None: identity)
+    doc_row: Optional[torch.Tensor] = None               # HDSG: supernode row of each document
     graph_sent_ptr: Optional[torch.Tensor] = None        # [B+1] sentence offsets per graph
     n_total_nodes: int = 0
     n_total_edges: int = 0
@@ -176,11 +183,37 @@ class HeteroBatch:
             return self._csc_word, self._csc_super
         raise NotImplementedError("GAT Layer has not been implemented!")   # module/GAT.py:41
 
+    def s2s_groups(self):
+        """(xgrp, xmember, mult) int32 maps of the implicit extra in-edges used by the S2S layer type
+        (csrc/hsg_s2s.cu): HSG - every sentence belongs to and reads its graph's group, each ordered pair twice
+        (dataloader.py:262-263); HDSG - sentences belong to their document's group, documents read it (:385)."""
+        cached = self.__dict__.get("_s2s_groups")
+        if cached is not None:
+            return cached
+        if self.sent_doc_row is None:                       # HSG: group id = first supernode row of the graph
+            grp = self.super_ptr[:-1][self.super_graph.long()].int().contiguous()
+            out = (grp, grp, 2)
+        else:
+            n = self.n_super
+            xgrp = torch.full((n,), -1, dtype=torch.int32, device=self.device)
+            xmember = torch.full((n,), -1, dtype=torch.int32, device=self.device)
+            drows = self.doc_rows()
+            xgrp[drows] = drows.int()
+            xmember[self.sentence_rows()] = self.sent_doc_row.int()
+            out = (xgrp, xmember, 1)
+        self.__dict__["_s2s_groups"] = out
+        return out
+
     def sentence_rows(self) -> torch.Tensor:
-        """rows of `s` that are sentence nodes (dtype == 1), ascending (HiGraph.py:191)."""
+        """rows of `s` that are sentence nodes (dtype == 1), ascending (HiGraph.py:191).  Taken from the builder's
+        maps when present (no host synchronisation), else derived from super_type."""
+        if self.sent_row is not None:
+            return self.sent_row.long()
         return torch.nonzero(self.super_type == 1).reshape(-1)
 
     def doc_rows(self) -> torch.Tensor:
+        if self.doc_row is not None:
+            return self.doc_row
         return torch.nonzero(self.super_type == 2).reshape(-1)
 
     # ---- construction -----------------------------------------------------------
@@ -284,6 +317,9 @@ class HeteroBatch:
             n_per = (dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1])[dtb.sent_graph]
             hb.sent_row = (base + dtb.sent_local[:dtb.n_sent]).int()
             hb.sent_doc_row = (base + n_per + dtb.sent_doc[:dtb.n_sent]).long()
+            if dtb.doc_graph is not None:                     # supernode row of every document, in document order
+                n_per_g = dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1]
+                hb.doc_row = (offs[1][:B][dtb.doc_graph] + n_per_g[dtb.doc_graph] + dtb.doc_local).long()
         return hb
 
     @staticmethod
@@ -396,7 +432,7 @@ class BuildPipeline:
         blob = getattr(hb._keepalive[0], "_blob", None)
         if blob is not None:
             bases.append(blob)
-        for extra in (hb.sent_row, hb.sent_doc_row):
+        for extra in (hb.sent_row, hb.sent_doc_row, hb.doc_row):
             if extra is not None:
                 bases.append(extra)
         for t in bases:

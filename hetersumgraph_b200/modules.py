@@ -17,7 +17,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .functional import AttnPrepFn, FFNFn, MultiHeadFn, UpdateLoopFn, WSWGATCoreFn
+from .functional import AttnPrepFn, FFNFn, MultiHeadFn, S2SFn, UpdateLoopFn, WSWGATCoreFn
 
 
 class WSGATLayer:
@@ -184,6 +184,48 @@ class MultiHeadLayer(nn.Module):
                                  self.feat_fc_bias, self.attn_fc_weight, g.tfidfembed_weight)
 
 
+class MultiHeadSGATLayer(nn.Module):
+    """num_heads sentence->sentence heads (reference: module/GATStackLayer.py:27-44 over SGATLayer,
+    module/GATLayer.py:49-78).  The reference's models never instantiate it (HiGraph.py:57-76)."""
+
+    def __init__(self, in_dim, out_dim, num_heads, attn_drop_out, merge='cat'):
+        super().__init__()
+        if merge != 'cat':
+            raise NotImplementedError("merge != 'cat' is a scalar-mean bug in the reference (GATStackLayer.py:44)")
+        self.in_dim, self.out_dim, self.num_heads, self.merge = in_dim, out_dim, num_heads, merge
+        self.fc_weight = nn.Parameter(torch.empty(out_dim * num_heads, in_dim))
+        self.attn_fc_weight = nn.Parameter(torch.empty(num_heads, 2 * out_dim))
+        self.dropout = nn.Dropout(attn_drop_out)
+        for w, fan_in in ((self.fc_weight, in_dim), (self.attn_fc_weight, 2 * out_dim)):
+            nn.init.uniform_(w, -1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        d = self.out_dim
+        for k in range(self.num_heads):
+            for name, t in (("fc.weight", self.fc_weight[k * d:(k + 1) * d]),
+                            ("attn_fc.weight", self.attn_fc_weight[k:k + 1])):
+                destination["%sheads.%d.%s" % (prefix, k, name)] = t if keep_vars else t.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        d = self.out_dim
+        with torch.no_grad():
+            for k in range(self.num_heads):
+                for name, dst in (("fc.weight", self.fc_weight[k * d:(k + 1) * d]),
+                                  ("attn_fc.weight", self.attn_fc_weight[k:k + 1])):
+                    key = "%sheads.%d.%s" % (prefix, k, name)
+                    if key not in state_dict:
+                        missing_keys.append(key)
+                    elif state_dict[key].shape != dst.shape:
+                        error_msgs.append("size mismatch for %s" % key)
+                    else:
+                        dst.copy_(state_dict[key])
+
+    def forward(self, g, h, origin=None):
+        _check_dropout(self, self.dropout.p, "attention-input")
+        return S2SFn.apply(g, self.num_heads, self.out_dim, h, origin, self.fc_weight, self.attn_fc_weight)
+
+
 class WSWGAT(nn.Module):
     """reference: module/GAT.py:30-59."""
 
@@ -197,8 +239,10 @@ class WSWGAT(nn.Module):
         elif layerType == "S2W":
             self.layer = MultiHeadLayer(in_dim, int(out_dim / num_heads), num_heads, attn_drop_out, feat_embed_size,
                                         layer=SWGATLayer)
+        elif layerType == "S2S":
+            # never instantiated by HSumGraph / HSumDocGraph (HiGraph.py:57-76); built for completeness
+            self.layer = MultiHeadSGATLayer(in_dim, int(out_dim / num_heads), num_heads, attn_drop_out)
         else:
-            # "S2S" (MultiHeadSGATLayer) is never instantiated by HSumGraph / HSumDocGraph (HiGraph.py:57-76)
             raise NotImplementedError("GAT Layer has not been implemented!")
         self.ffn = PositionwiseFeedForward(out_dim, ffn_inner_hidden_size, ffn_drop_out)
 
@@ -212,6 +256,10 @@ class WSWGAT(nn.Module):
                                 lay.attn_fc_weight, g.tfidfembed_weight)
 
     def forward(self, g, w, s, prepared=None):
+        if self.layerType == "S2S":
+            assert torch.equal(w, s)                                           # GAT.py:51
+            _check_dropout(self.ffn, self.ffn.dropout.p, "FFN")
+            return self.ffn(self.layer(g, s, origin=w))
         if self.layerType == "W2S":
             origin, neighbor = s, w
         else:

@@ -389,6 +389,30 @@ size_t hsg_adam_workspace_bytes(void);
 int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
                   float beta2, float eps, int step, float max_grad_norm, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * S2S layer type: SGATLayer / MultiHeadSGATLayer (module/GATLayer.py:49-78, module/GATStackLayer.py:27-44), the
+ * "S2S" branch of WSWGAT (module/GAT.py:38-39,50-52).  Never instantiated by the reference's models; built for
+ * completeness.  z = fc(h) (hsg_gemm_nt by the caller, head-major columns);
+ *     sh_v = mult * sum_{j: xmember[j] == xgrp[v]} z_j / (deg_v exp(leaky_relu(a[d:2d] . z_v)) + extra_v)
+ * (see csrc/hsg_s2s.cu for the derivation from DGL-0.4's pull over all in-edges); x = elu(sh) + origin (optional).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_graphs, n_super, H, d, mult, reserved;
+  const int32_t* super_ptr;   /* [n_graphs+1] supernode rows of every graph (contiguous) */
+  const int32_t* deg_indptr;  /* [n_super+1] indptr of the word->supernode CSC (deg_v = word in-degree) */
+  const int32_t* extra;       /* [n_super] number of non-word in-edges x_v */
+  const int32_t* xgrp;        /* [n_super] row id of the group whose member sum v reads, -1: none */
+  const int32_t* xmember;     /* [n_super] row id of the group v contributes its z to, -1: none */
+} hsg_s2s_graph;
+/* S [n_super, H*d]: group sums (saved for backward) */
+int hsg_s2s_fwd(const hsg_s2s_graph* g, const float* z, const float* a /* [H, 2d] */, const float* origin /* or NULL */,
+                float* S, float* sh, float* x /* or NULL */, void* stream);
+size_t hsg_s2s_bwd_workspace_bytes(int n_graphs, int H, int d);
+/* dx (gradient of x) or dsh (gradient of sh) given; dS: scratch [n_super, H*d]; dz [n_super, H*d]; da [H, 2d] */
+int hsg_s2s_bwd(const hsg_s2s_graph* g, const float* z, const float* a, const float* S, const float* dx,
+                const float* dsh, float* dS, float* dz, float* da, int accumulate, void* ws, size_t ws_bytes,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

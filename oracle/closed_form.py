@@ -125,3 +125,55 @@ def update_loop_cf(csc, word_feature, super_feature, params, n_iter, masks=None,
         word_state = wswgat_cf(csc, word_state, sent_state, params, "sent2word.", "S2W", T, nxt(), flips, nxd())
         sent_state = wswgat_cf(csc, word_state, sent_state, params, "word2sent.", "W2S", T, nxt(), flips, nxd())
     return word_state, sent_state
+
+
+# ---------------------------------------------------------------------------------------------------------
+# S2S layer type (module/GAT.py:38-39,50-52; SGATLayer module/GATLayer.py:49-78) - never instantiated by the
+# reference's models, restated for completeness.
+#   z = fc(h) on the supernodes only; attention logits are computed on the dtype == 0 edges (:71 - the
+#   word<->supernode edges, NOT the sent<->sent ones) from [z_src, z_dst]: for a word->supernode edge z_src is DGL's
+#   zero fill, so e_v = leaky_relu(a[d:2d] . z_v) for every word in-edge of v; pull(snode) reduces over ALL in-edges:
+#   deg_v word edges (logit e_v, message 0) and the extra edges (sent->sent twice per ordered pair in HSG,
+#   dataloader.py:262-263; sent->doc in HDSG, :385) with the never-written logit 0 and message z_src.  Hence
+#       sh_v = sum_{extra in-edges j->v} z_j / (deg_v exp(e_v) + x_v)        (0 when v has no extra in-edge).
+# ---------------------------------------------------------------------------------------------------------
+def extra_edges_of(g, csc):
+    """(src supernode row, dst supernode row) of every in-edge of a supernode that is not a word->supernode edge,
+    with multiplicity, from the literal graph arrays."""
+    import numpy as np
+    row = np.full(g.n_nodes, -1, np.int64)
+    row[csc["snode_id"]] = np.arange(len(csc["snode_id"]))
+    m = (g.unit[g.dst] == 1) & (g.unit[g.src] == 1)
+    return row[g.src[m]], row[g.dst[m]]
+
+
+def s2s_multi_head_cf(h, deg, xsrc, xdst, W, a):
+    """h [Ns, in]; deg [Ns] word in-degree; (xsrc, xdst) extra edges; W [H*d, in]; a [H, 2d]."""
+    H = a.shape[0]
+    d = a.shape[1] // 2
+    n = h.shape[0]
+    z = (h @ W.t()).reshape(n, H, d)
+    t = (z * a[:, d:].unsqueeze(0)).sum(-1)                                  # [Ns, H]
+    e = F.leaky_relu(t, LEAKY_SLOPE)
+    xsrc = torch.as_tensor(xsrc, dtype=torch.int64)
+    xdst = torch.as_tensor(xdst, dtype=torch.int64)
+    xcnt = torch.zeros(n, dtype=h.dtype).index_add(0, xdst, torch.ones(len(xdst), dtype=h.dtype))
+    A = torch.zeros(n, H, d, dtype=h.dtype).index_add(0, xdst, z[xsrc])
+    den = torch.as_tensor(deg, dtype=h.dtype).reshape(-1, 1) * torch.exp(e) + xcnt.reshape(-1, 1)
+    den = torch.where(xcnt.reshape(-1, 1) > 0, den, torch.ones_like(den))
+    return (A / den.unsqueeze(-1)).reshape(n, H * d)
+
+
+def s2s_cf(g, csc, s, params, prefix, mask=None, flips=None):
+    """WSWGAT(..., "S2S").forward(g, s, s) (GAT.py:45-59)."""
+    import numpy as np
+    H = n_heads_of(params, prefix + "layer.")
+    W = torch.cat([params[prefix + "layer.heads.%d.fc.weight" % k] for k in range(H)], 0)
+    a = torch.cat([params[prefix + "layer.heads.%d.attn_fc.weight" % k] for k in range(H)], 0)
+    xsrc, xdst = extra_edges_of(g, csc)
+    deg = np.diff(csc["super_indptr"])
+    sh = s2s_multi_head_cf(s, deg, xsrc, xdst, W, a)
+    h = F.elu(sh) + s
+    return ffn_cf(h, params[prefix + "ffn.w_1.weight"], params[prefix + "ffn.w_1.bias"],
+                  params[prefix + "ffn.w_2.weight"], params[prefix + "ffn.w_2.bias"],
+                  params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"], mask, flips)

@@ -643,3 +643,34 @@ def test_fused_train_step_equals_autograd_path():
     assert torch.equal(s1.grad, d_sf)
     assert torch.equal(g1, arena.flat)
     assert float(g1.abs().max()) > 0
+
+
+@pytest.mark.parametrize("name,hdsg", [("s2s_hsg.npz", False), ("s2s_hdsg.npz", True)])
+def test_s2s_layer_matches_reference_golden(name, hdsg):
+    """WSWGAT(..., "S2S") (GAT.py:38-39,50-52) on the device against the reference's own classes (golden)."""
+    z = dict(np.load(os.path.join(GOLD, name)))
+    hid, nh, ffn_h, _ = [int(v) for v in z["dims"]]
+    params = {k[2:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("p:")}
+    m = hb.WSWGAT(hid, hid, nh, 0.0, ffn_h, 0.0, 50, "S2S").cuda()
+    m.load_state_dict(params, strict=True)
+    exs = fx.examples_from_arrays(z, "ex")
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    assert tb.order == z["order"].tolist()
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    s = torch.from_numpy(z["in_s"]).cuda().requires_grad_(True)
+    out = m(batch, s, s)
+    assert nerr(out, z["out_s"]) <= TOL, nerr(out, z["out_s"])
+    (out * torch.from_numpy(z["cs"]).cuda()).sum().backward()
+    assert nerr(s.grad, z["grad_in_s"]) <= TOL
+    d = m.layer.out_dim
+    for k in range(nh):
+        assert nerr(m.layer.fc_weight.grad[k * d:(k + 1) * d], z["gp:layer.heads.%d.fc.weight" % k]) <= TOL
+        ga = m.layer.attn_fc_weight.grad[k:k + 1]
+        assert nerr(ga, z["gp:layer.heads.%d.attn_fc.weight" % k]) <= TOL
+        assert float(ga[:, :d].abs().max()) == 0.0                     # a_src multiplies the zero-filled word z
+    for key in ("ffn.w_1.weight", "ffn.w_1.bias", "ffn.w_2.weight", "ffn.w_2.bias", "ffn.layer_norm.weight",
+                "ffn.layer_norm.bias"):
+        obj = m
+        for part in key.split("."):
+            obj = getattr(obj, part)
+        assert nerr(obj.grad, z["gp:" + key]) <= TOL, key

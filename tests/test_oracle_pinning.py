@@ -266,3 +266,34 @@ def test_oracle_vs_live_reference():
         params["_TFembed.weight"] = T.weight
         ow, os_ = wr.update_loop(ga, w, s, params, 2)
     assert nerr(ow, rw) <= 1e-6 and nerr(os_, rs) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["s2s_hsg.npz", "s2s_hdsg.npz"])
+def test_s2s_closed_form_matches_reference_golden(name):
+    """S2S layer type (SGATLayer, GATLayer.py:49-78; never instantiated by the reference's models): the closed form
+    of oracle/closed_form.py against the reference's own classes run on the shim (tests/golden/make_golden_s2s.py)."""
+    import os
+    from oracle import closed_form as cf
+    from oracle import fixtures as fx
+    from oracle import graph_builder_ref as gb
+    z = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+    g = fx.graph_from_arrays(z, "g_")
+    csc = gb.derive_csc(g)
+    params = {"x." + k[2:]: torch.from_numpy(v).clone().requires_grad_(True) for k, v in z.items() if k.startswith("p:")}
+    s = torch.from_numpy(z["in_s"]).clone().requires_grad_(True)
+    out = cf.s2s_cf(g, csc, s, params, "x.")
+    (out * torch.from_numpy(z["cs"])).sum().backward()
+
+    def err(a, b):
+        return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    assert err(out.detach(), torch.from_numpy(z["out_s"])) <= 1e-6
+    assert err(s.grad, torch.from_numpy(z["grad_in_s"])) <= 1e-6
+    for k, v in z.items():
+        if k.startswith("gp:"):
+            ref = torch.from_numpy(v)
+            got = params["x." + k[3:]].grad
+            got = torch.zeros_like(ref) if got is None else got
+            if float(ref.abs().max()) == 0.0:
+                assert float(got.abs().max()) == 0.0, k
+            else:
+                assert err(got, ref) <= 1e-5, k
