@@ -96,6 +96,11 @@ class S2SGraphC(C.Structure):
                [(n, C.c_void_p) for n in ("super_ptr", "deg_indptr", "extra", "xgrp", "xmember")]
 
 
+class DocMapC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_sent", "n_doc", "hidden", "reserved")] + \
+               [(n, C.c_void_p) for n in ("sent_row", "doc_row", "sent_doc", "doc_graph", "graph_sent_ptr")]
+
+
 class HeadArgsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_sent", "n_super", "hidden", "two_part", "n_graphs", "reserved")] + \
                [(n, C.c_void_p) for n in ("state", "sent_row", "doc_row", "graph_sent_ptr", "wh_w", "wh_b", "labels")] + \
@@ -145,6 +150,9 @@ _PROTOS = {
     "hsg_head_workspace_bytes": (_Z, [_I, _I]),
     "hsg_head_fwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _Z, _P]),
     "hsg_head_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "hsg_doc_mean": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P]),
+    "hsg_super_assemble": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P, _P]),
+    "hsg_doc_init_bwd": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P, _P, _P]),
     "hsg_topm": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "hsg_adam_workspace_bytes": (_Z, []),
     "hsg_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P, _Z,

@@ -292,3 +292,120 @@ int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
 }
 
 }  // extern "C"
+
+// ---- HDSG document-node init ------------------------------------------------------------
+// HSumDocGraph.forward / set_dnfeature (HiGraph.py:196-203, 231-244): a document node starts from the MEAN of its
+// sentences' init features, projected by dn_feature_proj; the supernode init tensor interleaves sentence and
+// document rows per graph.  The reference does this with a Python loop over graph.predecessors(dnode).
+namespace hsg {
+
+// one block per document, thread per column: doc_mean[j] = mean_{i in graph(j): sent_doc[i] == j} sent_feature[i]
+__global__ void __launch_bounds__(256)
+doc_mean_kernel(hsg_doc_map m, const float* __restrict__ sent_feature, float* __restrict__ doc_mean) {
+  pdl_prologue();
+  const int j = blockIdx.x, g = m.doc_graph[j];
+  const int i0 = m.graph_sent_ptr[g], i1 = m.graph_sent_ptr[g + 1];
+  for (int c = threadIdx.x; c < m.hidden; c += blockDim.x) {
+    float s = 0.f;
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i)                                   // sentence order: fixed summation order
+      if (m.sent_doc[i] == j) {
+        s += sent_feature[(size_t)i * m.hidden + c];
+        ++cnt;
+      }
+    doc_mean[(size_t)j * m.hidden + c] = cnt > 0 ? s / (float)cnt : 0.f;
+  }
+}
+
+// rows 0..n_sent-1: super[sent_row[i]] = sent_feature[i]; rows n_sent..: super[doc_row[j]] = doc_feature[j]
+__global__ void __launch_bounds__(256)
+super_assemble_kernel(hsg_doc_map m, const float* __restrict__ sent_feature, const float* __restrict__ doc_feature,
+                      float* __restrict__ super_feature) {
+  pdl_prologue();
+  const int r = blockIdx.x;
+  const float* src;
+  int dst;
+  if (r < m.n_sent) {
+    src = sent_feature + (size_t)r * m.hidden;
+    dst = m.sent_row[r];
+  } else {
+    src = doc_feature + (size_t)(r - m.n_sent) * m.hidden;
+    dst = m.doc_row[r - m.n_sent];
+  }
+  for (int c = threadIdx.x; c < m.hidden; c += blockDim.x) super_feature[(size_t)dst * m.hidden + c] = src[c];
+}
+
+// d_doc_feature[j] = d_super[doc_row[j]]
+__global__ void __launch_bounds__(256)
+doc_gather_kernel(hsg_doc_map m, const float* __restrict__ d_super, float* __restrict__ d_doc_feature) {
+  pdl_prologue();
+  const int j = blockIdx.x;
+  for (int c = threadIdx.x; c < m.hidden; c += blockDim.x)
+    d_doc_feature[(size_t)j * m.hidden + c] = d_super[(size_t)m.doc_row[j] * m.hidden + c];
+}
+
+// d_sent[i] = d_super[sent_row[i]] + d_doc_mean[doc(i)] / #sentences(doc(i))
+__global__ void __launch_bounds__(256)
+doc_init_bwd_kernel(hsg_doc_map m, const float* __restrict__ d_super, const float* __restrict__ d_doc_mean,
+                    float* __restrict__ d_sent) {
+  pdl_prologue();
+  __shared__ int cnt_s;
+  const int i = blockIdx.x, j = m.sent_doc[i];
+  if (threadIdx.x == 0) {
+    const int g = m.doc_graph[j];
+    int cnt = 0;
+    for (int t = m.graph_sent_ptr[g]; t < m.graph_sent_ptr[g + 1]; ++t) cnt += m.sent_doc[t] == j ? 1 : 0;
+    cnt_s = cnt;
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)cnt_s;
+  for (int c = threadIdx.x; c < m.hidden; c += blockDim.x)
+    d_sent[(size_t)i * m.hidden + c] =
+        d_super[(size_t)m.sent_row[i] * m.hidden + c] + d_doc_mean[(size_t)j * m.hidden + c] * inv;
+}
+
+static bool doc_map_ok(const hsg_doc_map* m) {
+  return m && m->n_sent >= 0 && m->n_doc >= 0 && m->hidden > 0 && m->sent_row && m->doc_row && m->sent_doc &&
+         m->doc_graph && m->graph_sent_ptr;
+}
+
+}  // namespace hsg
+
+extern "C" {
+
+int hsg_doc_mean(const hsg_doc_map* m, const float* sent_feature, float* doc_mean, void* stream) {
+  if (!doc_map_ok(m) || !sent_feature || !doc_mean) return HSG_ERR_ARG;
+  if (m->n_doc == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(SLOT_HEAD, s);
+  launch_k(doc_mean_kernel, dim3(m->n_doc), dim3(256), 0, s, *m, sent_feature, doc_mean);
+  return check_launch();
+}
+
+int hsg_super_assemble(const hsg_doc_map* m, const float* sent_feature, const float* doc_feature,
+                       float* super_feature, void* stream) {
+  if (!doc_map_ok(m) || !sent_feature || !doc_feature || !super_feature) return HSG_ERR_ARG;
+  if (m->n_sent + m->n_doc == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(SLOT_HEAD, s);
+  launch_k(super_assemble_kernel, dim3(m->n_sent + m->n_doc), dim3(256), 0, s, *m, sent_feature, doc_feature,
+           super_feature);
+  return check_launch();
+}
+
+int hsg_doc_init_bwd(const hsg_doc_map* m, const float* d_super, const float* d_doc_mean /* or NULL: gather phase */,
+                     float* d_doc_feature /* gather phase */, float* d_sent /* scatter phase */, void* stream) {
+  if (!doc_map_ok(m) || !d_super) return HSG_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(SLOT_HEAD, s);
+  if (d_doc_mean == nullptr) {
+    if (!d_doc_feature) return HSG_ERR_ARG;
+    if (m->n_doc > 0) launch_k(doc_gather_kernel, dim3(m->n_doc), dim3(256), 0, s, *m, d_super, d_doc_feature);
+  } else {
+    if (!d_sent) return HSG_ERR_ARG;
+    if (m->n_sent > 0) launch_k(doc_init_bwd_kernel, dim3(m->n_sent), dim3(256), 0, s, *m, d_super, d_doc_mean, d_sent);
+  }
+  return check_launch();
+}
+
+}  // extern "C"

@@ -617,6 +617,47 @@ class SentenceLossFn(torch.autograd.Function):
         return None, None, None, d_state, d_w, d_b, None
 
 
+class DocInitFn(torch.autograd.Function):
+    """supernode init features of an HDSG batch (HSumDocGraph.forward + set_dnfeature, HiGraph.py:196-203,231-244):
+    sentence rows = sent_feature, document rows = dn_feature_proj(mean of the document's sentence features)."""
+
+    @staticmethod
+    def forward(ctx, batch, sent_feature, W):
+        _lib.require_device()
+        lib = _lib.load()
+        sent_feature, W = _f32c(sent_feature), _f32c(W)
+        n_sent, hid = sent_feature.shape
+        if batch.doc_row is None or batch.sent_doc_gidx is None:
+            raise ValueError("DocInitFn needs an HDSG batch built by the device builder")
+        doc_row32, sent_row32 = batch.doc_row.int(), batch.sent_row
+        n_doc = doc_row32.shape[0]
+        dm = _lib.DocMapC(n_sent, n_doc, hid, 0, _p(sent_row32), _p(doc_row32), _p(batch.sent_doc_gidx),
+                          _p(batch.doc_graph), _p(batch.graph_sent_ptr))
+        dev = sent_feature.device
+        doc_mean = torch.empty(n_doc, hid, dtype=torch.float32, device=dev)
+        _lib.check(lib.hsg_doc_mean(C.byref(dm), _p(sent_feature), _p(doc_mean), _st()))
+        doc_feature = gemm_nt(doc_mean, W)
+        sup = torch.empty(batch.n_super, hid, dtype=torch.float32, device=dev)
+        _lib.check(lib.hsg_super_assemble(C.byref(dm), _p(sent_feature), _p(doc_feature), _p(sup), _st()))
+        ctx.dm, ctx.keep = dm, (batch, doc_row32, sent_row32)
+        ctx.save_for_backward(doc_mean, W)
+        return sup
+
+    @staticmethod
+    def backward(ctx, d_sup):
+        lib = _lib.load()
+        doc_mean, W = ctx.saved_tensors
+        d_sup = _f32c(d_sup)
+        dm = ctx.dm
+        d_doc_feature = torch.empty_like(doc_mean)
+        _lib.check(lib.hsg_doc_init_bwd(C.byref(dm), _p(d_sup), None, _p(d_doc_feature), None, _st()))
+        d_doc_mean = gemm_nn(d_doc_feature, W)
+        dW, _ = gemm_tn(d_doc_feature, doc_mean)
+        d_sent = torch.empty(dm.n_sent, dm.hidden, dtype=torch.float32, device=d_sup.device)
+        _lib.check(lib.hsg_doc_init_bwd(C.byref(dm), _p(d_sup), _p(d_doc_mean), None, _p(d_sent), _st()))
+        return None, d_sent, dW
+
+
 def topm(logits, graph_sent_ptr, m):
     """[n_graphs, m] int32: per graph the local indices of the m sentences with the largest class-1 logit, in
     descending order, -1 padded (Tester.py:128 torch.topk(p_sent[:, 1], min(m, N)))."""

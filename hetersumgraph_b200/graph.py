@@ -55,9 +55,11 @@ class DeviceTokenBatch:
             per_d = np.diff(tb.graph_doc_ptr)
             doc_graph = np.repeat(np.arange(tb.n_graphs, dtype=np.int64), per_d)
             doc_local = (np.arange(int(per_d.sum()), dtype=np.int32) - np.repeat(tb.graph_doc_ptr[:-1], per_d)).astype(np.int32)
+            sent_doc_g = (tb.graph_doc_ptr[:-1][sent_graph] + tb.sent_doc[:len(sent_graph)]).astype(np.int32)
             arrays.update(graph_doc_ptr=tb.graph_doc_ptr, sent_doc=tb.sent_doc, doc_tok_ptr=tb.doc_tok_ptr,
                           doc_tokens=tb.doc_tokens, doc_bin=tb.doc_bin, sent_graph=sent_graph, sent_local=sent_local,
-                          doc_graph=doc_graph, doc_local=doc_local)
+                          doc_graph=doc_graph, doc_local=doc_local, sent_doc_g=sent_doc_g,
+                          doc_graph32=doc_graph.astype(np.int32))
         layout, off = {}, 0
         for name, a in arrays.items():
             a = np.ascontiguousarray(a)
@@ -105,13 +107,14 @@ class DeviceTokenBatch:
         if vocab_size is None:
             vocab_size = meta["vocab"]
         d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = d.sent_graph = d.sent_local = None
-        d.doc_graph = d.doc_local = None
+        d.doc_graph = d.doc_local = d.sent_doc_g = d.doc_graph32 = None
         d.n_sent = meta["S"]
         if tb.hdsg:
             d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = view("graph_doc_ptr"), view("sent_doc"), view("doc_tok_ptr")
             d.doc_tokens, d.doc_bin = view("doc_tokens"), view("doc_bin")
             d.sent_graph, d.sent_local = view("sent_graph"), view("sent_local")
             d.doc_graph, d.doc_local = view("doc_graph"), view("doc_local")
+            d.sent_doc_g, d.doc_graph32 = view("sent_doc_g"), view("doc_graph32")
         d.c_struct = _lib.TokenBatchC(tb.n_graphs, meta["S"], meta["L"], int(tb.hdsg), int(vocab_size), meta["n_doc"],
                                       meta["n_doc_tok"], meta["max_sent"],
                                       _ptr(d.tokens), _ptr(d.sent_bin), _ptr(d.graph_sent_ptr), _ptr(d.filter_bitmap),
@@ -154,6 +157,8 @@ class HeteroBatch:
     sent_doc_row: Optional[torch.Tensor] = None          # HDSG: supernode row of each sentence's document
     sent_row: Optional[torch.Tensor] = None              # HDSG: supernode row of each sentence (None: identity)
     doc_row: Optional[torch.Tensor] = None               # HDSG: supernode row of each document
+    sent_doc_gidx: Optional[torch.Tensor] = None         # HDSG: global document index of each sentence (int32)
+    doc_graph: Optional[torch.Tensor] = None             # HDSG: graph index of each document (int32)
     graph_sent_ptr: Optional[torch.Tensor] = None        # [B+1] sentence offsets per graph
     n_total_nodes: int = 0
     n_total_edges: int = 0
@@ -320,6 +325,7 @@ class HeteroBatch:
             if dtb.doc_graph is not None:                     # supernode row of every document, in document order
                 n_per_g = dtb.graph_sent_ptr[1:] - dtb.graph_sent_ptr[:-1]
                 hb.doc_row = (offs[1][:B][dtb.doc_graph] + n_per_g[dtb.doc_graph] + dtb.doc_local).long()
+                hb.sent_doc_gidx, hb.doc_graph = dtb.sent_doc_g, dtb.doc_graph32
         return hb
 
     @staticmethod

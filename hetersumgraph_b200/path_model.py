@@ -43,17 +43,10 @@ class HSGPath(nn.Module):
         if not self.hdsg:
             super_feature = sent_feature
         else:
-            srows, drows = g.sentence_rows(), g.doc_rows()
-            d_of_s = g.sent_doc_row                                   # [n_sent] supernode row of each sentence's doc
-            # doc init = mean of its sentences' init features (set_dnfeature, HiGraph.py:231-244)
-            dmap = torch.full((g.n_super,), -1, dtype=torch.long, device=sent_feature.device)
-            dmap[drows] = torch.arange(drows.shape[0], device=sent_feature.device)
-            didx = dmap[d_of_s]
-            sums = torch.zeros(drows.shape[0], sent_feature.shape[1], device=sent_feature.device).index_add(0, didx, sent_feature)
-            cnt = torch.zeros(drows.shape[0], device=sent_feature.device).index_add(0, didx, torch.ones_like(didx, dtype=torch.float32))
-            doc_feature = self.dn_feature_proj(sums / cnt.unsqueeze(1))
-            super_feature = torch.zeros(g.n_super, sent_feature.shape[1], device=sent_feature.device)
-            super_feature = super_feature.index_copy(0, srows, sent_feature).index_copy(0, drows, doc_feature)
+            # doc init = mean of its sentences' init features (set_dnfeature, HiGraph.py:231-244), projected, and the
+            # sentence / document rows interleaved per graph: hsg_doc_mean + hsg_gemm_nt + hsg_super_assemble
+            from .functional import DocInitFn
+            super_feature = DocInitFn.apply(g, sent_feature, self.dn_feature_proj.weight)
         return self.loop(g, word_feature, super_feature)
 
     def forward(self, g: HeteroBatch, sent_feature: torch.Tensor):

@@ -413,6 +413,29 @@ int hsg_s2s_bwd(const hsg_s2s_graph* g, const float* z, const float* a, const fl
                 const float* dsh, float* dS, float* dz, float* da, int accumulate, void* ws, size_t ws_bytes,
                 void* stream);
 
+/* ------------------------------------------------------------------------
+ * HDSG document-node init: HSumDocGraph.forward / set_dnfeature (HiGraph.py:196-203, 231-244).
+ *   doc_mean[j]   = mean of the init features of document j's sentences          hsg_doc_mean
+ *   doc_feature   = dn_feature_proj(doc_mean)                                     hsg_gemm_nt (caller)
+ *   super_feature = sentence / document rows interleaved per graph               hsg_super_assemble
+ * backward: hsg_doc_init_bwd in two phases around the caller's projection-backward products.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_sent, n_doc, hidden, reserved;
+  const int32_t* sent_row;        /* [n_sent] supernode row of every sentence */
+  const int32_t* doc_row;         /* [n_doc]  supernode row of every document */
+  const int32_t* sent_doc;        /* [n_sent] GLOBAL document index of every sentence */
+  const int32_t* doc_graph;       /* [n_doc]  graph index of every document */
+  const int32_t* graph_sent_ptr;  /* [n_graphs+1] */
+} hsg_doc_map;
+int hsg_doc_mean(const hsg_doc_map* m, const float* sent_feature, float* doc_mean, void* stream);
+int hsg_super_assemble(const hsg_doc_map* m, const float* sent_feature, const float* doc_feature,
+                       float* super_feature, void* stream);
+/* phase 1 (d_doc_mean == NULL): d_doc_feature[j] = d_super[doc_row[j]];
+ * phase 2: d_sent[i] = d_super[sent_row[i]] + d_doc_mean[doc(i)] / #sentences(doc(i)) */
+int hsg_doc_init_bwd(const hsg_doc_map* m, const float* d_super, const float* d_doc_mean, float* d_doc_feature,
+                     float* d_sent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

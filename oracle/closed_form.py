@@ -177,3 +177,16 @@ def s2s_cf(g, csc, s, params, prefix, mask=None, flips=None):
     return ffn_cf(h, params[prefix + "ffn.w_1.weight"], params[prefix + "ffn.w_1.bias"],
                   params[prefix + "ffn.w_2.weight"], params[prefix + "ffn.w_2.bias"],
                   params[prefix + "ffn.layer_norm.weight"], params[prefix + "ffn.layer_norm.bias"], mask, flips)
+
+
+def doc_init_ref(sent_feature, sent_rows, doc_rows, doc_of_sent_row, W, n_super):
+    """HSumDocGraph.forward / set_dnfeature (HiGraph.py:196-203, 231-244): supernode init features =
+    sentence rows <- sent_feature, document rows <- dn_feature_proj(mean of the document's sentences)."""
+    dmap = torch.full((n_super,), -1, dtype=torch.long)
+    dmap[doc_rows] = torch.arange(len(doc_rows))
+    didx = dmap[doc_of_sent_row]
+    sums = torch.zeros(len(doc_rows), sent_feature.shape[1], dtype=sent_feature.dtype).index_add(0, didx, sent_feature)
+    cnt = torch.zeros(len(doc_rows), dtype=sent_feature.dtype).index_add(0, didx, torch.ones(len(didx), dtype=sent_feature.dtype))
+    doc_feature = (sums / cnt.unsqueeze(1)) @ W.t()
+    out = torch.zeros(n_super, sent_feature.shape[1], dtype=sent_feature.dtype)
+    return out.index_copy(0, sent_rows, sent_feature).index_copy(0, doc_rows, doc_feature)

@@ -674,3 +674,32 @@ def test_s2s_layer_matches_reference_golden(name, hdsg):
         for part in key.split("."):
             obj = getattr(obj, part)
         assert nerr(obj.grad, z["gp:" + key]) <= TOL, key
+
+
+def test_hdsg_doc_init_matches_reference_restatement():
+    """hsg_doc_mean / hsg_super_assemble / hsg_doc_init_bwd against set_dnfeature + dn_feature_proj
+    (HiGraph.py:196-203, 231-244) restated in oracle/closed_form.py:doc_init_ref."""
+    from hetersumgraph_b200.functional import DocInitFn
+    exs = syn.make_examples(5, "multinews", seed=71, hdsg=True)
+    tb = syn.pack_token_batch(exs, hdsg=True)
+    batch = hb.HeteroBatch.from_token_batch(tb)
+    bg, _ = oracle_batch(exs, True)
+    csc = gb.derive_csc(bg)
+    # known answers for the row maps from the literal graph
+    row = np.full(bg.n_nodes, -1, np.int64)
+    row[csc["snode_id"]] = np.arange(len(csc["snode_id"]))
+    assert np.array_equal(batch.sentence_rows().cpu().numpy(), row[csc["sent_id"]])
+    assert np.array_equal(batch.doc_rows().cpu().numpy(), row[csc["doc_id"]])
+    torch.manual_seed(0)
+    n_sent = batch.labels.shape[0]
+    sf = torch.randn(n_sent, 64)
+    W = torch.randn(64, 64) * 0.2
+    c = torch.randn(batch.n_super, 64)
+    sfg, Wg = sf.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    got = DocInitFn.apply(batch, sfg, Wg)
+    (got * c.cuda()).sum().backward()
+    sfc, Wc = sf.clone().requires_grad_(True), W.clone().requires_grad_(True)
+    want = cf.doc_init_ref(sfc, batch.sentence_rows().cpu(), batch.doc_rows().cpu(), batch.sent_doc_row.cpu(), Wc,
+                           batch.n_super)
+    (want * c).sum().backward()
+    assert nerr(got, want) <= TOL and nerr(sfg.grad, sfc.grad) <= TOL and nerr(Wg.grad, Wc.grad) <= TOL
