@@ -198,8 +198,18 @@ def map_sent2doc(doc_len: List[int], n_sent: int) -> Dict[int, int]:
     return out
 
 
+def bitmap_of(ids, vocab_size: int) -> np.ndarray:
+    """bit set = filtered id (the builder's filter_bitmap input)."""
+    ids = np.asarray(sorted(set(int(i) for i in ids if 0 <= int(i) < vocab_size)), np.int64)
+    bm = np.zeros((vocab_size + 31) // 32, np.uint32)
+    np.bitwise_or.at(bm, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+    return bm
+
+
 def pack_token_batch(examples: List[DocExample], hdsg: bool = False, vocab_size: int = VOCAB_SIZE,
-                     order: Optional[List[int]] = None, doc_max_timesteps: int = DOC_MAX_TIMESTEPS) -> TokenBatch:
+                     order: Optional[List[int]] = None, doc_max_timesteps: int = DOC_MAX_TIMESTEPS,
+                     filter_ids_list=None) -> TokenBatch:
+    """filter_ids_list: the dataset's filter ids (dataloader.py:167-182); None = the synthetic generator's set."""
     if order is None:
         order = stable_desc_order([min(e.n_sent, doc_max_timesteps) for e in examples]).tolist()
     toks, bins, labels, sent_doc = [], [], [], []
@@ -229,7 +239,7 @@ def pack_token_batch(examples: List[DocExample], hdsg: bool = False, vocab_size:
         tokens=np.concatenate(toks).astype(np.int32) if toks else np.zeros((0, L), np.int32),
         sent_bin=np.concatenate(bins).astype(np.int8) if bins else np.zeros((0, L), np.int8),
         graph_sent_ptr=np.asarray(gsp, np.int32),
-        filter_bitmap=filter_bitmap(vocab_size),
+        filter_bitmap=filter_bitmap(vocab_size) if filter_ids_list is None else bitmap_of(filter_ids_list, vocab_size),
         labels=np.concatenate(labels).astype(np.int64) if labels else np.zeros(0, np.int64))
     if hdsg:
         tb.graph_doc_ptr = np.asarray(gdp, np.int32)
