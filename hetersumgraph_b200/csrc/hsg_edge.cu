@@ -881,9 +881,10 @@ int hsg_edge_perm(int H, int d, int col) {
 
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q, const float* origin,
                  float* sh, float* x, float* stat, void* stream) {
-  if (!csc || !zp || !q || !sh || !stat || csc->n_dst < 0) return HSG_ERR_ARG;
+  if (!csc || csc->n_dst < 0) return HSG_ERR_ARG;
+  if (csc->n_dst == 0) return HSG_OK;                 // empty destination set (row pointers may be NULL)
+  if (!zp || !q || !sh || !stat) return HSG_ERR_ARG;
   if (x != nullptr && origin == nullptr) return HSG_ERR_ARG;
-  if (csc->n_dst == 0) return HSG_OK;
   if (!csc->indptr || (csc->n_edges > 0 && (!csc->nbr || !csc->bin))) return HSG_ERR_ARG;
   if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(sh) || (x && (!aligned16(x) || !aligned16(origin))))
     return HSG_ERR_ALIGN;

@@ -352,7 +352,7 @@ static int launch_ffma(bool small, bool vec, int M, int N, int K, const float* A
 
 int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
-  if (M < 0 || N1 <= 0 || N2 <= 0 || !A || !B || !C || !ws) return HSG_ERR_ARG;
+  if (M < 0 || N1 <= 0 || N2 <= 0 || !C || !ws || (M > 0 && (!A || !B))) return HSG_ERR_ARG;
   if (ws_bytes < hsg_gemm_tn_workspace_bytes(M, N1, N2)) return HSG_ERR_WORKSPACE;
   if (M > 0 && is_small(M, N1, N2)) {   // cluster split over the node rows: no partials, no reduce launch
     LaunchScope ls(SLOT_GEMM_TN, s);
@@ -403,10 +403,11 @@ extern "C" {
 
 int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const float* bias, const float* R, int ldr, int epi, void* stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if (M < 0 || N <= 0 || K <= 0) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;                          // empty node set: nothing to do (pointers may be NULL)
+  if (!A || !B || !C) return HSG_ERR_ARG;
   if ((epi & HSG_EPI_BIAS) && !bias) return HSG_ERR_ARG;
   if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
-  if (M == 0) return HSG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(C) &&
              (R == nullptr || aligned16(R));
@@ -420,10 +421,11 @@ int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, in
 
 int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const float* R, int ldr, int epi, void* stream) {
-  if (M < 0 || N <= 0 || K <= 0 || !A || !B || !C) return HSG_ERR_ARG;
+  if (M < 0 || N <= 0 || K <= 0) return HSG_ERR_ARG;
   if (epi & (HSG_EPI_BIAS | HSG_EPI_RELU)) return HSG_ERR_ARG;
+  if (M == 0) return HSG_OK;                          // empty node set: nothing to do (pointers may be NULL)
+  if (!A || !B || !C) return HSG_ERR_ARG;
   if ((epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) && !R) return HSG_ERR_ARG;
-  if (M == 0) return HSG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   bool vec = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B) &&
              aligned16(C) && (R == nullptr || aligned16(R));

@@ -175,8 +175,8 @@ bool grads_ok(const hsg_layer_grads& G, bool need_bf) {
 }
 
 int common_checks(const hsg_loop_args* a, const Layout& L) {
-  if (!a->csc_super || !a->csc_word || !a->T || !a->word_feature || !a->super_feature || !a->state)
-    return HSG_ERR_ARG;
+  if (!a->csc_super || !a->csc_word || !a->T || !a->state) return HSG_ERR_ARG;
+  if ((a->n_word > 0 && !a->word_feature) || (a->n_super > 0 && !a->super_feature)) return HSG_ERR_ARG;
   for (int k = 0; k < 2; ++k)
     if (L.has[k] && !params_ok(layer(a, k))) return HSG_ERR_ARG;
   if (a->state_floats < L.state_total) return HSG_ERR_WORKSPACE;

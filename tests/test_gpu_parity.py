@@ -703,3 +703,36 @@ def test_hdsg_doc_init_matches_reference_restatement():
                            batch.n_super)
     (want * c).sum().backward()
     assert nerr(got, want) <= TOL and nerr(sfg.grad, sfc.grad) <= TOL and nerr(Wg.grad, Wc.grad) <= TOL
+
+
+def test_update_loop_degenerate_batches():
+    """Ragged / empty inputs through the whole-loop entry points: a batch whose graphs have NO word nodes at all
+    (every token filtered: n_word = 0, no edges) and a batch mixing such a graph with ordinary ones."""
+    L = 100
+    empty = syn.DocExample(sents=np.zeros((3, L), np.int32), w2s=[{}, {}, {}], labels=np.zeros(3, np.int64))
+    empty.sents[:, :2] = [[5, 6], [7, 8], [9, 10]]                      # stop-word surrogates: filtered ids
+    normal = syn.make_examples(2, "tiny", seed=81)
+    for exs in ([empty], [empty, normal[0], normal[1]]):
+        tb = syn.pack_token_batch(exs)
+        batch = hb.HeteroBatch.from_token_batch(tb)
+        bg, _ = oracle_batch(exs, False)
+        assert_batch_equals_oracle(batch, bg)
+        csc = gb.derive_csc(bg)
+        torch.manual_seed(4)
+        m = hb.WSWGATUpdateLoop(n_iter=1, atten_dropout_prob=0.0, ffn_dropout_prob=0.0)
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        m = m.cuda()
+        w, s = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+        cs = torch.randn(batch.n_super, 64)
+        wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+        gw, gs = m(batch, wg, sg)
+        (gs * cs.cuda()).sum().backward()
+        wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+        ow, os_ = cf.update_loop_cf(csc, wc, sc, params, 1)
+        (os_ * cs).sum().backward()
+        assert gw.shape == ow.shape and nerr(gs, os_) <= TOL
+        if batch.n_word > 0:
+            assert nerr(gw, ow) <= TOL
+        assert nerr(sg.grad, sc.grad) <= TOL
+        assert torch.isfinite(m.word2sent.layer.fc_weight.grad).all()
+        assert nerr(m.word2sent.ffn.w_1.weight.grad, params["word2sent.ffn.w_1.weight"].grad) <= TOL
