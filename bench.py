@@ -290,8 +290,9 @@ def run_ours(args):
     def upload():
         return DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
 
-    loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
-    loss_ev = [None, None]
+    LAG = 2                                      # the host reads the loss of step i - LAG (asynchronous logging)
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(LAG + 1)]
+    loss_ev = [None] * (LAG + 1)
     e2e_state = {"i": 0, "last": None}
 
     def step_e2e():
@@ -299,14 +300,16 @@ def run_ours(args):
         pipe.submit(upload)                      # pinned host -> device copy of the next batch's tokens, then its build
         sf = sf_host.to(dev, non_blocking=True)
         loss = compute(batch, sf)
-        k = e2e_state["i"] & 1
+        k = e2e_state["i"] % (LAG + 1)
         loss_host[k].copy_(loss.detach().view(1), non_blocking=True)   # D2H of this step's loss into pinned memory
-        loss_ev[k] = torch.cuda.Event()
-        loss_ev[k].record()
+        if loss_ev[k] is None:
+            loss_ev[k] = torch.cuda.Event()
+        loss_ev[k].record(pipe.main)
         pipe.finish()
-        if loss_ev[k ^ 1] is not None:           # the host consumes the PREVIOUS step's loss (one-step lag, like an
-            loss_ev[k ^ 1].synchronize()         # asynchronous training logger): no pipeline drain per step
-            e2e_state["last"] = float(loss_host[k ^ 1])
+        j = (e2e_state["i"] - LAG) % (LAG + 1)
+        if e2e_state["i"] >= LAG and loss_ev[j] is not None:   # consume an OLDER step's loss: no pipeline drain per step
+            loss_ev[j].synchronize()
+            e2e_state["last"] = float(loss_host[j])
         e2e_state["i"] += 1
         return e2e_state["last"], batch
 
@@ -459,9 +462,9 @@ def run_ours(args):
                                    "dgl_edges": batch.n_total_edges},
                    "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3)},
         "e2e": {"value": n_graphs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 24,
-                "d2h": "loss -> pinned host memory every step (async copy), read by the host one step later; "
-                       "builder totals (24 B) read every step"},
+                "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 4 * (5 * (tb.n_graphs + 1) + 1),
+                "d2h": "loss -> pinned host memory every step (async copy), read by the host two steps later; "
+                       "builder totals read every step"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,
         "large_shard": large,

@@ -11,6 +11,10 @@
 // neighbor = current word state, origin = current supernode state -> new supernode state), kind 1 = S2W
 // (destinations = words, neighbor = supernode state, origin = word state -> new word state).
 // HSG / HDSG: start_kind 0, n_apps = 1 + 2 n_iter.  (1, kind) is one stand-alone WSWGAT.forward.
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
 #include "hsg_common.cuh"
 #include "hsg_edge_layout.cuh"
 #include "hsg_internal.cuh"
@@ -24,6 +28,48 @@ using namespace hsg;
   } while (0)
 
 namespace {
+
+// ---- side stream for the weight-gradient products of the backward pass -------------------------------------------
+// In every application's backward the three weight-gradient products (dW2 = dr^T hdn, dW1 = dhp^T x,
+// dW_aug = dzp^T neighbor) feed nothing downstream except the final attention-prep backward, while the chain
+// dhp -> dx -> edge backward -> d_neighbor is strictly serial and made of kernels that leave most SMs idle at
+// batch 32 (64-127 CTAs).  They are forked onto a second stream (own reduction workspace) and joined by events:
+// same kernels, same per-buffer order, bitwise identical results.
+struct SideRes {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, dzp = nullptr, done[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static SideRes g_side[32];
+static std::mutex g_side_mu;
+static std::atomic<int> g_overlap{-1};
+
+bool overlap_enabled() {
+  int v = g_overlap.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HSG_BWD_OVERLAP");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_overlap.store(v);
+  }
+  return v != 0;
+}
+
+SideRes* side_res() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  SideRes& r = g_side[dev];
+  if (!r.ok) {
+    if (cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool good = cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&r.dzp, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&r.done[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) return nullptr;
+    r.ok = true;
+  }
+  return &r;
+}
 
 inline size_t r4(size_t n) { return (n + 3) & ~(size_t)3; }
 inline size_t mx(size_t a, size_t b) { return a > b ? a : b; }
@@ -64,7 +110,7 @@ struct Layout {
   size_t dWaug[2], dq[2], zero_out;
   KindBuf kb[2];
   size_t aexp_b;            // backward: regenerated A'
-  size_t scratch_total, ws_bytes;
+  size_t scratch_total, ws_bytes, ws_half;
 
   int kind(int i) const { return (i + start) & 1; }
   size_t app_start(int i) const {
@@ -162,7 +208,8 @@ int make_layout(const hsg_loop_args* a, Layout* L) {
     w = mx(w, hsg_wswgat_bwd_workspace_bytes(P.H, P.d, P.in_dim, P.d_hid, L->n_src[k], L->n_dst[k]));
     if (L->drop_attn) w = mx(w, hsg_gemm_tn_workspace_bytes(L->n_src[k], L->ldz[k], P.H * P.in_dim));
   }
-  L->ws_bytes = w;
+  L->ws_half = (w + 255) & ~(size_t)255;
+  L->ws_bytes = 2 * L->ws_half;              // second half: reduction workspace of the side stream
   return HSG_OK;
 }
 
@@ -228,9 +275,11 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
 }
 
 // backward of application i.  dnb == nullptr skips the d_neighbor product; dnb_add (may be nullptr) is summed into it.
+// sd != nullptr: weight-gradient products go to the side stream (workspace ws2); side_pending[k] tells whether an
+// earlier application of the same kind still has side work in flight on this kind's scratch buffers.
 int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbor, const float* dout, float* dx,
             float* dnb, const float* dnb_add, float* sc, int acc_aug, const hsg_layer_grads& G, int acc_ffn, void* ws,
-            size_t ws_bytes, cudaStream_t s) {
+            size_t ws_bytes, void* ws2, SideRes* sd, bool* side_pending, cudaStream_t s) {
   const int k = L.kind(i);
   const hsg_layer_params& P = layer(a, k);
   const AppOff& o = L.app[k];
@@ -243,6 +292,12 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   float* stat = blk + o.stat;
   float *dr = sc + b.dr, *dhp = sc + b.dhp, *g = sc + b.g, *dzp = sc + b.dzp;
   float *dW_aug = sc + L.dWaug[k], *dq = sc + L.dq[k];
+  cudaStream_t s2 = sd ? sd->stream : s;            // stream of the weight-gradient products
+  void* wsw = sd ? ws2 : ws;
+  if (sd && side_pending[k]) {                      // this kind's dr / dhp / dzp are about to be overwritten
+    if (cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
+    side_pending[k] = false;
+  }
   // LayerNorm
   HSG_TRY(layernorm_bwd_ex(n_dst, F, dout, r, ln, P.gamma, dr, G.dgamma, G.dbeta, ws, ws_bytes, acc_ffn, s));
   // FFN dropout: the residual path keeps dr, the W2 path sees dr * mask / (1-p)
@@ -253,13 +308,18 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   }
   // FFN: dhp = (drm . W2) * relu', dW2 = drm^T hdn, dW1 = dhp^T x, dx = dhp . W1 + dr
   HSG_TRY(hsg_gemm_nn(n_dst, P.d_hid, F, drm, F, P.w2, P.d_hid, dhp, P.d_hid, hdn, P.d_hid, HSG_EPI_RELU_MASK, s));
-  HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, ws, ws_bytes, acc_ffn, s));
-  HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, ws, ws_bytes, acc_ffn, s));
+  if (sd) {
+    if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->fork, 0) != cudaSuccess)
+      return HSG_ERR_CUDA;
+  }
+  HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, wsw, ws_bytes, acc_ffn, s2));
+  HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2));
   HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
   HSG_TRY(hsg_edge_bwd_prep(n_dst, P.H, P.d, dx, nullptr, sh, g, stat, s));
   HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, ws, ws_bytes, acc_aug, s));
   // projection backward
+  int rc;
   if (L.drop_attn) {
     const int KW = P.H * P.in_dim;
     const DropCfg dc = make_drop(a->attn_p, a->seed, stream_attn(i));
@@ -267,21 +327,38 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
       HSG_TRY(hsg_gemm_nn(n_src, KW, ldz, dzp, ldz, st + L.wblk[k], KW, sc + b.dA, KW, nullptr, 0, 0, s));
       HSG_TRY(dropout_reduce(n_src, P.in_dim, P.H, sc + b.dA, dnb_add, dnb, dc, s));
     }
-    float* aexp = sc + L.aexp_b;
+    float* aexp = sc + L.aexp_b;                    // shared by both kinds: stays on the main stream
     HSG_TRY(dropout_expand(n_src, P.in_dim, P.H, neighbor, aexp, dc, s));
     HSG_TRY(gemm_tn_ex(n_src, ldz, KW, dzp, ldz, aexp, KW, sc + b.dWblk, KW, nullptr, ws, ws_bytes, 0, s));
-    return wblk_gather(P.H, P.d, P.in_dim, ldz, sc + b.dWblk, dW_aug, acc_aug, s);
+    rc = wblk_gather(P.H, P.d, P.in_dim, ldz, sc + b.dWblk, dW_aug, acc_aug, s);
+  } else {
+    if (sd) {
+      if (cudaEventRecord(sd->dzp, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->dzp, 0) != cudaSuccess)
+        return HSG_ERR_CUDA;
+    }
+    HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr, wsw, ws_bytes,
+                       acc_aug, s2));
+    rc = HSG_OK;
+    if (dnb)
+      rc = hsg_gemm_nn(n_src, P.in_dim, ldz, dzp, ldz, st + L.waug[k], P.in_dim, dnb, P.in_dim, dnb_add, P.in_dim,
+                       dnb_add ? HSG_EPI_ADD : 0, s);
   }
-  if (dnb)
-    HSG_TRY(hsg_gemm_nn(n_src, P.in_dim, ldz, dzp, ldz, st + L.waug[k], P.in_dim, dnb, P.in_dim, dnb_add, P.in_dim,
-                        dnb_add ? HSG_EPI_ADD : 0, s));
-  return gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr, ws, ws_bytes,
-                    acc_aug, s);
+  if (rc) return rc;
+  if (sd) {
+    if (cudaEventRecord(sd->done[k], s2) != cudaSuccess) return HSG_ERR_CUDA;
+    side_pending[k] = true;
+  }
+  return HSG_OK;
 }
 
 }  // namespace
 
 extern "C" {
+
+int hsg_set_bwd_overlap(int on) {
+  g_overlap.store(on ? 1 : 0);
+  return HSG_OK;
+}
 
 int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan) {
   if (!plan) return HSG_ERR_ARG;
@@ -346,6 +423,9 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
   // (0: supernode state, 1: word state); NULL = zero
   const float* gst[2] = {b->d_super_state, b->d_word_state};
   int done[2] = {0, 0};
+  SideRes* sd = overlap_enabled() ? side_res() : nullptr;
+  bool side_pending[2] = {false, false};
+  void* ws2 = reinterpret_cast<char*>(b->ws) + L.ws_half;
   for (int i = L.n_apps - 1; i >= 0; --i) {
     const int k = L.kind(i);
     const hsg_layer_params& P = layer(a, k);
@@ -370,11 +450,14 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
     }
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
     HSG_TRY(app_bwd(a, L, i, neighbor, dout, dx, dnb, gst[k ^ 1], sc, done[k] > 0, G, acc || done[k] > 0, b->ws,
-                    b->ws_bytes, s));
+                    L.ws_half, ws2, sd, side_pending, s));
     ++done[k];
     gst[k] = dx;
     gst[k ^ 1] = dnb;
   }
+  if (sd)                                               // join: every weight gradient is complete from here on
+    for (int k = 0; k < 2; ++k)
+      if (side_pending[k] && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
   // attention-prep backward: (dW_aug, dq) summed over the applications -> fc / feat_fc / attn_fc / TF-IDF table
   int t_written = 0;
   for (int k = 0; k < 2; ++k) {

@@ -234,7 +234,7 @@ class HeteroBatch:
         return HeteroBatch._build_fill(HeteroBatch._build_count(dtb))
 
     @staticmethod
-    def _build_count(dtb: "DeviceTokenBatch"):
+    def _build_count(dtb: "DeviceTokenBatch", stream_obj=None):
         """Phase 1 on the current stream: per-graph counts + offsets; the totals start their way to pinned host
         memory.  Returns the state _build_fill needs."""
         _lib.require_device()
@@ -255,7 +255,7 @@ class HeteroBatch:
         totals_host.copy_(meta, non_blocking=True)                       # the one D2H of the build
         totals_dev = meta
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(stream_obj) if stream_obj is not None else ev.record()
         return dict(dtb=dtb, ws=ws, ws_bytes=ws_bytes, offs=offs, status=status, off_c=off_c,
                     totals_dev=totals_dev, totals_host=totals_host, event=ev)
 
@@ -267,11 +267,11 @@ class HeteroBatch:
         dtb, ws, ws_bytes, offs, status, off_c = c["dtb"], c["ws"], c["ws_bytes"], c["offs"], c["status"], c["off_c"]
         dev, B, tbc = dtb.device, dtb.n_graphs, dtb.c_struct
         c["event"].synchronize()
-        th = c["totals_host"]
-        status_h = int(th[5 * (B + 1)])
+        th = c["totals_host"].tolist()
+        status_h = th[5 * (B + 1)]
         if status_h != 0:
             _lib.check(status_h)
-        n_word, n_super, n_node, n_edge, n_pair = [int(th[i * (B + 1) + B]) for i in range(5)]
+        n_word, n_super, n_node, n_edge, n_pair = [th[i * (B + 1) + B] for i in range(5)]
         st = _stream()
         i32 = dict(dtype=torch.int32, device=dev)
         # one int32 arena for every 4-byte array, one byte arena for the rest: 2 allocations instead of 14
@@ -281,18 +281,14 @@ class HeteroBatch:
                    ("word_src", max(n_pair, 1)), ("word_eid", max(n_pair, 1))]
         sizes8 = [("super_type", max(n_super, 1)), ("super_bin", max(n_pair, 1)), ("word_bin", max(n_pair, 1))]
         out = {}
-        tot = sum((n + 3) & ~3 for _, n in sizes32)
-        a32 = torch.empty(tot, **i32)
-        off = 0
-        for name, n in sizes32:
-            out[name] = a32[off:off + n]
-            off += (n + 3) & ~3
-        tot = sum((n + 15) & ~15 for _, n in sizes8)
-        a8 = torch.empty(tot, dtype=torch.uint8, device=dev)
-        off = 0
-        for name, n in sizes8:
-            out[name] = a8[off:off + n]
-            off += (n + 15) & ~15
+        pad32 = [(n + 3) & ~3 for _, n in sizes32]
+        a32 = torch.empty(sum(pad32), **i32)
+        for (name, n), part in zip(sizes32, a32.split_with_sizes(pad32)):     # one call -> all the views
+            out[name] = part[:n] if part.shape[0] != n else part
+        pad8 = [(n + 15) & ~15 for _, n in sizes8]
+        a8 = torch.empty(sum(pad8), dtype=torch.uint8, device=dev)
+        for (name, n), part in zip(sizes8, a8.split_with_sizes(pad8)):
+            out[name] = part[:n] if part.shape[0] != n else part
         out["super_type"] = out["super_type"].view(torch.int8)
         if B == 0:
             out["super_indptr"].zero_()
@@ -400,6 +396,9 @@ class BuildPipeline:
     def __init__(self, device="cuda"):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
+        # the compute stream is sampled once: torch.cuda.current_stream() costs ~12 us per call, the stream context
+        # manager three of them, and a training loop does not change its compute stream between steps
+        self.main = torch.cuda.current_stream(self.device)
         self._pending = None
         self._ready = None
 
@@ -408,18 +407,24 @@ class BuildPipeline:
         on the side stream."""
         if self._pending is not None or self._ready is not None:
             raise RuntimeError("BuildPipeline: previous batch not taken yet")
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self.stream):
+        self.stream.wait_stream(self.main)
+        torch.cuda.set_stream(self.stream)
+        try:
             dtb = source() if callable(source) else source
-            self._pending = HeteroBatch._build_count(dtb)
+            self._pending = HeteroBatch._build_count(dtb, self.stream)
+        finally:
+            torch.cuda.set_stream(self.main)
 
     def finish(self):
         if self._pending is None:
             return
-        with torch.cuda.stream(self.stream):
+        torch.cuda.set_stream(self.stream)
+        try:
             hb = HeteroBatch._build_fill(self._pending)
             ev = torch.cuda.Event()
-            ev.record()
+            ev.record(self.stream)
+        finally:
+            torch.cuda.set_stream(self.main)
         self._pending = None
         self._ready = (hb, ev)
 
@@ -430,7 +435,7 @@ class BuildPipeline:
             raise RuntimeError("BuildPipeline: nothing submitted")
         hb, ev = self._ready
         self._ready = None
-        cur = torch.cuda.current_stream(self.device)
+        cur = self.main
         cur.wait_event(ev)
         # allocated on the side stream, consumed on the compute stream: tell the caching allocator.  Every field of
         # the batch is a view of one of these few storages.

@@ -343,6 +343,11 @@ typedef struct {
   size_t ws_bytes;
 } hsg_loop_bwd_args;
 
+/* hsg_update_loop_bwd forks the weight-gradient products (dW2, dW1, dW_aug of every application) onto an internal
+ * second stream, joined by events before the call's last kernels, so they overlap the serial dx -> edge backward ->
+ * d_neighbor chain (default on; HSG_BWD_OVERLAP=0 or hsg_set_bwd_overlap(0): everything on the caller's stream).
+ * Same kernels and per-buffer order either way: bitwise identical results. */
+int hsg_set_bwd_overlap(int on);
 /* Sizes/offsets for the given dimensions (pointers inside `a` are not read). */
 int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan);
 int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream);
