@@ -122,16 +122,21 @@ head_bwd_doc_kernel(hsg_head_args a, const float* __restrict__ dlogits, const fl
   }
 }
 
+// one warp per output: lanes take the block partials strided, then a fixed-order shuffle tree
 __global__ void __launch_bounds__(256)
 head_bwd_reduce_kernel(int nblocks, int n_out, const float* __restrict__ part, float* __restrict__ d_w,
                        float* __restrict__ d_b, int accumulate) {
   pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n_out) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n_out + i];   // fixed order
-  float* o = i < n_out - 2 ? d_w + i : d_b + (i - (n_out - 2));
-  *o = accumulate ? *o + s : s;
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * n_out + i];
+  s = warp_sum(s);
+  if (lane == 0) {
+    float* o = i < n_out - 2 ? d_w + i : d_b + (i - (n_out - 2));
+    *o = accumulate ? *o + s : s;
+  }
 }
 
 // one warp per graph: out[g, rank] = local sentence index with the rank-th largest class-1 logit (ties: lower index
@@ -253,7 +258,7 @@ int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout
     if (a->two_part && a->n_graphs > 0) launch_k(head_bwd_doc_kernel, dim3(a->n_graphs), dim3(256), 0, s, *a, dlogits, gout, d_state);
   }
   const int n_out = 2 * width + 2;
-  launch_k(head_bwd_reduce_kernel, dim3(ceil_div(n_out, 256)), dim3(256), 0, s, blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
+  launch_k(head_bwd_reduce_kernel, dim3(ceil_div(n_out, 8)), dim3(256), 0, s, blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
   return check_launch();
 }
 
