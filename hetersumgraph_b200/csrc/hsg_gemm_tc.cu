@@ -277,6 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_main = tmem_d + acc * acc_cols, d_corr = d_main + BN_MAX;
         const uint32_t idesc = make_idesc(A_MN, B_MN, ti.n_mma);
+        // precise mode: A_hi.B_hi and A_hi.B_lo in ONE instruction of N = 128 + n_mma - the B_lo tile directly
+        // follows the B_hi tile in shared memory and the correction accumulator directly follows the main one in
+        // TMEM, so [B_hi | B_lo] is one operand and [main | corr] one accumulator: A_hi is read from shared memory
+        // once instead of twice (the pipeline is shared-memory-bandwidth bound).  Columns n_mma..127 are scratch.
+        const uint32_t idesc_wide = make_idesc(A_MN, B_MN, BN_MAX + ti.n_mma);
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait((use_conv ? bar_ready : bar_full) + 8 * slot, ph);
@@ -290,12 +295,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t b_off = B_MN ? ks * 1024u : ks * 32u;
             const uint64_t dah = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lay),
                            dbh = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lay);
-            tc_mma_tf32(d_main, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
             if (want_lo) {
-              const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay),
-                             dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lay);
-              tc_mma_tf32(d_corr, dah, dbl, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-              tc_mma_tf32(d_corr, dal, dbh, idesc, 1u);
+              const uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lay);
+              tc_mma_tf32(d_main, dah, dbh, idesc_wide, (kb > 0 || ks > 0) ? 1u : 0u);   // [main | corr] (+)= A_hi [B_hi | B_lo]
+              tc_mma_tf32(d_corr, dal, dbh, idesc, 1u);                                   // corr += A_lo B_hi
+            } else {
+              tc_mma_tf32(d_main, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
             }
           }
           tc_commit(bar_empty + 8 * slot);                                  // frees the slot when the MMAs retire
