@@ -780,7 +780,8 @@ static int edge_grid(int n_rows_steps, int cap = EDGE_DEFAULT_BLOCKS) {
 
 // (H, D) instantiations: defaults (8,8) W2S and (6,50) S2W (HiGraph.py:57-76), plus
 // other hidden/embedding sizes and the small shapes used by the test fixtures.
-#define HSG_EDGE_CONFIGS(X) X(8, 8) X(6, 50) X(8, 16) X(6, 16) X(8, 32) X(6, 32) X(4, 4) X(6, 8) X(4, 16) X(1, 64)
+#define HSG_EDGE_CONFIGS(X) \
+  X(8, 8) X(6, 50) X(8, 16) X(6, 16) X(8, 32) X(6, 32) X(4, 4) X(6, 8) X(4, 16) X(1, 64) X(16, 4) X(2, 32) X(4, 32) X(12, 25)
 
 // unroll depth: deep for high-degree rows (supernodes), shallow for low-degree rows (words)
 template <int H, int D>

@@ -736,3 +736,49 @@ def test_update_loop_degenerate_batches():
         assert nerr(sg.grad, sc.grad) <= TOL
         assert torch.isfinite(m.word2sent.layer.fc_weight.grad).all()
         assert nerr(m.word2sent.ffn.w_1.weight.grad, params["word2sent.ffn.w_1.weight"].grad) <= TOL
+
+
+ALL_EDGE_CONFIGS = [(8, 8), (6, 50), (8, 16), (6, 16), (8, 32), (6, 32), (4, 4), (6, 8), (4, 16), (1, 64), (16, 4),
+                    (2, 32), (4, 32), (12, 25)]
+
+
+@pytest.mark.parametrize("H,d", ALL_EDGE_CONFIGS)
+@pytest.mark.parametrize("kind", ["W2S", "S2W"])
+def test_every_instantiated_head_shape_matches_closed_form(H, d, kind):
+    """Every (heads, head_dim) instantiation of the edge kernels (HSG_EDGE_CONFIGS), both layer types, forward and
+    all gradients of MultiHeadLayer against the closed form on a small HSG batch."""
+    exs = syn.make_examples(4, "tiny", seed=91)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    bg, _ = oracle_batch(exs, False)
+    csc = gb.derive_csc(bg)
+    in_dim, fe = 20, 12
+    torch.manual_seed(H * 100 + d)
+    lay = hb.MultiHeadLayer(in_dim, d, H, 0.0, fe, layer=hb.WSGATLayer if kind == "W2S" else hb.SWGATLayer)
+    W, Wf, a = lay.fc_weight.detach().clone(), lay.feat_fc_weight.detach().clone(), lay.attn_fc_weight.detach().clone()
+    bf = lay.feat_fc_bias.detach().clone() if lay.feat_fc_bias is not None else torch.zeros(H * d)
+    lay = lay.cuda()
+    T = torch.randn(10, fe)
+    batch.set_tfidf_embedding(T.cuda().requires_grad_(True))
+    n_src, n_dst = (batch.n_word, batch.n_super) if kind == "W2S" else (batch.n_super, batch.n_word)
+    h = torch.randn(n_src, in_dim)
+    c = torch.randn(n_dst, H * d)
+    hg = h.cuda().requires_grad_(True)
+    out = lay(batch, hg)
+    (out * c.cuda()).sum().backward()
+    hc = h.clone().requires_grad_(True)
+    Wc, Wfc, bfc, ac, Tc = (t.clone().requires_grad_(True) for t in (W, Wf, bf, a, T))
+    if kind == "W2S":
+        ref = cf.multi_head_cf(hc, n_dst, csc["super_indptr"], csc["super_src"], csc["super_bin"], csc["extra_cnt"],
+                               Wc, Wfc, bfc, ac, Tc)
+    else:
+        ref = cf.multi_head_cf(hc, n_dst, csc["word_indptr"], csc["word_src"], csc["word_bin"], csc["extra_cnt_word"],
+                               Wc, Wfc, bfc, ac, Tc)
+    (ref * c).sum().backward()
+    assert nerr(out, ref) <= TOL, (H, d, kind, nerr(out, ref))
+    assert nerr(hg.grad, hc.grad) <= TOL
+    assert nerr(lay.fc_weight.grad, Wc.grad) <= TOL
+    assert nerr(lay.feat_fc_weight.grad, Wfc.grad) <= TOL
+    assert nerr(lay.attn_fc_weight.grad, ac.grad) <= TOL
+    assert nerr(batch.tfidfembed_weight.grad, Tc.grad) <= TOL
+    if lay.feat_fc_bias is not None:
+        assert nerr(lay.feat_fc_bias.grad, bfc.grad) <= TOL
