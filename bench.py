@@ -357,6 +357,7 @@ def run_ours(args):
     # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
     _, batch = step_resident()
     torch.cuda.synchronize()
+    lib.hsg_set_bwd_overlap(0)      # per-kernel events are only meaningful when the kernels do not share the GPU
     lib.hsg_profile_reset()
     lib.hsg_profile_enable(1)
     for _ in range(args.steps):
@@ -364,6 +365,7 @@ def run_ours(args):
         step_resident()
     torch.cuda.synchronize()
     lib.hsg_profile_enable(0)
+    lib.hsg_set_bwd_overlap(1)
     prof = _lib.profile_snapshot()
     acct = accounting.step_accounting(batch.n_word, batch.n_super, batch.n_pair, n_iter)
     kernels = []

@@ -732,6 +732,157 @@ edge_bwd_rowpar_kernel(int n_src, const int32_t* __restrict__ indptr, const int3
   }
 }
 
+// ---------------------------------------------------------------------------
+// backward over FEW, HIGH-degree rows (batch 32: 1 009 supernode rows of ~17, at most ~60, word neighbours): with a
+// warp per row only n_rows/8 CTAs exist and the kernel lasts as long as its longest row.  Here a whole CTA walks one
+// row: warp w takes the w-th contiguous slice of the edge list, the eight partial [dz | dp] rows meet in shared
+// memory and are summed in warp order (fixed, deterministic).
+// ---------------------------------------------------------------------------
+template <int H, int D>
+__global__ void __launch_bounds__(EDGE_THREADS, 3)
+edge_bwd_blockrow_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                         const uint8_t* __restrict__ bin, const float* __restrict__ zp, int ldz,
+                         const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ stat,
+                         float* __restrict__ dzp, float* __restrict__ dq_part) {
+  pdl_prologue();
+  using C = EdgeCfg<H, D>;
+  constexpr int NQ = HSG_N_BINS * H;
+  constexpr int U = 2;
+  constexpr int PW = C::FP + H;                      // floats of one partial row
+  __shared__ float q_s[NQ];
+  __shared__ float dq_s[EDGE_WARPS][C::EPS][NQ];
+  __shared__ __align__(16) float part_s[EDGE_WARPS][PW + 2];
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) q_s[i] = q[i];
+  for (int i = threadIdx.x; i < EDGE_WARPS * C::EPS * NQ; i += blockDim.x) (&dq_s[0][0][0])[i] = 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int grp = lane / C::GROUP;
+  const int gl = lane % C::GROUP;
+  const int k = gl / C::LPH;
+  const int l = gl % C::LPH;
+  const bool lane_on = grp < C::EPS;
+  float* my_dq = &dq_s[wib][lane_on ? grp : 0][0];
+
+  for (int u = blockIdx.x; u < n_src; u += gridDim.x) {
+    const int beg = __ldg(indptr + u), end = __ldg(indptr + u + 1);
+    const int per = (end - beg + EDGE_WARPS - 1) / EDGE_WARPS;
+    const int my_beg = min(end, beg + wib * per), my_end = min(end, my_beg + per);
+    const float* zrow = zp + (size_t)u * ldz;
+    float zv[C::NE], acc[C::NE];
+    float pu = 0.f, acc_dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::NE; ++i) {
+      zv[i] = 0.f;
+      acc[i] = 0.f;
+    }
+    if (lane_on && my_end > my_beg) {
+      pu = __ldg(zrow + C::FP + k);
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i)
+        if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(zrow + (i * C::GROUP + gl) * C::VEC, zv + i * C::VEC);
+    }
+    for (int c0 = my_beg; c0 < my_end; c0 += 32) {
+      const int cnt = min(32, my_end - c0);
+      int my_v = 0, my_b = 0;
+      if (lane < cnt) {
+        my_v = __ldg(nbr + c0 + lane);
+        my_b = __ldg(bin + c0 + lane);
+      }
+      for (int j0 = 0; j0 < cnt; j0 += C::EPS * U) {   // warp-uniform (shuffles inside)
+        float gv[U][C::NE], mk[U], dk[U], sk[U];
+        int bb[U];
+        bool ok[U];
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+          const int j = j0 + uu * C::EPS + grp;
+          const int v = __shfl_sync(0xffffffffu, my_v, j & 31);
+          bb[uu] = __shfl_sync(0xffffffffu, my_b, j & 31);
+          ok[uu] = lane_on && j < cnt;
+          mk[uu] = 0.f;
+          dk[uu] = 1.f;
+          sk[uu] = 0.f;
+#pragma unroll
+          for (int i = 0; i < C::NE; ++i) gv[uu][i] = 0.f;
+          if (ok[uu]) {
+            const float* grow = g + (size_t)v * C::FP;
+            const float* stp = stat + (size_t)v * 3 * H;
+            mk[uu] = __ldg(stp + k);
+            dk[uu] = __ldg(stp + H + k);
+            sk[uu] = __ldg(stp + 2 * H + k);
+#pragma unroll
+            for (int i = 0; i < C::VPL; ++i)
+              if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(grow + (i * C::GROUP + gl) * C::VEC, gv[uu] + i * C::VEC);
+          }
+        }
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < C::NE; ++i) part = fmaf(gv[uu][i], zv[i], part);
+          const float t = head_sum<C::LPH>(part, lane, l);
+          if (ok[uu]) {
+            const float pre = pu + q_s[bb[uu] * H + k];
+            const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
+            const float alpha = __expf(lg - mk[uu]) / dk[uu];
+            const float de = alpha * (t - sk[uu]);
+            const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
+#pragma unroll
+            for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(alpha, gv[uu][i], acc[i]);
+            acc_dp += dpre;
+            if (l == 0) my_dq[bb[uu] * H + k] += dpre;
+          }
+        }
+      }
+    }
+    // merge the EPS groups of this warp (fixed order), park the warp's partial row in shared memory
+#pragma unroll
+    for (int g2 = 1; g2 < C::EPS; ++g2) {
+      const int src = (gl + g2 * C::GROUP) & 31;
+      const float dp2 = __shfl_sync(0xffffffffu, acc_dp, src);
+      if (grp == 0) acc_dp += dp2;
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) {
+        const float a2 = __shfl_sync(0xffffffffu, acc[i], src);
+        if (grp == 0) acc[i] += a2;
+      }
+    }
+    if (grp == 0) {
+      float* pr = &part_s[wib][0];
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) {
+        if (l + C::LPH * i >= C::NV) {
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) acc[i * C::VEC + t] = 0.f;   // layout holes must be finite zeros
+        }
+#pragma unroll
+        for (int t = 0; t < C::VEC; ++t) pr[(i * C::GROUP + gl) * C::VEC + t] = acc[i * C::VEC + t];
+      }
+      if (l == 0) pr[C::FP + k] = acc_dp;
+    }
+    __syncthreads();
+    float* drow = dzp + (size_t)u * ldz;
+    for (int t = threadIdx.x; t < ldz; t += blockDim.x) {
+      float sres = 0.f;
+      if (t < PW) {
+#pragma unroll
+        for (int w = 0; w < EDGE_WARPS; ++w) sres += part_s[w][t];   // warp order: fixed
+      }
+      drow[t] = sres;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+    float sres = 0.f;
+#pragma unroll
+    for (int w = 0; w < EDGE_WARPS; ++w)
+#pragma unroll
+      for (int g2 = 0; g2 < C::EPS; ++g2) sres += dq_s[w][g2][i];
+    dq_part[(size_t)blockIdx.x * NQ + i] = sres;
+  }
+}
+
 // dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
 __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
                                                           float* __restrict__ dq, int accumulate) {
@@ -810,6 +961,8 @@ static int launch_prep(int n_dst, const float* dx, const float* dsh, const float
 }
 
 static std::atomic<int> g_rowpar{-1};   // -1 auto (low average degree), 0 never, 1 whenever the layout allows
+static std::atomic<int> g_blockrow{-1}; // -1 auto (few high-degree rows), 0 never, 1 always
+constexpr int BLOCKROW_MAX_ROWS = 8192;
 
 template <int H, int D>
 static void launch_rowpar(int blocks, const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g,
@@ -828,10 +981,17 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
   const int rp = g_rowpar.load(std::memory_order_relaxed);
   const bool rowpar = C::EPS > 1 && !C::STAGED && (rp == 1 || (rp < 0 && !deep));
-  const int blocks = rowpar ? edge_grid(ceil_div(c->n_dst, C::EPS)) : edge_grid(c->n_dst);
+  // few high-degree rows (a warp per row would leave most SMs idle and last as long as the longest row): CTA per row
+  const int br = g_blockrow.load(std::memory_order_relaxed);
+  const bool blockrow = !rowpar && (br == 1 || (br < 0 && deep && c->n_dst <= BLOCKROW_MAX_ROWS));
+  const int blocks = blockrow ? min(c->n_dst, edge_block_cap(EDGE_DEFAULT_BLOCKS))
+                              : (rowpar ? edge_grid(ceil_div(c->n_dst, C::EPS)) : edge_grid(c->n_dst));
   {
     LaunchScope ls(SLOT_EDGE_BWD, s);
-    if (rowpar)
+    if (blockrow)
+      launch_k(edge_bwd_blockrow_kernel<H, D>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
+               zp, ldz, q, g, stat, dzp, ws);
+    else if (rowpar)
       launch_rowpar<H, D>(blocks, c, zp, ldz, q, g, stat, dzp, ws, s);
     else if (deep)
       launch_k(edge_bwd_kernel<H, D, UHI>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin, zp, ldz, q, g,
@@ -912,6 +1072,11 @@ int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx, const float* dsh
 
 int hsg_set_edge_rowpar(int mode) {
   g_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  return HSG_OK;
+}
+
+int hsg_set_edge_blockrow(int mode) {
+  g_blockrow.store(mode < 0 ? -1 : (mode ? 1 : 0));
   return HSG_OK;
 }
 

@@ -230,6 +230,10 @@ size_t hsg_edge_bwd_workspace_bytes(int H);
  * own row when the average degree is low - word rows; the groups share one row's edge list otherwise), 0 never,
  * 1 always.  Same results either way (tested); a tuning / test knob. */
 int hsg_set_edge_rowpar(int mode);
+/* CTA-per-row mapping of hsg_edge_bwd for FEW high-degree rows (<= 8 192 rows, average degree above 4 per group -
+ * the supernode rows of a small batch): the eight warps of a CTA share one row's edge list and their partial rows are
+ * summed in warp order.  -1 auto, 0 never, 1 always (overrides the warp-per-row mappings). */
+int hsg_set_edge_blockrow(int mode);
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,
                  const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
                  void* ws, size_t ws_bytes, void* stream);

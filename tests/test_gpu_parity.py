@@ -580,17 +580,18 @@ def test_standalone_wswgat_module_with_dropout():
         assert nerr(got, want) <= TOL, kind
 
 
-def test_edge_bwd_row_mappings_agree():
-    """hsg_edge_bwd's two row mappings for multi-group layouts ((8,8): two groups per warp) - groups sharing one
-    row's edge list vs. each group walking its own row - give the same dzp / dq up to summation order."""
+@pytest.mark.parametrize("kind,H,d", [("W2S", 8, 8), ("S2W", 6, 50)])
+def test_edge_bwd_row_mappings_agree(kind, H, d):
+    """hsg_edge_bwd's row mappings - warp per row with the groups sharing the row's edge list (baseline), each group
+    walking its own row (low-degree rows), a whole CTA per row (few high-degree rows) - give the same dzp / dq up to
+    summation order."""
     import ctypes as C
     from hetersumgraph_b200 import _lib
     from hetersumgraph_b200.functional import _Workspace
     lib = _lib.load()
     exs = syn.make_examples(16, "cnndm", seed=5)
     batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
-    H, d = 8, 8
-    csc, csc_t = batch.csc("W2S")
+    csc, csc_t = batch.csc(kind)
     fp, ldz = _lib.edge_layout(H, d)
     torch.manual_seed(0)
     dev = "cuda"
@@ -608,8 +609,9 @@ def test_edge_bwd_row_mappings_agree():
     ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), torch.device(dev), "edge")
     outs = []
     try:
-        for mode in (0, 1):
-            lib.hsg_set_edge_rowpar(mode)
+        for rowpar, blockrow in ((0, 0), (1, 0), (0, 1)):
+            lib.hsg_set_edge_rowpar(rowpar)
+            lib.hsg_set_edge_blockrow(blockrow)
             dzp = torch.full((csc.n_src, ldz), float("nan"), device=dev)
             dq = torch.empty(10, H, device=dev)
             _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(), g.data_ptr(),
@@ -617,8 +619,10 @@ def test_edge_bwd_row_mappings_agree():
             outs.append((dzp, dq))
     finally:
         lib.hsg_set_edge_rowpar(-1)
-    assert torch.isfinite(outs[1][0]).all()
-    assert nerr(outs[1][0], outs[0][0]) <= 2e-6 and nerr(outs[1][1], outs[0][1]) <= 2e-6
+        lib.hsg_set_edge_blockrow(-1)
+    for dzp, dq in outs[1:]:
+        assert torch.isfinite(dzp).all()
+        assert nerr(dzp, outs[0][0]) <= 2e-6 and nerr(dq, outs[0][1]) <= 2e-6
 
 
 def test_fused_train_step_equals_autograd_path():
