@@ -182,7 +182,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -290,7 +290,7 @@ def run_ours(args):
     def upload():
         return DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
 
-    LAG = 2                                      # the host reads the loss of step i - LAG (asynchronous logging)
+    LAG = 8                                      # the host reads the loss of step i - LAG (asynchronous logging ring)
     loss_host = [torch.zeros(1).pin_memory() for _ in range(LAG + 1)]
     loss_ev = [None] * (LAG + 1)
     e2e_state = {"i": 0, "last": None}
@@ -345,13 +345,15 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
-    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    # at least 10 untimed steps each: the caching allocator needs a few steps per leg before its cross-stream block
+    # reuse pattern (side-stream builds, pinned uploads) is stable - a cudaMalloc inside the timed region costs ms
+    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 10))
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 10))
     clk = clocks.stop() if rank == 0 else None
     # informational: the same step with single-pass TF32 products (the "bf16 projections <= 2e-2" error class of
     # BASELINE.json); NOT the headline - value / e2e above are measured in the fp32-parity mode
     hb.set_gemm_mode("tf32")
-    ms_fast, _ = timed(step_resident, args.steps, 3)
+    ms_fast, _ = timed(step_resident, args.steps, 5)
     hb.set_gemm_mode("tf32x3")
 
     # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
@@ -453,7 +455,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": n_graphs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 10), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if args.global_batch > 0 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": n_graphs_global, "n_iter": n_iter,
                    "dropout": 0.0, "l2": "flushed between steps (256 MiB memset outside the timed events)",
@@ -465,7 +467,7 @@ def run_ours(args):
                    "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3)},
         "e2e": {"value": n_graphs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 4 * (5 * (tb.n_graphs + 1) + 1),
-                "d2h": "loss -> pinned host memory every step (async copy), read by the host two steps later; "
+                "d2h": "loss -> pinned host memory every step (async copy), read by the host eight steps later (logging ring); "
                        "builder totals read every step"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,

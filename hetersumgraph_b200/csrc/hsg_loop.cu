@@ -60,7 +60,11 @@ SideRes* side_res() {
   std::lock_guard<std::mutex> lk(g_side_mu);
   SideRes& r = g_side[dev];
   if (!r.ok) {
-    if (cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // lowest priority: when SMs free up, the critical-path kernels of the caller's stream (dx, edge backward,
+    // d_neighbor) are scheduled before the weight-gradient products
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&r.stream, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
     bool good = cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r.dzp, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming) == cudaSuccess &&
