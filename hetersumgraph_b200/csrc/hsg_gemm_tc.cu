@@ -407,6 +407,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        // bias of this lane's four columns: loaded once per chunk (not once per row group)
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ep.epi & HSG_EPI_BIAS) {
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt)
+            if (col + tt < n_out) bz[tt] = __ldg(ep.bias + col + tt);
+        }
         float v[32];
         if (ti.nkb > 0) {
           tc_ld32(d_main + (uint32_t)c0, v);
@@ -423,39 +430,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];           // bank (lane + i) % 32: conflict-free
         __syncwarp();
+        const bool do_relu = (ep.epi & HSG_EPI_RELU) != 0, do_add = (ep.epi & HSG_EPI_ADD) != 0,
+                   do_mask = (ep.epi & HSG_EPI_RELU_MASK) != 0;
+        const bool vec_col = col + 3 < n_out && ld_vec;
+        const int ones_d = ep.colsum_part != nullptr ? ep.ones_col - col : -1;   // 0..3 when this lane holds the sums
+        // everything below stays in registers: no dynamically indexed arrays (they would live in local memory)
 #pragma unroll
         for (int p8 = 0; p8 < 8; ++p8) {
           const int rl = p8 * 4 + r_sub;
           const int row = ti.m0 + lg * 32 + rl;
-          float o[4];
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) o[tt] = tile[rl * 33 + c_sub + tt];
+          float o0 = tile[rl * 33 + c_sub + 0], o1 = tile[rl * 33 + c_sub + 1], o2 = tile[rl * 33 + c_sub + 2],
+                o3 = tile[rl * 33 + c_sub + 3];
+          if (ones_d >= 0 && ones_d < 4 && row < Md)
+            ep.colsum_part[(size_t)ti.z * Md + row] = ones_d == 0 ? o0 : (ones_d == 1 ? o1 : (ones_d == 2 ? o2 : o3));
+          o0 += bz[0]; o1 += bz[1]; o2 += bz[2]; o3 += bz[3];
+          if (do_relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
+          if (do_add) { o0 += rv4[p8].x; o1 += rv4[p8].y; o2 += rv4[p8].z; o3 += rv4[p8].w; }
+          if (do_mask) {
+            o0 = rv4[p8].x > 0.f ? o0 : 0.f; o1 = rv4[p8].y > 0.f ? o1 : 0.f;
+            o2 = rv4[p8].z > 0.f ? o2 : 0.f; o3 = rv4[p8].w > 0.f ? o3 : 0.f;
+          }
           if (row < Md) {
-            const bool vec = col + 3 < n_out && ld_vec;
-            if (ep.epi != 0) {
-              const float rv[4] = {rv4[p8].x, rv4[p8].y, rv4[p8].z, rv4[p8].w};
-#pragma unroll
-              for (int tt = 0; tt < 4; ++tt) {
-                const int cc = col + tt;
-                if (cc < n_out) {
-                  float c = o[tt];
-                  if (ep.epi & HSG_EPI_BIAS) c += __ldg(ep.bias + cc);
-                  if (ep.epi & HSG_EPI_RELU) c = fmaxf(c, 0.f);
-                  if (ep.epi & HSG_EPI_ADD) c += rv[tt];
-                  if (ep.epi & HSG_EPI_RELU_MASK) c = rv[tt] > 0.f ? c : 0.f;
-                  o[tt] = c;
-                }
-              }
-            }
-            if (vec) {
-              *reinterpret_cast<float4*>(Dz + (size_t)row * ep.ldd + col) = make_float4(o[0], o[1], o[2], o[3]);
+            float* dp = Dz + (size_t)row * ep.ldd + col;
+            if (vec_col) {
+              *reinterpret_cast<float4*>(dp) = make_float4(o0, o1, o2, o3);
             } else {
-#pragma unroll
-              for (int tt = 0; tt < 4; ++tt)
-                if (col + tt < n_out) Dz[(size_t)row * ep.ldd + col + tt] = o[tt];
+              if (col + 0 < n_out) dp[0] = o0;
+              if (col + 1 < n_out) dp[1] = o1;
+              if (col + 2 < n_out) dp[2] = o2;
+              if (col + 3 < n_out) dp[3] = o3;
             }
-            if (ep.colsum_part != nullptr && ep.ones_col >= col && ep.ones_col < col + 4)
-              ep.colsum_part[(size_t)ti.z * Md + row] = o[ep.ones_col - col];
           }
         }
         __syncwarp();
