@@ -37,14 +37,15 @@ struct EdgeCfg {
   static constexpr int H = H_, D = D_, F = H_ * D_;
   static constexpr int VEC = (D_ % 4 == 0) ? 4 : ((D_ % 2 == 0) ? 2 : 1);
   static constexpr int NV = D_ / VEC;                       // vectors per head
-  static constexpr int LPH_MAX = 32 / H_;
-  static constexpr int LPH = NV < LPH_MAX ? NV : LPH_MAX;   // lanes per head
+  static constexpr int LPH = edge_lph(H_, NV);              // lanes per head (hsg_edge_layout.cuh)
   static constexpr int VPL = (NV + LPH - 1) / LPH;          // vectors per lane
   static constexpr int GROUP = H_ * LPH;                    // lanes per edge row
   static constexpr int EPS = 32 / GROUP;                    // edge rows per warp step
   static constexpr int NE = VPL * VEC;                      // elements per lane
   static constexpr int FP = VPL * GROUP * VEC;              // permuted row width
-  static constexpr bool STAGED = VPL > 1;                   // lane layout != row layout -> smem staging
+  // a lane's elements are original columns k*D + VEC*(l + LPH*i) + t: with LPH == 1 (lane owns its whole head) or
+  // VPL == 1 every lane vector is a contiguous piece of the row; otherwise row I/O is staged through shared memory
+  static constexpr bool STAGED = VPL > 1 && LPH > 1;
   static_assert(H_ <= 32 && LPH >= 1 && EPS >= 1, "bad edge config");
   static_assert(!STAGED || (EPS == 1 && F % 4 == 0), "staged epilogue assumes one row per warp step");
 };
@@ -105,7 +106,7 @@ __device__ __forceinline__ float elu1(float o) {            // F.elu, alpha = 1 
 }
 
 template <int H, int D, int U>
-__global__ void __launch_bounds__(EDGE_THREADS, (EdgeCfg<H, D>::NE <= 4) ? 4 : 3)
+__global__ void __launch_bounds__(EDGE_THREADS, (EdgeCfg<H, D>::NE <= 8) ? 4 : 3)
 edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
                 const uint8_t* __restrict__ bin, const int32_t* __restrict__ extra, const float* __restrict__ zp,
                 int ldz, const float* __restrict__ q, const float* __restrict__ origin, float* __restrict__ sh,
@@ -157,11 +158,17 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
     const float xcnt = extra ? (float)__ldg(extra + v) : 0.f;
     // origin row of this destination: issued now, consumed in the epilogue
     float4 og[OV];
+    float ogd[C::STAGED ? 1 : C::NE];
     if (x != nullptr) {
       if (!C::STAGED) {
-        float t[4] = {0.f, 0.f, 0.f, 0.f};
-        if (grp == 0) ld_vec<C::VEC>(origin + (size_t)v * C::F + gl * C::VEC, t);
-        og[0] = make_float4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) ogd[i] = 0.f;
+        if (grp == 0) {
+#pragma unroll
+          for (int i = 0; i < C::VPL; ++i)
+            if (l + C::LPH * i < C::NV)
+              ld_vec<C::VEC>(origin + (size_t)v * C::F + k * D + C::VEC * (l + C::LPH * i), ogd + i * C::VEC);
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < OV; ++i) {
@@ -208,22 +215,25 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
               if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(row + (i * C::GROUP + gl) * C::VEC, zv[uu] + i * C::VEC);
           }
         }
+        // consume them: online softmax with ONE rescale per U rows (maximum first), branch-free
+        float lgv[U];
+        float mx = m;
 #pragma unroll
-        for (int uu = 0; uu < U; ++uu) {                // then consume them (online softmax)
-          if (ok[uu]) {
-            const float lg = leaky(pe[uu] + q_s[bb[uu] * H + k]);
-            if (lg > m) {
-              const float sc = __expf(m - lg);
-              den *= sc;
+        for (int uu = 0; uu < U; ++uu) {
+          lgv[uu] = ok[uu] ? leaky(pe[uu] + q_s[bb[uu] * H + k]) : -CUDART_INF_F;
+          mx = fmaxf(mx, lgv[uu]);
+        }
+        const float sc = (m == mx) ? 1.f : __expf(m - mx);   // m == mx also covers -inf == -inf (no row seen yet)
+        den *= sc;
 #pragma unroll
-              for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
-              m = lg;
-            }
-            const float w = __expf(lg - m);
-            den += w;
+        for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
+        m = mx;
 #pragma unroll
-            for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
-          }
+        for (int uu = 0; uu < U; ++uu) {
+          const float w = ok[uu] ? __expf(lgv[uu] - mx) : 0.f;
+          den += w;
+#pragma unroll
+          for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
         }
       }
     }
@@ -259,18 +269,22 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
       stat[(size_t)v * 3 * H + H + k] = den;
     }
     if (!C::STAGED) {
-      if (grp == 0) {                                   // lane layout == row layout: direct 128-bit stores
-        const size_t off = (size_t)v * C::F + gl * C::VEC;
-        float o[C::VEC];
+      if (grp == 0) {                                   // every lane vector is a contiguous piece of the row
 #pragma unroll
-        for (int t = 0; t < C::VEC; ++t) o[t] = acc[t] * inv;
-        st_vec<C::VEC>(sh + off, o);
-        if (x != nullptr) {
-          const float ogv[4] = {og[0].x, og[0].y, og[0].z, og[0].w};
-          float xo[C::VEC];
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i < C::NV) {
+            const size_t off = (size_t)v * C::F + k * D + C::VEC * (l + C::LPH * i);
+            float o[C::VEC];
 #pragma unroll
-          for (int t = 0; t < C::VEC; ++t) xo[t] = ogv[t] + elu1(o[t]);
-          st_vec<C::VEC>(x + off, xo);
+            for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
+            st_vec<C::VEC>(sh + off, o);
+            if (x != nullptr) {
+              float xo[C::VEC];
+#pragma unroll
+              for (int t = 0; t < C::VEC; ++t) xo[t] = ogd[i * C::VEC + t] + elu1(o[t]);
+              st_vec<C::VEC>(x + off, xo);
+            }
+          }
         }
       }
     } else {
@@ -312,6 +326,173 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
 }
 
 // ---------------------------------------------------------------------------
+// forward, ROW-PARALLEL: every GROUP-lane group of a warp walks ITS OWN destination row (EPS rows per warp in flight,
+// U gathered rows each).  No merge of partial softmax states, no index shuffles: on the W2S default (8,8) (one lane
+// per head, four rows per warp) this executes ~2.5x fewer instructions per edge than the shared-row mapping, which
+// ncu showed issue-bound on large shards.  Used when there are enough rows to fill the machine (hsg_edge_fwd picks).
+// Same arithmetic per row as edge_fwd_kernel with one group (edges in CSC order, one rescale per U rows).
+// ---------------------------------------------------------------------------
+template <int H, int D, int U>
+__global__ void __launch_bounds__(EDGE_THREADS, (U * EdgeCfg<H, D>::NE <= 16) ? 4 : 3)
+edge_fwd_rowpar_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                       const uint8_t* __restrict__ bin, const int32_t* __restrict__ extra,
+                       const float* __restrict__ zp, int ldz, const float* __restrict__ q,
+                       const float* __restrict__ origin, float* __restrict__ sh, float* __restrict__ x,
+                       float* __restrict__ stat) {
+  pdl_prologue();
+  using C = EdgeCfg<H, D>;
+  static_assert(!C::STAGED && C::EPS > 1, "row-parallel forward needs direct row I/O and several groups per warp");
+  __shared__ float q_s[HSG_N_BINS * H];
+  for (int i = threadIdx.x; i < HSG_N_BINS * H; i += blockDim.x) q_s[i] = q[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int grp = lane / C::GROUP;
+  const int gl = lane % C::GROUP;
+  const int k = gl / C::LPH;
+  const int l = gl % C::LPH;
+  const bool lane_on = grp < C::EPS;
+  const int nsteps = ceil_div(n_dst, C::EPS);
+
+  int st = warp;
+  int beg = 0, end = 0;
+  {
+    const int v = st * C::EPS + grp;
+    if (lane_on && st < nsteps && v < n_dst) {
+      beg = __ldg(indptr + v);
+      end = __ldg(indptr + v + 1);
+    }
+  }
+  while (st < nsteps) {
+    const int v = st * C::EPS + grp;
+    const bool row_on = lane_on && v < n_dst;
+    int begn = 0, endn = 0;                              // next step's edge range: issued now, used at the bottom
+    {
+      const int vn = (st + nwarps) * C::EPS + grp;
+      if (lane_on && st + nwarps < nsteps && vn < n_dst) {
+        begn = __ldg(indptr + vn);
+        endn = __ldg(indptr + vn + 1);
+      }
+    }
+    const int deg = row_on ? end - beg : 0;
+    int maxdeg = deg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    // ids / bins of the first U edges of this group's row
+    int un[U], bn[U];
+#pragma unroll
+    for (int uu = 0; uu < U; ++uu) {
+      un[uu] = 0;
+      bn[uu] = 0;
+      if (uu < deg) {
+        un[uu] = __ldg(nbr + beg + uu);
+        bn[uu] = __ldg(bin + beg + uu);
+      }
+    }
+    const float xcnt = (extra && row_on) ? (float)__ldg(extra + v) : 0.f;
+    float ogd[C::NE];
+#pragma unroll
+    for (int i = 0; i < C::NE; ++i) ogd[i] = 0.f;
+    if (x != nullptr && row_on) {
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i)
+        if (l + C::LPH * i < C::NV)
+          ld_vec<C::VEC>(origin + (size_t)v * C::F + k * D + C::VEC * (l + C::LPH * i), ogd + i * C::VEC);
+    }
+    float m = -CUDART_INF_F, den = 0.f;
+    float acc[C::NE];
+#pragma unroll
+    for (int i = 0; i < C::NE; ++i) acc[i] = 0.f;
+
+    for (int j0 = 0; j0 < maxdeg; j0 += U) {             // warp-uniform trip count
+      float zv[U][C::NE], pe[U];
+      int bb[U];
+      bool ok[U];
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {                  // gathers of this round
+        ok[uu] = j0 + uu < deg;
+        bb[uu] = bn[uu];
+        pe[uu] = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) zv[uu][i] = 0.f;
+        if (ok[uu]) {
+          const float* row = zp + (size_t)un[uu] * ldz;
+          pe[uu] = __ldg(row + C::FP + k);
+#pragma unroll
+          for (int i = 0; i < C::VPL; ++i)
+            if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(row + (i * C::GROUP + gl) * C::VEC, zv[uu] + i * C::VEC);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {                  // ids of the next round, in flight with the gathers
+        const int j = j0 + U + uu;
+        un[uu] = 0;
+        bn[uu] = 0;
+        if (j < deg) {
+          un[uu] = __ldg(nbr + beg + j);
+          bn[uu] = __ldg(bin + beg + j);
+        }
+      }
+      float lgv[U];
+      float mx = m;
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        lgv[uu] = ok[uu] ? leaky(pe[uu] + q_s[bb[uu] * H + k]) : -CUDART_INF_F;
+        mx = fmaxf(mx, lgv[uu]);
+      }
+      const float sc = (m == mx) ? 1.f : __expf(m - mx);
+      den *= sc;
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
+      m = mx;
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        const float w = ok[uu] ? __expf(lgv[uu] - mx) : 0.f;
+        den += w;
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
+      }
+    }
+    float mf = 0.f, inv = 0.f;
+    if (m == -CUDART_INF_F) {  // no word<->supernode in-edge: DGL's zero fill (or softmax over z = 0 extras)
+      den = xcnt > 0.f ? xcnt : 1.f;
+    } else {
+      mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
+      const float sc = __expf(m - mf);
+      den = den * sc + xcnt * __expf(-mf);
+      inv = sc / den;
+    }
+    if (row_on) {
+      if (l == 0) {
+        stat[(size_t)v * 3 * H + k] = mf;
+        stat[(size_t)v * 3 * H + H + k] = den;
+      }
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) {
+        if (l + C::LPH * i < C::NV) {
+          const size_t off = (size_t)v * C::F + k * D + C::VEC * (l + C::LPH * i);
+          float o[C::VEC];
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
+          st_vec<C::VEC>(sh + off, o);
+          if (x != nullptr) {
+            float xo[C::VEC];
+#pragma unroll
+            for (int t = 0; t < C::VEC; ++t) xo[t] = ogd[i * C::VEC + t] + elu1(o[t]);
+            st_vec<C::VEC>(x + off, xo);
+          }
+        }
+      }
+    }
+    st += nwarps;
+    beg = begn;
+    end = endn;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // backward prep: g = dx * elu'(sh)  (or g = dsh) written lane-interleaved [n_dst, FP],
 //                s[v,k] = g_v[k] . sh_v[k]
 // ---------------------------------------------------------------------------
@@ -340,18 +521,24 @@ edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __res
     for (int i = 0; i < C::NE; ++i) gv[i] = 0.f;
     if (!C::STAGED) {
       if (on) {
-        const size_t off = (size_t)v * C::F + gl * C::VEC;
-        float s_[C::VEC];
-        ld_vec<C::VEC>(sh + off, s_);
-        if (dx != nullptr) {
-          ld_vec<C::VEC>(dx + off, gv);
 #pragma unroll
-          for (int t = 0; t < C::VEC; ++t) gv[t] *= (s_[t] > 0.f ? 1.f : __expf(s_[t]));
-        } else {
-          ld_vec<C::VEC>(dsh + off, gv);
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i < C::NV) {
+            const size_t off = (size_t)v * C::F + k * D + C::VEC * (l + C::LPH * i);
+            float s_[C::VEC];
+            float* gi = gv + i * C::VEC;
+            ld_vec<C::VEC>(sh + off, s_);
+            if (dx != nullptr) {
+              ld_vec<C::VEC>(dx + off, gi);
+#pragma unroll
+              for (int t = 0; t < C::VEC; ++t) gi[t] *= (s_[t] > 0.f ? 1.f : __expf(s_[t]));
+            } else {
+              ld_vec<C::VEC>(dsh + off, gi);
+            }
+#pragma unroll
+            for (int t = 0; t < C::VEC; ++t) part = fmaf(gi[t], s_[t], part);
+          }
         }
-#pragma unroll
-        for (int t = 0; t < C::VEC; ++t) part = fmaf(gv[t], s_[t], part);
       }
     } else {
       float* g_row = stage + (2 * wib) * C::F;
@@ -516,7 +703,7 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
           if (ok[uu]) {
             const float pre = pu + q_s[bb[uu] * H + k];
             const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-            const float alpha = __expf(lg - mk[uu]) / dk[uu];
+            const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
             const float de = alpha * (t - sk[uu]);
             const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -688,7 +875,7 @@ edge_bwd_rowpar_kernel(int n_src, const int32_t* __restrict__ indptr, const int3
         if (ok[uu]) {
           const float pre = pu + q_s[bb[uu] * H + k];
           const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-          const float alpha = __expf(lg - mk[uu]) / dk[uu];
+          const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
           const float de = alpha * (t - sk[uu]);
           const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -825,7 +1012,7 @@ edge_bwd_blockrow_kernel(int n_src, const int32_t* __restrict__ indptr, const in
           if (ok[uu]) {
             const float pre = pu + q_s[bb[uu] * H + k];
             const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-            const float alpha = __expf(lg - mk[uu]) / dk[uu];
+            const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
             const float de = alpha * (t - sk[uu]);
             const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -934,6 +1121,25 @@ static int edge_grid(int n_rows_steps, int cap = EDGE_DEFAULT_BLOCKS) {
 #define HSG_EDGE_CONFIGS(X) \
   X(8, 8) X(6, 50) X(8, 16) X(6, 16) X(8, 32) X(6, 32) X(4, 4) X(6, 8) X(4, 16) X(1, 64) X(16, 4) X(2, 32) X(4, 32) X(12, 25)
 
+static std::atomic<int> g_fwd_rowpar{-1};   // -1 auto (many rows), 0 never, 1 whenever the layout allows
+constexpr int FWD_ROWPAR_MIN_ROWS = 16384;
+
+template <int H, int D>
+static bool launch_fwd_rowpar(int blocks, bool deep, const hsg_csc* c, const float* zp, int ldz, const float* q,
+                              const float* origin, float* sh, float* x, float* stat, cudaStream_t s) {
+  if constexpr (EdgeCfg<H, D>::EPS > 1 && !EdgeCfg<H, D>::STAGED) {
+    constexpr int UR = EdgeCfg<H, D>::NE <= 8 ? 4 : 2;
+    if (deep)
+      launch_k(edge_fwd_rowpar_kernel<H, D, UR>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr,
+               c->bin, c->extra, zp, ldz, q, origin, sh, x, stat);
+    else
+      launch_k(edge_fwd_rowpar_kernel<H, D, 2>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr,
+               c->bin, c->extra, zp, ldz, q, origin, sh, x, stat);
+    return true;
+  }
+  return false;
+}
+
 // unroll depth: deep for high-degree rows (supernodes), shallow for low-degree rows (words)
 template <int H, int D>
 static int launch_fwd(const hsg_csc* c, const float* zp, int ldz, const float* q, const float* origin, float* sh,
@@ -941,7 +1147,13 @@ static int launch_fwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   using C = EdgeCfg<H, D>;
   constexpr int UHI = C::NE <= 4 ? 4 : 2, ULO = C::NE <= 4 ? 2 : 1;
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
+  const bool deep_row = (double)c->n_edges > 4.0 * (double)c->n_dst;
+  const int rp = g_fwd_rowpar.load(std::memory_order_relaxed);
+  const bool rowpar = C::EPS > 1 && !C::STAGED && (rp == 1 || (rp < 0 && c->n_dst >= FWD_ROWPAR_MIN_ROWS));
   LaunchScope ls(SLOT_EDGE_FWD, s);
+  if (rowpar && launch_fwd_rowpar<H, D>(edge_grid(ceil_div(c->n_dst, C::EPS)), deep_row, c, zp, ldz, q, origin, sh, x,
+                                        stat, s))
+    return check_launch();
   if (deep)
     launch_k(edge_fwd_kernel<H, D, UHI>, dim3(edge_grid(c->n_dst, C::STAGED ? EDGE_MAX_BLOCKS : EDGE_DEFAULT_BLOCKS)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
@@ -1072,6 +1284,11 @@ int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx, const float* dsh
 
 int hsg_set_edge_rowpar(int mode) {
   g_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  return HSG_OK;
+}
+
+int hsg_set_edge_fwd_rowpar(int mode) {
+  g_fwd_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
   return HSG_OK;
 }
 

@@ -18,14 +18,20 @@ struct EdgeLayout {
   int H, D, vec, nv, lph, vpl, group, eps, fp, ldz;
 };
 
+// lanes per head.  Short heads (at most two vectors, e.g. the W2S default D = 8) are owned by ONE lane: the logit,
+// softmax weight and the backward dot product of a head then need no cross-lane traffic and no redundant math, and
+// 32/H edge rows are in flight per warp instruction.  Longer heads are spread over up to 32/H lanes.
+__host__ __device__ constexpr int edge_lph(int H, int nv) {
+  return nv <= 2 ? 1 : (nv < 32 / H ? nv : 32 / H);
+}
+
 __host__ __device__ inline EdgeLayout make_edge_layout(int H, int D) {
   EdgeLayout L;
   L.H = H;
   L.D = D;
   L.vec = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
   L.nv = D / L.vec;
-  const int lph_max = 32 / H;
-  L.lph = L.nv < lph_max ? L.nv : lph_max;
+  L.lph = edge_lph(H, L.nv);
   L.vpl = (L.nv + L.lph - 1) / L.lph;
   L.group = H * L.lph;
   L.eps = 32 / L.group;

@@ -214,6 +214,10 @@ int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, 
  * torch.cat(head_outs), GATStackLayer.py:59) to its position inside a gathered row. */
 int hsg_edge_layout(int H, int d, int* host_fp, int* host_ldz);
 int hsg_edge_perm(int H, int d, int col);
+/* Row mapping of hsg_edge_fwd when a warp holds several GROUP-lane groups: -1 auto (each group walks its own
+ * destination row when there are >= 16 384 rows - large shards; the groups share one row's edge list otherwise),
+ * 0 never, 1 whenever the layout allows.  Same results up to summation order (tested). */
+int hsg_set_edge_fwd_rowpar(int mode);
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
                  const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F] */,
                  float* x /* [n_dst,F] or NULL */, float* stat /* [n_dst,3H] */, void* stream);

@@ -746,11 +746,29 @@ ALL_EDGE_CONFIGS = [(8, 8), (6, 50), (8, 16), (6, 16), (8, 32), (6, 32), (4, 4),
                     (2, 32), (4, 32), (12, 25)]
 
 
+@pytest.fixture
+def row_mapping(request):
+    """Forces the edge kernels' row mapping ("auto", "shared" = groups share a row, "rowpar" = a row per group)."""
+    from hetersumgraph_b200 import _lib
+    lib = _lib.load()
+    mode = {"auto": -1, "shared": 0, "rowpar": 1}[request.param]
+    lib.hsg_set_edge_fwd_rowpar(mode)
+    lib.hsg_set_edge_rowpar(mode)
+    if mode >= 0:
+        lib.hsg_set_edge_blockrow(0)
+    yield request.param
+    lib.hsg_set_edge_fwd_rowpar(-1)
+    lib.hsg_set_edge_rowpar(-1)
+    lib.hsg_set_edge_blockrow(-1)
+
+
 @pytest.mark.parametrize("H,d", ALL_EDGE_CONFIGS)
 @pytest.mark.parametrize("kind", ["W2S", "S2W"])
-def test_every_instantiated_head_shape_matches_closed_form(H, d, kind):
-    """Every (heads, head_dim) instantiation of the edge kernels (HSG_EDGE_CONFIGS), both layer types, forward and
-    all gradients of MultiHeadLayer against the closed form on a small HSG batch."""
+@pytest.mark.parametrize("row_mapping", ["auto", "shared", "rowpar"], indirect=True)
+def test_every_instantiated_head_shape_matches_closed_form(H, d, kind, row_mapping):
+    """Every (heads, head_dim) instantiation of the edge kernels (HSG_EDGE_CONFIGS), both layer types, every row
+    mapping of the forward and backward kernels: forward and all gradients of MultiHeadLayer against the closed form
+    on a small HSG batch."""
     exs = syn.make_examples(4, "tiny", seed=91)
     batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
     bg, _ = oracle_batch(exs, False)
