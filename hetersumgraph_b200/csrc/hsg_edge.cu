@@ -1070,6 +1070,234 @@ edge_bwd_blockrow_kernel(int n_src, const int32_t* __restrict__ indptr, const in
   }
 }
 
+// ---------------------------------------------------------------------------
+// backward over HIGH-degree rows with ASYNCHRONOUS gathers (the supernode rows of the S2W layer on a large shard:
+// ~17 word neighbours of 1.2 KB each).  ncu showed edge_bwd_kernel latency-bound there (long-scoreboard stalls on the
+// first use of a gathered row, 24 warps/SM x 2 rows in flight because the gathered rows live in registers).  Here the
+// neighbour rows [g_v | (m, den, s)_v] are copied global -> shared with cp.async into a per-warp ring of R slots,
+// R - 1 rows ahead of the row being consumed, across row boundaries: a warp owns a CHUNK of consecutive rows, whose
+// edge lists are one contiguous range of the CSC, and streams through that range.  Same arithmetic and summation
+// order per row as edge_bwd_kernel (one group per warp).  Layouts with one GROUP per warp (EPS == 1) only.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int ASYNC_ROWS_PER_CHUNK = 8;
+
+template <int H, int D>
+struct AsyncCfg {
+  using C = EdgeCfg<H, D>;
+  static constexpr int SLOT = (C::FP + 3 * H + 1 + 3) & ~3;          // floats: [g row | m den s | bin], 16-byte multiple
+  // ring depth: as deep as ~7.5 KB per warp allows (3 CTAs of 8 warps per SM), at least 3, at most 8
+  static constexpr int R_FIT = (7680 / 4) / SLOT;
+#ifdef HSG_ASYNC_R
+  static constexpr int R = HSG_ASYNC_R;
+#else
+  static constexpr int R = R_FIT < 3 ? 3 : (R_FIT > 8 ? 8 : R_FIT);
+#endif
+  static constexpr size_t SMEM = (size_t)EDGE_WARPS * R * SLOT * sizeof(float);
+};
+
+template <int H, int D>
+__global__ void __launch_bounds__(EDGE_THREADS, 3)
+edge_bwd_async_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                      const uint8_t* __restrict__ bin, const float* __restrict__ zp, int ldz,
+                      const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ stat,
+                      float* __restrict__ dzp, float* __restrict__ dq_part, int RC) {
+  pdl_prologue();
+  using C = EdgeCfg<H, D>;
+  using A = AsyncCfg<H, D>;
+  static_assert(C::EPS == 1 && C::FP % 4 == 0, "one group per warp, 16-byte row copies");
+  constexpr int NQ = HSG_N_BINS * H;
+  constexpr int R = A::R, SLOT = A::SLOT;
+  extern __shared__ float4 ring_raw[];
+  __shared__ float q_s[NQ];
+  __shared__ float dq_s[EDGE_WARPS][NQ];
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) q_s[i] = q[i];
+  for (int i = threadIdx.x; i < EDGE_WARPS * NQ; i += blockDim.x) (&dq_s[0][0])[i] = 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int gl = lane % C::GROUP;
+  const int k = gl / C::LPH;
+  const int l = gl % C::LPH;
+  const bool lane_on = lane < C::GROUP;
+  float* my_dq = &dq_s[wib][0];
+  float* ring = reinterpret_cast<float*>(ring_raw) + (size_t)wib * R * SLOT;
+  const int nchunks = ceil_div(n_src, RC);
+
+  for (int chunk = warp; chunk < nchunks; chunk += nwarps) {
+    const int r0 = chunk * RC, nrows = min(RC, n_src - r0);
+    const int my_ip = lane <= nrows ? __ldg(indptr + r0 + lane) : 0;        // row pointers of the chunk
+    const int e_beg = __shfl_sync(0xffffffffu, my_ip, 0), e_end = __shfl_sync(0xffffffffu, my_ip, nrows);
+    // ---- producer state: neighbour ids / bins in blocks of 32 edges, one block ahead ----
+    int pblk = e_beg;
+    int p_ids = 0, p_bins = 0, p_ids_n = 0, p_bins_n = 0;
+    if (pblk + lane < e_end) {
+      p_ids = __ldg(nbr + pblk + lane);
+      p_bins = __ldg(bin + pblk + lane);
+    }
+    if (pblk + 32 + lane < e_end) {
+      p_ids_n = __ldg(nbr + pblk + 32 + lane);
+      p_bins_n = __ldg(bin + pblk + 32 + lane);
+    }
+    int pe = e_beg;
+    auto issue = [&]() {                                   // copies of edge pe into its ring slot (warp-uniform)
+      if (pe < e_end) {
+        if (pe - pblk >= 32) {
+          pblk += 32;
+          p_ids = p_ids_n;
+          p_bins = p_bins_n;
+          p_ids_n = 0;
+          p_bins_n = 0;
+          if (pblk + 32 + lane < e_end) {
+            p_ids_n = __ldg(nbr + pblk + 32 + lane);
+            p_bins_n = __ldg(bin + pblk + 32 + lane);
+          }
+        }
+        const int v = __shfl_sync(0xffffffffu, p_ids, pe - pblk);
+        const int b = __shfl_sync(0xffffffffu, p_bins, pe - pblk);
+        float* slot = ring + ((pe - e_beg) % R) * SLOT;
+        const float* grow = g + (size_t)v * C::FP;
+        for (int c4 = lane; c4 < C::FP / 4; c4 += 32) cp_async_16(slot + 4 * c4, grow + 4 * c4);
+        const float* srow = stat + (size_t)v * 3 * H;
+        for (int c = lane; c < 3 * H; c += 32) cp_async_4(slot + C::FP + c, srow + c);
+        if (lane == 0) slot[C::FP + 3 * H] = __int_as_float(b);
+      }
+      cp_async_commit();                                   // one group per edge slot, empty or not
+      ++pe;
+    };
+#pragma unroll 1
+    for (int i = 0; i < R - 1; ++i) issue();
+
+    // ---- consumer state ----
+    int row = 0;                                            // row index inside the chunk
+    int row_end = __shfl_sync(0xffffffffu, my_ip, 1);
+    float zv[C::NE], zn[C::NE], acc[C::NE];
+    float pu = 0.f, pn = 0.f, acc_dp = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::NE; ++i) {
+      zv[i] = 0.f;
+      zn[i] = 0.f;
+      acc[i] = 0.f;
+    }
+    auto load_z = [&](int r, float* zdst, float& pdst) {    // [z | p] of source row r0 + r (zeros past the chunk)
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) zdst[i] = 0.f;
+      pdst = 0.f;
+      if (lane_on && r < nrows) {
+        const float* zrow = zp + (size_t)(r0 + r) * ldz;
+        pdst = __ldg(zrow + C::FP + k);
+#pragma unroll
+        for (int i = 0; i < C::VPL; ++i)
+          if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(zrow + (i * C::GROUP + gl) * C::VEC, zdst + i * C::VEC);
+      }
+    };
+    auto finalize = [&]() {                                 // write [dz | dp | 0] of the current row, reset
+      float* drow = dzp + (size_t)(r0 + row) * ldz;
+      if (lane_on) {
+#pragma unroll
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i >= C::NV) {
+#pragma unroll
+            for (int t = 0; t < C::VEC; ++t) acc[i * C::VEC + t] = 0.f;   // layout holes must be finite zeros
+          }
+          st_vec<C::VEC>(drow + (i * C::GROUP + gl) * C::VEC, acc + i * C::VEC);
+        }
+        if (l == 0) drow[C::FP + k] = acc_dp;
+      }
+      for (int c = C::FP + H + lane; c < ldz; c += 32) drow[c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) acc[i] = 0.f;
+      acc_dp = 0.f;
+      ++row;
+      row_end = __shfl_sync(0xffffffffu, my_ip, min(row + 1, 31));
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) zv[i] = zn[i];
+      pu = pn;
+      load_z(row + 1, zn, pn);                             // one row ahead
+    };
+    load_z(0, zv, pu);
+    load_z(1, zn, pn);
+
+    for (int ce = e_beg; ce < e_end; ++ce) {
+      issue();
+      cp_async_wait<R - 1>();
+      __syncwarp();
+      while (ce >= row_end) finalize();                    // rows that ended (or are empty) before this edge
+      const float* slot = ring + ((ce - e_beg) % R) * SLOT;
+      float gv[C::NE];
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) gv[i] = 0.f;
+      float mk = 0.f, dk = 1.f, sk = 0.f;
+      int bb = 0;
+      if (lane_on) {
+        mk = slot[C::FP + k];
+        dk = slot[C::FP + H + k];
+        sk = slot[C::FP + 2 * H + k];
+        bb = __float_as_int(slot[C::FP + 3 * H]);
+#pragma unroll
+        for (int i = 0; i < C::VPL; ++i) {
+          if (l + C::LPH * i < C::NV) {
+            const float* sp = slot + (i * C::GROUP + gl) * C::VEC;
+            if (C::VEC == 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(sp);
+              gv[i * C::VEC] = t4.x; gv[i * C::VEC + 1] = t4.y; gv[i * C::VEC + 2] = t4.z; gv[i * C::VEC + 3] = t4.w;
+            } else if (C::VEC == 2) {
+              const float2 t2 = *reinterpret_cast<const float2*>(sp);
+              gv[i * C::VEC] = t2.x; gv[i * C::VEC + 1] = t2.y;
+            } else {
+              gv[i * C::VEC] = sp[0];
+            }
+          }
+        }
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < C::NE; ++i) part = fmaf(gv[i], zv[i], part);
+      const float t = head_sum<C::LPH>(part, lane, l);
+      if (lane_on) {
+        const float pre = pu + q_s[bb * H + k];
+        const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
+        const float alpha = __fdividef(__expf(lg - mk), dk);
+        const float de = alpha * (t - sk);
+        const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
+#pragma unroll
+        for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(alpha, gv[i], acc[i]);
+        acc_dp += dpre;
+        if (l == 0) my_dq[bb * H + k] += dpre;
+      }
+      __syncwarp();                                        // the slot is free for the copy issued next iteration
+    }
+    while (row < nrows) finalize();                        // last row with edges and trailing empty rows
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) {
+    float sres = 0.f;
+#pragma unroll
+    for (int w = 0; w < EDGE_WARPS; ++w) sres += dq_s[w][i];
+    dq_part[(size_t)blockIdx.x * NQ + i] = sres;
+  }
+}
+
 // dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
 __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
                                                           float* __restrict__ dq, int accumulate) {
@@ -1185,6 +1413,39 @@ static void launch_rowpar(int blocks, const hsg_csc* c, const float* zp, int ldz
   }
 }
 
+// -1 auto, 0 never, 1 whenever the layout allows.  Auto NEVER picks this mapping: measured on the 2 048-graph shard
+// (S2W backward, 35 k rows x ~30 neighbours of 1.2 KB) it takes 414 us against 360 us for the register-gather kernel -
+// ncu (profiles/r01k_full_edge_bwd_async.txt): issue slots 69 % busy, DRAM 38 %: the ring bookkeeping and the shared-
+// memory round trip cost more issue slots than the removed scoreboard stalls gave back.  Kept as a parity-tested opt-in.
+static std::atomic<int> g_bwd_async{-1};
+
+template <int H, int D>
+static bool launch_bwd_async(int* blocks_out, const hsg_csc* c, const float* zp, int ldz, const float* q,
+                             const float* g, const float* stat, float* dzp, float* ws, cudaStream_t s) {
+  if constexpr (EdgeCfg<H, D>::EPS == 1 && EdgeCfg<H, D>::FP % 4 == 0) {
+    using A = AsyncCfg<H, D>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(edge_bwd_async_kernel<H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)A::SMEM) != cudaSuccess)
+        return false;
+      attr_done = true;
+    }
+    static int rc = 0;
+    if (!rc) {
+      const char* e = getenv("HSG_ASYNC_RC");
+      rc = e ? atoi(e) : ASYNC_ROWS_PER_CHUNK;
+      if (rc < 1 || rc > 30) rc = ASYNC_ROWS_PER_CHUNK;
+    }
+    const int blocks = edge_grid(ceil_div(c->n_dst, rc), 148 * 3);
+    launch_k(edge_bwd_async_kernel<H, D>, dim3(blocks), dim3(EDGE_THREADS), A::SMEM, s, c->n_dst, c->indptr, c->nbr,
+             c->bin, zp, ldz, q, g, stat, dzp, ws, rc);
+    *blocks_out = blocks;
+    return true;
+  }
+  return false;
+}
+
 template <int H, int D>
 static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g, const float* stat,
                       float* dzp, float* dq, float* ws, int accumulate_dq, cudaStream_t s) {
@@ -1196,11 +1457,14 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   // few high-degree rows (a warp per row would leave most SMs idle and last as long as the longest row): CTA per row
   const int br = g_blockrow.load(std::memory_order_relaxed);
   const bool blockrow = !rowpar && (br == 1 || (br < 0 && deep && c->n_dst <= BLOCKROW_MAX_ROWS));
-  const int blocks = blockrow ? min(c->n_dst, edge_block_cap(EDGE_DEFAULT_BLOCKS))
-                              : (rowpar ? edge_grid(ceil_div(c->n_dst, C::EPS)) : edge_grid(c->n_dst));
+  int blocks = blockrow ? min(c->n_dst, edge_block_cap(EDGE_DEFAULT_BLOCKS))
+                        : (rowpar ? edge_grid(ceil_div(c->n_dst, C::EPS)) : edge_grid(c->n_dst));
+  const int as = g_bwd_async.load(std::memory_order_relaxed);
+  const bool async = !rowpar && !blockrow && as == 1;
   {
     LaunchScope ls(SLOT_EDGE_BWD, s);
-    if (blockrow)
+    if (async && launch_bwd_async<H, D>(&blocks, c, zp, ldz, q, g, stat, dzp, ws, s)) {
+    } else if (blockrow)
       launch_k(edge_bwd_blockrow_kernel<H, D>, dim3(blocks), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                zp, ldz, q, g, stat, dzp, ws);
     else if (rowpar)
@@ -1289,6 +1553,11 @@ int hsg_set_edge_rowpar(int mode) {
 
 int hsg_set_edge_fwd_rowpar(int mode) {
   g_fwd_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  return HSG_OK;
+}
+
+int hsg_set_edge_bwd_async(int mode) {
+  g_bwd_async.store(mode < 0 ? -1 : (mode ? 1 : 0));
   return HSG_OK;
 }
 

@@ -238,6 +238,11 @@ int hsg_set_edge_rowpar(int mode);
  * the supernode rows of a small batch): the eight warps of a CTA share one row's edge list and their partial rows are
  * summed in warp order.  -1 auto, 0 never, 1 always (overrides the warp-per-row mappings). */
 int hsg_set_edge_blockrow(int mode);
+/* Asynchronous-gather mapping of hsg_edge_bwd (layouts with one lane group per warp, e.g. the S2W default (6,50)):
+ * neighbour rows are copied global -> shared with cp.async into a per-warp ring several rows ahead, across row
+ * boundaries.  Opt-in only: -1 auto (= never: measured slower than the register-gather kernel, see hsg_edge.cu),
+ * 0 never, 1 whenever the layout allows (and neither the row-parallel nor the CTA-per-row mapping is forced). */
+int hsg_set_edge_bwd_async(int mode);
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,
                  const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
                  void* ws, size_t ws_bytes, void* stream);

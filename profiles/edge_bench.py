@@ -29,14 +29,20 @@ def main():
     tb = syn.pack_token_batch(exs)
     batch = HeteroBatch.build(DeviceTokenBatch.upload(tb, dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    variants = [("auto", -1, -1, -1), ("shared-row fwd, shared-row bwd", 0, 0, 0), ("row-parallel fwd+bwd", 1, 1, 0)]
-    for name, fr, br, blk in variants:
+    variants = [("auto", -1, -1, -1, -1), ("shared-row fwd, shared-row bwd", 0, 0, 0, 0),
+                ("row-parallel fwd+bwd", 1, 1, 0, 0), ("async-gather bwd", 0, 0, 0, 1)]
+    only = os.environ.get("EDGE_BENCH_VARIANTS")
+    if only:
+        variants = [v for v in variants if v[0].split()[0] in only.split(",")]
+    for name, fr, br, blk, asy in variants:
+        lib.hsg_set_edge_bwd_async(asy)
         lib.hsg_set_edge_fwd_rowpar(fr)
         lib.hsg_set_edge_rowpar(br)
         lib.hsg_set_edge_blockrow(blk)
         for r in bench._time_edge_kernels(batch, "%d cnndm graphs" % n_graphs, dev, pk, flush, iters):
             print(json.dumps({"mapping": name, "kernel": r["kernel"], "layer": r["layer"], "us": round(r["ms"] * 1e3, 1),
                               "MB": round(r["algorithmic_MB"], 1), "frac": round(r["frac_of_hbm_peak"], 3)}))
+    lib.hsg_set_edge_bwd_async(-1)
     lib.hsg_set_edge_fwd_rowpar(-1)
     lib.hsg_set_edge_rowpar(-1)
     lib.hsg_set_edge_blockrow(-1)

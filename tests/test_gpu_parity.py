@@ -609,9 +609,10 @@ def test_edge_bwd_row_mappings_agree(kind, H, d):
     ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), torch.device(dev), "edge")
     outs = []
     try:
-        for rowpar, blockrow in ((0, 0), (1, 0), (0, 1)):
+        for rowpar, blockrow, asy in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)):
             lib.hsg_set_edge_rowpar(rowpar)
             lib.hsg_set_edge_blockrow(blockrow)
+            lib.hsg_set_edge_bwd_async(asy)
             dzp = torch.full((csc.n_src, ldz), float("nan"), device=dev)
             dq = torch.empty(10, H, device=dev)
             _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(), g.data_ptr(),
@@ -620,6 +621,7 @@ def test_edge_bwd_row_mappings_agree(kind, H, d):
     finally:
         lib.hsg_set_edge_rowpar(-1)
         lib.hsg_set_edge_blockrow(-1)
+        lib.hsg_set_edge_bwd_async(-1)
     for dzp, dq in outs[1:]:
         assert torch.isfinite(dzp).all()
         assert nerr(dzp, outs[0][0]) <= 2e-6 and nerr(dq, outs[0][1]) <= 2e-6
@@ -748,23 +750,26 @@ ALL_EDGE_CONFIGS = [(8, 8), (6, 50), (8, 16), (6, 16), (8, 32), (6, 32), (4, 4),
 
 @pytest.fixture
 def row_mapping(request):
-    """Forces the edge kernels' row mapping ("auto", "shared" = groups share a row, "rowpar" = a row per group)."""
+    """Forces the edge kernels' row mapping: "auto"; "shared" = the lane groups of a warp share one row; "rowpar" = a
+    row per lane group (forward and backward); "async" = backward with cp.async gathers through a shared-memory ring."""
     from hetersumgraph_b200 import _lib
     lib = _lib.load()
-    mode = {"auto": -1, "shared": 0, "rowpar": 1}[request.param]
-    lib.hsg_set_edge_fwd_rowpar(mode)
-    lib.hsg_set_edge_rowpar(mode)
-    if mode >= 0:
-        lib.hsg_set_edge_blockrow(0)
+    fwd_rp, bwd_rp, blk, asy = {"auto": (-1, -1, -1, -1), "shared": (0, 0, 0, 0), "rowpar": (1, 1, 0, 0),
+                                "async": (0, 0, 0, 1)}[request.param]
+    lib.hsg_set_edge_fwd_rowpar(fwd_rp)
+    lib.hsg_set_edge_rowpar(bwd_rp)
+    lib.hsg_set_edge_blockrow(blk)
+    lib.hsg_set_edge_bwd_async(asy)
     yield request.param
     lib.hsg_set_edge_fwd_rowpar(-1)
     lib.hsg_set_edge_rowpar(-1)
     lib.hsg_set_edge_blockrow(-1)
+    lib.hsg_set_edge_bwd_async(-1)
 
 
 @pytest.mark.parametrize("H,d", ALL_EDGE_CONFIGS)
 @pytest.mark.parametrize("kind", ["W2S", "S2W"])
-@pytest.mark.parametrize("row_mapping", ["auto", "shared", "rowpar"], indirect=True)
+@pytest.mark.parametrize("row_mapping", ["auto", "shared", "rowpar", "async"], indirect=True)
 def test_every_instantiated_head_shape_matches_closed_form(H, d, kind, row_mapping):
     """Every (heads, head_dim) instantiation of the edge kernels (HSG_EDGE_CONFIGS), both layer types, every row
     mapping of the forward and backward kernels: forward and all gradients of MultiHeadLayer against the closed form
