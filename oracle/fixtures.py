@@ -72,3 +72,70 @@ def graph_from_arrays(z, prefix="g_"):
     g.batch_num_nodes = z[prefix + "batch_num_nodes"].tolist()
     g.batch_num_edges = z[prefix + "batch_num_edges"].tolist()
     return g
+
+
+# --------------------------------------------------------------------------------------------
+# sentence-encoder fixtures (tests/golden/make_golden_encoder.py and the tests share these)
+# --------------------------------------------------------------------------------------------
+def encoder_param_shapes(vocab, emb, sent_max_len, doc_max, n_feature, hidden, lstm_hidden, lstm_layers=2):
+    """state_dict keys / shapes of the sentence-encoder part of the reference's HSumGraph (HiGraph.py:112-125,
+    Encoder.py:41-54, HiGraph.py:53), bidirectional LSTM."""
+    shapes = {"ngram_enc.embed.weight": (vocab, emb), "sent_pos_embed.weight": (doc_max + 1, emb),
+              "ngram_enc.position_embedding.weight": (sent_max_len + 1, emb),
+              "cnn_proj.weight": (n_feature, emb), "cnn_proj.bias": (n_feature,),
+              "lstm_proj.weight": (n_feature, 2 * lstm_hidden), "lstm_proj.bias": (n_feature,),
+              "n_feature_proj.weight": (hidden, 2 * n_feature)}
+    for i, h in enumerate(range(2, 8)):
+        shapes["ngram_enc.convs.%d.weight" % i] = (50, 1, h, emb)
+        shapes["ngram_enc.convs.%d.bias" % i] = (50,)
+    for layer in range(lstm_layers):
+        for sfx in ("", "_reverse"):
+            n_in = emb if layer == 0 else 2 * lstm_hidden
+            shapes["lstm.weight_ih_l%d%s" % (layer, sfx)] = (4 * lstm_hidden, n_in)
+            shapes["lstm.weight_hh_l%d%s" % (layer, sfx)] = (4 * lstm_hidden, lstm_hidden)
+            shapes["lstm.bias_ih_l%d%s" % (layer, sfx)] = (4 * lstm_hidden,)
+            shapes["lstm.bias_hh_l%d%s" % (layer, sfx)] = (4 * lstm_hidden,)
+    return shapes
+
+
+def seeded_encoder_params(shapes, seed, zero_pad_row=True):
+    """Deterministic parameter values from the shapes alone (so that a fixture need not store megabytes of weights):
+    tensor number i is drawn from its own torch.Generator(seed * 1000 + i).  The two sinusoid tables are the
+    reference's (frozen, PositionEmbedding.py); weights ~ N(0, 1/fan_in), biases ~ N(0, 0.1), embedding ~ N(0, 1)."""
+    import torch
+    from oracle import encoder_ref as er
+    out = {}
+    for i, (k, shp) in enumerate(sorted(shapes.items())):
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        if k in ("sent_pos_embed.weight", "ngram_enc.position_embedding.weight"):
+            out[k] = er.sinusoid_table(shp[0], shp[1], padding_idx=0)
+        elif k == "ngram_enc.embed.weight":
+            w = torch.randn(shp, generator=g)
+            if zero_pad_row:
+                w[0] = 0.0
+            out[k] = w
+        elif len(shp) == 1:
+            out[k] = 0.1 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            out[k] = torch.randn(shp, generator=g) / fan_in ** 0.5
+    return out
+
+
+def encoder_tokens(n_sent_per_graph, L, vocab, seed):
+    """Token matrix [S, L] (trailing PAD = 0) with the edge cases of the n-gram encoder: an empty sentence, a full one,
+    lengths within 7 of L, length 1; graph_sent_ptr for graphs given in batch order."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    S = int(sum(n_sent_per_graph))
+    lens = rng.integers(1, max(2, L // 2), size=S)
+    special = [0, L, L - 1, L - 6, L - 7, 1, 2, 7]
+    for i, v in enumerate(special[:S]):
+        lens[(3 * i + 1) % S] = max(0, min(L, v))
+    tokens = np.zeros((S, L), np.int32)
+    for s in range(S):
+        tokens[s, :lens[s]] = rng.integers(1, vocab, size=lens[s])
+    ptr = np.concatenate([[0], np.cumsum(n_sent_per_graph)]).astype(np.int32)
+    return tokens, ptr

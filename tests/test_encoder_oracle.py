@@ -1,0 +1,101 @@
+"""CPU tests: pin oracle/encoder_ref.py (restatement of module/Encoder.py + HiGraph.py:112-161) against the golden
+vectors generated from the UNMODIFIED reference (tests/golden/make_golden_encoder.py) and, when /root/reference is
+present (build container), against the live reference classes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder_ref as er
+from oracle import fixtures as fx
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-5   # BASELINE.json: fp32 normalised max error
+
+
+def nerr(a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def load_encoder_fixture(name):
+    z = dict(np.load(os.path.join(GOLD, name)))
+    vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden = [int(v) for v in z["dims"]]
+    shapes = fx.encoder_param_shapes(vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden)
+    params = fx.seeded_encoder_params(shapes, int(z["seed"]), bool(z["zero_pad_row"]))
+    return z, params
+
+
+def golden_grad(z, key, g):
+    """the fixture stores large gradients sub-sampled"""
+    ref = z["gp:" + key]
+    g = g.detach()
+    return (g if ref.shape == tuple(g.shape) else g.flatten()[::int(z["stride"])]), torch.from_numpy(ref)
+
+
+@pytest.mark.parametrize("name", ["encoder_small.npz", "encoder_default.npz"])
+def test_encoder_restatement_matches_reference_golden(name):
+    z, params = load_encoder_fixture(name)
+    frozen = ("ngram_enc.embed.weight", "sent_pos_embed.weight", "ngram_enc.position_embedding.weight")
+    p = {k: (v.clone().requires_grad_(True) if k not in frozen else v) for k, v in params.items()}
+    sf, ngram = er.sent_feature(z["tokens"], z["graph_sent_ptr"], p)
+    assert nerr(ngram, z["ngram"]) <= 2e-6
+    assert nerr(sf, z["sent_feature"]) <= 2e-6
+    (sf * torch.from_numpy(z["cot"])).sum().backward()
+    for k, v in p.items():
+        if k in frozen:
+            continue
+        got, ref = golden_grad(z, k, v.grad)
+        assert nerr(got, ref) <= TOL, k
+
+
+def test_lstm_restatement_matches_torch_lstm():
+    """the cell-by-cell LSTM against torch.nn.LSTM on a packed sequence (what HiGraph.py:135-142 calls)."""
+    torch.manual_seed(3)
+    lstm = torch.nn.LSTM(12, 5, num_layers=2, batch_first=True, bidirectional=True)
+    lens = [4, 4, 2, 1]
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    feats = torch.randn(int(ptr[-1]), 12)
+    seqs = [feats[ptr[i]:ptr[i + 1]] for i in range(len(lens))]
+    packed = torch.nn.utils.rnn.pack_padded_sequence(torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True), lens,
+                                                     batch_first=True)
+    out, _ = lstm(packed)
+    unp, ulen = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+    ref = torch.cat([unp[i][:ulen[i]] for i in range(len(lens))], 0)
+    got = er.lstm_packed(feats, ptr, dict(lstm.named_parameters()), 2, True)
+    assert nerr(got, ref) <= 1e-6
+
+
+def test_token_positions_edge_cases():
+    L = 10
+    tok = np.zeros((3, L), np.int64)
+    tok[1, :] = 5                       # full sentence
+    tok[2, :3] = 7
+    pos = er.token_positions(tok, L)
+    assert pos[0].tolist() == [0] * L
+    assert pos[1].tolist() == list(range(1, L + 1))
+    assert pos[2].tolist() == [1, 2, 3] + [0] * (L - 3)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only in the build container")
+def test_ngram_encode_matches_live_reference_sentencoder():
+    """module.Encoder.sentEncoder (Encoder.py:18-76) run live on random tokens."""
+    import types
+    sys.path.insert(0, "/root/reference")
+    from module.Encoder import sentEncoder
+    torch.manual_seed(11)
+    L, V = 30, 90
+    hps = types.SimpleNamespace(sent_max_len=L, word_emb_dim=300, cuda=False)
+    embed = torch.nn.Embedding(V, 300, padding_idx=0)
+    enc = sentEncoder(hps, embed)
+    with torch.no_grad():
+        for c in enc.convs:
+            c.bias.normal_(0, 0.3)
+    tokens, _ = fx.encoder_tokens([9], L, V, seed=2)
+    ref = enc(torch.from_numpy(tokens).long())
+    got = er.ngram_encode(tokens, embed.weight, enc.position_embedding.weight, [c.weight for c in enc.convs],
+                          [c.bias for c in enc.convs])
+    assert nerr(got, ref) <= 2e-6
+    assert torch.equal(er.sinusoid_table(L + 1, 300, padding_idx=0), enc.position_embedding.weight)
