@@ -143,6 +143,14 @@ _PROTOS = {
     "hsg_set_edge_fwd_rowpar": (C.c_int, [_I]),
     "hsg_set_edge_blockrow": (C.c_int, [_I]),
     "hsg_set_edge_bwd_async": (C.c_int, [_I]),
+    "hsg_enc_gather": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_enc_pack_weights": (C.c_int, [_I, _P, _P, _P]),
+    "hsg_enc_pool_fwd": (C.c_int, [_I, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "hsg_enc_conv_wgrad_workspace_bytes": (_Z, [_I, _I]),
+    "hsg_enc_conv_wgrad": (C.c_int, [_I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _Z, _P]),
+    "hsg_add_rows": (C.c_int, [_I, _I, _P, _I, _P, _P, _P, _I, _P]),
+    "hsg_lstm_fwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hsg_lstm_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "hsg_wswgat_fwd": (C.c_int, [C.POINTER(WswgatFwdArgsC), _P]),
     "hsg_wswgat_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),

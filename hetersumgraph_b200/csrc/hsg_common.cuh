@@ -29,6 +29,8 @@ enum Slot {
   SLOT_ADAM,
   SLOT_DROPOUT,
   SLOT_S2S,
+  SLOT_ENCODER,
+  SLOT_LSTM,
   SLOT_COUNT
 };
 

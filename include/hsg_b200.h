@@ -454,6 +454,58 @@ int hsg_super_assemble(const hsg_doc_map* m, const float* sent_feature, const fl
 int hsg_doc_init_bwd(const hsg_doc_map* m, const float* d_super, const float* d_doc_mean, float* d_doc_feature,
                      float* d_sent, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Sentence encoder in front of the path: the n-gram CNN of module/Encoder.py:56-76
+ * (sentEncoder.forward), called from HSumGraph._sent_cnn_feature, HiGraph.py:127-133.
+ *   x[s,t,:]   = embed[tok[s,t]] + pos_table[t < len_s ? t+1 : 0]                       Encoder.py:58-69
+ *   out[s, (h-2)*50 + c] = max_t relu(conv_h(x)[s,c,t]),  h = 2..7, 50 channels each    Encoder.py:71-73
+ * Sentences are stored COMPACT: sentence s keeps its first n_s = min(tail_s + 7, L) rows (tail_s = index after its
+ * last non-zero id; every window behind it sees the same PAD row and gives the same value), rows back to back in
+ * xc [n_rows + 8, D] (8 zeroed tail rows), row_ptr [n_sent+1].  The six convolutions are the product
+ *   y [n_rows, 312] = A [n_rows, 7D] . wpad [312, 7D]^T   with A = xc and lda = D (overlapping rows, no im2col),
+ * wpad = the kernels zero-padded to height 7 (hsg_enc_pack_weights); height h occupies columns (h-2)*52 .. +49
+ * (52-column groups start 16-byte aligned).  The caller issues it as K-chunks of hsg_gemm_nt over kernel rows
+ * {0,1}, {2,3}, {4,5}, {6}, each restricted to the column groups whose kernels reach those rows and accumulated
+ * in place (HSG_EPI_ADD with R == C).  D % 4 == 0, L >= 7.
+ * Backward (frozen embedding, train.py:340-342): only the kernels and biases get gradients; d out / d y is one-hot
+ * per (sentence, channel), so dW is a sparse accumulation of <= n_sent*300 input slabs in a fixed order.
+ * ------------------------------------------------------------------------ */
+int hsg_enc_gather(int n_sent, int L, int D, int n_rows, const int32_t* tokens /* [n_sent, L] */,
+                   const int32_t* sent_len /* [n_sent] non-zero ids, Encoder.py:58 */, const int32_t* row_ptr,
+                   const float* embed, const float* pos_table /* [L+1, D] */, float* xc, void* stream);
+/* conv_w[i]: [50, 1, i+2, D] (Conv2d weight of height i+2) -> wpad [312, 7D] */
+int hsg_enc_pack_weights(int D, const float* const* conv_w, float* wpad, void* stream);
+/* out[s, (h-2)*50 + c] = relu(max over the valid windows of y[row_ptr[s]+t, (h-2)*52 + c] + bias);
+ * arg_t [300, n_sent] = compact row of the maximum (first one), -1 where the ReLU is inactive */
+int hsg_enc_pool_fwd(int n_sent, const int32_t* row_ptr, const float* y, int ldy, const float* const* conv_b,
+                     float* out, int ldo, int32_t* arg_t, void* stream);
+size_t hsg_enc_conv_wgrad_workspace_bytes(int n_sent, int D);
+/* d_conv_w[i] [50, 1, i+2, D], d_conv_b[i] [50]: written (accumulate = 0) or added to (accumulate = 1) */
+int hsg_enc_conv_wgrad(int n_sent, int D, const float* xc, const float* d_out, int ldo, const int32_t* arg_t,
+                       float* const* d_conv_w, float* const* d_conv_b, int accumulate, void* ws, size_t ws_bytes,
+                       void* stream);
+/* out[r,:] = x[r,:] + table[idx[r],:]   (ngram_feature + sent_pos_embed(position), HiGraph.py:130-132) */
+int hsg_add_rows(int n, int D, const float* x, int ldx, const int32_t* idx, const float* table, float* out, int ldo,
+                 void* stream);
+
+/* ------------------------------------------------------------------------
+ * Recurrent part of the sentence-level (Bi)LSTM - torch.nn.LSTM on the packed per-graph sentence sequences,
+ * HiGraph.py:118-119,135-142 (get_snode_feat :247-255).  One layer per call; gate order i, f, g, o.
+ * Rows of graph b are graph_sent_ptr[b] .. graph_sent_ptr[b+1]-1 (batched sentence order), direction 1 walks them
+ * backwards.  The caller computes the input products of all time steps with hsg_gemm_nt:
+ *   xproj [S, ndir*4H] (direction d in columns d*4H .., NO bias: b_ih + b_hh are added here).
+ * forward : out [S, ndir*H] (= cat(h_fwd, h_bwd), the layer output), and saved for backward:
+ *           gates [S, ndir, 4H] (post-activation), cst [S, ndir, H] (cell states), hprev [S, ndir, H] (h_{t-1}).
+ * backward: da [S, ndir*4H] = gradient of the pre-activation gates (xproj layout); the caller finishes with GEMMs:
+ *           dW_ih = da_d^T x, dW_hh = da_d^T hprev_d, db_ih = db_hh = colsum(da_d), dx = sum_d da_d W_ih_d.
+ * H <= 128, H % 4 == 0; ndir 1 or 2; w_hh / b_ih / b_hh: arrays of ndir device pointers.
+ * ------------------------------------------------------------------------ */
+int hsg_lstm_fwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, const float* xproj,
+                 const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, float* out,
+                 float* gates, float* cst, float* hprev, void* stream);
+int hsg_lstm_bwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, const float* d_out, const float* gates,
+                 const float* cst, const float* const* w_hh, float* da, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

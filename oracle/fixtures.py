@@ -139,3 +139,22 @@ def encoder_tokens(n_sent_per_graph, L, vocab, seed):
         tokens[s, :lens[s]] = rng.integers(1, vocab, size=lens[s])
     ptr = np.concatenate([[0], np.cumsum(n_sent_per_graph)]).astype(np.int32)
     return tokens, ptr
+
+
+def load_encoder_fixture(gold_dir, name):
+    """(arrays, seeded parameters) of tests/golden/encoder_*.npz"""
+    import os
+    import numpy as np
+    z = dict(np.load(os.path.join(gold_dir, name)))
+    vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden = [int(v) for v in z["dims"]]
+    shapes = encoder_param_shapes(vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden)
+    params = seeded_encoder_params(shapes, int(z["seed"]), bool(z["zero_pad_row"]))
+    return z, params
+
+
+def golden_grad(z, key, g):
+    """(gradient as stored, golden gradient): the encoder fixtures store large gradients sub-sampled"""
+    import torch
+    ref = z["gp:" + key]
+    g = g.detach()
+    return (g if ref.shape == tuple(g.shape) else g.flatten()[::int(z["stride"])]), torch.from_numpy(ref)

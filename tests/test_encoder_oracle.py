@@ -20,19 +20,8 @@ def nerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-def load_encoder_fixture(name):
-    z = dict(np.load(os.path.join(GOLD, name)))
-    vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden = [int(v) for v in z["dims"]]
-    shapes = fx.encoder_param_shapes(vocab, emb, L, doc_max, n_feature, hidden, lstm_hidden)
-    params = fx.seeded_encoder_params(shapes, int(z["seed"]), bool(z["zero_pad_row"]))
-    return z, params
-
-
-def golden_grad(z, key, g):
-    """the fixture stores large gradients sub-sampled"""
-    ref = z["gp:" + key]
-    g = g.detach()
-    return (g if ref.shape == tuple(g.shape) else g.flatten()[::int(z["stride"])]), torch.from_numpy(ref)
+load_encoder_fixture = lambda name: fx.load_encoder_fixture(GOLD, name)  # noqa: E731
+golden_grad = fx.golden_grad
 
 
 @pytest.mark.parametrize("name", ["encoder_small.npz", "encoder_default.npz"])

@@ -129,3 +129,28 @@ def test_stress_edges_and_csc_pair():
     # twins: pair t = (word, sup) appears in both CSCs
     t = seid // 2
     assert np.array_equal(ssrc, word[t]) and np.array_equal(wsrc, sup[weid // 2])
+
+
+def test_encoder_plan_host_logic():
+    """EncoderPlan (host side of the sentence encoder): lengths, compact rows, positions and the PackedSequence order."""
+    from hetersumgraph_b200.encoder import EncoderPlan
+    L = 12
+    tokens = np.zeros((7, L), np.int32)
+    lens = [12, 0, 3, 6, 5, 1, 9]
+    for s, n in enumerate(lens):
+        tokens[s, :n] = 5
+    tokens[2, 1] = 0                                   # interior zero: len 2, tail 3
+    ptr = np.asarray([0, 3, 6, 7])
+    plan = EncoderPlan(tokens, ptr, "cpu")
+    assert plan.sent_len.tolist() == [12, 0, 2, 6, 5, 1, 9]
+    assert np.diff(plan.row_ptr.numpy()).tolist() == [12, 7, 10, 12, 12, 8, 12]
+    assert plan.sent_pos.tolist() == [1, 2, 3, 1, 2, 3, 1]
+    # same order as torch's pack_padded_sequence over the per-graph lists
+    seqs = [torch.arange(ptr[i], ptr[i + 1]).float()[:, None] for i in range(3)]
+    packed = torch.nn.utils.rnn.pack_padded_sequence(torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True), [3, 3, 1],
+                                                     batch_first=True)
+    assert packed.data[:, 0].long().tolist() == plan.perm.tolist()
+    assert packed.batch_sizes.tolist() == plan.batch_sizes.tolist()
+    assert plan.perm[plan.inv_perm].tolist() == list(range(7))
+    with pytest.raises(ValueError):
+        EncoderPlan(tokens, np.asarray([0, 1, 7]), "cpu")       # not in batch order
