@@ -50,6 +50,7 @@ def parse():
                     help="strong scaling (BASELINE.json configs[4]): total graphs per step, split evenly over the GPUs")
     ap.add_argument("--no-stress", action="store_true", help="skip the stress-graph edge-kernel roofline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the sentence-encoder leg (SURVEY 8-f rank 1)")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--stress-only", action="store_true", help="run only the stress-graph edge-kernel leg (for ncu)")
     ap.add_argument("--stress-scale", type=int, default=4)
@@ -441,6 +442,9 @@ def run_ours(args):
     large = None
     if not args.no_stress and world == 1:
         large = large_shard_leg(dev, pk)
+    encoder = None
+    if not args.no_encoder and world == 1 and not hdsg:
+        encoder = encoder_leg(dev, pk, exs, tb, n_iter, args.steps)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -471,7 +475,7 @@ def run_ours(args):
                        "builder totals read every step"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,
-        "large_shard": large,
+        "large_shard": large, "with_sentence_encoder": encoder,
         "single_pass_tf32_mode": {"graphs_per_s": n_graphs_global / (ms_fast * 1e-3), "ms_per_step": ms_fast,
                                   "note": "informational, tolerance class 2e-2; not the headline"},
     }
@@ -479,6 +483,88 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
+    """the sentence encoder (n-gram CNN + BiLSTM + projections) in front of the path, same batch.
+    (i) encoder alone fwd+bwd, (ii) encoder -> update loop -> loss, backward through both (autograd path, parameter
+    gradients of every stage), (iii) the oracle restatement of the encoder on the host cores, (iv) per-kernel split."""
+    from hetersumgraph_b200 import _lib
+    from hetersumgraph_b200.encoder import EncoderPlan, SentenceEncoder
+    from hetersumgraph_b200.graph import DeviceTokenBatch, HeteroBatch
+    from hetersumgraph_b200.path_model import HSGPath, fused_loss
+    lib = _lib.load()
+    torch.manual_seed(1234)
+    model = HSGPath(n_iter=n_iter).to(dev)
+    enc = SentenceEncoder(model._embed, lstm_dropout=0.0).to(dev)
+    dtb = DeviceTokenBatch.upload(tb, dev)
+    batch = HeteroBatch.build(dtb)
+    S, L = tb.tokens.shape
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cot = torch.randn(S, 64, device=dev)
+    params = [q for q in list(enc.parameters()) + list(model.parameters()) if q.requires_grad]
+
+    def enc_only():
+        plan = EncoderPlan.from_token_batch(tb, dev, tokens_dev=dtb.tokens)      # host plan + one small H2D per step
+        enc(plan).backward(cot)
+
+    def full():
+        plan = EncoderPlan.from_token_batch(tb, dev, tokens_dev=dtb.tokens)
+        for q in params:
+            q.grad = None
+        loss, _ = fused_loss(model, batch, enc(plan))
+        loss.backward()
+        return loss
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / steps
+
+    ms_enc = timed(enc_only)
+    ms_full = timed(full)
+    lib.hsg_profile_reset()
+    lib.hsg_profile_enable(1)
+    for _ in range(steps):
+        flush.zero_()
+        enc_only()
+    torch.cuda.synchronize()
+    lib.hsg_profile_enable(0)
+    slots = {k: {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps} for k, v in _lib.profile_snapshot().items()}
+    plan = EncoderPlan.from_token_batch(tb, dev, tokens_dev=dtb.tokens)
+    useful = S * sum((L + 1 - h) * h for h in range(2, 8)) * 50 * 300 * 2.0      # what the reference's Conv2d executes
+    executed = plan.n_rows * 300.0 * 2.0 * (312 * 2 + 260 * 2 + 156 * 2 + 52)
+    out = {"what": "sentEncoder + cnn_proj + BiLSTM + lstm_proj + n_feature_proj (Encoder.py:56-76, HiGraph.py:112-161, :96) "
+                   "fwd+bwd on the same %d-graph batch; L2 flushed; inter-layer LSTM dropout 0 in both arms" % tb.n_graphs,
+           "sentences": S, "compact_rows": plan.n_rows, "padded_rows": S * L,
+           "encoder_fwd_bwd_ms": ms_enc, "encoder_graphs_per_s": tb.n_graphs / (ms_enc * 1e-3),
+           "encoder_plus_path_fwd_bwd_ms": ms_full, "encoder_plus_path_graphs_per_s": tb.n_graphs / (ms_full * 1e-3),
+           "conv_fwd_gflop_reference": useful / 1e9, "conv_fwd_gflop_executed": executed / 1e9, "kernels": slots}
+    # host-cores arm: the oracle restatement of the same stage (oracle/encoder_ref.py), forward + backward
+    from oracle import encoder_ref as er
+    frozen = ("ngram_enc.embed.weight", "sent_pos_embed.weight", "ngram_enc.position_embedding.weight")
+    sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    p = {k: (v.clone().requires_grad_(True) if k not in frozen else v) for k, v in sd.items()}
+    cot_c = cot.cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    for _ in range(cpu_steps):
+        sf, _ = er.sent_feature(tb.tokens, tb.graph_sent_ptr, p)
+        sf.backward(cot_c)
+    sec = (time.perf_counter() - t0) / cpu_steps
+    out["cpu_baseline"] = {"value": tb.n_graphs / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": "the whole %d-graph batch, %d step(s), %.2f s/step" % (tb.n_graphs, cpu_steps, sec)}
+    return out
 
 
 def _time_edge_kernels(batch, label, dev, pk, flush, iters):

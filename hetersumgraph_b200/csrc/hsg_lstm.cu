@@ -24,6 +24,31 @@ constexpr int LSTM_KR = 32;          // W_hh columns kept in registers (k = KS .
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
+// W_hh[:, 0:KS] -> shared memory rows of `pitch` floats: float4 copies, 8 independent loads in flight per thread (a
+// scalar load -> store loop costs ~100 serial L2 latencies per thread, ncu: 17 % of the kernel's samples)
+__device__ __forceinline__ void load_whh_smem(float* W_s, const float* __restrict__ whh, int H, int KS, int pitch) {
+  const int nk4 = KS >> 2, tot4 = 4 * H * nk4;
+  for (int base = threadIdx.x; base < tot4; base += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i4 = base + q * blockDim.x;
+      if (i4 < tot4) {
+        const int jj = i4 / nk4, k4 = i4 - jj * nk4;
+        v[q] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)jj * H) + k4);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i4 = base + q * blockDim.x;
+      if (i4 < tot4) {
+        const int jj = i4 / nk4, k4 = i4 - jj * nk4;
+        *reinterpret_cast<float4*>(W_s + (size_t)jj * pitch + 4 * k4) = v[q];
+      }
+    }
+  }
+}
+
 struct LstmDirPtrs {
   const float* w_hh[2];   // [4H, H]
   const float* b_ih[2];   // [4H]
@@ -48,10 +73,7 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
   const int j = threadIdx.x;
   const bool on = j < G4;
   const float* whh = p.w_hh[dir];
-  for (int idx = threadIdx.x; idx < G4 * KS; idx += blockDim.x) {
-    const int jj = idx / KS, k = idx - jj * KS;
-    W_s[jj * pitch + k] = __ldg(whh + (size_t)jj * H + k);
-  }
+  load_whh_smem(W_s, whh, H, KS, pitch);
   for (int i = threadIdx.x; i < LSTM_MAX_H + LSTM_KR; i += blockDim.x) h_s[i] = 0.f;
   float wreg[LSTM_KR];
 #pragma unroll
@@ -110,6 +132,14 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
 }
 
 // d_out [S, ndir*H]; da [S, ndir*4H] (pre-activation gate gradients, the x-projection layout)
+//
+// The transposed product dh_{t-1}[k] = sum_j da[j] W_hh[j][k] uses the SAME on-chip copy of W_hh as the forward:
+//   * columns k < KS (shared memory): thread (kg, jc) owns 4 consecutive columns and a chunk of H/4 gate rows -
+//     float4 reads along k (conflict-free), 16 row chunks reduced through shared memory;
+//   * columns k >= KS (registers of the thread that owns gate row j): every thread forms da[j] * W[j][KS..KS+31]
+//     and the 32 column sums are reduced across the warp with a 31-shuffle butterfly, then across the 16 warps.
+constexpr int LSTM_NJ = 16;          // gate-row chunks of the shared-memory part
+
 __global__ void __launch_bounds__(512, 1)
 lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* __restrict__ d_out,
                 const float* __restrict__ gates, const float* __restrict__ cst, LstmDirPtrs p,
@@ -121,23 +151,28 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const int pitch = KS + 4;
   float* W_s = smem;                               // [4H][pitch]
-  float* da_s = W_s + (size_t)G4 * pitch;          // [4H]
-  float* part_s = da_s + 4 * LSTM_MAX_H;           // [4][LSTM_MAX_H]
+  float* da_s = W_s + (size_t)G4 * pitch;          // [4 * LSTM_MAX_H]
+  float* part_s = da_s + 4 * LSTM_MAX_H;           // [LSTM_NJ][LSTM_KS_MAX]  partial sums, columns k < KS
+  float* regp_s = part_s + LSTM_NJ * LSTM_KS_MAX;  // [16 warps][LSTM_KR]     partial sums, columns k >= KS
   const int b = blockIdx.x, dir = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool on = tid < G4;
   const float* whh = p.w_hh[dir];
-  for (int idx = threadIdx.x; idx < G4 * KS; idx += blockDim.x) {
-    const int jj = idx / KS, k = idx - jj * KS;
-    W_s[jj * pitch + k] = __ldg(whh + (size_t)jj * H + k);
-  }
-  for (int i = threadIdx.x; i < 4 * LSTM_MAX_H; i += blockDim.x) part_s[i] = 0.f;
+  load_whh_smem(W_s, whh, H, KS, pitch);
+  for (int i = threadIdx.x; i < LSTM_NJ * LSTM_KS_MAX + 16 * LSTM_KR; i += blockDim.x) part_s[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * LSTM_MAX_H; i += blockDim.x) da_s[i] = 0.f;
+  const bool has_reg = H > KS;
+  float wreg[LSTM_KR];
+#pragma unroll
+  for (int i = 0; i < LSTM_KR; ++i) wreg[i] = (on && KS + i < H) ? __ldg(whh + (size_t)tid * H + KS + i) : 0.f;
+  const int nkg = KS >> 2;                                    // float4 column groups in shared memory
+  const int kg = tid % nkg, jc = tid / nkg;                   // this thread's column group and gate-row chunk
+  const bool smem_on = jc < LSTM_NJ;
+  const int jper = G4 / LSTM_NJ;                              // gate rows per chunk (= H / 4)
   const int r0 = gptr[b], T = gptr[b + 1] - r0;
-  const int k = on ? tid % H : 0, jq = on ? tid / H : 0;     // transposed product: thread (k, quarter of the gate rows)
-  const int u = tid;                                         // pointwise: hidden unit (u < H)
+  const int u = tid;                                          // pointwise: hidden unit (u < H)
   float dc_carry = 0.f;
   __syncthreads();
-  // operands of the first step (the LAST time step of the forward order)
   float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cc = 0.f, cp = 0.f, go = 0.f;
   auto load_step = [&](int step) {
     const int row = r0 + (dir ? T - 1 - step : step);
@@ -155,7 +190,15 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
   for (int step = T - 1; step >= 0; --step) {
     const int row = r0 + (dir ? T - 1 - step : step);
     if (u < H) {
-      const float dh = go + ((part_s[u] + part_s[LSTM_MAX_H + u]) + (part_s[2 * LSTM_MAX_H + u] + part_s[3 * LSTM_MAX_H + u]));
+      float rec = 0.f;                                        // dh from step + 1, fixed summation order
+      if (u < KS) {
+#pragma unroll
+        for (int q = 0; q < LSTM_NJ; ++q) rec += part_s[q * LSTM_KS_MAX + u];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) rec += regp_s[q * LSTM_KR + (u - KS)];
+      }
+      const float dh = go + rec;
       const float tc = tanhf(cc);
       const float d_o = dh * tc;
       const float dc = fmaf(dh * og, 1.f - tc * tc, dc_carry);
@@ -175,24 +218,39 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
       if (step > 0) load_step(step - 1);                      // prefetch: lands during the product below
     }
     __syncthreads();
-    if (on) {                                                 // dh_{t-1}[k] = sum_j da[j] W_hh[j][k], quarter jq of j
-      float acc0 = 0.f, acc1 = 0.f;
-      const int j0 = jq * H;
-      if (k < KS) {
-        const float* wc = W_s + (size_t)j0 * pitch + k;
-        for (int jj = 0; jj < H; jj += 2) {
-          acc0 = fmaf(da_s[j0 + jj], wc[(size_t)jj * pitch], acc0);
-          acc1 = fmaf(da_s[j0 + jj + 1], wc[(size_t)(jj + 1) * pitch], acc1);
+    if (step > 0) {                                           // the product feeds the next (earlier) step only
+      if (has_reg) {                                          // columns KS .. KS+31 from registers, butterfly reduce
+        const float dj = on ? da_s[tid] : 0.f;
+        float v[LSTM_KR];
+#pragma unroll
+        for (int i = 0; i < LSTM_KR; ++i) v[i] = dj * wreg[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float keep = up ? v[i + off] : v[i];
+            const float send = up ? v[i] : v[i + off];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
         }
-      } else {
-        const float* wc = whh + (size_t)j0 * H + k;          // columns kept out of shared memory: L2, coalesced over k
-#pragma unroll 8
-        for (int jj = 0; jj < H; jj += 2) {
-          acc0 = fmaf(da_s[j0 + jj], __ldg(wc + (size_t)jj * H), acc0);
-          acc1 = fmaf(da_s[j0 + jj + 1], __ldg(wc + (size_t)(jj + 1) * H), acc1);
-        }
+        regp_s[warp * LSTM_KR + lane] = v[0];                 // lane l holds column KS + l (warps past 4H hold zeros)
       }
-      part_s[jq * LSTM_MAX_H + k] = acc0 + acc1;
+      if (smem_on) {                                          // columns k < KS from shared memory
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int j0 = jc * jper;
+        const float* wp = W_s + (size_t)j0 * pitch + 4 * kg;
+#pragma unroll 4
+        for (int jj = 0; jj < jper; ++jj) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + (size_t)jj * pitch);
+          const float dj = da_s[j0 + jj];
+          acc.x = fmaf(dj, w4.x, acc.x);
+          acc.y = fmaf(dj, w4.y, acc.y);
+          acc.z = fmaf(dj, w4.z, acc.z);
+          acc.w = fmaf(dj, w4.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(part_s + jc * LSTM_KS_MAX + 4 * kg) = acc;
+      }
     }
     __syncthreads();
   }
@@ -202,7 +260,7 @@ static size_t lstm_smem_bytes(int H) {
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const size_t w = (size_t)4 * H * (KS + 4);
   const size_t fwd = w + LSTM_MAX_H + LSTM_KR + 4 * H;
-  const size_t bwd = w + 4 * LSTM_MAX_H + 4 * LSTM_MAX_H;
+  const size_t bwd = w + 4 * LSTM_MAX_H + LSTM_NJ * LSTM_KS_MAX + 16 * LSTM_KR;
   return (fwd > bwd ? fwd : bwd) * sizeof(float);
 }
 
@@ -236,6 +294,7 @@ int hsg_lstm_fwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
   for (int d = 0; d < 2; ++d) {
     const int s = d < ndir ? d : 0;
     if (!w_hh[s] || !b_ih[s] || !b_hh[s]) return HSG_ERR_ARG;
+    if (!aligned16(w_hh[s])) return HSG_ERR_ALIGN;
     p.w_hh[d] = w_hh[s];
     p.b_ih[d] = b_ih[s];
     p.b_hh[d] = b_hh[s];
@@ -259,6 +318,7 @@ int hsg_lstm_bwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
   for (int d = 0; d < 2; ++d) {
     const int s = d < ndir ? d : 0;
     if (!w_hh[s]) return HSG_ERR_ARG;
+    if (!aligned16(w_hh[s])) return HSG_ERR_ALIGN;
     p.w_hh[d] = w_hh[s];
     p.b_ih[d] = nullptr;
     p.b_hh[d] = nullptr;

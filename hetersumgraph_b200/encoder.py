@@ -78,22 +78,33 @@ class EncoderPlan:
         if np.any(counts[1:] > counts[:-1]):
             raise ValueError("graphs must be in batch order (#sentences descending, dataloader.py:479)")
         sent_pos = (np.arange(S, dtype=np.int64) - np.repeat(ptr[:-1], counts) + 1).astype(np.int32)
-        t_max = int(counts[0]) if len(counts) else 0
-        batch_sizes = (counts[None, :] > np.arange(t_max)[:, None]).sum(axis=1).astype(np.int64)
-        perm = np.concatenate([ptr[:b] + t for t, b in enumerate(batch_sizes)]) if t_max else np.zeros(0, np.int64)
-        inv = np.empty_like(perm)
-        inv[perm] = np.arange(len(perm))
         self.n_sent, self.L, self.n_rows = S, L, int(row_ptr[-1])
-        self.batch_sizes = torch.from_numpy(batch_sizes)                       # stays on the host (PackedSequence)
+        self._ptr, self._counts, self._device, self._packed = ptr, counts, device, None
         blob = np.concatenate([sent_len, row_ptr, sent_pos, ptr]).astype(np.int32)   # one H2D for the int32 arrays
         dev = torch.from_numpy(blob).to(device, non_blocking=True)
         self.sent_len, self.row_ptr, self.sent_pos = dev[:S], dev[S:2 * S + 1], dev[2 * S + 1:3 * S + 1]
         self.graph_sent_ptr = dev[3 * S + 1:]
         self.n_graphs = len(ptr) - 1
-        both = torch.from_numpy(np.concatenate([perm, inv])).to(device, non_blocking=True)
-        self.perm, self.inv_perm = both[:S], both[S:]
         self.tokens = tokens_dev if tokens_dev is not None else torch.from_numpy(tokens).to(device, non_blocking=True)
         self.real_windows = int(np.sum(np.maximum(n_rows, 0)))
+
+    def _packed_order(self):
+        """(batch_sizes on the host, perm, inv_perm): the time-major order of a PackedSequence over the per-graph sentence
+        lists - only the use_cudnn_lstm comparison path needs it, so it is built on first use."""
+        if self._packed is None:
+            ptr, counts, S = self._ptr, self._counts, self.n_sent
+            t_max = int(counts[0]) if len(counts) else 0
+            batch_sizes = (counts[None, :] > np.arange(t_max)[:, None]).sum(axis=1).astype(np.int64)
+            perm = np.concatenate([ptr[:b] + t for t, b in enumerate(batch_sizes)]) if t_max else np.zeros(0, np.int64)
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(len(perm))
+            both = torch.from_numpy(np.concatenate([perm, inv])).to(self._device)
+            self._packed = (torch.from_numpy(batch_sizes), both[:S], both[S:])
+        return self._packed
+
+    batch_sizes = property(lambda self: self._packed_order()[0])
+    perm = property(lambda self: self._packed_order()[1])
+    inv_perm = property(lambda self: self._packed_order()[2])
 
     @staticmethod
     def from_token_batch(tb, device="cuda", tokens_dev=None):
