@@ -10,5 +10,8 @@ from .graph import BuildPipeline, DeviceTokenBatch, HeteroBatch, csc_pair_from_e
 from .modules import (MultiHeadLayer, MultiHeadSGATLayer, PositionwiseFeedForward, SWGATLayer, WSGATLayer, WSWGAT,  # noqa: F401
                       WSWGATUpdateLoop)
 
-__all__ = ["BuildPipeline", "DeviceTokenBatch", "HeteroBatch", "csc_pair_from_edges", "MultiHeadLayer", "MultiHeadSGATLayer", "PositionwiseFeedForward", "SWGATLayer",
+from .encoder import EncoderPlan, SentenceEncoder  # noqa: F401,E402
+from .model import HSumDocGraph, HSumGraph  # noqa: F401,E402
+
+__all__ = ["EncoderPlan", "SentenceEncoder", "HSumGraph", "HSumDocGraph", "BuildPipeline", "DeviceTokenBatch", "HeteroBatch", "csc_pair_from_edges", "MultiHeadLayer", "MultiHeadSGATLayer", "PositionwiseFeedForward", "SWGATLayer",
            "WSGATLayer", "WSWGAT", "WSWGATUpdateLoop", "synthetic"]

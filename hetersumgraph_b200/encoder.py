@@ -305,6 +305,13 @@ class SentenceEncoder(nn.Module):
     def __init__(self, embed, word_emb_dim=300, sent_max_len=100, doc_max_timesteps=50, n_feature_size=128,
                  hidden_size=64, lstm_hidden_state=128, lstm_layers=2, bidirectional=True, lstm_dropout=0.1):
         super().__init__()
+        self._build_sn_param(embed, word_emb_dim, sent_max_len, doc_max_timesteps, n_feature_size, lstm_hidden_state,
+                             lstm_layers, bidirectional, lstm_dropout)
+        self._build_n_feature_proj(n_feature_size, hidden_size)
+
+    def _build_sn_param(self, embed, word_emb_dim, sent_max_len, doc_max_timesteps, n_feature_size, lstm_hidden_state,
+                        lstm_layers, bidirectional, lstm_dropout):
+        """HSumGraph._init_sn_param (HiGraph.py:112-125), same creation order."""
         if word_emb_dim != NGRAM_DIM:
             # HiGraph.py:131-132 adds the 300-wide n-gram feature to a word_emb_dim-wide position embedding
             raise ValueError("word_emb_dim must be 300 (= 50 channels x 6 kernel heights), as in the reference")
@@ -321,7 +328,9 @@ class SentenceEncoder(nn.Module):
                             batch_first=True, bidirectional=bidirectional)
         self.lstm_proj = nn.Linear(lstm_hidden_state * (2 if bidirectional else 1), n_feature_size)
         self.ngram_enc = _NgramParams(embed, sent_max_len, word_emb_dim)
-        self.n_feature_proj = nn.Linear(n_feature_size * 2, hidden_size, bias=False)
+
+    def _build_n_feature_proj(self, n_feature_size, hidden_size):
+        self.n_feature_proj = nn.Linear(n_feature_size * 2, hidden_size, bias=False)      # HiGraph.py:53
 
     def ngram(self, plan: EncoderPlan):
         if plan.L != self.sent_max_len:
@@ -346,6 +355,9 @@ class SentenceEncoder(nn.Module):
         return out.data.index_select(0, plan.inv_perm)
 
     def forward(self, plan: EncoderPlan):
+        return self.encode(plan)
+
+    def encode(self, plan: EncoderPlan):
         ngram = self.ngram(plan)
         lstm_out = self.lstm_feature(plan, ngram)
         return SentHeadFn.apply(ngram, lstm_out, plan.sent_pos, self.sent_pos_embed.weight, self.cnn_proj.weight,

@@ -90,6 +90,7 @@ class DeviceTokenBatch:
             host, _ = DeviceTokenBatch.host_buffers(tb)
         d = DeviceTokenBatch()
         d.device, d.hdsg, d.n_graphs = dev, bool(tb.hdsg), tb.n_graphs
+        d.host_tb = tb                                  # host arrays: the sentence encoder's plan is made from them
         blob = host["blob"].to(dev, non_blocking=True)                 # the ONE host -> device copy of the batch
         d._blob = blob
         lay, meta = host["layout"], host["meta"]
@@ -208,6 +209,22 @@ class HeteroBatch:
             out = (xgrp, xmember, 1)
         self.__dict__["_s2s_groups"] = out
         return out
+
+    @property
+    def encoder_plan(self):
+        """EncoderPlan of this batch for encoder.SentenceEncoder (the counterpart of the `words` / `position` node data
+        the reference's set_snfeature reads, HiGraph.py:128-131): made on first use from the host token matrix the
+        batch was built from, sharing the device copy of the tokens."""
+        plan = self.__dict__.get("_encoder_plan")
+        if plan is None:
+            dtb = self.__dict__.get("_keepalive", (None,))[0]
+            tb = getattr(dtb, "host_tb", None)
+            if tb is None:
+                raise RuntimeError("this HeteroBatch was not built from a TokenBatch: pass an EncoderPlan explicitly")
+            from .encoder import EncoderPlan
+            plan = EncoderPlan.from_token_batch(tb, self.device, tokens_dev=dtb.tokens)
+            self.__dict__["_encoder_plan"] = plan
+        return plan
 
     def sentence_rows(self) -> torch.Tensor:
         """rows of `s` that are sentence nodes (dtype == 1), ascending (HiGraph.py:191).  Taken from the builder's

@@ -293,8 +293,16 @@ class WSWGATUpdateLoop(nn.Module):
     def __init__(self, word_emb_dim=300, hidden_size=64, n_head=8, atten_dropout_prob=0.1,
                  ffn_inner_hidden_size=512, ffn_dropout_prob=0.1, feat_embed_size=50, n_iter=1):
         super().__init__()
+        self._build_tfembed(feat_embed_size, n_iter)
+        self._build_layers(word_emb_dim, hidden_size, n_head, atten_dropout_prob, ffn_inner_hidden_size,
+                           ffn_dropout_prob, feat_embed_size)
+
+    def _build_tfembed(self, feat_embed_size, n_iter):
         self._n_iter = n_iter
         self._TFembed = nn.Embedding(10, feat_embed_size)   # box=10 (HiGraph.py:52)
+
+    def _build_layers(self, word_emb_dim, hidden_size, n_head, atten_dropout_prob, ffn_inner_hidden_size,
+                      ffn_dropout_prob, feat_embed_size):
         self.word2sent = WSWGAT(word_emb_dim, hidden_size, n_head, atten_dropout_prob, ffn_inner_hidden_size,
                                 ffn_dropout_prob, feat_embed_size, "W2S")
         self.sent2word = WSWGAT(hidden_size, word_emb_dim, 6, atten_dropout_prob, ffn_inner_hidden_size,
@@ -339,6 +347,9 @@ class WSWGATUpdateLoop(nn.Module):
         return cfg, (self._TFembed.weight,) + pw + ps
 
     def forward(self, graph, word_feature, sent_feature):
+        return self.update(graph, word_feature, sent_feature)
+
+    def update(self, graph, word_feature, sent_feature):
         cfg, tensors = self.loop_call(graph)
         return UpdateLoopFn.apply(graph, cfg, word_feature, sent_feature, *tensors)
 

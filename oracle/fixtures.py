@@ -158,3 +158,34 @@ def golden_grad(z, key, g):
     ref = z["gp:" + key]
     g = g.detach()
     return (g if ref.shape == tuple(g.shape) else g.flatten()[::int(z["stride"])]), torch.from_numpy(ref)
+
+
+def seeded_state_dict(shapes, seed, keep=()):
+    """Deterministic values for a whole-model state_dict from (key -> shape) alone: tensor number i (keys sorted) is
+    drawn from torch.Generator(seed * 100003 + i).  Matrices ~ N(0, 1/fan_in), vectors ~ N(0, 0.1), LayerNorm gains
+    1 + N(0, 0.1), word embedding ~ N(0, 1) with a zero PAD row; keys in `keep` (frozen sinusoid tables) are skipped."""
+    import torch
+    out = {}
+    for i, (k, shp) in enumerate(sorted(shapes.items())):
+        if k in keep:
+            continue
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        if k.endswith("embed.weight") and "TFembed" not in k and "pos" not in k and "position" not in k:
+            w = torch.randn(shp, generator=g)
+            w[0] = 0.0
+        elif k.endswith("layer_norm.weight"):
+            w = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:
+            w = 0.1 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            w = torch.randn(shp, generator=g) / fan_in ** 0.5
+        out[k] = w
+    if "_embed.weight" in out and "ngram_enc.embed.weight" in out:
+        out["ngram_enc.embed.weight"] = out["_embed.weight"]          # one shared table (HiGraph.py:125)
+    return out
+
+
+FROZEN_MODEL_KEYS = ("sent_pos_embed.weight", "ngram_enc.position_embedding.weight")

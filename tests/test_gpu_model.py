@@ -1,0 +1,83 @@
+"""GPU parity test (-m gpu) of the whole drop-in models against the UNMODIFIED reference run end to end:
+hetersumgraph_b200.HSumGraph / HSumDocGraph `forward(graph)` vs HiGraph.HSumGraph / HSumDocGraph `forward(graph)`
+(HiGraph.py:82-110, :175-228) on the same tokens, TF-IDF tables and weights, default hyper-parameters.  Goldens:
+tests/golden/model_*.npz (tests/golden/make_golden_model.py).  The reference's state_dict loads with its own keys.
+
+Tolerance (BASELINE.json): logits and every parameter gradient <= 1e-5 normalised max error.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import hetersumgraph_b200 as hb
+from hetersumgraph_b200 import synthetic as syn
+from oracle import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-5
+
+
+def nerr(a, b):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def hps_default(n_iter):
+    return types.SimpleNamespace(n_iter=n_iter, word_emb_dim=300, sent_max_len=100, doc_max_timesteps=50,
+                                 n_feature_size=128, hidden_size=64, lstm_hidden_state=128, lstm_layers=2,
+                                 bidirectional=True, n_head=8, atten_dropout_prob=0.0, ffn_inner_hidden_size=512,
+                                 ffn_dropout_prob=0.0, feat_embed_size=50, cuda=True)
+
+
+def reference_keyed_grads(model):
+    """gradients under the reference's per-head state_dict keys (the modules store the heads packed)."""
+    out = {k: v.grad for k, v in model.state_dict(keep_vars=True).items() if getattr(v, "grad", None) is not None}
+    for pre in ("word2sent.", "sent2word."):
+        lay = getattr(model, pre[:-1]).layer
+        d = lay.out_dim
+        for k in range(lay.num_heads):
+            out[pre + "layer.heads.%d.fc.weight" % k] = lay.fc_weight.grad[k * d:(k + 1) * d]
+            out[pre + "layer.heads.%d.feat_fc.weight" % k] = lay.feat_fc_weight.grad[k * d:(k + 1) * d]
+            if lay.feat_fc_bias is not None:
+                out[pre + "layer.heads.%d.feat_fc.bias" % k] = lay.feat_fc_bias.grad[k * d:(k + 1) * d]
+            out[pre + "layer.heads.%d.attn_fc.weight" % k] = lay.attn_fc_weight.grad[k:k + 1]
+    return out
+
+
+@pytest.mark.parametrize("name", ["model_hsg_default.npz", "model_hdsg_default.npz"])
+def test_whole_model_matches_reference_forward_and_gradients(name):
+    z = dict(np.load(os.path.join(GOLD, name)))
+    hdsg, n_iter, seed = bool(z["hdsg"]), int(z["n_iter"]), int(z["seed"])
+    exs = fx.examples_from_arrays(z, "ex")
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    assert tb.order == z["order"].tolist()
+    embed = torch.nn.Embedding(50000, 300, padding_idx=0)
+    embed.weight.requires_grad_(False)                       # train.py:340-342 default
+    model = (hb.HSumDocGraph if hdsg else hb.HSumGraph)(hps_default(n_iter), embed)
+    model.lstm.dropout = 0.0                                 # the golden ran the reference in .eval(): dropout off
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = fx.seeded_state_dict(shapes, seed, keep=fx.FROZEN_MODEL_KEYS)
+    missing, unexpected = model.load_state_dict(sd, strict=False)       # the reference's own keys
+    assert sorted(missing) == sorted(fx.FROZEN_MODEL_KEYS) and not unexpected
+    model = model.cuda()
+    batch = hb.HeteroBatch.from_token_batch(tb, "cuda")
+    logits = model(batch)
+    assert logits.shape == z["logits"].shape
+    assert nerr(logits, z["logits"]) <= TOL, nerr(logits, z["logits"])
+    (logits * torch.from_numpy(z["cot"]).cuda()).sum().backward()
+    grads = reference_keyed_grads(model)
+    checked = 0
+    for key in [k[3:] for k in z if k.startswith("gp:")]:
+        assert key in grads, key
+        got, ref = fx.golden_grad(z, key, grads[key].cpu())
+        if float(ref.abs().max()) == 0.0:
+            assert float(got.abs().max()) <= 1e-12, key
+        else:
+            assert nerr(got, ref) <= TOL, (key, nerr(got, ref))
+        checked += 1
+    assert checked >= 60
