@@ -5,11 +5,14 @@
 // sequence per step (measured here: ~9 ms per training step at 32 graphs, 12x the whole WSWGAT path).  Every graph is
 // an independent sequence whose rows are already contiguous in the batched sentence order, so:
 //   * the input products  x . W_ih^T  of ALL time steps are one GEMM per direction (caller, hsg_gemm_nt);
-//   * the recurrence runs in ONE persistent kernel per layer: CTA (graph, direction), one thread per gate row
-//     (4H <= 512 threads).  W_hh stays on chip for the whole sequence: columns k < 96 in shared memory (row pitch
-//     KS + 4 floats: the float4 reads of 8 consecutive rows cover all 32 banks), columns 96..127 in 32 registers
-//     per thread; h in shared memory, c in a register.  No global traffic on the critical path except the
-//     prefetched x-projection row;
+//   * the recurrence runs in ONE persistent kernel per layer: CTA (graph, direction), 2H threads, each owning TWO gate
+//     rows (t and t + 2H).  W_hh stays on chip for the whole sequence, HALF of it in registers: columns k < 64 in
+//     shared memory (row pitch KS + 4 floats: the float4 reads of 8 consecutive rows cover all 32 banks), columns
+//     64..127 in 2 x 64 registers per thread.  The step time is the shared-memory read of W_hh (ncu: mio / short-
+//     scoreboard stalls on the LDS.128 stream), so moving half of it into the register file halves it
+//     (first version: 96 of 128 columns in shared memory, one row per thread: 2.0 us per step);
+//     h in shared memory, c in a register.  No global traffic on the critical path except the prefetched
+//     x-projection values;
 //   * backward: the same CTA walks its sequence in reverse, recomputes nothing (post-activation gates, c and
 //     h_{t-1} were saved by the forward), keeps dh / dc on chip and writes the pre-activation gradients da [S, 4H]
 //     per direction; the weight / input gradients are GEMMs over all time steps at once (caller: gemm_tn, gemm_nn).
@@ -19,8 +22,10 @@
 namespace hsg {
 
 constexpr int LSTM_MAX_H = 128;
-constexpr int LSTM_KS_MAX = 96;      // W_hh columns kept in shared memory
-constexpr int LSTM_KR = 32;          // W_hh columns kept in registers (k = KS .. KS + 31)
+constexpr int LSTM_KS_MAX = 64;      // W_hh columns kept in shared memory
+constexpr int LSTM_KR = 64;          // W_hh columns kept in registers (k = KS .. KS + 63), per gate row
+constexpr int LSTM_NJ_MAX = 16;      // gate-row chunks of the shared-memory part of the transposed product
+constexpr int LSTM_MAX_WARPS = 8;    // 2 * LSTM_MAX_H / 32
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -49,6 +54,20 @@ __device__ __forceinline__ void load_whh_smem(float* W_s, const float* __restric
   }
 }
 
+// register-resident columns KS .. KS+63 of gate row j (zeros past H)
+__device__ __forceinline__ void load_whh_regs(float (&w)[LSTM_KR], const float* __restrict__ whh, int H, int KS, int j,
+                                              bool on) {
+#pragma unroll
+  for (int i = 0; i < LSTM_KR; i += 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on && KS + i < H) v = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * H + KS + i));   // H % 4 == 0
+    w[i] = v.x;
+    w[i + 1] = v.y;
+    w[i + 2] = v.z;
+    w[i + 3] = v.w;
+  }
+}
+
 struct LstmDirPtrs {
   const float* w_hh[2];   // [4H, H]
   const float* b_ih[2];   // [4H]
@@ -56,77 +75,104 @@ struct LstmDirPtrs {
 };
 
 // xproj [S, ndir*4H] (no bias), out [S, ndir*H], gates [S, ndir, 4H], cst [S, ndir, H], hprev [S, ndir, H]
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(2 * LSTM_MAX_H, 1)
 lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* __restrict__ xproj, LstmDirPtrs p,
                 float* __restrict__ out, float* __restrict__ gates, float* __restrict__ cst,
                 float* __restrict__ hprev) {
   pdl_prologue();
   extern __shared__ float4 lstm_smem4[];
   float* smem = reinterpret_cast<float*>(lstm_smem4);
-  const int G4 = 4 * H;
+  const int G4 = 4 * H, H2 = 2 * H;
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const int pitch = KS + 4;
   float* W_s = smem;                               // [4H][pitch]
-  float* h_s = W_s + (size_t)G4 * pitch;           // [LSTM_MAX_H + LSTM_KR] zero padded
-  float* a_s = h_s + LSTM_MAX_H + LSTM_KR;         // [4H]
+  float* h_s = W_s + (size_t)G4 * pitch;           // [LSTM_KS_MAX + LSTM_KR] zero padded
+  float* a_s = h_s + LSTM_KS_MAX + LSTM_KR;        // [4H]
   const int b = blockIdx.x, dir = blockIdx.y;
-  const int j = threadIdx.x;
-  const bool on = j < G4;
+  const int t = threadIdx.x;
+  const bool on = t < H2;
+  const int j0 = t, j1 = t + H2;                   // the two gate rows of this thread
   const float* whh = p.w_hh[dir];
   load_whh_smem(W_s, whh, H, KS, pitch);
-  for (int i = threadIdx.x; i < LSTM_MAX_H + LSTM_KR; i += blockDim.x) h_s[i] = 0.f;
-  float wreg[LSTM_KR];
-#pragma unroll
-  for (int i = 0; i < LSTM_KR; ++i) wreg[i] = (on && KS + i < H) ? __ldg(whh + (size_t)j * H + KS + i) : 0.f;
-  const float bias = on ? __ldg(p.b_ih[dir] + j) + __ldg(p.b_hh[dir] + j) : 0.f;
-  const bool is_g = on && (j / H) == 2;
+  for (int i = threadIdx.x; i < LSTM_KS_MAX + LSTM_KR; i += blockDim.x) h_s[i] = 0.f;
+  float wr0[LSTM_KR], wr1[LSTM_KR];
+  load_whh_regs(wr0, whh, H, KS, j0, on);
+  load_whh_regs(wr1, whh, H, KS, j1, on);
+  const float bias0 = on ? __ldg(p.b_ih[dir] + j0) + __ldg(p.b_hh[dir] + j0) : 0.f;
+  const float bias1 = on ? __ldg(p.b_ih[dir] + j1) + __ldg(p.b_hh[dir] + j1) : 0.f;
+  const bool tanh1 = on && t < H;                  // row t + 2H is a g-gate row (tanh) for t < H, an o-gate row otherwise
   const int r0 = gptr[b], T = gptr[b + 1] - r0;
   const int ldx = ndir * G4;
   float c = 0.f;
   __syncthreads();
-  float xa = (on && T > 0) ? __ldg(xproj + (size_t)(r0 + (dir ? T - 1 : 0)) * ldx + dir * G4 + j) : 0.f;
+  float xa0 = 0.f, xa1 = 0.f;
+  if (on && T > 0) {
+    const float* xr = xproj + (size_t)(r0 + (dir ? T - 1 : 0)) * ldx + dir * G4;
+    xa0 = __ldg(xr + j0);
+    xa1 = __ldg(xr + j1);
+  }
   for (int step = 0; step < T; ++step) {
     const int row = r0 + (dir ? T - 1 - step : step);
-    float xa_next = 0.f;
-    if (on && step + 1 < T) xa_next = __ldg(xproj + (size_t)(r0 + (dir ? T - 2 - step : step + 1)) * ldx + dir * G4 + j);
-    float acc0 = 0.f, acc1 = 0.f;
+    float xn0 = 0.f, xn1 = 0.f;
+    if (on && step + 1 < T) {
+      const float* xr = xproj + (size_t)(r0 + (dir ? T - 2 - step : step + 1)) * ldx + dir * G4;
+      xn0 = __ldg(xr + j0);
+      xn1 = __ldg(xr + j1);
+    }
     if (on) {
-      const float* wr = W_s + j * pitch;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // two partial sums per row
+      const float* w0 = W_s + (size_t)j0 * pitch;
+      const float* w1 = W_s + (size_t)j1 * pitch;
+#pragma unroll 4
       for (int k = 0; k < KS; k += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
         const float4 h4 = *reinterpret_cast<const float4*>(h_s + k);
-        acc0 = fmaf(w4.x, h4.x, acc0);
-        acc1 = fmaf(w4.y, h4.y, acc1);
-        acc0 = fmaf(w4.z, h4.z, acc0);
-        acc1 = fmaf(w4.w, h4.w, acc1);
+        const float4 u4 = *reinterpret_cast<const float4*>(w0 + k);
+        const float4 v4 = *reinterpret_cast<const float4*>(w1 + k);
+        a0 = fmaf(u4.x, h4.x, a0);
+        a1 = fmaf(u4.y, h4.y, a1);
+        a0 = fmaf(u4.z, h4.z, a0);
+        a1 = fmaf(u4.w, h4.w, a1);
+        b0 = fmaf(v4.x, h4.x, b0);
+        b1 = fmaf(v4.y, h4.y, b1);
+        b0 = fmaf(v4.z, h4.z, b0);
+        b1 = fmaf(v4.w, h4.w, b1);
       }
       if (H > KS) {
 #pragma unroll
         for (int i = 0; i < LSTM_KR; i += 4) {
           const float4 h4 = *reinterpret_cast<const float4*>(h_s + KS + i);
-          acc0 = fmaf(wreg[i], h4.x, acc0);
-          acc1 = fmaf(wreg[i + 1], h4.y, acc1);
-          acc0 = fmaf(wreg[i + 2], h4.z, acc0);
-          acc1 = fmaf(wreg[i + 3], h4.w, acc1);
+          a0 = fmaf(wr0[i], h4.x, a0);
+          a1 = fmaf(wr0[i + 1], h4.y, a1);
+          a0 = fmaf(wr0[i + 2], h4.z, a0);
+          a1 = fmaf(wr0[i + 3], h4.w, a1);
+          b0 = fmaf(wr1[i], h4.x, b0);
+          b1 = fmaf(wr1[i + 1], h4.y, b1);
+          b0 = fmaf(wr1[i + 2], h4.z, b0);
+          b1 = fmaf(wr1[i + 3], h4.w, b1);
         }
       }
-      const float a = (acc0 + acc1) + xa + bias;
-      const float act = is_g ? tanhf(a) : sigmoid_acc(a);
-      a_s[j] = act;
-      gates[((size_t)row * ndir + dir) * G4 + j] = act;
+      const float act0 = sigmoid_acc((a0 + a1) + xa0 + bias0);            // rows < 2H: i and f gates
+      const float pre1 = (b0 + b1) + xa1 + bias1;
+      const float act1 = tanh1 ? tanhf(pre1) : sigmoid_acc(pre1);
+      a_s[j0] = act0;
+      a_s[j1] = act1;
+      float* gr = gates + ((size_t)row * ndir + dir) * G4;
+      gr[j0] = act0;
+      gr[j1] = act1;
     }
     __syncthreads();
-    if (j < H) {
-      const float ig = a_s[j], fg = a_s[H + j], gg = a_s[2 * H + j], og = a_s[3 * H + j];
-      const size_t o = ((size_t)row * ndir + dir) * H + j;
-      hprev[o] = h_s[j];
+    if (t < H) {
+      const float ig = a_s[t], fg = a_s[H + t], gg = a_s[2 * H + t], og = a_s[3 * H + t];
+      const size_t o = ((size_t)row * ndir + dir) * H + t;
+      hprev[o] = h_s[t];
       c = fmaf(fg, c, ig * gg);
       const float hv = og * tanhf(c);
       cst[o] = c;
       out[o] = hv;
-      h_s[j] = hv;
+      h_s[t] = hv;
     }
-    xa = xa_next;
+    xa0 = xn0;
+    xa1 = xn1;
     __syncthreads();
   }
 }
@@ -134,41 +180,41 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
 // d_out [S, ndir*H]; da [S, ndir*4H] (pre-activation gate gradients, the x-projection layout)
 //
 // The transposed product dh_{t-1}[k] = sum_j da[j] W_hh[j][k] uses the SAME on-chip copy of W_hh as the forward:
-//   * columns k < KS (shared memory): thread (kg, jc) owns 4 consecutive columns and a chunk of H/4 gate rows -
-//     float4 reads along k (conflict-free), 16 row chunks reduced through shared memory;
-//   * columns k >= KS (registers of the thread that owns gate row j): every thread forms da[j] * W[j][KS..KS+31]
-//     and the 32 column sums are reduced across the warp with a 31-shuffle butterfly, then across the 16 warps.
-constexpr int LSTM_NJ = 16;          // gate-row chunks of the shared-memory part
-
-__global__ void __launch_bounds__(512, 1)
+//   * columns k < KS (shared memory): thread (kg, jc) owns 4 consecutive columns and a chunk of gate rows - float4
+//     reads along k (conflict-free), the row chunks reduced through shared memory;
+//   * columns k >= KS (registers of the thread that owns gate rows t, t + 2H): every thread forms
+//     da[t] W[t][k] + da[t+2H] W[t+2H][k] for its 64 columns, and the column sums are reduced across the warp with two
+//     31-shuffle butterflies (32 columns each), then across the warps through shared memory.
+__global__ void __launch_bounds__(2 * LSTM_MAX_H, 1)
 lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* __restrict__ d_out,
                 const float* __restrict__ gates, const float* __restrict__ cst, LstmDirPtrs p,
                 float* __restrict__ da) {
   pdl_prologue();
   extern __shared__ float4 lstm_smem4[];
   float* smem = reinterpret_cast<float*>(lstm_smem4);
-  const int G4 = 4 * H;
+  const int G4 = 4 * H, H2 = 2 * H;
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const int pitch = KS + 4;
-  float* W_s = smem;                               // [4H][pitch]
-  float* da_s = W_s + (size_t)G4 * pitch;          // [4 * LSTM_MAX_H]
-  float* part_s = da_s + 4 * LSTM_MAX_H;           // [LSTM_NJ][LSTM_KS_MAX]  partial sums, columns k < KS
-  float* regp_s = part_s + LSTM_NJ * LSTM_KS_MAX;  // [16 warps][LSTM_KR]     partial sums, columns k >= KS
+  float* W_s = smem;                                    // [4H][pitch]
+  float* da_s = W_s + (size_t)G4 * pitch;               // [4 * LSTM_MAX_H]
+  float* part_s = da_s + 4 * LSTM_MAX_H;                // [LSTM_NJ_MAX][LSTM_KS_MAX]  partial sums, columns k < KS
+  float* regp_s = part_s + LSTM_NJ_MAX * LSTM_KS_MAX;   // [LSTM_MAX_WARPS][LSTM_KR]   partial sums, columns k >= KS
   const int b = blockIdx.x, dir = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool on = tid < G4;
+  const bool on = tid < H2;
   const float* whh = p.w_hh[dir];
   load_whh_smem(W_s, whh, H, KS, pitch);
-  for (int i = threadIdx.x; i < LSTM_NJ * LSTM_KS_MAX + 16 * LSTM_KR; i += blockDim.x) part_s[i] = 0.f;
+  for (int i = threadIdx.x; i < LSTM_NJ_MAX * LSTM_KS_MAX + LSTM_MAX_WARPS * LSTM_KR; i += blockDim.x) part_s[i] = 0.f;
   for (int i = threadIdx.x; i < 4 * LSTM_MAX_H; i += blockDim.x) da_s[i] = 0.f;
   const bool has_reg = H > KS;
-  float wreg[LSTM_KR];
-#pragma unroll
-  for (int i = 0; i < LSTM_KR; ++i) wreg[i] = (on && KS + i < H) ? __ldg(whh + (size_t)tid * H + KS + i) : 0.f;
+  float wr0[LSTM_KR], wr1[LSTM_KR];
+  load_whh_regs(wr0, whh, H, KS, tid, on);
+  load_whh_regs(wr1, whh, H, KS, tid + H2, on);
   const int nkg = KS >> 2;                                    // float4 column groups in shared memory
+  const int nj = (H2 >= LSTM_NJ_MAX * nkg) ? LSTM_NJ_MAX : LSTM_NJ_MAX / 2;   // gate-row chunks (2H >= 8 nkg always)
   const int kg = tid % nkg, jc = tid / nkg;                   // this thread's column group and gate-row chunk
-  const bool smem_on = jc < LSTM_NJ;
-  const int jper = G4 / LSTM_NJ;                              // gate rows per chunk (= H / 4)
+  const bool smem_on = jc < nj;
+  const int jper = G4 / nj;                                   // gate rows per chunk
   const int r0 = gptr[b], T = gptr[b + 1] - r0;
   const int u = tid;                                          // pointwise: hidden unit (u < H)
   float dc_carry = 0.f;
@@ -192,11 +238,10 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
     if (u < H) {
       float rec = 0.f;                                        // dh from step + 1, fixed summation order
       if (u < KS) {
-#pragma unroll
-        for (int q = 0; q < LSTM_NJ; ++q) rec += part_s[q * LSTM_KS_MAX + u];
+        for (int q = 0; q < nj; ++q) rec += part_s[q * LSTM_KS_MAX + u];
       } else {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) rec += regp_s[q * LSTM_KR + (u - KS)];
+        for (int q = 0; q < LSTM_MAX_WARPS; ++q) rec += regp_s[q * LSTM_KR + (u - KS)];
       }
       const float dh = go + rec;
       const float tc = tanhf(cc);
@@ -219,31 +264,34 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
     }
     __syncthreads();
     if (step > 0) {                                           // the product feeds the next (earlier) step only
-      if (has_reg) {                                          // columns KS .. KS+31 from registers, butterfly reduce
-        const float dj = on ? da_s[tid] : 0.f;
-        float v[LSTM_KR];
+      if (has_reg) {                                          // columns KS .. KS+63 from registers, butterfly reduce
+        const float d0 = on ? da_s[tid] : 0.f, d1 = on ? da_s[tid + H2] : 0.f;
 #pragma unroll
-        for (int i = 0; i < LSTM_KR; ++i) v[i] = dj * wreg[i];
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool up = (lane & off) != 0;
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(d0, wr0[half * 32 + i], d1 * wr1[half * 32 + i]);
 #pragma unroll
-          for (int i = 0; i < off; ++i) {
-            const float keep = up ? v[i + off] : v[i];
-            const float send = up ? v[i] : v[i + off];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float keep = up ? v[i + off] : v[i];
+              const float send = up ? v[i] : v[i + off];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
           }
+          regp_s[warp * LSTM_KR + half * 32 + lane] = v[0];   // lane l holds column KS + 32 half + l
         }
-        regp_s[warp * LSTM_KR + lane] = v[0];                 // lane l holds column KS + l (warps past 4H hold zeros)
       }
       if (smem_on) {                                          // columns k < KS from shared memory
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int j0 = jc * jper;
-        const float* wp = W_s + (size_t)j0 * pitch + 4 * kg;
+        const int jb = jc * jper;
+        const float* wp = W_s + (size_t)jb * pitch + 4 * kg;
 #pragma unroll 4
         for (int jj = 0; jj < jper; ++jj) {
           const float4 w4 = *reinterpret_cast<const float4*>(wp + (size_t)jj * pitch);
-          const float dj = da_s[j0 + jj];
+          const float dj = da_s[jb + jj];
           acc.x = fmaf(dj, w4.x, acc.x);
           acc.y = fmaf(dj, w4.y, acc.y);
           acc.z = fmaf(dj, w4.z, acc.z);
@@ -259,8 +307,8 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
 static size_t lstm_smem_bytes(int H) {
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const size_t w = (size_t)4 * H * (KS + 4);
-  const size_t fwd = w + LSTM_MAX_H + LSTM_KR + 4 * H;
-  const size_t bwd = w + 4 * LSTM_MAX_H + LSTM_NJ * LSTM_KS_MAX + 16 * LSTM_KR;
+  const size_t fwd = w + LSTM_KS_MAX + LSTM_KR + 4 * H;
+  const size_t bwd = w + 4 * LSTM_MAX_H + LSTM_NJ_MAX * LSTM_KS_MAX + LSTM_MAX_WARPS * LSTM_KR;
   return (fwd > bwd ? fwd : bwd) * sizeof(float);
 }
 
@@ -302,7 +350,7 @@ int hsg_lstm_fwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
   if ((rc = lstm_attr(lstm_fwd_kernel, H)) != HSG_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_LSTM, s);
-  const int threads = ((4 * H + 31) / 32) * 32;
+  const int threads = ((2 * H + 31) / 32) * 32;
   launch_k(lstm_fwd_kernel, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir, graph_sent_ptr, xproj, p,
            out, gates, cst, hprev);
   return check_launch();
@@ -326,7 +374,7 @@ int hsg_lstm_bwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
   if ((rc = lstm_attr(lstm_bwd_kernel, H)) != HSG_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_LSTM, s);
-  const int threads = ((4 * H + 31) / 32) * 32;
+  const int threads = ((2 * H + 31) / 32) * 32;
   launch_k(lstm_bwd_kernel, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir, graph_sent_ptr, d_out,
            gates, cst, p, da);
   return check_launch();

@@ -171,6 +171,16 @@ class NgramEncodeFn(torch.autograd.Function):
         return tuple(grads)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class LstmFn(torch.autograd.Function):
     """out [S, ndir * H] = the last layer's output of nn.LSTM run on every graph's sentence rows as one sequence
     (pack_padded_sequence semantics, HiGraph.py:135-141).  Arguments: x [S, in], graph_sent_ptr (device int32 [B+1]),
@@ -178,6 +188,8 @@ class LstmFn(torch.autograd.Function):
     weight_ih, weight_hh, bias_ih, bias_hh).  p > 0: inter-layer dropout (nn.LSTM(dropout=0.1), HiGraph.py:118) with
     the library's counter-based masks (hsg_dropout_mask, stream 1000 + layer), applied by two elementwise torch ops -
     training-mode only, off in every parity test and in both bench arms."""
+
+    overlap_weight_grads = True       # class-level switch (tests compare both settings)
 
     @staticmethod
     def forward(ctx, x, gptr, cfg, *params):
@@ -225,6 +237,11 @@ class LstmFn(torch.autograd.Function):
         S = d_cur.shape[0]
         grads = [None] * len(params)
         G4 = 4 * H
+        # weight-gradient products (dW_ih, dW_hh, db of both directions) run on a side stream: only dx is on the chain
+        # to the next (lower) layer's recurrence, which occupies n_graphs * ndir CTAs and leaves most SMs idle.  Same
+        # kernels, same results; the main stream joins before backward returns.
+        main = torch.cuda.current_stream()
+        side = _side_stream(d_cur.device) if LstmFn.overlap_weight_grads else None
         for layer in range(n_layers - 1, -1, -1):
             if ctx.scales and layer + 1 < n_layers:
                 d_cur = d_cur * ctx.scales[layer]
@@ -233,16 +250,32 @@ class LstmFn(torch.autograd.Function):
             da = torch.empty(S, ndir * G4, dtype=torch.float32, device=d_cur.device)
             _lib.check(lib.hsg_lstm_bwd(n_graphs, H, ndir, _p(gptr), _p(d_cur), _p(gates), _p(cst),
                                         _ptr_array([q[1] for q in pl]), _p(da), _st()))
+
+            def weight_grads(tag):
+                for d in range(ndir):
+                    da_d = da[:, d * G4:(d + 1) * G4]
+                    dW_ih, db = gemm_tn(da_d, inp, want_colsum=True, ws_tag=tag)
+                    dW_hh, _ = gemm_tn(da_d, hprev[:, d, :], ws_tag=tag)
+                    base = (layer * ndir + d) * 4
+                    grads[base], grads[base + 1], grads[base + 2], grads[base + 3] = dW_ih, dW_hh, db, db.clone()
+                    if tag != "tn":                  # allocated on the side stream, consumed on the main stream
+                        for g in grads[base:base + 4]:
+                            g.record_stream(main)
+
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    weight_grads("tn_side")
+            else:
+                weight_grads("tn")
             dx = None
-            for d in range(ndir):
-                da_d = da[:, d * G4:(d + 1) * G4]
-                dW_ih, db = gemm_tn(da_d, inp, want_colsum=True)
-                dW_hh, _ = gemm_tn(da_d, hprev[:, d, :])
-                base = (layer * ndir + d) * 4
-                grads[base], grads[base + 1], grads[base + 2], grads[base + 3] = dW_ih, dW_hh, db, db.clone()
-                if layer > 0 or ctx.need_dx:
+            if layer > 0 or ctx.need_dx:
+                for d in range(ndir):
+                    da_d = da[:, d * G4:(d + 1) * G4]
                     dx = gemm_nn(da_d, pl[d][0]) if dx is None else gemm_nn(da_d, pl[d][0], R=dx, epi=_lib.EPI_ADD)
             d_cur = dx
+        if side is not None:
+            main.wait_stream(side)
         return (d_cur if ctx.need_dx else None, None, None) + tuple(grads)
 
 
@@ -273,12 +306,26 @@ class SentHeadFn(torch.autograd.Function):
         d_sf = _f32c(d_sf)
         nf = Wc.shape[0]
         d_node = gemm_nn(d_sf, Wn)
-        dWn, _ = gemm_tn(d_sf, node)
         d_cnn, d_lf = d_node[:, :nf], d_node[:, nf:]
+        # the three weight-gradient products run on the side stream next to the two input-gradient products (all five
+        # are small launches that leave most SMs idle); joined before returning, because autograd accumulates the
+        # returned gradients on the main stream
+        main = torch.cuda.current_stream()
+        side = _side_stream(d_sf.device) if LstmFn.overlap_weight_grads else None
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            tag = "tn_side" if side is not None else "tn"
+            dWn, _ = gemm_tn(d_sf, node, ws_tag=tag)
+            dWc, dbc = gemm_tn(d_cnn, cnn_in, want_colsum=True, ws_tag=tag)
+            dWl, dbl = gemm_tn(d_lf, lstm_out, want_colsum=True, ws_tag=tag)
+            if side is not None:
+                for g in (dWn, dWc, dbc, dWl, dbl):
+                    g.record_stream(main)
         d_ngram = gemm_nn(d_cnn, Wc)
-        dWc, dbc = gemm_tn(d_cnn, cnn_in, want_colsum=True)
         d_lstm_out = gemm_nn(d_lf, Wl)
-        dWl, dbl = gemm_tn(d_lf, lstm_out, want_colsum=True)
+        if side is not None:
+            main.wait_stream(side)
         return d_ngram, d_lstm_out, None, None, dWc, dbc, dWl, dbl, dWn
 
 

@@ -187,7 +187,11 @@ int hsg_set_gemm_small_flops(double flops);
 /* Profiling aid for the tensor-core pipeline: on = 1/0 arms/disarms a trace of CTA 0 (synchronous call); on < 0 reads
  * up to max_events (event id, k-block counter, SM clock) triples into host_out and returns their number. */
 int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events);
-/* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward) */
+/* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward).
+ * lda may be SMALLER than K: rows of A then overlap (row m = the K floats starting at A + m*lda) - the sentence
+ * encoder's convolution windows (hsg_enc_* below) are read that way without an im2col copy.
+ * With HSG_EPI_ADD, R may be the same buffer as C (ldr == ldc): every element is read and then written by one thread
+ * (in-place accumulation of K-chunks). */
 int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const float* bias, const float* R, int ldr, int epi, void* stream);
 /* C[M,N] = A[M,K] . B[K,N]    (input gradient) */

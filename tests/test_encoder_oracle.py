@@ -88,3 +88,35 @@ def test_ngram_encode_matches_live_reference_sentencoder():
                           [c.bias for c in enc.convs])
     assert nerr(got, ref) <= 2e-6
     assert torch.equal(er.sinusoid_table(L + 1, 300, padding_idx=0), enc.position_embedding.weight)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only in the build container")
+@pytest.mark.parametrize("hdsg", [False, True])
+def test_dropin_models_have_the_reference_state_dict(hdsg):
+    """hetersumgraph_b200.HSumGraph / HSumDocGraph: same keys, key order and shapes as HiGraph.HSumGraph / HSumDocGraph
+    (so a reference checkpoint loads with strict=True), 1 762 166 / 1 766 390 trainable parameters at the defaults."""
+    import types
+    sys.path.insert(0, "/root/reference")
+    from oracle import dgl04_shim as shim
+    shim.install()
+    import HiGraph
+    import hetersumgraph_b200 as hb
+    hps = types.SimpleNamespace(n_iter=1, word_emb_dim=300, sent_max_len=100, doc_max_timesteps=50, n_feature_size=128,
+                                hidden_size=64, lstm_hidden_state=128, lstm_layers=2, bidirectional=True, n_head=8,
+                                atten_dropout_prob=0.1, ffn_inner_hidden_size=512, ffn_dropout_prob=0.1,
+                                feat_embed_size=50, cuda=False)
+    e1 = torch.nn.Embedding(1000, 300, padding_idx=0)
+    e1.weight.requires_grad_(False)
+    ref = (HiGraph.HSumDocGraph if hdsg else HiGraph.HSumGraph)(hps, e1)
+    e2 = torch.nn.Embedding(1000, 300, padding_idx=0)
+    e2.weight.requires_grad_(False)
+    mine = (hb.HSumDocGraph if hdsg else hb.HSumGraph)(hps, e2)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    missing, unexpected = mine.load_state_dict(a, strict=True)
+    assert not missing and not unexpected
+    back = mine.state_dict()
+    assert all(torch.equal(a[k], back[k]) for k in a)          # packed <-> per-head round trip is lossless
+    n_train = sum(p.numel() for p in mine.parameters() if p.requires_grad)
+    assert n_train == sum(p.numel() for p in ref.parameters() if p.requires_grad) == (1766390 if hdsg else 1762166)

@@ -154,6 +154,16 @@ def test_lstm_kernels_match_oracle(H, n_in, layers, bidir, lens):
         assert nerr(g, po[name].grad) <= TOL, name
     assert torch.equal(out, runs[1][0]) and torch.equal(dx, runs[1][1])
     assert all(torch.equal(a, b) for a, b in zip(grads, runs[1][2]))
+    # weight-gradient products on the side stream (default) vs everything on one stream: bitwise identical
+    LstmFn.overlap_weight_grads = False
+    try:
+        xd = x.cuda().requires_grad_(True)
+        pd = [v.detach().clone().cuda().requires_grad_(True) for v in ref._flat_weights]
+        (LstmFn.apply(xd, gptr, cfg, *pd) * cot.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert torch.equal(xd.grad, dx) and all(torch.equal(q.grad, g) for q, g in zip(pd, grads))
+    finally:
+        LstmFn.overlap_weight_grads = True
 
 
 def test_cudnn_lstm_option_agrees_with_kernels():
