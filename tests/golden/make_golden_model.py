@@ -58,10 +58,29 @@ def run(name, hdsg, n_iter, seed):
     out = {"seed": np.int64(seed), "n_iter": np.int64(n_iter), "hdsg": np.int64(hdsg), "stride": np.int64(STRIDE),
            "order": np.asarray(order, np.int64), "logits": logits.detach().numpy(), "cot": cot.numpy()}
     out.update(fx.examples_to_arrays(exs, "ex"))
+
+    def sub(g):
+        return g.numpy() if g.numel() <= 2048 else g.flatten()[::STRIDE].numpy()
+
     for k, p in model.named_parameters():
         if p.requires_grad:
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
-            out["gp:" + k] = g.numpy() if g.numel() <= 2048 else g.flatten()[::STRIDE].numpy()
+            out["gp:" + k] = sub(p.grad if p.grad is not None else torch.zeros_like(p))
+    # the SAME reference code evaluated in float64: tells how far the reference's own fp32 run is from the exact value
+    # of every gradient (some are sums that cancel to ~1e-7 of their terms - e.g. feat_fc.bias of sent2word, whose
+    # gradient is a softmax-shift direction - and carry no significant digit in fp32)
+    graphs64 = [(mg.ref_graph_hdsg if hdsg else mg.ref_graph_hsg)(e, filt) for e in exs]
+    BG64 = mg.shim.batch([graphs64[i] for i in order])
+    model64 = (HiGraph.HSumDocGraph if hdsg else HiGraph.HSumGraph)(hps_default(n_iter),
+                                                                    torch.nn.Embedding(VOCAB, 300, padding_idx=0)).eval()
+    model64.load_state_dict(sd, strict=False)
+    model64 = model64.double()
+    model64._embed.weight.requires_grad_(False)
+    logits64 = model64(BG64)
+    (logits64 * cot.double()).sum().backward()
+    out["logits64"] = logits64.detach().numpy()
+    for k, p in model64.named_parameters():
+        if p.requires_grad:
+            out["g64:" + k] = sub(p.grad if p.grad is not None else torch.zeros_like(p))
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, "sentences", logits.shape[0], "bytes", os.path.getsize(os.path.join(HERE, name)))
 
