@@ -29,10 +29,11 @@ constexpr int LSTM_MAX_WARPS = 8;    // 2 * LSTM_MAX_H / 32
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
-// W_hh[:, 0:KS] -> shared memory rows of `pitch` floats: float4 copies, 8 independent loads in flight per thread (a
-// scalar load -> store loop costs ~100 serial L2 latencies per thread, ncu: 17 % of the kernel's samples)
-__device__ __forceinline__ void load_whh_smem(float* W_s, const float* __restrict__ whh, int H, int KS, int pitch) {
-  const int nk4 = KS >> 2, tot4 = 4 * H * nk4;
+// W_hh[:, col0 : col0 + ncols] -> shared memory rows of `pitch` floats: coalesced float4 copies, 8 independent loads in
+// flight per thread (a scalar load -> store loop costs ~100 serial L2 latencies per thread, ncu: 17 % of the samples)
+__device__ __forceinline__ void load_whh_cols(float* W_s, const float* __restrict__ whh, int H, int col0, int ncols,
+                                              int pitch) {
+  const int nk4 = ncols >> 2, tot4 = 4 * H * nk4;
   for (int base = threadIdx.x; base < tot4; base += 8 * blockDim.x) {
     float4 v[8];
 #pragma unroll
@@ -40,7 +41,7 @@ __device__ __forceinline__ void load_whh_smem(float* W_s, const float* __restric
       const int i4 = base + q * blockDim.x;
       if (i4 < tot4) {
         const int jj = i4 / nk4, k4 = i4 - jj * nk4;
-        v[q] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)jj * H) + k4);
+        v[q] = __ldg(reinterpret_cast<const float4*>(whh + (size_t)jj * H + col0) + k4);
       }
     }
 #pragma unroll
@@ -54,18 +55,37 @@ __device__ __forceinline__ void load_whh_smem(float* W_s, const float* __restric
   }
 }
 
-// register-resident columns KS .. KS+63 of gate row j (zeros past H)
-__device__ __forceinline__ void load_whh_regs(float (&w)[LSTM_KR], const float* __restrict__ whh, int H, int KS, int j,
-                                              bool on) {
+// On-chip copy of W_hh for this CTA: columns [KS, H) into the registers of the threads that own gate rows j0 / j1
+// (zeros past H), columns [0, KS) into shared memory.  The register part is staged through the shared-memory region
+// first, so that every global read is a coalesced float4 stream (per-thread row reads of 256 B each thrash the small
+// L1 next to a 147 KB shared-memory carve-out: ncu showed ~20 % of the kernel in this prologue).  Ends with a barrier.
+__device__ __forceinline__ void load_whh_onchip(float* W_s, float (&wr0)[LSTM_KR], float (&wr1)[LSTM_KR],
+                                                const float* __restrict__ whh, int H, int KS, int pitch, int j0, int j1,
+                                                bool on) {
 #pragma unroll
-  for (int i = 0; i < LSTM_KR; i += 4) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on && KS + i < H) v = __ldg(reinterpret_cast<const float4*>(whh + (size_t)j * H + KS + i));   // H % 4 == 0
-    w[i] = v.x;
-    w[i + 1] = v.y;
-    w[i + 2] = v.z;
-    w[i + 3] = v.w;
+  for (int i = 0; i < LSTM_KR; ++i) {
+    wr0[i] = 0.f;
+    wr1[i] = 0.f;
   }
+  if (H > KS) {
+    const int nr = H - KS;                                   // <= LSTM_KR <= pitch
+    load_whh_cols(W_s, whh, H, KS, nr, pitch);
+    __syncthreads();
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < LSTM_KR; i += 4) {
+        if (i < nr) {
+          const float4 a = *reinterpret_cast<const float4*>(W_s + (size_t)j0 * pitch + i);
+          const float4 b = *reinterpret_cast<const float4*>(W_s + (size_t)j1 * pitch + i);
+          wr0[i] = a.x; wr0[i + 1] = a.y; wr0[i + 2] = a.z; wr0[i + 3] = a.w;
+          wr1[i] = b.x; wr1[i + 1] = b.y; wr1[i + 2] = b.z; wr1[i + 3] = b.w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  load_whh_cols(W_s, whh, H, 0, KS, pitch);
+  __syncthreads();
 }
 
 struct LstmDirPtrs {
@@ -75,13 +95,18 @@ struct LstmDirPtrs {
 };
 
 // xproj [S, ndir*4H] (no bias), out [S, ndir*H], gates [S, ndir, 4H], cst [S, ndir, H], hprev [S, ndir, H]
+// HT: compile-time hidden size (128: every loop bound is a constant, the shared-memory and register halves of the product
+// are interleaved k-block by k-block and fully unrolled so that the LDS.128 stream runs ahead of the FMAs - ncu showed
+// 26 % short-scoreboard stalls on the first FMA after each shared-memory read), 0: runtime H.
+template <int HT>
 __global__ void __launch_bounds__(2 * LSTM_MAX_H, 1)
-lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* __restrict__ xproj, LstmDirPtrs p,
+lstm_fwd_kernel(int Hrt, int ndir, const int32_t* __restrict__ gptr, const float* __restrict__ xproj, LstmDirPtrs p,
                 float* __restrict__ out, float* __restrict__ gates, float* __restrict__ cst,
                 float* __restrict__ hprev) {
   pdl_prologue();
   extern __shared__ float4 lstm_smem4[];
   float* smem = reinterpret_cast<float*>(lstm_smem4);
+  const int H = HT ? HT : Hrt;
   const int G4 = 4 * H, H2 = 2 * H;
   const int KS = H < LSTM_KS_MAX ? H : LSTM_KS_MAX;
   const int pitch = KS + 4;
@@ -93,11 +118,9 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
   const bool on = t < H2;
   const int j0 = t, j1 = t + H2;                   // the two gate rows of this thread
   const float* whh = p.w_hh[dir];
-  load_whh_smem(W_s, whh, H, KS, pitch);
   for (int i = threadIdx.x; i < LSTM_KS_MAX + LSTM_KR; i += blockDim.x) h_s[i] = 0.f;
   float wr0[LSTM_KR], wr1[LSTM_KR];
-  load_whh_regs(wr0, whh, H, KS, j0, on);
-  load_whh_regs(wr1, whh, H, KS, j1, on);
+  load_whh_onchip(W_s, wr0, wr1, whh, H, KS, pitch, j0, j1, on);
   const float bias0 = on ? __ldg(p.b_ih[dir] + j0) + __ldg(p.b_hh[dir] + j0) : 0.f;
   const float bias1 = on ? __ldg(p.b_ih[dir] + j1) + __ldg(p.b_hh[dir] + j1) : 0.f;
   const bool tanh1 = on && t < H;                  // row t + 2H is a g-gate row (tanh) for t < H, an o-gate row otherwise
@@ -123,6 +146,31 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
       float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;      // two partial sums per row
       const float* w0 = W_s + (size_t)j0 * pitch;
       const float* w1 = W_s + (size_t)j1 * pitch;
+      if constexpr (HT == 2 * LSTM_KS_MAX) {
+#pragma unroll
+        for (int k = 0; k < LSTM_KS_MAX; k += 4) {
+          const float4 h4 = *reinterpret_cast<const float4*>(h_s + k);
+          const float4 g4 = *reinterpret_cast<const float4*>(h_s + LSTM_KS_MAX + k);
+          const float4 u4 = *reinterpret_cast<const float4*>(w0 + k);
+          const float4 v4 = *reinterpret_cast<const float4*>(w1 + k);
+          a0 = fmaf(wr0[k], g4.x, a0);
+          a1 = fmaf(wr0[k + 1], g4.y, a1);
+          b0 = fmaf(wr1[k], g4.x, b0);
+          b1 = fmaf(wr1[k + 1], g4.y, b1);
+          a0 = fmaf(wr0[k + 2], g4.z, a0);
+          a1 = fmaf(wr0[k + 3], g4.w, a1);
+          b0 = fmaf(wr1[k + 2], g4.z, b0);
+          b1 = fmaf(wr1[k + 3], g4.w, b1);
+          a0 = fmaf(u4.x, h4.x, a0);
+          a1 = fmaf(u4.y, h4.y, a1);
+          b0 = fmaf(v4.x, h4.x, b0);
+          b1 = fmaf(v4.y, h4.y, b1);
+          a0 = fmaf(u4.z, h4.z, a0);
+          a1 = fmaf(u4.w, h4.w, a1);
+          b0 = fmaf(v4.z, h4.z, b0);
+          b1 = fmaf(v4.w, h4.w, b1);
+        }
+      } else {
 #pragma unroll 4
       for (int k = 0; k < KS; k += 4) {
         const float4 h4 = *reinterpret_cast<const float4*>(h_s + k);
@@ -150,6 +198,7 @@ lstm_fwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
           b0 = fmaf(wr1[i + 2], h4.z, b0);
           b1 = fmaf(wr1[i + 3], h4.w, b1);
         }
+      }
       }
       const float act0 = sigmoid_acc((a0 + a1) + xa0 + bias0);            // rows < 2H: i and f gates
       const float pre1 = (b0 + b1) + xa1 + bias1;
@@ -203,13 +252,11 @@ lstm_bwd_kernel(int H, int ndir, const int32_t* __restrict__ gptr, const float* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool on = tid < H2;
   const float* whh = p.w_hh[dir];
-  load_whh_smem(W_s, whh, H, KS, pitch);
   for (int i = threadIdx.x; i < LSTM_NJ_MAX * LSTM_KS_MAX + LSTM_MAX_WARPS * LSTM_KR; i += blockDim.x) part_s[i] = 0.f;
   for (int i = threadIdx.x; i < 4 * LSTM_MAX_H; i += blockDim.x) da_s[i] = 0.f;
   const bool has_reg = H > KS;
   float wr0[LSTM_KR], wr1[LSTM_KR];
-  load_whh_regs(wr0, whh, H, KS, tid, on);
-  load_whh_regs(wr1, whh, H, KS, tid + H2, on);
+  load_whh_onchip(W_s, wr0, wr1, whh, H, KS, pitch, tid, tid + H2, on);
   const int nkg = KS >> 2;                                    // float4 column groups in shared memory
   const int nj = (H2 >= LSTM_NJ_MAX * nkg) ? LSTM_NJ_MAX : LSTM_NJ_MAX / 2;   // gate-row chunks (2H >= 8 nkg always)
   const int kg = tid % nkg, jc = tid / nkg;                   // this thread's column group and gate-row chunk
@@ -347,12 +394,19 @@ int hsg_lstm_fwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
     p.b_ih[d] = b_ih[s];
     p.b_hh[d] = b_hh[s];
   }
-  if ((rc = lstm_attr(lstm_fwd_kernel, H)) != HSG_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  LaunchScope ls(SLOT_LSTM, s);
   const int threads = ((2 * H + 31) / 32) * 32;
-  launch_k(lstm_fwd_kernel, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir, graph_sent_ptr, xproj, p,
-           out, gates, cst, hprev);
+  if (H == 2 * LSTM_KS_MAX) {
+    if ((rc = lstm_attr(lstm_fwd_kernel<2 * LSTM_KS_MAX>, H)) != HSG_OK) return rc;
+    LaunchScope ls(SLOT_LSTM, s);
+    launch_k(lstm_fwd_kernel<2 * LSTM_KS_MAX>, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir,
+             graph_sent_ptr, xproj, p, out, gates, cst, hprev);
+  } else {
+    if ((rc = lstm_attr(lstm_fwd_kernel<0>, H)) != HSG_OK) return rc;
+    LaunchScope ls(SLOT_LSTM, s);
+    launch_k(lstm_fwd_kernel<0>, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir, graph_sent_ptr,
+             xproj, p, out, gates, cst, hprev);
+  }
   return check_launch();
 }
 
