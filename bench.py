@@ -533,6 +533,42 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
 
     ms_enc = timed(enc_only)
     ms_full = timed(full)
+
+    # ---- the whole model through the public drop-in class, one TRAINING step from host buffers: pinned-host token blob
+    # -> H2D -> device graph build -> HSumGraph.forward (encoder, embedding, update loop, classifier) -> the reference's
+    # loss (train.py:114-119) -> backward -> Adam over the flat arena; the loss goes back to pinned host memory ----
+    import types
+
+    import hetersumgraph_b200 as hb
+    from hetersumgraph_b200.dist import FlatGradArena
+    from hetersumgraph_b200.functional import FusedAdam
+    from hetersumgraph_b200.path_model import graph_loss
+    hps = types.SimpleNamespace(n_iter=n_iter, word_emb_dim=300, sent_max_len=L, doc_max_timesteps=50, n_feature_size=128,
+                                hidden_size=64, lstm_hidden_state=128, lstm_layers=2, bidirectional=True, n_head=8,
+                                atten_dropout_prob=0.0, ffn_inner_hidden_size=512, ffn_dropout_prob=0.0,
+                                feat_embed_size=50, cuda=True)
+    torch.manual_seed(1234)
+    embed = torch.nn.Embedding(50000, 300, padding_idx=0)
+    embed.weight.requires_grad_(False)
+    whole = hb.HSumGraph(hps, embed).to(dev)
+    whole.lstm.dropout = 0.0
+    arena = FlatGradArena(whole.parameters(), flatten_params=True)
+    opt = FusedAdam(arena.flat_param.data, arena.flat, lr=5e-4)
+    host, h2d_bytes = DeviceTokenBatch.host_buffers(tb)
+    bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def train_step():
+        dtb_i = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
+        b = HeteroBatch.build(dtb_i)
+        arena.flat.zero_()
+        loss = graph_loss(b, whole(b), b.labels)
+        loss.backward()
+        opt.step()
+        loss_host.copy_(loss.detach().view(1), non_blocking=True)
+        return loss
+
+    ms_train = timed(train_step)
     lib.hsg_profile_reset()
     lib.hsg_profile_enable(1)
     for _ in range(steps):
@@ -549,6 +585,12 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
            "sentences": S, "compact_rows": plan.n_rows, "padded_rows": S * L,
            "encoder_fwd_bwd_ms": ms_enc, "encoder_graphs_per_s": tb.n_graphs / (ms_enc * 1e-3),
            "encoder_plus_path_fwd_bwd_ms": ms_full, "encoder_plus_path_graphs_per_s": tb.n_graphs / (ms_full * 1e-3),
+           "whole_model_train_step": {
+               "what": "hetersumgraph_b200.HSumGraph (drop-in for HiGraph.HSumGraph) from HOST buffers: H2D of the token "
+                       "blob, device graph build, forward, loss, backward, Adam; loss copied to pinned host memory",
+               "ms_per_step": ms_train, "graphs_per_s": tb.n_graphs / (ms_train * 1e-3),
+               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4 + 4 * (5 * (tb.n_graphs + 1) + 1),
+               "trainable_parameters": int(arena.flat.numel())},
            "conv_fwd_gflop_reference": useful / 1e9, "conv_fwd_gflop_executed": executed / 1e9, "kernels": slots}
     # host-cores arm: the oracle restatement of the same stage (oracle/encoder_ref.py), forward + backward
     from oracle import encoder_ref as er

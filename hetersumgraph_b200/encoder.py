@@ -75,8 +75,6 @@ class EncoderPlan:
         row_ptr = np.zeros(S + 1, np.int32)
         np.cumsum(n_rows, out=row_ptr[1:])
         counts = np.diff(ptr)
-        if np.any(counts[1:] > counts[:-1]):
-            raise ValueError("graphs must be in batch order (#sentences descending, dataloader.py:479)")
         sent_pos = (np.arange(S, dtype=np.int64) - np.repeat(ptr[:-1], counts) + 1).astype(np.int32)
         self.n_sent, self.L, self.n_rows = S, L, int(row_ptr[-1])
         self._ptr, self._counts, self._device, self._packed = ptr, counts, device, None
@@ -86,13 +84,15 @@ class EncoderPlan:
         self.graph_sent_ptr = dev[3 * S + 1:]
         self.n_graphs = len(ptr) - 1
         self.tokens = tokens_dev if tokens_dev is not None else torch.from_numpy(tokens).to(device, non_blocking=True)
-        self.real_windows = int(np.sum(np.maximum(n_rows, 0)))
 
     def _packed_order(self):
         """(batch_sizes on the host, perm, inv_perm): the time-major order of a PackedSequence over the per-graph sentence
         lists - only the use_cudnn_lstm comparison path needs it, so it is built on first use."""
         if self._packed is None:
             ptr, counts, S = self._ptr, self._counts, self.n_sent
+            if np.any(counts[1:] > counts[:-1]):
+                raise ValueError("a PackedSequence needs the graphs in batch order (#sentences descending, "
+                                 "dataloader.py:479)")
             t_max = int(counts[0]) if len(counts) else 0
             batch_sizes = (counts[None, :] > np.arange(t_max)[:, None]).sum(axis=1).astype(np.int64)
             perm = np.concatenate([ptr[:b] + t for t, b in enumerate(batch_sizes)]) if t_max else np.zeros(0, np.int64)
