@@ -557,17 +557,25 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
     host, h2d_bytes = DeviceTokenBatch.host_buffers(tb)
     bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
     loss_host = torch.zeros(1).pin_memory()
+    from hetersumgraph_b200.graph import BuildPipeline
+    pipe = BuildPipeline(dev)      # upload + build of batch i+1 on a side stream while batch i trains (one build per step)
+
+    def upload():
+        return DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
 
     def train_step():
-        dtb_i = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
-        b = HeteroBatch.build(dtb_i)
+        b = pipe.take()
+        pipe.submit(upload)
         arena.flat.zero_()
         loss = graph_loss(b, whole(b), b.labels)
         loss.backward()
         opt.step()
         loss_host.copy_(loss.detach().view(1), non_blocking=True)
+        pipe.finish()
         return loss
 
+    pipe.submit(upload)
+    pipe.finish()
     ms_train = timed(train_step)
     lib.hsg_profile_reset()
     lib.hsg_profile_enable(1)
@@ -587,7 +595,8 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
            "encoder_plus_path_fwd_bwd_ms": ms_full, "encoder_plus_path_graphs_per_s": tb.n_graphs / (ms_full * 1e-3),
            "whole_model_train_step": {
                "what": "hetersumgraph_b200.HSumGraph (drop-in for HiGraph.HSumGraph) from HOST buffers: H2D of the token "
-                       "blob, device graph build, forward, loss, backward, Adam; loss copied to pinned host memory",
+                       "blob + device graph build of the NEXT batch on a side stream (one per step), forward, loss, "
+                       "backward, Adam; loss copied to pinned host memory every step",
                "ms_per_step": ms_train, "graphs_per_s": tb.n_graphs / (ms_train * 1e-3),
                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4 + 4 * (5 * (tb.n_graphs + 1) + 1),
                "trainable_parameters": int(arena.flat.numel())},

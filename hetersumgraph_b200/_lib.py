@@ -143,6 +143,7 @@ _PROTOS = {
     "hsg_set_edge_fwd_rowpar": (C.c_int, [_I]),
     "hsg_set_edge_blockrow": (C.c_int, [_I]),
     "hsg_set_edge_bwd_async": (C.c_int, [_I]),
+    "hsg_enc_plan_host": (C.c_int, [_I, _I, _P, _I, _P, _P, _P, _P]),
     "hsg_enc_gather": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "hsg_enc_pack_weights": (C.c_int, [_I, _P, _P, _P]),
     "hsg_enc_pool_fwd": (C.c_int, [_I, _P, _P, _I, _P, _P, _I, _P, _P]),

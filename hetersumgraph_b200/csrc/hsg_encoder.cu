@@ -237,6 +237,37 @@ using namespace hsg;
 
 extern "C" {
 
+// Host-side plan of a batch (plain C loop over the host token matrix; no device work, no synchronisation).
+int hsg_enc_plan_host(int n_sent, int L, const int32_t* tokens, int n_graphs, const int32_t* graph_sent_ptr,
+                      int32_t* sent_len, int32_t* row_ptr, int32_t* sent_pos) {
+  if (n_sent < 0 || L < ENC_HMAX || n_graphs < 0 || !row_ptr) return HSG_ERR_ARG;
+  if (n_sent > 0 && (!tokens || !sent_len || !sent_pos)) return HSG_ERR_ARG;
+  if (n_graphs > 0 && (!graph_sent_ptr || graph_sent_ptr[0] != 0 || graph_sent_ptr[n_graphs] != n_sent)) return HSG_ERR_ARG;
+  long long rows = 0;
+  row_ptr[0] = 0;
+  for (int s = 0; s < n_sent; ++s) {
+    const int32_t* t = tokens + (size_t)s * L;
+    int len = 0, tail = 0;
+    for (int i = 0; i < L; ++i) {
+      if (t[i] != 0) {
+        ++len;
+        tail = i + 1;
+      }
+    }
+    sent_len[s] = len;
+    const int n = tail + ENC_HMAX < L ? tail + ENC_HMAX : L;
+    rows += n;
+    if (rows > 0x7fffffffLL) return HSG_ERR_CAPACITY;
+    row_ptr[s + 1] = (int32_t)rows;
+  }
+  for (int g = 0; g < n_graphs; ++g) {
+    const int b = graph_sent_ptr[g], e = graph_sent_ptr[g + 1];
+    if (e < b || e > n_sent) return HSG_ERR_ARG;
+    for (int s = b; s < e; ++s) sent_pos[s] = s - b + 1;       // dataloader.py:241
+  }
+  return HSG_OK;
+}
+
 int hsg_enc_gather(int n_sent, int L, int D, int n_rows, const int32_t* tokens, const int32_t* sent_len,
                    const int32_t* row_ptr, const float* embed, const float* pos_table, float* xc, void* stream) {
   if (n_sent < 0 || L < ENC_HMAX || D <= 0 || n_rows < 0) return HSG_ERR_ARG;

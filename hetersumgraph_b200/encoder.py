@@ -68,17 +68,18 @@ class EncoderPlan:
             raise ValueError("sent_max_len must be >= 7 (the largest convolution kernel, Encoder.py:37)")
         if int(ptr[-1]) != S:
             raise ValueError("graph_sent_ptr does not cover the token matrix")
-        nz = tokens != 0
-        sent_len = nz.sum(axis=1).astype(np.int32)
-        tail = np.where(nz.any(axis=1), L - np.argmax(nz[:, ::-1], axis=1), 0).astype(np.int64)   # index after last id
-        n_rows = np.minimum(tail + H_MAX, L)
-        row_ptr = np.zeros(S + 1, np.int32)
-        np.cumsum(n_rows, out=row_ptr[1:])
+        B = len(ptr) - 1
+        # one int32 host blob [sent_len | row_ptr | sent_pos | graph_sent_ptr], filled by the library's host routine
+        # (one pass over the token matrix in C instead of several numpy passes) and uploaded with ONE copy
+        blob = np.empty(3 * S + 1 + B + 1, np.int32)
+        gptr32 = blob[3 * S + 1:]
+        gptr32[:] = ptr
+        base = blob.ctypes.data
+        _lib.check(_lib.load().hsg_enc_plan_host(S, L, tokens.ctypes.data, B, gptr32.ctypes.data, base, base + 4 * S,
+                                                  base + 4 * (2 * S + 1)))
         counts = np.diff(ptr)
-        sent_pos = (np.arange(S, dtype=np.int64) - np.repeat(ptr[:-1], counts) + 1).astype(np.int32)
-        self.n_sent, self.L, self.n_rows = S, L, int(row_ptr[-1])
+        self.n_sent, self.L, self.n_rows = S, L, int(blob[2 * S])
         self._ptr, self._counts, self._device, self._packed = ptr, counts, device, None
-        blob = np.concatenate([sent_len, row_ptr, sent_pos, ptr]).astype(np.int32)   # one H2D for the int32 arrays
         dev = torch.from_numpy(blob).to(device, non_blocking=True)
         self.sent_len, self.row_ptr, self.sent_pos = dev[:S], dev[S:2 * S + 1], dev[2 * S + 1:3 * S + 1]
         self.graph_sent_ptr = dev[3 * S + 1:]

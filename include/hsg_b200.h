@@ -474,6 +474,12 @@ int hsg_doc_init_bwd(const hsg_doc_map* m, const float* d_super, const float* d_
  * Backward (frozen embedding, train.py:340-342): only the kernels and biases get gradients; d out / d y is one-hot
  * per (sentence, channel), so dW is a sparse accumulation of <= n_sent*300 input slabs in a fixed order.
  * ------------------------------------------------------------------------ */
+/* HOST function (all pointers are host memory, no device work): per sentence the number of non-zero ids
+ * (sent_len, Encoder.py:58), the compact row offsets (row_ptr [n_sent+1], row_ptr[n_sent] = n_rows) and the position
+ * of the sentence inside its graph, 1-based (sent_pos, dataloader.py:241).  Replaces the reference's per-sentence host
+ * loop with a device sync per sentence (Encoder.py:61-66). */
+int hsg_enc_plan_host(int n_sent, int L, const int32_t* tokens, int n_graphs, const int32_t* graph_sent_ptr,
+                      int32_t* sent_len, int32_t* row_ptr, int32_t* sent_pos);
 int hsg_enc_gather(int n_sent, int L, int D, int n_rows, const int32_t* tokens /* [n_sent, L] */,
                    const int32_t* sent_len /* [n_sent] non-zero ids, Encoder.py:58 */, const int32_t* row_ptr,
                    const float* embed, const float* pos_table /* [L+1, D] */, float* xc, void* stream);
