@@ -542,7 +542,6 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
     import hetersumgraph_b200 as hb
     from hetersumgraph_b200.dist import FlatGradArena
     from hetersumgraph_b200.functional import FusedAdam
-    from hetersumgraph_b200.path_model import graph_loss
     hps = types.SimpleNamespace(n_iter=n_iter, word_emb_dim=300, sent_max_len=L, doc_max_timesteps=50, n_feature_size=128,
                                 hidden_size=64, lstm_hidden_state=128, lstm_layers=2, bidirectional=True, n_head=8,
                                 atten_dropout_prob=0.0, ffn_inner_hidden_size=512, ffn_dropout_prob=0.0,
@@ -567,7 +566,7 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
         b = pipe.take()
         pipe.submit(upload)
         arena.flat.zero_()
-        loss = graph_loss(b, whole(b), b.labels)
+        loss, _logits = whole.loss(b)                 # forward + the reference's loss (train.py:113-119)
         loss.backward()
         opt.step()
         loss_host.copy_(loss.detach().view(1), non_blocking=True)

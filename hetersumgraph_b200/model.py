@@ -46,11 +46,25 @@ class HSumGraph(SentenceEncoder, WSWGATUpdateLoop):
         """n_feature_proj(set_snfeature(graph)) (HiGraph.py:96,154-161)."""
         return self.encode(plan if plan is not None else graph.encoder_plan)
 
-    def forward(self, graph: HeteroBatch, plan=None):
+    def supernode_state(self, graph: HeteroBatch, plan=None):
+        """state of the supernodes after the update loop (HiGraph.py:98-106)."""
         word_feature = self.set_wnfeature(graph)
         sent_feature = self.set_snfeature_proj(graph, plan)
-        _, sent_state = self.update(graph, word_feature, sent_feature)          # HiGraph.py:98-106
-        return self.wh(sent_state)                                              # :108
+        return self.update(graph, word_feature, sent_feature)[1]
+
+    def forward(self, graph: HeteroBatch, plan=None):
+        return self.wh(self.supernode_state(graph, plan))                       # HiGraph.py:108
+
+    def loss(self, graph: HeteroBatch, plan=None, n_graphs_global=None):
+        """(loss, logits): `outputs = model.forward(G)` followed by the reference's training loss - per-sentence
+        cross-entropy, dgl.sum_nodes per graph, mean over graphs (train.py:113-119) - with the classifier, the loss and
+        their backward in the library's head kernels (hsg_head_fwd/bwd) instead of ~20 stock launches.  Same values as
+        path_model.graph_loss(graph, self(graph), graph.labels); `logits` is returned for extraction only.
+        n_graphs_global: the divisor of the mean when the batch is one shard of a data-parallel step."""
+        from .functional import SentenceLossFn
+        state = self.supernode_state(graph, plan)
+        n = n_graphs_global if n_graphs_global is not None else graph.n_graphs
+        return SentenceLossFn.apply(graph, n, None, state, self.wh.weight, self.wh.bias, graph.labels)
 
 
 class HSumDocGraph(HSumGraph):
@@ -61,11 +75,14 @@ class HSumDocGraph(HSumGraph):
         self.dn_feature_proj = nn.Linear(hps.hidden_size, hps.hidden_size, bias=False)     # HiGraph.py:173
         self.wh = nn.Linear(self.n_feature * 2, 2)
 
-    def forward(self, graph: HeteroBatch, plan=None):
+    def supernode_state(self, graph: HeteroBatch, plan=None):
         from .functional import DocInitFn
         word_feature = self.set_wnfeature(graph)
         sent_feature = self.set_snfeature_proj(graph, plan)
         super_feature = DocInitFn.apply(graph, sent_feature, self.dn_feature_proj.weight)   # HiGraph.py:196-203,231-244
-        _, state = self.update(graph, word_feature, super_feature)                          # :205-214
+        return self.update(graph, word_feature, super_feature)[1]                           # :205-214
+
+    def forward(self, graph: HeteroBatch, plan=None):
+        state = self.supernode_state(graph, plan)
         s_state = torch.cat([state[graph.sentence_rows()], state[graph.sent_doc_row]], dim=-1)   # :216-228
         return self.wh(s_state)

@@ -91,4 +91,11 @@ def test_whole_model_matches_reference_forward_and_gradients(name):
             cancelling.append(key)
         checked += 1
     assert len(cancelling) <= 8, cancelling          # only the few cancelling sums may use the second criterion
+    # model.loss(graph): the library's fused classifier + loss against the stock formulation on the same logits
+    from hetersumgraph_b200.path_model import graph_loss
+    with torch.no_grad():
+        ref_loss = graph_loss(batch, model(batch), batch.labels)
+    loss, logits2 = model.loss(batch)
+    assert nerr(logits2, z["logits"]) <= TOL
+    assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
     assert checked >= 60
