@@ -552,6 +552,7 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
     whole = hb.HSumGraph(hps, embed).to(dev)
     whole.lstm.dropout = 0.0
     arena = FlatGradArena(whole.parameters(), flatten_params=True)
+    whole.fuse_grad_accumulation = True    # kernels add parameter gradients straight into the arena views
     opt = FusedAdam(arena.flat_param.data, arena.flat, lr=5e-4)
     host, h2d_bytes = DeviceTokenBatch.host_buffers(tb)
     bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)

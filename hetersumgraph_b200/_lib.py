@@ -134,6 +134,7 @@ _PROTOS = {
     "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
     "hsg_gemm_tn_workspace_bytes": (_Z, [_I, _I, _I]),
     "hsg_gemm_tn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _Z, _P]),
+    "hsg_gemm_tn_acc": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _Z, _P]),
     "hsg_edge_layout": (C.c_int, [_I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hsg_edge_perm": (C.c_int, [_I, _I, _I]),
     "hsg_edge_fwd": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P]),

@@ -462,6 +462,11 @@ size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
   return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
 }
 
+int hsg_gemm_tn_acc(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                    float* colsum, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, accumulate ? 1 : 0, (cudaStream_t)stream);
+}
+
 int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, void* ws, size_t ws_bytes, void* stream) {
   return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, 0, (cudaStream_t)stream);

@@ -122,9 +122,11 @@ class NgramEncodeFn(torch.autograd.Function):
     position table, train.py:340-342 / Encoder.py:44-45)."""
 
     @staticmethod
-    def forward(ctx, plan, embed_w, pos_table, *conv):
+    def forward(ctx, plan, targets, embed_w, pos_table, *conv):
+        """targets: None, or the twelve existing .grad buffers (w0, b0, ..., w5, b5) the backward ADDS into."""
         _lib.require_device()
         lib = _lib.load()
+        ctx.targets = targets
         ws_, bs_ = [_f32c(t) for t in conv[0::2]], [_f32c(t) for t in conv[1::2]]
         embed_w, pos_table = _f32c(embed_w), _f32c(pos_table)
         D = embed_w.shape[1]
@@ -160,15 +162,19 @@ class NgramEncodeFn(torch.autograd.Function):
         xc, arg_t = ctx.saved_tensors
         d_out = _f32c(d_out)
         dev = d_out.device
-        dws = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes[0::2]]
-        dbs = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes[1::2]]
+        fused = ctx.targets is not None
+        if fused:
+            dws, dbs = list(ctx.targets[0::2]), list(ctx.targets[1::2])
+        else:
+            dws = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes[0::2]]
+            dbs = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes[1::2]]
         nbytes = lib.hsg_enc_conv_wgrad_workspace_bytes(ctx.S, ctx.D)
         ws = _Workspace.get(nbytes, dev, "enc_wgrad")
         _lib.check(lib.hsg_enc_conv_wgrad(ctx.S, ctx.D, _p(xc), _p(d_out), d_out.stride(0), _p(arg_t), _ptr_array(dws),
-                                          _ptr_array(dbs), 0, _p(ws), ws.numel(), _st()))
-        grads = [None, None, None]
+                                          _ptr_array(dbs), 1 if fused else 0, _p(ws), ws.numel(), _st()))
+        grads = [None, None, None, None]
         for w, b in zip(dws, dbs):
-            grads += [w, b]
+            grads += [None, None] if fused else [w, b]
         return tuple(grads)
 
 
@@ -196,7 +202,8 @@ class LstmFn(torch.autograd.Function):
     def forward(ctx, x, gptr, cfg, *params):
         _lib.require_device()
         lib = _lib.load()
-        n_graphs, H, n_layers, ndir, p_drop, seed = cfg
+        n_graphs, H, n_layers, ndir, p_drop, seed = cfg[:6]
+        ctx.targets = cfg[6] if len(cfg) > 6 else None       # existing .grad buffers in nn.LSTM's parameter order
         x = _f32c(x)
         params = [_f32c(p) for p in params]
         S = x.shape[0]
@@ -255,9 +262,14 @@ class LstmFn(torch.autograd.Function):
             def weight_grads(tag):
                 for d in range(ndir):
                     da_d = da[:, d * G4:(d + 1) * G4]
+                    base = (layer * ndir + d) * 4
+                    if ctx.targets is not None:      # added straight into the .grad buffers; db goes to both biases
+                        t = ctx.targets[base:base + 4]
+                        gemm_tn(da_d, inp, ws_tag=tag, out=t[0], cs_out=t[2])
+                        gemm_tn(da_d, hprev[:, d, :], ws_tag=tag, out=t[1], cs_out=t[3])
+                        continue
                     dW_ih, db = gemm_tn(da_d, inp, want_colsum=True, ws_tag=tag)
                     dW_hh, _ = gemm_tn(da_d, hprev[:, d, :], ws_tag=tag)
-                    base = (layer * ndir + d) * 4
                     grads[base], grads[base + 1], grads[base + 2], grads[base + 3] = dW_ih, dW_hh, db, db.clone()
                     if tag != "tn":                  # allocated on the side stream, consumed on the main stream
                         for g in grads[base:base + 4]:
@@ -285,9 +297,11 @@ class SentHeadFn(torch.autograd.Function):
     (HiGraph.py:130-132, :141, :160, :96).  The concatenation is the column layout of one [S, 2 nf] buffer."""
 
     @staticmethod
-    def forward(ctx, ngram, lstm_out, sent_pos, pos_table, Wc, bc, Wl, bl, Wn):
+    def forward(ctx, targets, ngram, lstm_out, sent_pos, pos_table, Wc, bc, Wl, bl, Wn):
+        """targets: None, or the existing .grad buffers of (Wc, bc, Wl, bl, Wn) the backward ADDS into."""
         _lib.require_device()
         lib = _lib.load()
+        ctx.targets = targets
         ngram, lstm_out = _f32c(ngram), _f32c(lstm_out)
         Wc, bc, Wl, bl, Wn, pos_table = [_f32c(t) for t in (Wc, bc, Wl, bl, Wn, pos_table)]
         S, D = ngram.shape
@@ -317,17 +331,24 @@ class SentHeadFn(torch.autograd.Function):
             side.wait_stream(main)
         with torch.cuda.stream(side if side is not None else main):
             tag = "tn_side" if side is not None else "tn"
-            dWn, _ = gemm_tn(d_sf, node, ws_tag=tag)
-            dWc, dbc = gemm_tn(d_cnn, cnn_in, want_colsum=True, ws_tag=tag)
-            dWl, dbl = gemm_tn(d_lf, lstm_out, want_colsum=True, ws_tag=tag)
-            if side is not None:
-                for g in (dWn, dWc, dbc, dWl, dbl):
-                    g.record_stream(main)
+            if ctx.targets is not None:
+                tWc, tbc, tWl, tbl, tWn = ctx.targets
+                gemm_tn(d_sf, node, ws_tag=tag, out=tWn)
+                gemm_tn(d_cnn, cnn_in, ws_tag=tag, out=tWc, cs_out=tbc)
+                gemm_tn(d_lf, lstm_out, ws_tag=tag, out=tWl, cs_out=tbl)
+                dWn = dWc = dbc = dWl = dbl = None
+            else:
+                dWn, _ = gemm_tn(d_sf, node, ws_tag=tag)
+                dWc, dbc = gemm_tn(d_cnn, cnn_in, want_colsum=True, ws_tag=tag)
+                dWl, dbl = gemm_tn(d_lf, lstm_out, want_colsum=True, ws_tag=tag)
+                if side is not None:
+                    for g in (dWn, dWc, dbc, dWl, dbl):
+                        g.record_stream(main)
         d_ngram = gemm_nn(d_cnn, Wc)
         d_lstm_out = gemm_nn(d_lf, Wl)
         if side is not None:
             main.wait_stream(side)
-        return d_ngram, d_lstm_out, None, None, dWc, dbc, dWl, dbl, dWn
+        return None, d_ngram, d_lstm_out, None, None, dWc, dbc, dWl, dbl, dWn
 
 
 class _NgramParams(nn.Module):
@@ -386,7 +407,21 @@ class SentenceEncoder(nn.Module):
         conv = []
         for c in self.ngram_enc.convs:
             conv += [c.weight, c.bias]
-        return NgramEncodeFn.apply(plan, self.ngram_enc.embed.weight, self.ngram_enc.position_embedding.weight, *conv)
+        return NgramEncodeFn.apply(plan, self._targets(conv), self.ngram_enc.embed.weight,
+                                   self.ngram_enc.position_embedding.weight, *conv)
+
+    # When True, backward ADDS the parameter gradients straight into the existing `.grad` buffers (e.g. the views of a
+    # dist.FlatGradArena) from inside the library's kernels instead of returning them to autograd, which would launch
+    # one add per parameter (33 here).  Same arithmetic; requires every parameter to have a `.grad` tensor.  Same
+    # switch as WSWGATUpdateLoop.fuse_grad_accumulation (the whole-model classes share it).
+    fuse_grad_accumulation = False
+
+    def _targets(self, params):
+        if not (self.fuse_grad_accumulation and torch.is_grad_enabled()):
+            return None
+        if any(p.grad is None for p in params):
+            raise RuntimeError("fuse_grad_accumulation needs a .grad buffer on every parameter")
+        return [p.grad for p in params]
 
     def lstm_feature(self, plan: EncoderPlan, ngram):
         """LSTM over every graph's sentence sequence (HiGraph.py:135-141), rows in batch order."""
@@ -394,7 +429,8 @@ class SentenceEncoder(nn.Module):
         if not self.use_cudnn_lstm:
             p_drop = float(lstm.dropout) if (self.training and lstm.num_layers > 1) else 0.0
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0.0 else 0     # CPU generator: no sync
-            cfg = (plan.n_graphs, lstm.hidden_size, lstm.num_layers, 2 if lstm.bidirectional else 1, p_drop, seed)
+            cfg = (plan.n_graphs, lstm.hidden_size, lstm.num_layers, 2 if lstm.bidirectional else 1, p_drop, seed,
+                   self._targets(lstm._flat_weights))
             return LstmFn.apply(ngram, plan.graph_sent_ptr, cfg, *lstm._flat_weights)
         packed = torch.nn.utils.rnn.PackedSequence(ngram.index_select(0, plan.perm), plan.batch_sizes)
         # cuDNN's RNN would otherwise run its products in TF32 (error class 1e-3, outside the fp32 bound of 1e-5)
@@ -408,6 +444,6 @@ class SentenceEncoder(nn.Module):
     def encode(self, plan: EncoderPlan):
         ngram = self.ngram(plan)
         lstm_out = self.lstm_feature(plan, ngram)
-        return SentHeadFn.apply(ngram, lstm_out, plan.sent_pos, self.sent_pos_embed.weight, self.cnn_proj.weight,
-                                self.cnn_proj.bias, self.lstm_proj.weight, self.lstm_proj.bias,
-                                self.n_feature_proj.weight)
+        head = [self.cnn_proj.weight, self.cnn_proj.bias, self.lstm_proj.weight, self.lstm_proj.bias,
+                self.n_feature_proj.weight]
+        return SentHeadFn.apply(self._targets(head), ngram, lstm_out, plan.sent_pos, self.sent_pos_embed.weight, *head)

@@ -81,16 +81,21 @@ def gemm_nn(A, B, R=None, epi=0):
     return Cm
 
 
-def gemm_tn(A, B, want_colsum=False, ws_tag="tn"):
+def gemm_tn(A, B, want_colsum=False, ws_tag="tn", out=None, cs_out=None):
     """C = A.T @ B  (and column sums of A), deterministic.  `ws_tag` names the scratch buffer: calls that may run
-    concurrently on different streams must use different tags."""
+    concurrently on different streams must use different tags.  out / cs_out: existing buffers the product (and the
+    column sums) are ADDED to (gradient accumulation straight into .grad, hsg_gemm_tn_acc)."""
     lib = _lib.load()
     M, N1 = A.shape
     N2 = B.shape[1]
-    Cm = torch.empty(N1, N2, dtype=torch.float32, device=A.device)
-    cs = torch.empty(N1, dtype=torch.float32, device=A.device) if want_colsum else None
     nbytes = lib.hsg_gemm_tn_workspace_bytes(M, N1, N2)
     ws = _Workspace.get(nbytes, A.device, ws_tag)
+    if out is not None:
+        _lib.check(lib.hsg_gemm_tn_acc(M, N1, N2, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0),
+                                       _p(cs_out), 1, _p(ws), ws.numel(), _st()))
+        return out, cs_out
+    Cm = torch.empty(N1, N2, dtype=torch.float32, device=A.device)
+    cs = torch.empty(N1, dtype=torch.float32, device=A.device) if want_colsum else None
     _lib.check(lib.hsg_gemm_tn(M, N1, N2, _p(A), A.stride(0), _p(B), B.stride(0), _p(Cm), Cm.stride(0), _p(cs), _p(ws),
                                ws.numel(), _st()))
     return Cm, cs

@@ -64,7 +64,10 @@ class HSumGraph(SentenceEncoder, WSWGATUpdateLoop):
         from .functional import SentenceLossFn
         state = self.supernode_state(graph, plan)
         n = n_graphs_global if n_graphs_global is not None else graph.n_graphs
-        return SentenceLossFn.apply(graph, n, None, state, self.wh.weight, self.wh.bias, graph.labels)
+        targets = None
+        if self.fuse_grad_accumulation and torch.is_grad_enabled():
+            targets = (self.wh.weight.grad, self.wh.bias.grad)
+        return SentenceLossFn.apply(graph, n, targets, state, self.wh.weight, self.wh.bias, graph.labels)
 
 
 class HSumDocGraph(HSumGraph):

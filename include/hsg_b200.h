@@ -202,6 +202,10 @@ int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, in
 size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2);
 int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, void* ws, size_t ws_bytes, void* stream);
+/* same product; accumulate != 0 ADDS the result to C (and to colsum): a weight gradient accumulated straight into an
+ * existing .grad buffer (what autograd's AccumulateGrad would do with one more launch per parameter) */
+int hsg_gemm_tn_acc(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                    float* colsum, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K3  fused edge kernel (forward): for every destination row v
