@@ -120,3 +120,35 @@ def test_dropin_models_have_the_reference_state_dict(hdsg):
     assert all(torch.equal(a[k], back[k]) for k in a)          # packed <-> per-head round trip is lossless
     n_train = sum(p.numel() for p in mine.parameters() if p.requires_grad)
     assert n_train == sum(p.numel() for p in ref.parameters() if p.requires_grad) == (1766390 if hdsg else 1762166)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only in the build container")
+def test_ngram_blocking_and_label_metric_match_live_reference():
+    """extraction.ngram_blocking / eval_label against SLTester.ngram_blocking (Tester.py:155-184) and tools.utils.eval_label
+    (the reference modules import `rouge`, absent here: a stub module stands in, nothing of it is called)."""
+    import types
+    sys.path.insert(0, "/root/reference")
+    from oracle import dgl04_shim as shim
+    shim.install()
+    for name in ("rouge", "pyrouge"):
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            stub.Rouge = stub.Rouge155 = object
+            sys.modules[name] = stub
+    from Tester import SLTester
+    from tools.utils import eval_label as ref_eval
+    from hetersumgraph_b200.extraction import eval_label, ngram_blocking
+    rng = np.random.default_rng(3)
+    words = ["w%d" % i for i in range(12)]
+    tester = SLTester(model=None, m=3)
+    for trial in range(30):
+        n = int(rng.integers(1, 9))
+        sents = [" ".join(rng.choice(words, size=int(rng.integers(0, 9)))) for _ in range(n)]
+        p = torch.from_numpy(rng.permutation(n).astype(np.float32))          # distinct scores: the order is unique
+        n_win, k = int(rng.integers(2, 5)), int(rng.integers(1, n + 1))
+        ref = tester.ngram_blocking(sents, p, n_win, k).tolist()
+        order = p.sort(descending=True)[1].tolist()
+        assert ngram_blocking(sents, order, n_win, k) == ref
+    a = ref_eval(torch.tensor(7), torch.tensor(10), torch.tensor(14), 50, torch.tensor(40))
+    b = eval_label(7, 10, 14, 50, 40)
+    assert all(abs(float(x) - y) < 1e-6 for x, y in zip(a, b))
