@@ -12,8 +12,8 @@
 //     UMMA layouts - K-major operands with SWIZZLE_128B (8-row x 128 B atoms), MN-major operands with
 //     SWIZZLE_128B_ATOM_32B (4-k x 128 B atoms: the only MN-major layout the tensor core takes for 32-bit
 //     data); tile edges are zero-filled by the TMA unit;
-//   * six converter warps sweep the landed tile linearly and split every value into hi = x rounded to the
-//     nearest TF32 value (in place) and lo = x - hi (second tile);
+//   * six converter warps sweep the landed tile linearly and split every value into hi = x truncated to the
+//     TF32 grid (what the tensor core reads from the raw tile: nothing to store) and lo = x - hi (second tile);
 //   * one thread issues   D += A_hi B_hi ;  D' += A_hi B_lo ;  D' += A_lo B_hi     (precise mode, "3xTF32")
 //     with tcgen05.mma.kind::tf32 - error ~2^-22 relative, inside BASELINE.json's fp32 bound of 1e-5 - or
 //     only the first product on the raw tile in fast mode (TF32, the tensor core truncates itself);
@@ -129,6 +129,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+
+// hi as the tensor core itself sees a raw fp32 operand: kind::tf32 ignores the low 13 mantissa bits (truncation).  With
+// HSG_TC_HI_INPLACE == 0 the converters leave the landed tile untouched (it IS the hi operand) and only write
+// lo = x - trunc(x): one shared-memory store per chunk instead of two.  |lo| < 2^-10 |x| instead of 2^-11 with
+// round-to-nearest; the dropped lo*lo term and the hardware's truncation of lo stay at ~2^-20 relative.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+#ifndef HSG_TC_HI_INPLACE
+#define HSG_TC_HI_INPLACE 0
+#endif
 
 struct Epilogue {
   float* D;            // output (or split-K partial base)
@@ -349,8 +358,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int id = ct + i * NCONV;
               if (id < total) {
                 char* hi = id < TM * 8 ? st + id * 16 : st + 2 * TILE_BYTES + (id - TM * 8) * 16;
+#if HSG_TC_HI_INPLACE
                 const float4 h = make_float4(tf32_rn(v[i].x), tf32_rn(v[i].y), tf32_rn(v[i].z), tf32_rn(v[i].w));
                 *reinterpret_cast<float4*>(hi) = h;
+#else
+                const float4 h = make_float4(tf32_trunc(v[i].x), tf32_trunc(v[i].y), tf32_trunc(v[i].z),
+                                             tf32_trunc(v[i].w));
+#endif
                 *reinterpret_cast<float4*>(hi + TILE_BYTES) =
                     make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
               }
