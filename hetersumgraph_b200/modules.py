@@ -316,7 +316,10 @@ class WSWGATUpdateLoop(nn.Module):
     def _grad_targets(self):
         """[dT, 10 x word2sent, 10 x sent2word] .grad buffers in packed shapes; the views are rebuilt only when a
         .grad tensor has been replaced."""
-        leaves = [self._TFembed.weight] + [p for m in (self.word2sent, self.sent2word) for p in m.parameters()]
+        leaves = self.__dict__.get("_gt_leaves")       # parameter objects never change identity: walk the modules once
+        if leaves is None:
+            leaves = [self._TFembed.weight] + [p for m in (self.word2sent, self.sent2word) for p in m.parameters()]
+            self.__dict__["_gt_leaves"] = leaves
         sig = tuple(-1 if p.grad is None else p.grad.data_ptr() for p in leaves)
         ent = self.__dict__.get("_gt_cache")
         if ent is None or ent[0] != sig:
