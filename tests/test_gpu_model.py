@@ -99,3 +99,39 @@ def test_whole_model_matches_reference_forward_and_gradients(name):
     assert nerr(logits2, z["logits"]) <= TOL
     assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
     assert checked >= 60
+
+
+@pytest.mark.parametrize("hdsg", [False, True])
+def test_whole_model_training_mode_with_the_reference_dropout_rates(hdsg):
+    """the reference's default rates (atten_dropout_prob = ffn_dropout_prob = 0.1, LSTM inter-layer dropout 0.1,
+    train.py:279-309) in training mode, n_iter = 2: finite loss and gradients on every trainable parameter, the same
+    torch seed reproduces the step bit for bit, eval mode switches every mask off."""
+    exs = syn.make_examples(4, "multinews" if hdsg else "cnndm", seed=5, hdsg=hdsg)
+    tb = syn.pack_token_batch(exs, hdsg=hdsg)
+    hps = hps_default(2)
+    hps.atten_dropout_prob = hps.ffn_dropout_prob = 0.1
+    embed = torch.nn.Embedding(50000, 300, padding_idx=0)
+    embed.weight.requires_grad_(False)
+    torch.manual_seed(3)
+    model = (hb.HSumDocGraph if hdsg else hb.HSumGraph)(hps, embed).cuda().train()
+    batch = hb.HeteroBatch.from_token_batch(tb, "cuda")
+
+    def step(seed):
+        torch.manual_seed(seed)
+        for p in model.parameters():
+            p.grad = None
+        loss, logits = model.loss(batch)
+        loss.backward()
+        return float(loss), logits.clone(), [p.grad.clone() for p in model.parameters() if p.requires_grad]
+
+    l1, lg1, g1 = step(11)
+    l2, lg2, g2 = step(11)
+    l3, lg3, _ = step(12)
+    assert np.isfinite(l1) and all(torch.isfinite(g).all() for g in g1)
+    assert l1 == l2 and torch.equal(lg1, lg2) and all(torch.equal(a, b) for a, b in zip(g1, g2))
+    assert not torch.equal(lg1, lg3)                     # another seed, other masks
+    model.eval()
+    with torch.no_grad():
+        a = model(batch)
+        b = model(batch)
+    assert torch.equal(a, b) and a.shape == (tb.tokens.shape[0], 2)
