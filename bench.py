@@ -163,9 +163,10 @@ def run_reference(args):
 
 
 def workload_name(args, cfg_idx):
-    return ("BASELINE.json configs[%d]: HSG WSWGAT update loop fwd+bwd, %d %s-shaped graphs per GPU, seed-0 synthetic "
-            "tokens, random-init embeddings, sentence-encoder output replaced by a fixed random sent_feature"
-            % (cfg_idx, args.graphs_per_gpu, args.workload))
+    return ("BASELINE.json configs[%d]: %s WSWGAT update loop fwd+bwd, %d %s-shaped graphs per GPU, seed-0 synthetic "
+            "tokens, random-init embeddings, sentence-encoder output replaced by a fixed random sent_feature (the "
+            "whole model incl. the encoder: key with_sentence_encoder)"
+            % (cfg_idx, "HDSG" if args.workload == "multinews" else "HSG", args.graphs_per_gpu, args.workload))
 
 
 # ------------------------------------------------------------------------------------------------
