@@ -444,8 +444,8 @@ def run_ours(args):
     if not args.no_stress and world == 1:
         large = large_shard_leg(dev, pk)
     encoder = None
-    if not args.no_encoder and world == 1 and not hdsg:
-        encoder = encoder_leg(dev, pk, exs, tb, n_iter, args.steps)
+    if not args.no_encoder and world == 1:
+        encoder = encoder_leg(dev, pk, exs, tb, n_iter, args.steps, hdsg=hdsg)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -486,7 +486,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
+def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1, hdsg=False):
     """the sentence encoder (n-gram CNN + BiLSTM + projections) in front of the path, same batch.
     (i) encoder alone fwd+bwd, (ii) encoder -> update loop -> loss, backward through both (autograd path, parameter
     gradients of every stage), (iii) the oracle restatement of the encoder on the host cores, (iv) per-kernel split."""
@@ -496,7 +496,7 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
     from hetersumgraph_b200.path_model import HSGPath, fused_loss
     lib = _lib.load()
     torch.manual_seed(1234)
-    model = HSGPath(n_iter=n_iter).to(dev)
+    model = HSGPath(n_iter=n_iter, hdsg=hdsg).to(dev)
     enc = SentenceEncoder(model._embed, lstm_dropout=0.0).to(dev)
     dtb = DeviceTokenBatch.upload(tb, dev)
     batch = HeteroBatch.build(dtb)
@@ -550,7 +550,7 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
     torch.manual_seed(1234)
     embed = torch.nn.Embedding(50000, 300, padding_idx=0)
     embed.weight.requires_grad_(False)
-    whole = hb.HSumGraph(hps, embed).to(dev)
+    whole = (hb.HSumDocGraph if hdsg else hb.HSumGraph)(hps, embed).to(dev)
     whole.lstm.dropout = 0.0
     arena = FlatGradArena(whole.parameters(), flatten_params=True)
     whole.fuse_grad_accumulation = True    # kernels add parameter gradients straight into the arena views
@@ -595,7 +595,7 @@ def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1):
            "encoder_fwd_bwd_ms": ms_enc, "encoder_graphs_per_s": tb.n_graphs / (ms_enc * 1e-3),
            "encoder_plus_path_fwd_bwd_ms": ms_full, "encoder_plus_path_graphs_per_s": tb.n_graphs / (ms_full * 1e-3),
            "whole_model_train_step": {
-               "what": "hetersumgraph_b200.HSumGraph (drop-in for HiGraph.HSumGraph) from HOST buffers: H2D of the token "
+               "what": "hetersumgraph_b200.HSumGraph / HSumDocGraph (drop-ins for HiGraph.HSumGraph / HSumDocGraph) from HOST buffers: H2D of the token "
                        "blob + device graph build of the NEXT batch on a side stream (one per step), forward, loss, "
                        "backward, Adam; loss copied to pinned host memory every step",
                "ms_per_step": ms_train, "graphs_per_s": tb.n_graphs / (ms_train * 1e-3),
