@@ -267,7 +267,7 @@ def run_ours(args):
     pipe = BuildPipeline(dev)          # build of batch i+1 on a side stream while batch i computes (one build per step)
 
     from hetersumgraph_b200.path_model import FusedTrainStep
-    fused_step = FusedTrainStep(model, n_graphs_global) if not hdsg else None
+    fused_step = FusedTrainStep(model, n_graphs_global)
 
     def compute(batch, sf):
         flat.zero_()

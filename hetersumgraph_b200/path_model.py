@@ -97,12 +97,11 @@ class FusedTrainStep:
     whose CUDA worker-thread hand-off costs about as much host time per step as all the kernel launches together
     at batch 32.  d_sent_feature is what the sentence encoder's backward consumes (HiGraph.py:96).
 
-    HSG with a frozen embedding (the reference default, train.py:340-342); other configurations use the autograd
-    path.  Gradient parity with the autograd path is tested."""
+    HSG and HDSG (document-node init through DocInitFn's kernels, dn_feature_proj gradient added into its .grad) with
+    a frozen embedding (the reference default, train.py:340-342); a trainable embedding uses the autograd path.
+    Gradient parity with the autograd path is tested."""
 
     def __init__(self, model: "HSGPath", n_graphs_global=None):
-        if model.hdsg:
-            raise NotImplementedError("FusedTrainStep covers HSG; HDSG goes through fused_loss(...).backward()")
         if model._embed.weight.requires_grad:
             raise NotImplementedError("FusedTrainStep assumes the frozen word embedding of the reference default")
         self.model, self.n_graphs_global = model, n_graphs_global
@@ -122,13 +121,23 @@ class FusedTrainStep:
         n = self.n_graphs_global if self.n_graphs_global is not None else g.n_graphs
         with torch.no_grad():
             word_feature = F.embedding(g.word_wid, m._embed.weight)
+            super_feature = sent_feature
+            if m.hdsg:                                   # HiGraph.py:196-203,231-244
+                from .functional import DocInitFn
+                if m.dn_feature_proj.weight.grad is None:
+                    raise RuntimeError("FusedTrainStep needs .grad buffers on every parameter (dist.FlatGradArena)")
+                c0 = _Ctx([False, True, True])
+                super_feature = DocInitFn.forward(c0, g, sent_feature, m.dn_feature_proj.weight)
             c1 = _Ctx([False, False, False, True] + [False] * len(tensors))
-            _, super_state = UpdateLoopFn.forward(c1, g, cfg, word_feature, sent_feature, *tensors)
+            _, super_state = UpdateLoopFn.forward(c1, g, cfg, word_feature, super_feature, *tensors)
             c2 = _Ctx([False] * 7)
             loss, logits = SentenceLossFn.forward(c2, g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
                                                   m.wh.weight, m.wh.bias, g.labels)
             d_state = SentenceLossFn.backward(c2, None, None)[3]
             d_sent_feature = UpdateLoopFn.backward(c1, None, d_state)[3]
+            if m.hdsg:
+                _, d_sent_feature, dW = DocInitFn.backward(c0, d_sent_feature)
+                m.dn_feature_proj.weight.grad.add_(dW)
         return loss, logits, d_sent_feature
 
 

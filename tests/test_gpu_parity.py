@@ -627,15 +627,19 @@ def test_edge_bwd_row_mappings_agree(kind, H, d):
         assert nerr(dzp, outs[0][0]) <= 2e-6 and nerr(dq, outs[0][1]) <= 2e-6
 
 
-def test_fused_train_step_equals_autograd_path():
+@pytest.mark.parametrize("hdsg", [False, True])
+def test_fused_train_step_equals_autograd_path(hdsg):
     """path_model.FusedTrainStep (forward + backward driven without the autograd engine) against
-    fused_loss(...).backward(): same loss, same d_sent_feature, same gradients in the flat arena."""
+    fused_loss(...).backward(): same loss, same d_sent_feature, same gradients in the flat arena (HSG and HDSG)."""
     from hetersumgraph_b200.dist import FlatGradArena
     from hetersumgraph_b200.path_model import FusedTrainStep, HSGPath, fused_loss
-    exs = syn.make_examples(6, "tiny", seed=51)
-    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    if hdsg:
+        exs = syn.make_examples(6, "multinews", seed=51, hdsg=True)
+    else:
+        exs = syn.make_examples(6, "tiny", seed=51)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
     torch.manual_seed(9)
-    model = HSGPath(n_iter=1).cuda()
+    model = HSGPath(n_iter=1, hdsg=hdsg).cuda()
     arena = FlatGradArena(model.parameters())
     sf = torch.randn(batch.labels.shape[0], 64, device="cuda")
     model.loop.fuse_grad_accumulation = True
