@@ -173,22 +173,32 @@ __device__ __forceinline__ void trace(int ev, uint32_t it) {   // fire-and-forge
 }
 
 struct TileInfo {
-  int m0, n0, n_valid, n_mma, k_beg, nkb, z;
+  int m0, n0, n_valid, n_mma, k_beg, nkb, z, chunk;
 };
 
-__device__ __forceinline__ TileInfo tile_info(int t, int m_tiles, int n_tiles, int Nd, int bn, int K, int k_per_split) {
+// Work item w = (n tile, m tile, split z) as before; with k_chunk > 0 a split's K range is cut into chunks of k_chunk
+// and tile index t = chunk * n_items + w: launched with exactly n_items CTAs, CTA w walks ALL chunks of its own item
+// one after the other and its epilogue ADDS chunk > 0 onto what it stored for chunk 0.  The tensor core's fp32
+// accumulation truncates, so the error of one accumulation chain grows linearly with its length (measured on the
+// weight-gradient products: 2.8e-6 at 1 k rows per chain, 2.2e-5 at 8 k, 1.5e-4 at 63 k - a 2 048-graph shard);
+// chunks keep every chain at <= k_chunk / 8 updates and the chunks are summed in fp32 with round-to-nearest.
+__device__ __forceinline__ TileInfo tile_info(int t, int m_tiles, int n_tiles, int Nd, int bn, int K, int k_per_split,
+                                              int k_chunk, int n_items) {
   TileInfo ti;
-  const int nt = t % n_tiles;
-  const int r = t / n_tiles;
+  ti.chunk = k_chunk > 0 ? t / n_items : 0;
+  const int w = k_chunk > 0 ? t - ti.chunk * n_items : t;
+  const int nt = w % n_tiles;
+  const int r = w / n_tiles;
   const int mt = r % m_tiles;
   ti.z = r / m_tiles;
   ti.m0 = mt * TM;
   ti.n0 = nt * bn;
   ti.n_valid = min(bn, Nd - ti.n0);
   ti.n_mma = (ti.n_valid + 15) & ~15;
-  ti.k_beg = ti.z * k_per_split;
-  const int k_end = min(K, ti.k_beg + k_per_split);
-  ti.nkb = (k_end - ti.k_beg + BK - 1) / BK;
+  const int split_end = min(K, ti.z * k_per_split + k_per_split);
+  ti.k_beg = ti.z * k_per_split + ti.chunk * k_chunk;
+  const int k_end = k_chunk > 0 ? min(split_end, ti.k_beg + k_chunk) : split_end;
+  ti.nkb = k_end > ti.k_beg ? (k_end - ti.k_beg + BK - 1) / BK : 0;
   return ti;
 }
 
@@ -196,7 +206,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Md, int Nd,
                int K, int bn, int nb_box, int k_per_split, int m_tiles, int n_tiles, int total_tiles, int precise,
-               Epilogue ep) {
+               int k_chunk, int n_items, Epilogue ep) {
   extern __shared__ char smem_raw[];
   char* smem = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -247,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split, k_chunk, n_items);
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_empty + 8 * slot, ph ^ 1);                          // MMAs drained the slot
@@ -280,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t b_sbo = B_MN ? 512u : 1024u, b_lbo = B_MN ? 4096u : 16u, b_lay = B_MN ? 1u : 2u;
       uint32_t it = 0, tl = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split, k_chunk, n_items);
         const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);                           // epilogue drained this accumulator set
         tc_fence_after();
@@ -325,9 +335,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b_chunks = nb_box * 8;
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+        const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split, k_chunk, n_items);
         const bool ones_here = B_MN && ep.ones_col >= ti.n0 && ep.ones_col < ti.n0 + nb_box;
-        const int k_end = min(K, ti.k_beg + k_per_split);
+        const int k_end = min(min(K, ti.z * k_per_split + k_per_split), k_chunk > 0 ? ti.k_beg + k_chunk : K);
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * slot, ph);                                // this k-block has landed
@@ -381,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lg = warp & 3;                     // TMEM lane group of this warp (warp 8 -> lanes 0..31, ...)
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split);
+      const TileInfo ti = tile_info(t, m_tiles, n_tiles, Nd, bn, K, k_per_split, k_chunk, n_items);
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(bar_tfull + 8 * acc, aph);
       if (tid == 256) trace(6, tl);
@@ -396,8 +406,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // SM as full 128-byte lines: 8 lanes x 16 B per row, 4 rows per store instruction.
       float* tile = epi_stage + (warp - 8) * (32 * 33);
       const int r_sub = lane >> 3, c_sub = (lane & 7) * 4;
-      const bool has_r = (ep.epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) != 0;
-      const bool ld_vec = (ep.ldd & 3) == 0, lr_vec = (ep.ldr & 3) == 0;
+      // chunk > 0 of a K-chunked item: add onto what THIS thread stored for the previous chunk (plain loads: the data
+      // was written by this kernel, the read-only path must not be used for it)
+      const bool acc_chunk = ti.chunk > 0;
+      const float* r_base = acc_chunk ? Dz : ep.R;
+      const int r_ld = acc_chunk ? ep.ldd : ep.ldr;
+      const bool has_r = acc_chunk || (ep.epi & (HSG_EPI_ADD | HSG_EPI_RELU_MASK)) != 0;
+      const bool ld_vec = (ep.ldd & 3) == 0, lr_vec = (r_ld & 3) == 0;
       for (int c0 = 0; c0 < ti.n_mma; c0 += 32) {
         const int col = ti.n0 + c0 + c_sub;
         // residual / ReLU-mask operand of the whole 32x32 chunk first: eight independent 16-byte loads per lane in
@@ -409,8 +424,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row = ti.m0 + lg * 32 + p8 * 4 + r_sub;
             rv4[p8] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < Md) {
-              const float* rp = ep.R + (size_t)row * ep.ldr + col;
-              if (lr_vec && col + 3 < n_out) {
+              const float* rp = r_base + (size_t)row * r_ld + col;
+              if (acc_chunk) {
+                if (lr_vec && col + 3 < n_out) {
+                  rv4[p8] = *reinterpret_cast<const float4*>(rp);
+                } else {
+                  if (col + 0 < n_out) rv4[p8].x = rp[0];
+                  if (col + 1 < n_out) rv4[p8].y = rp[1];
+                  if (col + 2 < n_out) rv4[p8].z = rp[2];
+                  if (col + 3 < n_out) rv4[p8].w = rp[3];
+                }
+              } else if (lr_vec && col + 3 < n_out) {
                 rv4[p8] = __ldg(reinterpret_cast<const float4*>(rp));
               } else {
                 if (col + 0 < n_out) rv4[p8].x = __ldg(rp + 0);
@@ -444,7 +468,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];           // bank (lane + i) % 32: conflict-free
         __syncwarp();
-        const bool do_relu = (ep.epi & HSG_EPI_RELU) != 0, do_add = (ep.epi & HSG_EPI_ADD) != 0,
+        const bool do_relu = (ep.epi & HSG_EPI_RELU) != 0, do_add = acc_chunk || (ep.epi & HSG_EPI_ADD) != 0,
                    do_mask = (ep.epi & HSG_EPI_RELU_MASK) != 0;
         const bool vec_col = col + 3 < n_out && ld_vec;
         const int ones_d = ep.colsum_part != nullptr ? ep.ones_col - col : -1;   // 0..3 when this lane holds the sums
@@ -456,7 +480,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float o0 = tile[rl * 33 + c_sub + 0], o1 = tile[rl * 33 + c_sub + 1], o2 = tile[rl * 33 + c_sub + 2],
                 o3 = tile[rl * 33 + c_sub + 3];
           if (ones_d >= 0 && ones_d < 4 && row < Md)
-            ep.colsum_part[(size_t)ti.z * Md + row] = ones_d == 0 ? o0 : (ones_d == 1 ? o1 : (ones_d == 2 ? o2 : o3));
+          {
+            float* cp = ep.colsum_part + (size_t)ti.z * Md + row;
+            const float cv = ones_d == 0 ? o0 : (ones_d == 1 ? o1 : (ones_d == 2 ? o2 : o3));
+            *cp = acc_chunk ? *cp + cv : cv;
+          }
           o0 += bz[0]; o1 += bz[1]; o2 += bz[2]; o3 += bz[3];
           if (do_relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f); }
           if (do_add) { o0 += rv4[p8].x; o1 += rv4[p8].y; o2 += rv4[p8].z; o3 += rv4[p8].w; }
@@ -582,9 +610,13 @@ struct Operand {
 
 static bool g_attr_done[3] = {false, false, false};
 
+// longest accumulation chain of one TMEM accumulator, in K elements (see tile_info): weight-gradient splits longer
+// than this are walked in chunks by their CTA
+constexpr int K_CHUNK = 1024;
+
 template <bool A_MN, bool B_MN>
 static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, int K, int bn, int k_per_split,
-                  int precise, Epilogue ep, cudaStream_t s) {
+                  int precise, Epilogue ep, cudaStream_t s, int k_chunk = 0) {
   if (!g_attr_done[which]) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
         cudaSuccess)
@@ -598,10 +630,20 @@ static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, in
   const bool okB = B_MN ? make_map(&tmB, B.p, B.ext_mn, B.ext_k, B.ld, 32, true)
                         : make_map(&tmB, B.p, B.ext_k, B.ext_mn, B.ld, nb_box, false);
   if (!okA || !okB) return HSG_ERR_CUDA;
-  const int m_tiles = (int)grid.x, n_tiles = (int)grid.y, total = m_tiles * n_tiles * (int)grid.z;
-  const int ctas = total < num_sms() ? total : num_sms();
+  const int m_tiles = (int)grid.x, n_tiles = (int)grid.y, n_items = m_tiles * n_tiles * (int)grid.z;
+  int total = n_items, ctas = n_items < num_sms() ? n_items : num_sms();
+  if (k_chunk > 0) {
+    // chunked items: CTA w must own every chunk of item w (its epilogue adds them up in place), i.e. exactly one CTA
+    // per item; the plan keeps n_items within one wave, otherwise run unchunked
+    if (n_items <= num_sms() && k_per_split > k_chunk) {
+      total = n_items * ((k_per_split + k_chunk - 1) / k_chunk);
+      ctas = n_items;
+    } else {
+      k_chunk = 0;
+    }
+  }
   launch_k(gemm_tc_kernel<A_MN, B_MN>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tmA, tmB, Md, Nd, K, bn, nb_box, k_per_split, m_tiles,
-                                                               n_tiles, total, precise, ep);
+                                                               n_tiles, total, precise, k_chunk, n_items, ep);
   return check_launch();
 }
 
@@ -638,7 +680,7 @@ int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int 
   const int bn = pick_bn(n_total);
   Epilogue ep{part, N2, (size_t)N1 * N2, nullptr, nullptr, 0, 0, part_col, part_col ? N2 : -1};
   dim3 grid(ceil_div(N1, TM), ceil_div(n_total, bn), splits);
-  return launch<true, true>(2, grid, a, b, N1, n_total, M, bn, rows_per_split, precise, ep, s);
+  return launch<true, true>(2, grid, a, b, N1, n_total, M, bn, rows_per_split, precise, ep, s, precise ? K_CHUNK : 0);
 }
 
 int trace_ctl(int on, unsigned long long* host_out, int max_events) {
