@@ -241,6 +241,23 @@ FWD_TOL = {"fp32": TOL, "tf32x3": TOL, "tf32": 2e-2}
 @pytest.mark.parametrize("shape,hdsg,n_iter,n,seed", [("cnndm", False, 1, 8, 0), ("nyt50", False, 3, 4, 1),
                                                       ("multinews", True, 1, 4, 2)])
 def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed, gemm_mode):
+    _check_against_closed_form(shape, hdsg, n_iter, n, seed, gemm_mode, torch.float32)
+
+
+def test_large_batch_gradients_match_float64_closed_form():
+    """A data-parallel shard's worth of graphs (160 CNN/DM-shaped graphs, ~60 k word rows): forward and every gradient
+    against the closed form evaluated in float64.  Catches errors that grow with the batch - e.g. a single tensor-core
+    accumulation chain over a weight-gradient product's rows drifts to 2e-5 at 8 k rows per split (K-chunked since).
+    The batch (seed) is one in which no edge logit lies within rounding distance of leaky_relu's kink at 0: about one
+    logit in 10^7 does (2 M logits here), and then fp32 and fp64 take different slopes (1 vs 0.01) for that edge, which
+    shows at ~1e-4 in every gradient downstream of it - batches 5, 6 and 8 have such an edge (word row 4 222, head 6 of
+    the first W2S application: logit -1.2e-7; that one row of ~57 000 is off by 6e-4, all others within 1e-5,
+    scratch/large_batch_debug.py); that is a property of the function, not of the kernels."""
+    seed = int(os.environ.get("HSG_LARGE_BATCH_SEED", "7"))
+    _check_against_closed_form("cnndm", False, 1, 160, seed, "tf32x3", torch.float64)
+
+
+def _check_against_closed_form(shape, hdsg, n_iter, n, seed, gemm_mode, oracle_dtype, kink_rows=0):
     """Whole update loop, forward and every gradient, in all three arithmetic modes.
 
     ReLU is the one discontinuous function on the path: an FFN unit whose pre-activation lies within rounding
@@ -256,7 +273,7 @@ def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed, gemm_mod
     csc = gb.derive_csc(bg)
     torch.manual_seed(1234)
     m = hb.WSWGATUpdateLoop(n_iter=n_iter, atten_dropout_prob=0.0, ffn_dropout_prob=0.0)
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    params = {k: v.detach().clone().to(oracle_dtype).requires_grad_(True) for k, v in m.state_dict().items()}
     m = m.cuda()
     w = torch.randn(batch.n_word, 300)
     s = torch.randn(batch.n_super, 64)
@@ -269,10 +286,10 @@ def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed, gemm_mod
     finally:
         fn.RELU_MASK_CAPTURE = None
     ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
-    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    wc, sc = w.clone().to(oracle_dtype).requires_grad_(True), s.clone().to(oracle_dtype).requires_grad_(True)
     flips = []
     ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter, masks=masks, flips=flips)
-    ((ow * cw).sum() + (os_ * cs).sum()).backward()
+    ((ow * cw.to(oracle_dtype)).sum() + (os_ * cs.to(oracle_dtype)).sum()).backward()
     n_flip, n_unit = sum(f[0] for f in flips), sum(f[1] for f in flips)
     pre_at_flip = max(f[2] for f in flips)
     limit = {"fp32": (2e-5, 1e-5), "tf32x3": (2e-5, 1e-5), "tf32": (5e-3, 2e-2)}[gemm_mode]
@@ -296,6 +313,19 @@ def test_configs_match_closed_form_oracle(shape, hdsg, n_iter, n, seed, gemm_mod
         if mod.layer.feat_fc_bias is not None:
             checks.append((pre + ".feat_fc_bias", mod.layer.feat_fc_bias.grad, cat("feat_fc.bias")))
     for name, got, ref in checks:
+        if kink_rows and name in ("d word", "d sent"):
+            # leaky_relu has a kink at 0: an edge logit within rounding distance of 0 takes the slope 1 in one
+            # arithmetic and 0.01 in the other, which changes the input gradient of that edge's source row only (about
+            # one in 10^7 logits: expected ~0.4 rows at this size; seen: one row, 6e-4).  Every other row must agree.
+            d = (got.detach().cpu().double() - ref.detach().double()).abs().max(dim=1).values / float(ref.abs().max())
+            bad = d > gtol
+            assert int(bad.sum()) <= kink_rows and float(d.max()) <= 1e-3, (name, int(bad.sum()), float(d.max()))
+            continue
+        if kink_rows and (name == "TFembed" or name.endswith((".feat_fc", ".attn_fc", ".feat_fc_bias"))):
+            # the same edge enters these through dq / dp: sums that largely cancel (softmax-shift directions), so one
+            # flipped slope shows at ~1e-4 of the tensor's maximum; bounded, not compared at full tolerance
+            assert nerr(got, ref) <= 1e-3, (name, nerr(got, ref), gemm_mode)
+            continue
         assert nerr(got, ref) <= gtol, (name, nerr(got, ref), gemm_mode)
 
 
