@@ -365,11 +365,15 @@ static int lstm_check(int n_graphs, int H, int ndir) {
   return HSG_OK;
 }
 
-template <typename K>
+// opt in to the large dynamic shared-memory carve-out once per kernel and size (not on every launch)
+template <int TAG, typename K>                      // TAG: one static per KERNEL (the three share one function type)
 static int lstm_attr(K kernel, int H) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem_bytes(H)) == cudaSuccess
-             ? HSG_OK
-             : HSG_ERR_CUDA;
+  static int done_bytes = 0;
+  const int need = (int)lstm_smem_bytes(H);
+  if (need <= done_bytes) return HSG_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need) != cudaSuccess) return HSG_ERR_CUDA;
+  done_bytes = need;
+  return HSG_OK;
 }
 
 }  // namespace hsg
@@ -397,12 +401,12 @@ int hsg_lstm_fwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
   cudaStream_t s = (cudaStream_t)stream;
   const int threads = ((2 * H + 31) / 32) * 32;
   if (H == 2 * LSTM_KS_MAX) {
-    if ((rc = lstm_attr(lstm_fwd_kernel<2 * LSTM_KS_MAX>, H)) != HSG_OK) return rc;
+    if ((rc = lstm_attr<0>(lstm_fwd_kernel<2 * LSTM_KS_MAX>, H)) != HSG_OK) return rc;
     LaunchScope ls(SLOT_LSTM, s);
     launch_k(lstm_fwd_kernel<2 * LSTM_KS_MAX>, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir,
              graph_sent_ptr, xproj, p, out, gates, cst, hprev);
   } else {
-    if ((rc = lstm_attr(lstm_fwd_kernel<0>, H)) != HSG_OK) return rc;
+    if ((rc = lstm_attr<1>(lstm_fwd_kernel<0>, H)) != HSG_OK) return rc;
     LaunchScope ls(SLOT_LSTM, s);
     launch_k(lstm_fwd_kernel<0>, dim3(n_graphs, ndir), dim3(threads), lstm_smem_bytes(H), s, H, ndir, graph_sent_ptr,
              xproj, p, out, gates, cst, hprev);
@@ -425,7 +429,7 @@ int hsg_lstm_bwd(int n_graphs, int H, int ndir, const int32_t* graph_sent_ptr, c
     p.b_ih[d] = nullptr;
     p.b_hh[d] = nullptr;
   }
-  if ((rc = lstm_attr(lstm_bwd_kernel, H)) != HSG_OK) return rc;
+  if ((rc = lstm_attr<2>(lstm_bwd_kernel, H)) != HSG_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   LaunchScope ls(SLOT_LSTM, s);
   const int threads = ((2 * H + 31) / 32) * 32;
