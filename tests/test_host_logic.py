@@ -47,6 +47,18 @@ def test_argument_validation_without_gpu():
     perm = sorted(lib.hsg_edge_perm(6, 50, c) for c in range(300))
     assert perm == list(range(300))                     # a bijection onto [0, fp) for the default S2W shape
     assert lib.hsg_edge_bwd_workspace_bytes(8) > 0 and lib.hsg_gemm_tn_workspace_bytes(1000, 64, 64) > 0
+    # sentence encoder / LSTM entry points (no device work on these argument errors)
+    assert lib.hsg_enc_gather(4, 100, 300, 40, None, None, None, None, None, None, None) == -1      # null pointers
+    assert lib.hsg_enc_gather(4, 5, 300, 40, 16, 16, 16, 16, 16, 16, None) == -1                     # L < 7
+    assert lib.hsg_enc_gather(4, 100, 302, 40, 16, 16, 16, 16, 16, 16, None) == -2                   # D % 4 != 0
+    assert lib.hsg_enc_conv_wgrad_workspace_bytes(1009, 300) > 0
+    assert lib.hsg_lstm_fwd(2, 130, 2, 16, 16, 16, 16, 16, 16, 16, 16, 16, None) == -2               # H > 128
+    assert lib.hsg_lstm_fwd(2, 128, 3, 16, 16, 16, 16, 16, 16, 16, 16, 16, None) == -1               # ndir not 1 / 2
+    assert lib.hsg_lstm_bwd(0, 128, 2, None, None, None, None, None, None, None) == 0                # empty batch
+    tok = np.zeros((2, 8), np.int32)
+    out = np.zeros(16, np.int32)
+    assert lib.hsg_enc_plan_host(2, 8, tok.ctypes.data, 1, np.asarray([0, 3], np.int32).ctypes.data, out.ctypes.data,
+                                 out.ctypes.data + 16, out.ctypes.data + 32) == -1                   # ptr does not cover S
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
