@@ -103,17 +103,44 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invD = 1.f / (float)D;
+  // software pipeline over rows: the NEXT grid-stride row of this warp is fetched into registers while the current one
+  // goes through its two warp reductions (measured at 756 k x 300: 3.5 TB/s = 0.53 of the HBM peak without it - a
+  // warp had loads in flight for only part of its load -> reduce -> store cycle)
+  float4 prv[NV4], pdv[NV4];
+  float pmean = 0.f, prstd = 0.f;
+  auto prefetch_row = [&](int rw) {
+    if (rw < N) {
+      const float4* rr = reinterpret_cast<const float4*>(r + (size_t)rw * D);
+      const float4* dd = reinterpret_cast<const float4*>(dy + (size_t)rw * D);
+      pmean = __ldg(stats + 2 * (size_t)rw);
+      prstd = __ldg(stats + 2 * (size_t)rw + 1);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D4) {
+          prv[i] = __ldg(rr + c);
+          pdv[i] = __ldg(dd + c);
+        }
+      }
+    }
+  };
+  prefetch_row(warp);
   for (int row = warp; row < N; row += nwarps) {
-    const float4* rr = reinterpret_cast<const float4*>(r + (size_t)row * D);
-    const float4* dd = reinterpret_cast<const float4*>(dy + (size_t)row * D);
-    const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
+    const float mean = pmean, rstd = prstd;
+    float4 crv[NV4], cdv[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      crv[i] = prv[i];
+      cdv[i] = pdv[i];
+    }
+    prefetch_row(row + nwarps);
     float4 xh[NV4], gy[NV4];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + 32 * i;
       if (c < D4) {
-        const float4 rv = __ldg(rr + c), dv = __ldg(dd + c);
+        const float4 rv = crv[i], dv = cdv[i];
         xh[i] = make_float4((rv.x - mean) * rstd, (rv.y - mean) * rstd, (rv.z - mean) * rstd, (rv.w - mean) * rstd);
         gy[i] = make_float4(dv.x * gm[i].x, dv.y * gm[i].y, dv.z * gm[i].z, dv.w * gm[i].w);
         dg[i].x = fmaf(dv.x, xh[i].x, dg[i].x);
