@@ -53,8 +53,10 @@ def parse():
     ap.add_argument("--no-encoder", action="store_true", help="skip the sentence-encoder leg (SURVEY 8-f rank 1)")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--stress-only", action="store_true", help="run only the stress-graph edge-kernel leg (for ncu)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-scaling-legs", action="store_true", help="skip the strong_4096 / weak_1024_per_gpu / grad_parity legs")
     ap.add_argument("--stress-scale", type=int, default=4)
-    ap.add_argument("--stress-iters", type=int, default=20)
+    ap.add_argument("--stress-iters", type=int, default=10)
     return ap.parse_args()
 
 
@@ -81,8 +83,9 @@ def make_workload(args, rank):
 # reference arm: the oracle port of the reference's CPU path (per head, degree-bucketed like DGL 0.4)
 # ------------------------------------------------------------------------------------------------
 class CpuReference:
-    def __init__(self, exs, tb, hdsg, n_iter, closed_form=False):
+    def __init__(self, exs, tb, hdsg, n_iter, closed_form=False, device=None):
         from hetersumgraph_b200 import synthetic as syn
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
         from hetersumgraph_b200.path_model import HSGPath
         from oracle import graph_builder_ref as gb
         self.closed_form = closed_form
@@ -110,23 +113,32 @@ class CpuReference:
         self.sent_rows = torch.from_numpy(np.nonzero(self.g.ndtype[self.csc["snode_id"]] == 1)[0])
         self.labels = torch.from_numpy(tb.labels)
         self.n_graphs = tb.n_graphs
+        if self.device.type != "cpu":            # stock PyTorch on the GPU (B-cf-gpu): everything resident on the device
+            d = self.device
+            mv = lambda t: t.detach().to(d).requires_grad_(t.requires_grad)   # noqa: E731
+            self.params = {k: mv(v) for k, v in self.params.items()}
+            self.wh_w, self.wh_b, self.sent_feature = mv(self.wh_w), mv(self.wh_b), mv(self.sent_feature)
+            self.embed, self.wid, self.sent_rows, self.labels = (t.to(d) for t in (self.embed, self.wid, self.sent_rows,
+                                                                                   self.labels))
+            self.csc = {k: (torch.as_tensor(v).to(d) if isinstance(v, np.ndarray) else v) for k, v in self.csc.items()}
         self.opt = torch.optim.Adam(list(self.params.values()) + [self.wh_w, self.wh_b], lr=5e-4)
 
-    def step(self):
+    def step(self, sync=True):
         from oracle import closed_form as cf
         from oracle import wswgat_ref as wr
-        self.opt.zero_grad(set_to_none=True)
-        self.sent_feature.grad = None
-        wfeat = self.embed[self.wid]
-        if self.closed_form:
-            _, ss = cf.update_loop_cf(self.csc, wfeat, self.sent_feature, self.params, self.n_iter)
-        else:
-            _, ss = wr.update_loop(self.g, wfeat, self.sent_feature, self.params, self.n_iter)
-        logits = ss[self.sent_rows] @ self.wh_w.t() + self.wh_b
-        loss = torch.nn.functional.cross_entropy(logits, self.labels, reduction="sum") / self.n_graphs
-        loss.backward()
-        self.opt.step()
-        return float(loss)
+        with torch.device(self.device):
+            self.opt.zero_grad(set_to_none=True)
+            self.sent_feature.grad = None
+            wfeat = self.embed[self.wid]
+            if self.closed_form:
+                _, ss = cf.update_loop_cf(self.csc, wfeat, self.sent_feature, self.params, self.n_iter)
+            else:
+                _, ss = wr.update_loop(self.g, wfeat, self.sent_feature, self.params, self.n_iter)
+            logits = ss[self.sent_rows] @ self.wh_w.t() + self.wh_b
+            loss = torch.nn.functional.cross_entropy(logits, self.labels, reduction="sum") / self.n_graphs
+            loss.backward()
+            self.opt.step()
+        return float(loss.detach()) if sync else loss
 
 
 def time_cpu(ref, steps, warmup):
@@ -151,8 +163,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": tb.n_graphs, "n_iter": n_iter,
-                   "dropout": 0.0},
+        "config": base_config(args, cfg_idx, n_iter),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "the whole %d-graph batch per step (graph prebuilt; reference CreateGraph restatement took %.2f s once)"
                                    % (tb.n_graphs, ref.builder_s),
@@ -173,53 +184,105 @@ def workload_name(args, cfg_idx):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons of ONE GPU, sampled in-process through NVML every `period` seconds (a Python thread
+    calling three NVML getters: no child process, no nvidia-smi start-up on the host cores the ranks share).  Falls back
+    to `nvidia-smi -lms 200` when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
-        self.index = index
+    def __init__(self, index, period=0.1):
+        self.index, self.period = index, period
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc = self.thread = None
+        self.stop_flag = threading.Event()
+        self.mode = None
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = self.handle
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _smi_read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+        for ln in self.proc.stdout:
+            f = [x.strip() for x in ln.strip().split(",")]
             if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                self.sm.append(float(f[0]))
+                self.mx.append(float(f[1]))
             except ValueError:
                 continue
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(n)
+
+    def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                parts = [x for x in vis.split(",") if x.strip() != ""]
+                if idx < len(parts) and parts[idx].strip().isdigit():
+                    idx = int(parts[idx])
+            self.handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = self.sm
+        # "under load": samples at or above 60 % of the highest clock seen (idle gaps between legs clock down)
+        hi = [x for x in sm if x >= 0.6 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "samples_under_load": len(hi),
+                "sampler": self.mode + (" thread, %.0f ms period" % (self.period * 1e3) if self.mode == "nvml" else " -lms 200")}
+
+
+def base_config(args, cfg_idx, n_iter):
+    """the `config` object BOTH arms print (identical keys and values, so the driver can compare them)"""
+    return {"workload": workload_name(args, cfg_idx), "graphs_per_gpu": args.graphs_per_gpu, "n_iter": n_iter,
+            "dropout": 0.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,8 +291,11 @@ class ClockSampler:
 def run_ours(args):
     import hetersumgraph_b200 as hb
     from hetersumgraph_b200 import _lib, accounting
-    from hetersumgraph_b200.graph import DeviceTokenBatch, HeteroBatch
-    from hetersumgraph_b200.path_model import HSGPath, fused_loss, graph_loss
+    from hetersumgraph_b200.dist import FlatGradArena
+    from hetersumgraph_b200.functional import FusedAdam
+    from hetersumgraph_b200.graph import BuildPipeline, DeviceTokenBatch
+    from hetersumgraph_b200.path_model import FusedTrainStep, HSGPath
+    from hetersumgraph_b200.step_graph import GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,75 +314,34 @@ def run_ours(args):
     n_graphs_global = tb.n_graphs * world
     torch.manual_seed(1234)
     model = HSGPath(n_iter=n_iter, hdsg=hdsg).to(dev)
-    from hetersumgraph_b200.dist import FlatGradArena
     arena = FlatGradArena(model.parameters(), flatten_params=True)         # contiguous gradient + parameter arenas
     flat = arena.flat
     model.loop.fuse_grad_accumulation = True     # kernels add parameter gradients straight into the arena views
-    from hetersumgraph_b200.functional import FusedAdam
     opt = FusedAdam(arena.flat_param.data, flat, lr=5e-4)                 # torch.optim.Adam semantics, one kernel over the flat arena
 
     host, h2d_tok_bytes = DeviceTokenBatch.host_buffers(tb)
     bitmap_dev = torch.from_numpy(tb.filter_bitmap.view(np.int32).copy()).to(dev)
-    dtb = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
     n_sent_rows = int(tb.tokens.shape[0])
     gen = torch.Generator().manual_seed(7 + rank)
     sf_host = torch.randn(n_sent_rows, 64, generator=gen).pin_memory()
-    sf_dev = sf_host.to(dev)
 
-    from hetersumgraph_b200.graph import BuildPipeline
-    pipe = BuildPipeline(dev)          # build of batch i+1 on a side stream while batch i computes (one build per step)
-
-    from hetersumgraph_b200.path_model import FusedTrainStep
-    fused_step = FusedTrainStep(model, n_graphs_global)
-
-    def compute(batch, sf):
-        flat.zero_()
-        if fused_step is not None:                # forward + backward without the autograd engine (same C entry points)
-            loss, _logits, _d_sf = fused_step(batch, sf)
-        else:
-            sf = sf.detach().requires_grad_(True)
-            loss, _logits = fused_loss(model, batch, sf, n_graphs_global, fuse_grad_accumulation=True)
-            loss.backward()
-        if dist is not None:
-            dist.all_reduce(flat)
-        opt.step()
-        return loss
+    all_reduce = (lambda t: dist.all_reduce(t)) if dist is not None else None
+    use_graph = not args.no_graph
+    # `value` leg: token blob and sent_feature resident in HBM before the timed region; `e2e` leg: both come from
+    # pinned host memory every step (H2D inside the step), the loss goes back to pinned host memory every step
+    gs_res = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=True)
+    gs_e2e = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=False)
+    gs_res.prime(host)
+    gs_e2e.prime(host)
+    gs_res._stage_sf(sf_host.to(dev))
+    sf_res = gs_res.sf_dev[:n_sent_rows]
 
     def step_resident():
-        batch = pipe.take()
-        pipe.submit(dtb)                         # token arrays already resident in HBM
-        loss = compute(batch, sf_dev)
-        pipe.finish()
-        return loss, batch
-
-    def upload():
-        return DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
-
-    LAG = 8                                      # the host reads the loss of step i - LAG (asynchronous logging ring)
-    loss_host = [torch.zeros(1).pin_memory() for _ in range(LAG + 1)]
-    loss_ev = [None] * (LAG + 1)
-    e2e_state = {"i": 0, "last": None}
+        return gs_res.step(host, sf_res)
 
     def step_e2e():
-        batch = pipe.take()
-        pipe.submit(upload)                      # pinned host -> device copy of the next batch's tokens, then its build
-        sf = sf_host.to(dev, non_blocking=True)
-        loss = compute(batch, sf)
-        k = e2e_state["i"] % (LAG + 1)
-        loss_host[k].copy_(loss.detach().view(1), non_blocking=True)   # D2H of this step's loss into pinned memory
-        if loss_ev[k] is None:
-            loss_ev[k] = torch.cuda.Event()
-        loss_ev[k].record(pipe.main)
-        pipe.finish()
-        j = (e2e_state["i"] - LAG) % (LAG + 1)
-        if e2e_state["i"] >= LAG and loss_ev[j] is not None:   # consume an OLDER step's loss: no pipeline drain per step
-            loss_ev[j].synchronize()
-            e2e_state["last"] = float(loss_host[j])
-        e2e_state["i"] += 1
-        return e2e_state["last"], batch
-
-    pipe.submit(dtb)
-    pipe.finish()
+        out = gs_e2e.step(host, sf_host)
+        return out
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)           # > 126 MB L2
 
@@ -325,53 +350,97 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
+    def timed(fn, steps, warmup, prewarm=0):
+        for _ in range(prewarm + warmup):
             fn()
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        l0 = lib.hsg_launch_count()
         for a, b in evs:
             flush.zero_()                                                    # L2 flush, outside the timed events
             a.record()
             fn()
             b.record()
         barrier()
-        launches = lib.hsg_launch_count() - l0
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, launches // steps
+        return float(t.item()) / steps
 
+    def wall(fn, steps):
+        """host wall clock around `steps` back-to-back calls, one device sync at the end, no L2 flush"""
+        for _ in range(5):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    PREWARM = 6      # untimed steps per leg before the driver's --warmup: first step eager, then one capture per slot parity
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    # at least 10 untimed steps each: the caching allocator needs a few steps per leg before its cross-stream block
-    # reuse pattern (side-stream builds, pinned uploads) is stable - a cudaMalloc inside the timed region costs ms
-    ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 10))
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 10))
+    ms_step = timed(step_resident, args.steps, args.warmup, PREWARM)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup, PREWARM)
+    loss_last = gs_e2e.sync_loss()
+    wall_steps = max(500, args.steps)
+    sec_wall = wall(step_e2e, wall_steps)
+    sec_wall_res = wall(step_resident, wall_steps)
     clk = clocks.stop() if rank == 0 else None
-    # informational: the same step with single-pass TF32 products (the "bf16 projections <= 2e-2" error class of
-    # BASELINE.json); NOT the headline - value / e2e above are measured in the fp32-parity mode
+    graph_launches = gs_res.launches_per_step
+    replays = (gs_res.replays, gs_e2e.replays)
+
+    # ---- the same step WITHOUT graph replay (round-1 path: FusedTrainStep enqueued from Python every step) ----
+    pipe = BuildPipeline(dev)
+    dtb = DeviceTokenBatch.upload(tb, dev, host=host, filter_bitmap_dev=bitmap_dev)
+    fused_step = FusedTrainStep(model, n_graphs_global)
+    sf_dev = sf_host.to(dev)
+
+    def step_eager():
+        batch = pipe.take()
+        pipe.submit(dtb)
+        loss, _logits, _d = fused_step(batch, sf_dev)
+        if dist is not None:
+            dist.all_reduce(flat)
+        opt.step_dev(zero_grad=True)
+        pipe.finish()
+        return loss, batch
+
+    pipe.submit(dtb)
+    pipe.finish()
+    l0 = lib.hsg_launch_count()
+    ms_eager = timed(step_eager, args.steps, 10)
+    eager_launches = (lib.hsg_launch_count() - l0) // (args.steps + 10)
+    # informational: the same step with single-pass TF32 products; NOT the headline
     hb.set_gemm_mode("tf32")
-    ms_fast, _ = timed(step_resident, args.steps, 5)
+    ms_fast = timed(step_eager, args.steps, 5)
     hb.set_gemm_mode("tf32x3")
 
     # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
-    _, batch = step_resident()
+    _, batch = step_eager()
     torch.cuda.synchronize()
     lib.hsg_set_bwd_overlap(0)      # per-kernel events are only meaningful when the kernels do not share the GPU
     lib.hsg_profile_reset()
     lib.hsg_profile_enable(1)
     for _ in range(args.steps):
         flush.zero_()
-        step_resident()
+        step_eager()
     torch.cuda.synchronize()
     lib.hsg_profile_enable(0)
     lib.hsg_set_bwd_overlap(1)
     prof = _lib.profile_snapshot()
-    acct = accounting.step_accounting(batch.n_word, batch.n_super, batch.n_pair, n_iter)
+    acct = dict(accounting.step_accounting(batch.n_word, batch.n_super, batch.n_pair, n_iter))
+    bb = accounting.builder_bytes(n_sent_rows, int(tb.tokens.shape[1]), batch.n_pair, batch.n_word, batch.n_super)
+    acct["build_count"] = (0, bb // 2, 1)
+    acct["build_fill"] = (0, bb - bb // 2, 1)
+    acct["build_scan"] = (0, 10 * (tb.n_graphs + 1) * 4, 1)
+    acct["adam"] = (0, flat.numel() * 4 * 7, 1)
     kernels = []
     for name, (cnt, ms) in prof.items():
         per_step_ms = ms / args.steps
@@ -389,6 +458,8 @@ def run_ours(args):
     for k in kernels:
         k["share"] = k["ms_per_step"] / tot
     kernels.sort(key=lambda k: -k["ms_per_step"])
+    step_bytes = sum(v[1] for v in acct.values())
+    step_flops = sum(v[0] for v in acct.values())
     # ---- roofline of the dominant kernel: the tcgen05 GEMM at its largest launch shape (FFN-1 on the word nodes,
     # GATLayer.py:38) timed live, one launch at a time, L2 flushed, CUDA events on the launching stream ----
     from hetersumgraph_b200.functional import gemm_nt
@@ -396,10 +467,10 @@ def run_ours(args):
     Mw, Kw, Nh = batch.n_word, 300, 512
     xa = torch.randn(Mw, Kw, device=dev)
     wb = torch.randn(Nh, Kw, device=dev) * 0.05
-    bb = torch.randn(Nh, device=dev)
+    bb_ = torch.randn(Nh, device=dev)
     outb = torch.empty(Mw, Nh, device=dev)
     for _ in range(3):
-        gemm_nt(xa, wb, bias=bb, epi=EPI_BIAS | EPI_RELU, out=outb)
+        gemm_nt(xa, wb, bias=bb_, epi=EPI_BIAS | EPI_RELU, out=outb)
     torch.cuda.synchronize()
     tsum = 0.0
     n_it = 20
@@ -407,13 +478,12 @@ def run_ours(args):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        gemm_nt(xa, wb, bias=bb, epi=EPI_BIAS | EPI_RELU, out=outb)
+        gemm_nt(xa, wb, bias=bb_, epi=EPI_BIAS | EPI_RELU, out=outb)
         e1.record()
         torch.cuda.synchronize()
         tsum += e0.elapsed_time(e1)
     ms_gemm = tsum / n_it
     fl_gemm = 2.0 * Mw * Kw * Nh
-    dom = next((k for k in kernels if k["kernel"].startswith("gemm")), None)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -429,7 +499,12 @@ def run_ours(args):
                 "note": "peak = measured sustained bf16 cuBLAS TFLOP/s; the fp32-parity scheme issues 3 TF32 MMAs per "
                         "product, so its ceiling is TF32-peak/3 (about 0.27 of this peak); "
                         "L2 flushed before every timed launch"}
-    del xa, wb, bb, outb
+    del xa, wb, bb_, outb
+
+    # ---- multi-GPU legs of BASELINE.json configs[4]: ONE global batch dealt by dist.shard_indices ----
+    scaling_legs = grad_par = None
+    if not args.no_scaling_legs:
+        scaling_legs, grad_par = scaling_legs_run(args, dev, rank, world, dist, timed)
 
     if rank != 0:
         if dist is not None:
@@ -439,13 +514,18 @@ def run_ours(args):
 
     stress = None
     if not args.no_stress and world == 1:
-        stress = stress_leg(dev, pk, args.stress_scale, args.stress_iters)
+        stress = []
+        for sc in (1, 4, 16):
+            stress += stress_leg(dev, pk, sc, args.stress_iters, flush)
     large = None
     if not args.no_stress and world == 1:
         large = large_shard_leg(dev, pk)
     encoder = None
     if not args.no_encoder and world == 1:
         encoder = encoder_leg(dev, pk, exs, tb, n_iter, args.steps, hdsg=hdsg)
+    stock = None
+    if not args.no_cpu_baseline and world == 1:
+        stock = stock_pytorch_gpu_leg(dev, exs, tb, hdsg, n_iter, flush, args.steps)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -457,33 +537,172 @@ def run_ours(args):
         refc = CpuReference(exs, tb, hdsg, n_iter, closed_form=True)
         secc = time_cpu(refc, args.cpu_steps, 1)
         cpu["closed_form_graphs_per_s"] = tb.n_graphs / secc
+        cpu["reference_verbatim_on_shim"] = verbatim_reference_leg(exs, tb, hdsg, n_iter)
 
+    d2h = 4 + 4 * (5 * (tb.n_graphs + 1) + 1)
     line = {
         "metric": METRIC, "value": n_graphs_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 10), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if args.global_batch > 0 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg_idx), "graphs_per_step": n_graphs_global, "n_iter": n_iter,
-                   "dropout": 0.0, "l2": "flushed between steps (256 MiB memset outside the timed events)",
-                   "build": "device-side (K0), double-buffered: batch i+1 is built on a side stream while batch i computes; "
-                            "exactly one build per timed step",
-                   "gemm_mode": "tf32x3 (tcgen05 kind::tf32, hi/lo split: fp32-parity mode)",
-                   "rank0_sizes": {"word_nodes": batch.n_word, "supernodes": batch.n_super, "pairs_per_direction": batch.n_pair,
-                                   "dgl_edges": batch.n_total_edges},
-                   "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3)},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": base_config(args, cfg_idx, n_iter),
+        "details": {"l2": "flushed between steps (256 MiB memset outside the timed events)",
+                    "step": ("one cudaGraphLaunch per step (step_graph.GraphedTrainStep): build of batch i+1 on a forked "
+                             "branch + embedding gather, update loop fwd, loss, update loop bwd, %sAdam+zero_grad of batch i"
+                             % ("NCCL all-reduce, " if world > 1 else "")) if use_graph else "eager enqueue (--no-graph)",
+                    "graph_replays_resident_e2e": replays,
+                    "prewarm_steps_per_leg": PREWARM,
+                    "build": "device-side (K0), double-buffered slots: batch i+1 is built while batch i computes; exactly one build per timed step",
+                    "gemm_mode": "tf32x3 (tcgen05 kind::tf32, hi/lo split: fp32-parity mode)",
+                    "rank0_sizes": {"word_nodes": batch.n_word, "supernodes": batch.n_super, "pairs_per_direction": batch.n_pair,
+                                    "dgl_edges": batch.n_total_edges},
+                    "edges_per_s": 2 * batch.n_pair * (1 + 2 * n_iter) * world / (ms_step * 1e-3),
+                    "step_algorithmic_MB": step_bytes / 1e6, "step_algorithmic_GFLOP": step_flops / 1e9,
+                    "step_frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm"],
+                    "step_frac_of_tensor_peak": step_flops / (ms_step * 1e-3) / 1e12 / pk["tf"],
+                    "last_loss": loss_last},
         "e2e": {"value": n_graphs_global / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": 4 + 4 * (5 * (tb.n_graphs + 1) + 1),
-                "d2h": "loss -> pinned host memory every step (async copy), read by the host eight steps later (logging ring); "
-                       "builder totals read every step"},
-        "gpu_launches": int(launches),
-        "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "edge_kernels_stress": stress,
-        "large_shard": large, "with_sentence_encoder": encoder,
+                "h2d_bytes_per_step": int(h2d_tok_bytes + sf_host.numel() * 4), "d2h_bytes_per_step": d2h,
+                "d2h": "loss -> pinned host memory every step (inside the step), read by the host after the next step; "
+                       "builder totals of the next batch read every step",
+                "wall_clock": {"steps": wall_steps, "seconds": sec_wall, "ms_per_step": sec_wall / wall_steps * 1e3,
+                               "graphs_per_s": n_graphs_global * wall_steps / sec_wall,
+                               "what": "time.perf_counter around %d back-to-back e2e steps (host memcpy into pinned staging, "
+                                       "H2D, step, D2H), one device sync at the end, no L2 flush" % wall_steps},
+                "wall_clock_resident": {"steps": wall_steps, "seconds": sec_wall_res,
+                                        "graphs_per_s": n_graphs_global * wall_steps / sec_wall_res}},
+        "gpu_launches": int(graph_launches if graph_launches is not None else eager_launches),
+        "eager_path": {"ms_per_step": ms_eager, "graphs_per_s": n_graphs_global / (ms_eager * 1e-3),
+                       "launches_per_step": int(eager_launches),
+                       "what": "the same step enqueued from Python every step (FusedTrainStep + BuildPipeline), resident inputs"},
+        "clocks": clk, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "stock_pytorch_gpu": stock,
+        "edge_kernels_stress": stress, "large_shard": large, "with_sentence_encoder": encoder,
+        "scaling_legs": scaling_legs, "grad_parity": grad_par,
         "single_pass_tf32_mode": {"graphs_per_s": n_graphs_global / (ms_fast * 1e-3), "ms_per_step": ms_fast,
-                                  "note": "informational, tolerance class 2e-2; not the headline"},
+                                  "note": "informational (eager path), tolerance class 2e-2; not the headline"},
     }
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def scaling_legs_run(args, dev, rank, world, dist, timed):
+    """BASELINE.json configs[4] in a driver-visible form: ONE seeded global batch, sorted and dealt to the ranks by
+    dist.shard_indices (dataloader.py:479-480 ordering + snake deal), each rank computes its shard with the loss scaled
+    by 1/B_global, one all-reduce of the arena, Adam.  strong: 4 096 graphs per step in total; weak: 1 024 per GPU.
+    grad_parity: the all-reduced gradient arena against rank 0 processing the whole (smaller) global batch alone."""
+    from hetersumgraph_b200 import synthetic as syn
+    from hetersumgraph_b200.dist import FlatGradArena, shard_indices
+    from hetersumgraph_b200.functional import FusedAdam
+    from hetersumgraph_b200.graph import HeteroBatch
+    from hetersumgraph_b200.path_model import FusedTrainStep, HSGPath
+
+    def model_pair():
+        torch.manual_seed(1234)
+        m = HSGPath(n_iter=1).to(dev)
+        ar = FlatGradArena(m.parameters(), flatten_params=True)
+        m.loop.fuse_grad_accumulation = True
+        return m, ar, FusedAdam(ar.flat_param.data, ar.flat, lr=5e-4)
+
+    def shard_of(exs_all, r, w):
+        sh = shard_indices([e.n_sent for e in exs_all], [float(sum(len(x) for x in e.w2s)) for e in exs_all], w)
+        return [exs_all[i] for i in sh[r]]
+
+    base = syn.make_examples(512, "cnndm", seed=3)     # the global batch tiles 512 distinct graphs (generation cost)
+
+    def leg(n_global, steps):
+        exs_all = [base[i % len(base)] for i in range(n_global)]
+        mine = shard_of(exs_all, rank, world)
+        tbs = syn.pack_token_batch(mine)
+        batch = HeteroBatch.from_token_batch(tbs, dev)
+        m, ar, op = model_pair()
+        step = FusedTrainStep(m, n_global)
+        sf = torch.randn(int(tbs.tokens.shape[0]), 64, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+
+        def fn():
+            step(batch, sf)
+            if dist is not None:
+                dist.all_reduce(ar.flat)
+            op.step_dev(zero_grad=True)
+        ms = timed(fn, steps, 3)
+        out = {"global_graphs": n_global, "graphs_this_rank": len(mine), "word_nodes_this_rank": batch.n_word,
+               "ms_per_step": ms, "graphs_per_s": n_global / (ms * 1e-3),
+               "what": "token arrays and the built batch resident; update loop fwd+bwd + loss + all-reduce + Adam per step"}
+        del batch, m, ar, op, step, sf
+        torch.cuda.empty_cache()
+        return out
+
+    legs = {"strong_4096": leg(4096, 5), "weak_1024_per_gpu": leg(1024 * world, 5)}
+
+    # gradient parity on a 256-graph global batch
+    n_par = 256
+    exs_all = base[:n_par]
+    sf_all = torch.randn(sum(e.n_sent for e in exs_all) + 8, 64, generator=torch.Generator().manual_seed(11))
+    # sentence rows follow the examples: give every example its own slice so shards see the same features
+    offs = np.concatenate([[0], np.cumsum([e.n_sent for e in exs_all])])
+
+    def run(exs_sub, idxs):
+        tbs = syn.pack_token_batch(exs_sub)
+        order = list(tbs.order) if getattr(tbs, "order", None) is not None else list(range(len(exs_sub)))
+        rows = np.concatenate([np.arange(offs[idxs[j]], offs[idxs[j]] + exs_sub[j].n_sent) for j in order]) \
+            if len(exs_sub) else np.zeros(0, np.int64)
+        batch = HeteroBatch.from_token_batch(tbs, dev)
+        m, ar, _ = model_pair()
+        FusedTrainStep(m, n_par)(batch, sf_all[rows].to(dev))
+        return ar.flat.clone()
+
+    sh = shard_indices([e.n_sent for e in exs_all], [float(sum(len(x) for x in e.w2s)) for e in exs_all], world)
+    g_shard = run([exs_all[i] for i in sh[rank]], sh[rank])
+    if dist is not None:
+        dist.all_reduce(g_shard)
+    par = None
+    if rank == 0:
+        g_full = run(exs_all, list(range(n_par)))
+        err = float((g_shard - g_full).abs().max() / g_full.abs().max())
+        par = {"global_graphs": n_par, "ranks": world, "normalised_max_error": err, "bound": 1e-6,
+               "ok": bool(err <= 1e-6),
+               "what": "all-reduced flat gradient arena of the N shards (dist.shard_indices) vs rank 0 running the whole "
+                       "global batch alone, same parameters and sent_feature rows"}
+    return legs, par
+
+
+def stock_pytorch_gpu_leg(dev, exs, tb, hdsg, n_iter, flush, steps):
+    """B-cf-gpu of BASELINE.md: the closed-form restatement (oracle/closed_form.py: index_add / scatter softmax in stock
+    PyTorch, no custom kernels) on the same B200 and batch - what eager PyTorch does with this path on this GPU."""
+    ref = CpuReference(exs, tb, hdsg, n_iter, closed_form=True, device=dev)
+    for _ in range(3):
+        ref.step()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ref.step(sync=False)
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    ms = tot / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step(sync=False)
+    torch.cuda.synchronize()
+    ms_wall = (time.perf_counter() - t0) / steps * 1e3
+    return {"what": "oracle/closed_form.py (vectorised torch restatement, fp32, TF32 off) fwd+bwd+torch.optim.Adam on the B200, "
+                    "stock PyTorch kernels only; graph prebuilt on the host",
+            "ms_per_step_events": ms, "ms_per_step_wall": ms_wall, "graphs_per_s": tb.n_graphs / (max(ms, ms_wall) * 1e-3)}
+
+
+def verbatim_reference_leg(exs, tb, hdsg, n_iter, steps=1):
+    """B-ref of BASELINE.md: the reference's own WSWGAT modules (module/GAT.py:45-59) UNMODIFIED on the DGL-0.4 shim,
+    1 thread and all threads.  Only where /root/reference exists (the build container); None on the GPU box."""
+    if not os.path.isdir("/root/reference/module"):
+        return None
+    try:
+        from oracle import fixtures as fx
+        return fx.time_verbatim_reference(exs, tb, hdsg, n_iter, steps)
+    except Exception as e:          # test infrastructure only: never fail the bench line
+        return {"unavailable": repr(e)[:200]}
 
 
 def encoder_leg(dev, pk, exs, tb, n_iter, steps, cpu_steps=1, hdsg=False):
@@ -655,26 +874,49 @@ def _time_edge_kernels(batch, label, dev, pk, flush, iters):
         nb = {"edge_fwd": accounting.edge_fwd_bytes(E, csc.n_src, csc.n_dst, H, d),
               "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
               "edge_bwd": accounting.edge_bwd_bytes(E, csc.n_src, csc.n_dst, H, d)}
-        for name, fn in fns.items():
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            tot = 0.0
-            for _ in range(iters):
-                flush.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                torch.cuda.synchronize()
-                tot += a.elapsed_time(b)
-            ms = tot / iters
-            gbs = nb[name] / (ms * 1e-3) / 1e9
-            out.append({"input": label, "kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": E,
-                        "n_src": csc.n_src, "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6,
-                        "GBps": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "l2": "flushed before every launch"})
+        out += _edge_rows(fns, nb, label, kind, H, d, E, csc, pk, flush, iters)
         del zp, origin, sh, x, g, dzp
     return out
+
+
+def _edge_rows(fns, nb, label, kind, H, d, E, csc, pk, flush, iters):
+    """time each edge kernel alone (CUDA events, L2 flushed before every launch) -> rows with two fractions of the HBM
+    peak: `frac_of_hbm_peak` over the bytes the kernel really moves (incl. the saved `sh`), and `frac_survey` over
+    SURVEY.md 8(d)'s B_fwd / B_bwd (the backward figure covers prep + the source-centric pass together)."""
+    from hetersumgraph_b200 import accounting
+    ms_of = {}
+    for name, fn in fns.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        ms_of[name] = tot / iters
+    rows = []
+    b_fwd = accounting.edge_fwd_bytes_survey(E, csc.n_src, csc.n_dst, H, d)
+    b_bwd = accounting.edge_bwd_bytes_survey(E, csc.n_src, csc.n_dst, H, d)
+    for name, ms in ms_of.items():
+        gbs = nb[name] / (ms * 1e-3) / 1e9
+        row = {"input": label, "kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": E,
+               "n_src": csc.n_src, "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6,
+               "GBps": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "l2": "flushed before every launch"}
+        if name == "edge_fwd":
+            row["survey_MB"] = b_fwd / 1e6
+            row["frac_survey"] = b_fwd / (ms * 1e-3) / 1e9 / pk["hbm"]
+        rows.append(row)
+    if "edge_bwd" in ms_of:
+        ms_pair = ms_of["edge_bwd"] + ms_of.get("edge_bwd_prep", 0.0)
+        rows.append({"input": label, "kernel": "edge_bwd_prep+edge_bwd", "layer": kind, "heads": H, "head_dim": d,
+                     "pairs": E, "ms": ms_pair, "survey_MB": b_bwd / 1e6,
+                     "frac_survey": b_bwd / (ms_pair * 1e-3) / 1e9 / pk["hbm"]})
+    return rows
 
 
 def large_shard_leg(dev, pk, n_graphs=2048, iters=10):
@@ -716,15 +958,18 @@ def large_shard_leg(dev, pk, n_graphs=2048, iters=10):
             "what": "device build + update loop fwd+bwd + loss (no optimizer), inputs resident"}
 
 
-def stress_leg(dev, pk, scale=4, iters=20):
-    """Edge kernels on the stress graph of SURVEY §8-d (x`scale`: working set > L2), timed alone with CUDA events."""
+def stress_leg(dev, pk, scale=4, iters=10, flush=None):
+    """Edge kernels on the stress graph of SURVEY 8-d (x1, x4, x16), each timed alone with CUDA events, L2 flushed before
+    every launch."""
     import ctypes as C
 
     import hetersumgraph_b200 as hb
     from hetersumgraph_b200 import _lib, accounting
     from hetersumgraph_b200 import synthetic as syn
-    from hetersumgraph_b200.functional import _Workspace, round_up
+    from hetersumgraph_b200.functional import _Workspace
     lib = _lib.load()
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_word, n_super, n_edges = 262144 * scale, 32768 * scale, 1048576 * scale
     word, sup, bins, extra = syn.stress_edges(n_word, n_super, n_edges, seed=4, extra=64)
     (sip, ssrc, sbin, _), (wip, wsrc, wbin, _) = hb.csc_pair_from_edges(word, sup, bins, n_word, n_super)
@@ -745,38 +990,22 @@ def stress_leg(dev, pk, scale=4, iters=20):
         dzp = torch.empty(csc.n_src, ldz, device=dev)
         dq = torch.empty(10, H, device=dev)
         ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
-
-        def fwd():
-            _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(),
-                                        sh.data_ptr(), x.data_ptr(), stat.data_ptr(), st))
-
-        def prep():
-            _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None, sh.data_ptr(), g.data_ptr(),
-                                             stat.data_ptr(), st))
-
-        def bwd():
-            _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(), g.data_ptr(),
-                                        stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), st))
-
+        fns = {
+            "edge_fwd": lambda: _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(),
+                                                            origin.data_ptr(), sh.data_ptr(), x.data_ptr(),
+                                                            stat.data_ptr(), st)),
+            "edge_bwd_prep": lambda: _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None,
+                                                                      sh.data_ptr(), g.data_ptr(), stat.data_ptr(), st)),
+            "edge_bwd": lambda: _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(),
+                                                            g.data_ptr(), stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(),
+                                                            ws.data_ptr(), ws.numel(), st))}
         nb = {"edge_fwd": accounting.edge_fwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d),
               "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
               "edge_bwd": accounting.edge_bwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d)}
-        for name, fn in (("edge_fwd", fwd), ("edge_bwd_prep", prep), ("edge_bwd", bwd)):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(iters):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / iters
-            gbs = nb[name] / (ms * 1e-3) / 1e9
-            out.append({"kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": n_edges, "n_src": csc.n_src,
-                        "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6, "GBps": gbs,
-                        "frac_of_hbm_peak": gbs / pk["hbm"], "working_set_gt_L2": True})
+        out += _edge_rows(fns, nb, "stress graph x%d" % scale, kind, H, d, n_edges, csc, pk, flush, iters)
         del zp, origin, sh, x, g, dzp
+    del batch
+    torch.cuda.empty_cache()
     return out
 
 

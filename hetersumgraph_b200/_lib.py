@@ -75,7 +75,7 @@ class LoopArgsC(C.Structure):
                 ("w2s", LayerParamsC), ("s2w", LayerParamsC),
                 ("T", C.c_void_p), ("word_feature", C.c_void_p), ("super_feature", C.c_void_p),
                 ("state", C.c_void_p), ("state_floats", C.c_size_t),
-                ("attn_p", C.c_float), ("ffn_p", C.c_float), ("seed", C.c_ulonglong)]
+                ("attn_p", C.c_float), ("ffn_p", C.c_float), ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p)]
 
 
 class LoopPlanC(C.Structure):
@@ -121,6 +121,7 @@ _PROTOS = {
     "hsg_profile_slot_name": (C.c_char_p, [_I]),
     "hsg_profile_read": (C.c_int, [_I, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "hsg_launch_count": (C.c_longlong, []),
+    "hsg_memset": (C.c_int, [_P, _I, _Z, _P]),
     "hsg_build_workspace_bytes": (_Z, [C.POINTER(TokenBatchC)]),
     "hsg_build_count": (C.c_int, [C.POINTER(TokenBatchC), GraphOffsetsC, _P, _P, _Z, _P]),
     "hsg_build_fill": (C.c_int, [C.POINTER(TokenBatchC), C.POINTER(GraphOutC), _P, _Z, _P]),
@@ -171,6 +172,9 @@ _PROTOS = {
     "hsg_adam_workspace_bytes": (_Z, []),
     "hsg_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float, _P, _Z,
                                 _P]),
+    "hsg_adam_step_dev": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _I, C.c_float, _P,
+                                    _Z, _P]),
+    "hsg_embed_gather": (C.c_int, [_I, _I, _P, _P, _P, _P]),
     "hsg_s2s_fwd": (C.c_int, [C.POINTER(S2SGraphC), _P, _P, _P, _P, _P, _P, _P]),
     "hsg_s2s_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "hsg_s2s_bwd": (C.c_int, [C.POINTER(S2SGraphC), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

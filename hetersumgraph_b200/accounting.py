@@ -38,6 +38,27 @@ def edge_bwd_bytes(E, n_src, n_dst, H, d):
     return b
 
 
+def edge_fwd_bytes_survey(E, n_src, n_dst, H, d):
+    """SURVEY.md 8(d) B_fwd: E(4+1) + N_dst(4+4) + N_src(F+H)4 + N_dst F 4 (origin) + N_dst F 4 (out) + N_dst H 8.
+    (edge_fwd_bytes above additionally counts the saved `sh` write, which the kernel really performs.)"""
+    F = H * d
+    return E * 5 + n_dst * 8 + n_src * (F + H) * 4 + 2 * n_dst * F * 4 + n_dst * H * 8
+
+
+def edge_bwd_bytes_survey(E, n_src, n_dst, H, d):
+    """SURVEY.md 8(d) B_bwd of the WHOLE edge backward (prep + source-centric pass) of one application whose forward
+    had n_src sources and n_dst destinations: 2E(4+1) + E 4 (eid map) + (N_src+N_dst) 4 + N_dst F 4 (g) + N_dst H 8 +
+    N_src(F+H)4 (z,p) + N_src(F+H)4 (dz,dp) + 10 H 4 (dq)."""
+    F = H * d
+    return (2 * E * 5 + E * 4 + (n_src + n_dst) * 4 + n_dst * F * 4 + n_dst * H * 8 + 2 * n_src * (F + H) * 4 +
+            10 * H * 4)
+
+
+def builder_bytes(n_sent, sent_len, n_pair, n_word, n_super):
+    """K0: S L 5 token + bin bytes read by each of the two passes, ~26 B per pair + the node maps written."""
+    return 2 * n_sent * sent_len * 5 + n_pair * 26 + n_word * 12 + n_super * 21
+
+
 def wswgat_application(E, n_src, n_dst, H, d, in_dim, d_hid):
     """{slot: [flops, bytes, launches]} of ONE WSWGAT application, forward + backward."""
     F = H * d
@@ -62,15 +83,16 @@ def wswgat_application(E, n_src, n_dst, H, d, in_dim, d_hid):
     add("layernorm_fwd", 0, 2 * n_dst * F * 4)
     # backward
     add("layernorm_bwd", 0, 3 * n_dst * F * 4)
-    add("layernorm_bwd_reduce", 0, 0)
+    add("layernorm_bwd_reduce", 0, 2 * F * 4 * 64)          # per-block partials of dgamma / dbeta (order of 64 blocks)
     gemm("gemm_nn", n_dst, d_hid, F)           # dhp = (dr W2) * relu'
     gemm("gemm_tn", n_dst, F, d_hid)           # dW2
     gemm("gemm_tn", n_dst, d_hid, F)           # dW1
     gemm("gemm_nn", n_dst, F, d_hid)           # dx = dhp W1 + dr
-    add("gemm_tn_reduce", 0, 0, 3)
+    # fixed-order second stage of the three weight-gradient products: partials read once, result written once
+    add("gemm_tn_reduce", 0, (F * d_hid * 2 + ldz * in_dim) * 4 * 9, 3)
     add("edge_bwd_prep", 0, edge_bwd_prep_bytes(n_dst, H, d))
     add("edge_bwd", 0, edge_bwd_bytes(E, n_src, n_dst, H, d))
-    add("edge_bwd_dq", 0, 0)
+    add("edge_bwd_dq", 0, 10 * H * 4 * 296)
     gemm("gemm_nn", n_src, in_dim, ldz)        # dh = dzp W_aug
     gemm("gemm_tn", n_src, ldz, in_dim)        # dW_aug
     return acc

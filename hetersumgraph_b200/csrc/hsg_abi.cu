@@ -38,8 +38,9 @@ static cudaEvent_t get_event() {
   return e;
 }
 
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 void prof_begin(int slot, cudaStream_t s) {
-  g_launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_prof) return;
   std::lock_guard<std::mutex> lk(g_mu);
   EventPair p;
@@ -165,5 +166,11 @@ int hsg_profile_read(int slot, int* host_count, float* host_ms) {
 }
 
 long long hsg_launch_count(void) { return g_launches.load(); }
+
+int hsg_memset(void* ptr, int value, size_t bytes, void* stream) {
+  if (!ptr && bytes) return HSG_ERR_ARG;
+  if (bytes == 0) return HSG_OK;
+  return cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream) == cudaSuccess ? HSG_OK : HSG_ERR_CUDA;
+}
 
 }  // extern "C"

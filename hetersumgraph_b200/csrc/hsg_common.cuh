@@ -60,6 +60,7 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_wait();
 }
 
+void count_launch();   // hsg_abi.cu: one tick per kernel launch of the library (hsg_launch_count)
 bool pdl_enabled();   // hsg_abi.cu (HSG_PDL=0 in the environment or hsg_set_pdl(0) turns it off)
 
 template <typename... P, typename... A>
@@ -74,6 +75,7 @@ inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
   cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 

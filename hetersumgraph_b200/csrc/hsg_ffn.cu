@@ -286,10 +286,10 @@ int hsg_layernorm_fwd(int N, int D, const float* r, const float* gamma, const fl
   const int grid = ln_grid(N);
   const int nv4 = ceil_div(D, 128);
   switch (nv4) {
-    case 1: launch_k(layernorm_fwd_kernel<1, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
-    case 2: launch_k(layernorm_fwd_kernel<2, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
-    case 3: launch_k(layernorm_fwd_kernel<3, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
-    default: launch_k(layernorm_fwd_kernel<4, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f}); break;
+    case 1: launch_k(layernorm_fwd_kernel<1, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f, nullptr}); break;
+    case 2: launch_k(layernorm_fwd_kernel<2, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f, nullptr}); break;
+    case 3: launch_k(layernorm_fwd_kernel<3, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f, nullptr}); break;
+    default: launch_k(layernorm_fwd_kernel<4, false>, dim3(grid), dim3(LN_THREADS), 0, s, N, D, r, gamma, beta, y, stats, nullptr, nullptr, DropCfg{0, 0, 1.f, nullptr}); break;
   }
   return check_launch();
 }

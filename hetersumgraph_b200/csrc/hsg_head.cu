@@ -209,11 +209,73 @@ adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float*
   }
 }
 
+// Same update with the step number read from DEVICE memory (state[0] = completed steps, state[1] = block ticket):
+// the kernel arguments are identical every step, so the launch can live in a replayed CUDA graph.  The last block to
+// finish advances the counter (every block has read it by then).  zero_grad: the gradient is cleared once consumed, so
+// the next step's kernels accumulate into a zeroed arena without a separate fill launch.
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(size_t n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float lr, float beta1, float beta2, float eps, const float* __restrict__ sumsq, float max_norm,
+                unsigned long long* __restrict__ state, int zero_grad) {
+  pdl_prologue();
+  const unsigned long long t = state[0] + 1ull;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  float coef = 1.f;
+  if (sumsq) coef = fminf(1.f, max_norm / (sqrtf(sumsq[0]) + 1e-6f));
+  for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    if (zero_grad) g[i] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&state[1], 1ull);
+    if (ticket == (unsigned long long)gridDim.x - 1ull) {
+      state[1] = 0ull;
+      state[0] = t;
+      __threadfence();
+    }
+  }
+}
+
+// out[i, :] = table[ids[i], :]   (the word-embedding lookup of set_wnfeature, HiGraph.py:147-148), float4 rows
+__global__ void __launch_bounds__(256)
+embed_gather_kernel(int n, int dim4, const int32_t* __restrict__ ids, const float4* __restrict__ table,
+                    float4* __restrict__ out) {
+  pdl_prologue();
+  const int rows_per_block = 256 / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * rows_per_block + warp; r < n; r += gridDim.x * rows_per_block) {
+    const float4* src = table + (size_t)__ldg(ids + r) * dim4;
+    float4* dst = out + (size_t)r * dim4;
+    for (int c = lane; c < dim4; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
 }  // namespace hsg
 
 using namespace hsg;
 
 extern "C" {
+
+int hsg_embed_gather(int n, int dim, const int32_t* ids, const float* table, float* out, void* stream) {
+  if (n < 0 || dim <= 0 || (dim & 3) || (n > 0 && (!ids || !table || !out))) return HSG_ERR_ARG;
+  if (!aligned16(table) || !aligned16(out)) return HSG_ERR_ALIGN;
+  if (n == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int blocks = ceil_div(n, 8);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  LaunchScope ls(SLOT_HEAD, s);
+  launch_k(embed_gather_kernel, dim3(blocks), dim3(256), 0, s, n, dim / 4, ids, reinterpret_cast<const float4*>(table),
+           reinterpret_cast<float4*>(out));
+  return check_launch();
+}
 
 size_t hsg_head_workspace_bytes(int n_sent, int width) {
   const int blocks = ceil_div(n_sent > 0 ? n_sent : 1, HEAD_ROWS_PER_BLOCK);
@@ -293,6 +355,28 @@ int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
   if (blocks > 1184) blocks = 1184;
   launch_k(adam_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n, param, grad, exp_avg, exp_avg_sq, beta1, beta2, step_size,
                                               inv_sqrt_bc2, eps, sumsq, max_grad_norm);
+  return check_launch();
+}
+
+int hsg_adam_step_dev(size_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                      float beta2, float eps, unsigned long long* step_state, int zero_grad, float max_grad_norm,
+                      void* ws, size_t ws_bytes, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step_state) return HSG_ERR_ARG;
+  if (n == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* sumsq = nullptr;
+  LaunchScope ls(SLOT_ADAM, s);
+  if (max_grad_norm > 0.f) {
+    if (!ws || ws_bytes < hsg_adam_workspace_bytes()) return HSG_ERR_WORKSPACE;
+    float* part = reinterpret_cast<float*>(ws);
+    launch_k(sumsq_part_kernel, dim3(SUMSQ_BLOCKS), dim3(256), 0, s, n, (const float*)grad, part);
+    launch_k(sumsq_final_kernel, dim3(1), dim3(512), 0, s, SUMSQ_BLOCKS, (const float*)part, part + SUMSQ_BLOCKS);
+    sumsq = part + SUMSQ_BLOCKS;
+  }
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  launch_k(adam_dev_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2,
+           eps, sumsq, max_grad_norm, step_state, zero_grad);
   return check_launch();
 }
 

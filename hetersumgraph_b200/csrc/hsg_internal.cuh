@@ -14,10 +14,15 @@ struct DropCfg {
   unsigned long long key;   // seed mixed with the stream id
   unsigned int thresh;      // drop when the 24-bit draw < thresh
   float scale;              // 1 / (1 - p)
+  // optional device-resident step counter mixed into the key at run time: a CUDA graph that replays the same kernel
+  // arguments every step still draws fresh masks (the counter is advanced by hsg_adam_step_dev).  NULL: key as is.
+  const unsigned long long* step;
 };
 
-inline DropCfg make_drop(float p, unsigned long long seed, unsigned int stream_id) {
+inline DropCfg make_drop(float p, unsigned long long seed, unsigned int stream_id,
+                         const unsigned long long* step = nullptr) {
   DropCfg c;
+  c.step = step;
   unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(stream_id + 1u);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -27,8 +32,12 @@ inline DropCfg make_drop(float p, unsigned long long seed, unsigned int stream_i
   return c;
 }
 
+__device__ __forceinline__ unsigned long long drop_key(const DropCfg& c) {
+  return c.step ? c.key + 0xD1B54A32D192ED03ull * (__ldg(c.step) + 1ull) : c.key;
+}
+
 __device__ __forceinline__ bool drop_keep(const DropCfg& c, unsigned long long idx) {
-  unsigned long long z = c.key + 0x9E3779B97F4A7C15ull * (idx + 1ull);
+  unsigned long long z = drop_key(c) + 0x9E3779B97F4A7C15ull * (idx + 1ull);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z ^= z >> 31;

@@ -258,7 +258,7 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   // per-head masked copies of the input multiply the head-blocked weight (hsg_dropout.cu)
   if (L.drop_attn) {
     float* aexp = st + L.aexp;
-    HSG_TRY(dropout_expand(n_src, P.in_dim, P.H, neighbor, aexp, make_drop(a->attn_p, a->seed, stream_attn(i)), s));
+    HSG_TRY(dropout_expand(n_src, P.in_dim, P.H, neighbor, aexp, make_drop(a->attn_p, a->seed, stream_attn(i), a->seed_dev), s));
     HSG_TRY(hsg_gemm_nt(n_src, ldz, P.H * P.in_dim, aexp, P.H * P.in_dim, st + L.wblk[k], P.H * P.in_dim, zp, ldz,
                         nullptr, nullptr, 0, 0, s));
   } else {
@@ -271,7 +271,7 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   HSG_TRY(hsg_gemm_nt(n_dst, P.d_hid, F, x, F, P.w1, F, hdn, P.d_hid, P.b1, nullptr, 0, HSG_EPI_BIAS | HSG_EPI_RELU, s));
   if (L.drop_ffn) {
     HSG_TRY(hsg_gemm_nt(n_dst, F, P.d_hid, hdn, P.d_hid, P.w2, P.d_hid, r, F, P.b2, nullptr, 0, HSG_EPI_BIAS, s));
-    return layernorm_fwd_dropres(n_dst, F, r, x, make_drop(a->ffn_p, a->seed, stream_ffn(i)), P.gamma, P.beta, out, ln,
+    return layernorm_fwd_dropres(n_dst, F, r, x, make_drop(a->ffn_p, a->seed, stream_ffn(i), a->seed_dev), P.gamma, P.beta, out, ln,
                                  s);
   }
   HSG_TRY(hsg_gemm_nt(n_dst, F, P.d_hid, hdn, P.d_hid, P.w2, P.d_hid, r, F, P.b2, x, F, HSG_EPI_BIAS | HSG_EPI_ADD, s));
@@ -307,7 +307,7 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   // FFN dropout: the residual path keeps dr, the W2 path sees dr * mask / (1-p)
   const float* drm = dr;
   if (L.drop_ffn) {
-    HSG_TRY(dropout_mul((size_t)n_dst * F, dr, sc + b.drm, make_drop(a->ffn_p, a->seed, stream_ffn(i)), s));
+    HSG_TRY(dropout_mul((size_t)n_dst * F, dr, sc + b.drm, make_drop(a->ffn_p, a->seed, stream_ffn(i), a->seed_dev), s));
     drm = sc + b.drm;
   }
   // FFN: dhp = (drm . W2) * relu', dW2 = drm^T hdn, dW1 = dhp^T x, dx = dhp . W1 + dr
@@ -326,7 +326,7 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   int rc;
   if (L.drop_attn) {
     const int KW = P.H * P.in_dim;
-    const DropCfg dc = make_drop(a->attn_p, a->seed, stream_attn(i));
+    const DropCfg dc = make_drop(a->attn_p, a->seed, stream_attn(i), a->seed_dev);
     if (dnb) {
       HSG_TRY(hsg_gemm_nn(n_src, KW, ldz, dzp, ldz, st + L.wblk[k], KW, sc + b.dA, KW, nullptr, 0, 0, s));
       HSG_TRY(dropout_reduce(n_src, P.in_dim, P.H, sc + b.dA, dnb_add, dnb, dc, s));

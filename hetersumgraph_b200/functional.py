@@ -475,6 +475,8 @@ class UpdateLoopFn(torch.autograd.Function):
         args.csc_super, args.csc_word = C.pointer(csc_s), C.pointer(csc_w)
         args.word_feature, args.super_feature = word_feature.data_ptr(), super_feature.data_ptr()
         args.attn_p, args.ffn_p, args.seed = float(cfg.get("attn_p", 0.0)), float(cfg.get("ffn_p", 0.0)), int(cfg.get("seed", 0))
+        sd = cfg.get("seed_dev")                    # device step counter mixed into the dropout key (CUDA-graph replay)
+        args.seed_dev = sd.data_ptr() if sd is not None else None
         pkey = (n_apps, start, n_word, n_super, args.attn_p > 0, args.ffn_p > 0, sig[1:])
         pent = cache.get("plan") if cache is not None else None
         if pent is not None and pent[0] == pkey:
@@ -685,9 +687,39 @@ class FusedAdam:
         self.m, self.v = torch.zeros_like(flat_param), torch.zeros_like(flat_param)
         self.lr, self.betas, self.eps, self.max_grad_norm, self.t = lr, betas, eps, float(max_grad_norm), 0
         self.ws = torch.empty(_lib.load().hsg_adam_workspace_bytes(), dtype=torch.uint8, device=flat_param.device)
+        self.step_state = None          # device-resident step counter (step_dev), created on first use
 
     def step(self):
+        if self.step_state is not None:
+            raise RuntimeError("FusedAdam: the step count lives on the device (step_dev was used); keep using step_dev")
         self.t += 1
         _lib.check(_lib.load().hsg_adam_step(self.p.numel(), _p(self.p), _p(self.g), _p(self.m), _p(self.v), self.lr,
                                              self.betas[0], self.betas[1], self.eps, self.t, self.max_grad_norm,
                                              self.ws.data_ptr(), self.ws.numel(), _st()))
+
+    def device_step_counter(self):
+        """[2] int64 on the device: [0] = completed steps (starts at the host count), [1] = kernel-internal ticket."""
+        if self.step_state is None:
+            self.step_state = torch.tensor([self.t, 0], dtype=torch.int64, device=self.p.device)
+        return self.step_state
+
+    def step_dev(self, zero_grad=True):
+        """The same update with the step number read from (and advanced in) device memory: identical kernel arguments
+        every step, so the launch can be replayed from a CUDA graph.  zero_grad clears the gradient arena after use."""
+        st = self.device_step_counter()
+        _lib.check(_lib.load().hsg_adam_step_dev(self.p.numel(), _p(self.p), _p(self.g), _p(self.m), _p(self.v), self.lr,
+                                                 self.betas[0], self.betas[1], self.eps, st.data_ptr(),
+                                                 1 if zero_grad else 0, self.max_grad_norm, self.ws.data_ptr(),
+                                                 self.ws.numel(), _st()))
+
+
+def embed_gather(ids, table, out=None):
+    """table[ids] for int32 ids (the frozen word-embedding lookup, HiGraph.py:147-148) in one library kernel."""
+    _lib.require_device()
+    n, dim = ids.shape[0], table.shape[1]
+    if ids.dtype != torch.int32:
+        raise TypeError("embed_gather expects int32 ids")
+    if out is None:
+        out = torch.empty(n, dim, dtype=torch.float32, device=table.device)
+    _lib.check(_lib.load().hsg_embed_gather(n, dim, _p(ids), _p(_f32c(table)), _p(out), _st()))
+    return out

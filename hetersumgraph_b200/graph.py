@@ -78,20 +78,32 @@ class DeviceTokenBatch:
         per_graph = np.diff(tb.graph_sent_ptr)
         meta = dict(S=int(S), L=int(L), max_sent=int(per_graph.max()) if tb.n_graphs > 0 else 0,
                     n_doc=int(tb.graph_doc_ptr[-1]) if tb.hdsg else 0, n_doc_tok=int(tb.doc_tok_ptr[-1]) if tb.hdsg else 0,
-                    vocab=int(tb.filter_bitmap.shape[0]) * 32)
+                    vocab=int(tb.filter_bitmap.shape[0]) * 32, n_graphs=int(tb.n_graphs), hdsg=bool(tb.hdsg))
         nbytes = sum(v[1] for v in layout.values())
-        return dict(blob=t, layout=layout, meta=meta), nbytes
+        return dict(blob=t, layout=layout, meta=meta, tb=tb), nbytes
 
     @staticmethod
     def upload(tb: TokenBatch, device="cuda", vocab_size: Optional[int] = None, host=None,
-               filter_bitmap_dev: Optional[torch.Tensor] = None) -> "DeviceTokenBatch":
+               filter_bitmap_dev: Optional[torch.Tensor] = None, blob_dev: Optional[torch.Tensor] = None,
+               copy: bool = True) -> "DeviceTokenBatch":
+        """blob_dev: an existing device byte buffer (>= the blob size) that receives the copy instead of a fresh
+        allocation - fixed addresses for CUDA-graph replay (step_graph.StaticBatchSlot); copy=False only creates the
+        views over it (the caller enqueues the copy itself)."""
         dev = torch.device(device)
         if host is None:
             host, _ = DeviceTokenBatch.host_buffers(tb)
         d = DeviceTokenBatch()
         d.device, d.hdsg, d.n_graphs = dev, bool(tb.hdsg), tb.n_graphs
         d.host_tb = tb                                  # host arrays: the sentence encoder's plan is made from them
-        blob = host["blob"].to(dev, non_blocking=True)                 # the ONE host -> device copy of the batch
+        if blob_dev is None:
+            blob = host["blob"].to(dev, non_blocking=True)             # the ONE host -> device copy of the batch
+        else:
+            nb = host["blob"].numel()
+            if blob_dev.numel() < nb:
+                raise ValueError("blob_dev holds %d bytes, the batch needs %d" % (blob_dev.numel(), nb))
+            blob = blob_dev[:nb]
+            if copy:
+                blob.copy_(host["blob"], non_blocking=True)
         d._blob = blob
         lay, meta = host["layout"], host["meta"]
 

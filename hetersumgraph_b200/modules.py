@@ -72,15 +72,18 @@ def _grad_buffers(mod):
     return out
 
 
-def _dropout_cfg(mods):
-    """(attn_p, ffn_p, seed) of a chain over `mods` (training mode only; the C loop takes one pair of rates)."""
+def _dropout_cfg(mods, fixed_seed=None):
+    """(attn_p, ffn_p, seed) of a chain over `mods` (training mode only; the C loop takes one pair of rates).
+    fixed_seed: callable returning the seed to use instead of drawing a fresh one (device-step-keyed masks)."""
     attn = {m.layer.dropout.p if m.layer.training else 0.0 for m in mods}
     ffn = {m.ffn.dropout.p if m.ffn.training else 0.0 for m in mods}
     if len(attn) > 1 or len(ffn) > 1:
         raise NotImplementedError("word2sent and sent2word must share their dropout rates (the reference builds both "
                                   "from hps.atten_dropout_prob / hps.ffn_dropout_prob, HiGraph.py:57-76)")
     attn_p, ffn_p = attn.pop(), ffn.pop()
-    seed = _next_dropout_seed() if (attn_p > 0.0 or ffn_p > 0.0) else 0
+    seed = 0
+    if attn_p > 0.0 or ffn_p > 0.0:
+        seed = fixed_seed() if fixed_seed is not None else _next_dropout_seed()
     return attn_p, ffn_p, seed
 
 
@@ -312,6 +315,9 @@ class WSWGATUpdateLoop(nn.Module):
     # of a dist.FlatGradArena) from inside the kernels' last stages instead of returning them to autograd, which
     # would launch one add per parameter.  Same arithmetic; requires every parameter to have a `.grad` tensor.
     fuse_grad_accumulation = False
+    # Optional int64 device tensor (FusedAdam.device_step_counter()) mixed into the dropout key at run time, so a
+    # CUDA-graph replay of the step draws fresh masks every step although its kernel arguments never change.
+    seed_dev = None
 
     def _grad_targets(self):
         """[dT, 10 x word2sent, 10 x sent2word] .grad buffers in packed shapes; the views are rebuilt only when a
@@ -335,7 +341,12 @@ class WSWGATUpdateLoop(nn.Module):
         path_model.FusedTrainStep (which drives the same functions without the autograd engine)."""
         graph.set_tfidf_embedding(self._TFembed.weight)
         mods = (self.word2sent, self.sent2word) if self._n_iter > 0 else (self.word2sent,)
-        attn_p, ffn_p, seed = _dropout_cfg(mods)
+        # with a device step counter the host seed is drawn ONCE (a replayed graph cannot take a new kernel argument
+        # per step); the per-step variation comes from the counter
+        fixed = None
+        if self.seed_dev is not None:
+            fixed = lambda: self.__dict__.setdefault("_base_seed", _next_dropout_seed())   # noqa: E731
+        attn_p, ffn_p, seed = _dropout_cfg(mods, fixed)
         pw, ps = _packed_params(self.word2sent), _packed_params(self.sent2word)
         targets = None
         if self.fuse_grad_accumulation and torch.is_grad_enabled():
@@ -344,7 +355,7 @@ class WSWGATUpdateLoop(nn.Module):
         n_apps = 1 + 2 * self._n_iter
         cfg = dict(n_apps=n_apps, start_kind=0, w2s=(lw.num_heads, lw.out_dim, self.word2sent.ffn.d_hid),
                    s2w=(ls.num_heads, ls.out_dim, self.sent2word.ffn.d_hid), grad_targets=targets, attn_p=attn_p,
-                   ffn_p=ffn_p, seed=seed, cache=self.__dict__.setdefault("_arg_cache", {}))
+                   ffn_p=ffn_p, seed=seed, seed_dev=self.seed_dev, cache=self.__dict__.setdefault("_arg_cache", {}))
         if DROPOUT_SEED_LOG is not None and seed:
             DROPOUT_SEED_LOG.append((seed, n_apps, 0))
         return cfg, (self._TFembed.weight,) + pw + ps

@@ -120,7 +120,8 @@ class FusedTrainStep:
             raise RuntimeError("FusedTrainStep needs .grad buffers on every parameter (dist.FlatGradArena)")
         n = self.n_graphs_global if self.n_graphs_global is not None else g.n_graphs
         with torch.no_grad():
-            word_feature = F.embedding(g.word_wid, m._embed.weight)
+            from .functional import embed_gather
+            word_feature = embed_gather(g.word_wid, m._embed.weight)     # own kernel: no stock ATen launch on the step
             super_feature = sent_feature
             if m.hdsg:                                   # HiGraph.py:196-203,231-244
                 from .functional import DocInitFn

@@ -67,6 +67,8 @@ const char* hsg_profile_slot_name(int slot);
 int hsg_profile_read(int slot, int* host_count, float* host_ms);
 /* total number of kernel launches issued by this library since load (always counted) */
 long long hsg_launch_count(void);
+/* cudaMemsetAsync on the given stream (a memset node under stream capture, not a kernel launch) */
+int hsg_memset(void* ptr, int value, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K0  device-side graph builder
@@ -336,6 +338,10 @@ typedef struct {
    * function of (seed, application index, element), regenerated in backward. */
   float attn_p, ffn_p;
   unsigned long long seed;
+  /* optional DEVICE step counter mixed into the mask key at run time (NULL: masks depend on `seed` only).  A CUDA
+   * graph replays identical kernel arguments every step; with this pointer (advanced by hsg_adam_step_dev) every
+   * replay still draws fresh masks, identical in forward and backward of the same step. */
+  const unsigned long long* seed_dev;
 } hsg_loop_args;
 
 typedef struct {
@@ -414,6 +420,16 @@ int hsg_topm(const float* logits, const int32_t* graph_sent_ptr, int n_graphs, i
 size_t hsg_adam_workspace_bytes(void);
 int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
                   float beta2, float eps, int step, float max_grad_norm, void* ws, size_t ws_bytes, void* stream);
+/* The same update with the step number kept on the DEVICE: step_state[0] = number of completed steps (the update uses
+ * step_state[0] + 1 and then advances it), step_state[1] = internal block ticket (must start at 0).  Identical
+ * arguments every step, so the launch can be replayed from a CUDA graph (train.py:131-135 as one captured step).
+ * zero_grad != 0 clears `grad` after use (the optimizer.zero_grad() of train.py:130 folded in).  The same counter is
+ * what hsg_loop_args.seed_dev reads for the dropout masks. */
+int hsg_adam_step_dev(size_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                      float beta2, float eps, unsigned long long* step_state, int zero_grad, float max_grad_norm,
+                      void* ws, size_t ws_bytes, void* stream);
+/* out[i, :] = table[ids[i], :]: the frozen word-embedding lookup of set_wnfeature (HiGraph.py:147-148).  dim % 4 == 0. */
+int hsg_embed_gather(int n, int dim, const int32_t* ids, const float* table, float* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * S2S layer type: SGATLayer / MultiHeadSGATLayer (module/GATLayer.py:49-78, module/GATStackLayer.py:27-44), the
