@@ -159,6 +159,8 @@ _PROTOS = {
     "hsg_wswgat_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "hsg_wswgat_bwd": (C.c_int, [C.POINTER(WswgatBwdArgsC), _P]),
     "hsg_set_bwd_overlap": (C.c_int, [_I]),
+    "hsg_set_side_ctas": (C.c_int, [_I]),
+    "hsg_set_tn_min_rows": (C.c_int, [_I]),
     "hsg_update_loop_plan": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopPlanC)]),
     "hsg_update_loop_fwd": (C.c_int, [C.POINTER(LoopArgsC), _P]),
     "hsg_update_loop_bwd": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopBwdArgsC), _P]),

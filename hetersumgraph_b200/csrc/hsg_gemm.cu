@@ -312,12 +312,21 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
 }
 
 // split of the node dimension for the tcgen05 weight-gradient kernel: 128 x 128 output tiles
-static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows) {
+// cta_budget: how many SMs the product may occupy (0 = all); g_tn_min_rows: shortest reduction range of one split.
+// Both are tuning knobs (hsg_set_side_ctas / hsg_set_tn_min_rows).  Measured on the 32-graph step (profiles/
+// r02c_sweep.jsonl): the step gets monotonically SLOWER when the side-stream weight-gradient products are confined to
+// fewer SMs (0.674 ms with all SMs, 0.746 ms with 72) or cut into fewer, longer splits - the step is bound by the sum of
+// the kernels' work, not by the small-kernel chain those products delay - so the defaults are "all SMs" and 256 rows.
+static std::atomic<int> g_tn_min_rows{256};
+
+static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows, int cta_budget = 0) {
   const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 128);
-  int want = 148 / tiles;   // floor: tiles * splits <= #SMs, ONE wave of the persistent kernel (ceil made 150 > 148)
+  const int sms = (cta_budget > 0 && cta_budget < 148) ? cta_budget : 148;
+  int want = sms / tiles;   // floor: tiles * splits <= budget, ONE wave of the persistent kernel (ceil made 150 > 148)
   if (want < 1) want = 1;
   int r = ceil_div(ceil_div(M, want), 32) * 32;
-  if (r < 256) r = 256;
+  const int min_rows = g_tn_min_rows.load(std::memory_order_relaxed);
+  if (r < min_rows) r = min_rows;
   *rows = r;
   *splits = ceil_div(M, r);
 }
@@ -351,7 +360,7 @@ static int launch_ffma(bool small, bool vec, int M, int N, int K, const float* A
 }
 
 int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-               float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+               float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s, int cta_budget) {
   if (M < 0 || N1 <= 0 || N2 <= 0 || !C || !ws || (M > 0 && (!A || !B))) return HSG_ERR_ARG;
   if (ws_bytes < hsg_gemm_tn_workspace_bytes(M, N1, N2)) return HSG_ERR_WORKSPACE;
   if (M > 0 && is_small(M, N1, N2)) {   // cluster split over the node rows: no partials, no reduce launch
@@ -365,7 +374,7 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
   const bool vec_tc = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
   if (M > 0 && mode != 0 && vec_tc) {
     int rows = 0;
-    tn_plan_tc(M, N1, N2, colsum != nullptr, &nsplit, &rows);
+    tn_plan_tc(M, N1, N2, colsum != nullptr, &nsplit, &rows, cta_budget);
     part_col = part + (size_t)nsplit * N1 * N2;
     LaunchScope ls(SLOT_GEMM_TN, s);
     int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, nsplit, rows, mode == 1, s);
@@ -437,6 +446,12 @@ int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, in
   return launch_ffma<false>(small, vec, M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi, s);
 }
 
+int hsg_set_tn_min_rows(int rows) {
+  if (rows < 32) return HSG_ERR_ARG;
+  g_tn_min_rows.store((rows + 31) & ~31);
+  return HSG_OK;
+}
+
 int hsg_set_gemm_mode(int mode) {
   if (mode < 0 || mode > 2) return HSG_ERR_ARG;
   g_gemm_mode.store(mode);
@@ -464,12 +479,12 @@ size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
 
 int hsg_gemm_tn_acc(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                     float* colsum, int accumulate, void* ws, size_t ws_bytes, void* stream) {
-  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, accumulate ? 1 : 0, (cudaStream_t)stream);
+  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, accumulate ? 1 : 0, (cudaStream_t)stream, 0);
 }
 
 int hsg_gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 float* colsum, void* ws, size_t ws_bytes, void* stream) {
-  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, 0, (cudaStream_t)stream);
+  return gemm_tn_ex(M, N1, N2, A, lda, B, ldb, C, ldc, colsum, ws, ws_bytes, 0, (cudaStream_t)stream, 0);
 }
 
 }  // extern "C"

@@ -56,7 +56,7 @@ int layernorm_fwd_dropres(int N, int D, float* r, const float* resid, DropCfg dc
 
 // C (+)= A^T B, colsum (+)= column sums of A
 int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-               float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+               float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s, int cta_budget = 0);
 
 // dgamma / dbeta (+)= ...
 int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,

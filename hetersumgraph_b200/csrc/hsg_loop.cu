@@ -43,6 +43,19 @@ struct SideRes {
 static SideRes g_side[32];
 static std::mutex g_side_mu;
 static std::atomic<int> g_overlap{-1};
+// SMs the side-stream weight-gradient products may occupy (see tn_plan_tc in hsg_gemm.cu)
+static std::atomic<int> g_side_ctas{-1};
+
+int side_ctas() {
+  int v = g_side_ctas.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HSG_SIDE_CTAS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    g_side_ctas.store(v);
+  }
+  return v;
+}
 
 bool overlap_enabled() {
   int v = g_overlap.load(std::memory_order_relaxed);
@@ -316,8 +329,9 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->fork, 0) != cudaSuccess)
       return HSG_ERR_CUDA;
   }
-  HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, wsw, ws_bytes, acc_ffn, s2));
-  HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2));
+  const int budget = sd ? side_ctas() : 0;
+  HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, wsw, ws_bytes, acc_ffn, s2, budget));
+  HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
   HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
   HSG_TRY(hsg_edge_bwd_prep(n_dst, P.H, P.d, dx, nullptr, sh, g, stat, s));
@@ -341,7 +355,7 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
         return HSG_ERR_CUDA;
     }
     HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr, wsw, ws_bytes,
-                       acc_aug, s2));
+                       acc_aug, s2, budget));
     rc = HSG_OK;
     if (dnb)
       rc = hsg_gemm_nn(n_src, P.in_dim, ldz, dzp, ldz, st + L.waug[k], P.in_dim, dnb, P.in_dim, dnb_add, P.in_dim,
@@ -361,6 +375,12 @@ extern "C" {
 
 int hsg_set_bwd_overlap(int on) {
   g_overlap.store(on ? 1 : 0);
+  return HSG_OK;
+}
+
+int hsg_set_side_ctas(int n) {
+  if (n < 0) return HSG_ERR_ARG;
+  g_side_ctas.store(n);
   return HSG_OK;
 }
 

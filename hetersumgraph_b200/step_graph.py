@@ -240,6 +240,11 @@ class GraphedTrainStep:
         # dropout under replay: masks are keyed by the optimizer's device step counter
         model.loop.seed_dev = opt.device_step_counter()
 
+    def _invalidate(self):
+        """drop every captured graph (a fixed buffer moved, or the cache is full); their memory pool dies with them"""
+        self.graphs.clear()
+        self.pool = None
+
     # -- staging --------------------------------------------------------------------------------------------------
     def _stage_blob(self, slot, host):
         nb = host["blob"].numel()
@@ -247,7 +252,7 @@ class GraphedTrainStep:
         if buf is None or buf.numel() < nb:
             buf = torch.empty(int(nb * StaticBatchSlot.GROW) + 64, dtype=torch.uint8).pin_memory()
             self.stage[slot] = buf
-            self.graphs.clear()
+            self._invalidate()
         buf[:nb].copy_(host["blob"])                  # host memcpy into the fixed pinned staging buffer
         return buf
 
@@ -257,7 +262,7 @@ class GraphedTrainStep:
             cap = int(n * StaticBatchSlot.GROW) + 8
             self.sf_dev = torch.zeros(cap, sent_feature.shape[1], dtype=torch.float32, device=self.dev)
             self.sf_stage = [torch.zeros(cap, sent_feature.shape[1], dtype=torch.float32).pin_memory() for _ in (0, 1)]
-            self.graphs.clear()
+            self._invalidate()
         if sent_feature.is_cuda:
             if sent_feature.data_ptr() != self.sf_dev.data_ptr():
                 self.sf_dev[:n].copy_(sent_feature)   # stream-ordered device copy (outside the graph)
@@ -329,7 +334,7 @@ class GraphedTrainStep:
             if self.capture and self.eager_steps >= 1:
                 # capture (no work is executed), then replay
                 if len(self.graphs) >= self.max_graphs:
-                    self.graphs.clear()
+                    self._invalidate()
                 g = torch.cuda.CUDAGraph()
                 cs = self.cap_stream
                 cs.wait_stream(main)

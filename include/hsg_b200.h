@@ -375,6 +375,11 @@ typedef struct {
  * d_neighbor chain (default on; HSG_BWD_OVERLAP=0 or hsg_set_bwd_overlap(0): everything on the caller's stream).
  * Same kernels and per-buffer order either way: bitwise identical results. */
 int hsg_set_bwd_overlap(int on);
+/* SMs the side-stream weight-gradient products may occupy (0 = all = default, or HSG_SIDE_CTAS).  Tuning knob: on
+ * the 32-graph step fewer SMs measured slower at every setting (profiles/r02c_sweep.jsonl). */
+int hsg_set_side_ctas(int n);
+/* shortest reduction range (rows) one split of a tensor-core weight-gradient product may have (default 256) */
+int hsg_set_tn_min_rows(int rows);
 /* Sizes/offsets for the given dimensions (pointers inside `a` are not read). */
 int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan);
 int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream);
