@@ -131,6 +131,7 @@ _PROTOS = {
     "hsg_get_gemm_mode": (C.c_int, []),
     "hsg_set_gemm_small_flops": (C.c_int, [C.c_double]),
     "hsg_gemm_trace": (C.c_int, [_I, C.POINTER(C.c_ulonglong), _I]),
+    "hsg_gemm_pair_trace": (C.c_int, [_I, C.POINTER(C.c_ulonglong), _I]),
     "hsg_gemm_nt": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _P]),
     "hsg_gemm_nn": (C.c_int, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _I, _P]),
     "hsg_gemm_tn_workspace_bytes": (_Z, [_I, _I, _I]),
@@ -161,6 +162,7 @@ _PROTOS = {
     "hsg_set_bwd_overlap": (C.c_int, [_I]),
     "hsg_set_side_ctas": (C.c_int, [_I]),
     "hsg_set_tn_min_rows": (C.c_int, [_I]),
+    "hsg_set_gemm_pair": (C.c_int, [_I]),
     "hsg_update_loop_plan": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopPlanC)]),
     "hsg_update_loop_fwd": (C.c_int, [C.POINTER(LoopArgsC), _P]),
     "hsg_update_loop_bwd": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopBwdArgsC), _P]),

@@ -54,7 +54,9 @@ struct LaunchScope {
 // prefetch, index loads of parameters) with its predecessor's execution.  Without the launch attribute both
 // instructions are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ void pdl_prologue() {
   pdl_trigger();
   pdl_wait();

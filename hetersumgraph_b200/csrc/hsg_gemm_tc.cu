@@ -23,6 +23,7 @@
 // extra all-ones B column.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -574,7 +575,8 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 static std::mutex g_maps_mu;
 
 static bool make_map(CUtensorMap* m, const float* ptr, int inner, int outer, int ld, int box_outer, bool mn_major) {
-  ReplaceAddrFn rep = replace_fn();
+  static const bool no_cache = getenv("HSG_TMAP_NOCACHE") != nullptr;     // debugging aid: encode every map afresh
+  ReplaceAddrFn rep = no_cache ? nullptr : replace_fn();
   const MapKey key{inner, outer, ld, box_outer, mn_major ? 1 : 0};
   if (rep) {
     std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -599,6 +601,11 @@ static bool make_map(CUtensorMap* m, const float* ptr, int inner, int outer, int
     if (g_maps.size() < 4096) g_maps.emplace(key, *m);
   }
   return ok;
+}
+
+// shared with the CTA-pair kernel (hsg_gemm_tc2.cu)
+bool make_tensor_map(CUtensorMap* m, const float* ptr, int inner, int outer, int ld, int box_outer, bool mn_major) {
+  return make_map(m, ptr, inner, outer, ld, box_outer, mn_major);
 }
 
 struct Operand {

@@ -189,6 +189,8 @@ int hsg_set_gemm_small_flops(double flops);
 /* Profiling aid for the tensor-core pipeline: on = 1/0 arms/disarms a trace of CTA 0 (synchronous call); on < 0 reads
  * up to max_events (event id, k-block counter, SM clock) triples into host_out and returns their number. */
 int hsg_gemm_trace(int on, unsigned long long* host_out, int max_events);
+/* the same for the first cluster of the CTA-pair kernel (events of the peer CTA carry id + 10) */
+int hsg_gemm_pair_trace(int on, unsigned long long* host_out, int max_events);
 /* C[M,N] = A[M,K] . B[N,K]^T  (nn.Linear / Conv1d(k=1) forward).
  * lda may be SMALLER than K: rows of A then overlap (row m = the K floats starting at A + m*lda) - the sentence
  * encoder's convolution windows (hsg_enc_* below) are read that way without an im2col copy.
@@ -378,6 +380,9 @@ int hsg_set_bwd_overlap(int on);
 /* SMs the side-stream weight-gradient products may occupy (0 = all = default, or HSG_SIDE_CTAS).  Tuning knob: on
  * the 32-graph step fewer SMs measured slower at every setting (profiles/r02c_sweep.jsonl). */
 int hsg_set_side_ctas(int n);
+/* 1 (default; HSG_GEMM_PAIR=0): NT / NN tensor-core products run on CTA pairs (tcgen05 cta_group::2, 256-row tiles,
+ * B tile shared by the two SMs); 0: the single-CTA kernel.  Bit-identical results either way. */
+int hsg_set_gemm_pair(int on);
 /* shortest reduction range (rows) one split of a tensor-core weight-gradient product may have (default 256) */
 int hsg_set_tn_min_rows(int rows);
 /* Sizes/offsets for the given dimensions (pointers inside `a` are not read). */

@@ -26,7 +26,13 @@ TOL = 1e-5
 def nerr(a, b):
     a = torch.as_tensor(a).detach().cpu().double()
     b = torch.as_tensor(b).detach().cpu().double()
-    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    e = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    if os.environ.get("HSG_DEBUG_NERR") and e > 1e-2 and a.dim() == 2:      # where are the wrong elements?
+        bad = (a - b).abs() > 1e-2 * float(b.abs().max())
+        rows, cols = bad.any(1).nonzero().flatten(), bad.any(0).nonzero().flatten()
+        print("NERR", tuple(a.shape), e, "nbad", int(bad.sum()), "rows", rows[:8].tolist(), rows[-4:].tolist(), len(rows),
+              "cols", cols[:8].tolist(), cols[-4:].tolist(), len(cols), "nan", int(torch.isnan(a).sum()))
+    return e
 
 
 def oracle_batch(exs, hdsg):
@@ -861,3 +867,64 @@ def test_weight_gradient_product_stays_in_tolerance_for_long_reductions(M, N1, N
     assert nerr(cs, ref_cs) <= TOL, nerr(cs, ref_cs)
     C2, cs2 = gemm_tn(A, B, want_colsum=True)
     assert torch.equal(Cm, C2) and torch.equal(cs, cs2)          # deterministic
+
+
+@pytest.mark.parametrize("M,N,K", [(11817, 512, 300), (11817, 300, 512), (5000, 72, 300), (700, 300, 72),
+                                   (513, 112, 300), (4099, 304, 64), (12001, 64, 512)])
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+def test_cta_pair_gemm_is_bit_identical_to_single_cta(M, N, K, mode):
+    """hsg_gemm_tc2.cu (tcgen05 cta_group::2: 256-row tiles over a CTA pair, B tile shared between the two SMs) against
+    the single-CTA kernel: same hi/lo split, same k order, same accumulators -> identical bits; and both against
+    float64.  Shapes: the FFN / projection products of the 32-graph step, ragged edges, odd tile counts."""
+    from hetersumgraph_b200 import _lib
+    lib = _lib.load()
+    prev = hb.get_gemm_mode()
+    hb.set_gemm_mode(mode)
+    try:
+        torch.manual_seed(3)
+        A = torch.randn(M, K, device="cuda")
+        B = torch.randn(N, K, device="cuda")
+        Bn = torch.randn(K, N, device="cuda")
+        bias = torch.randn(N, device="cuda")
+        R = torch.randn(M, N, device="cuda")
+        outs = []
+        for pair in (0, 1):
+            _lib.check(lib.hsg_set_gemm_pair(pair))
+            outs.append((gemm_nt(A, B), gemm_nt(A, B, bias=bias, epi=3), gemm_nt(A, B, bias=bias, R=R, epi=5),
+                         gemm_nn(A, Bn), gemm_nn(A, Bn, R=R, epi=8), gemm_nn(A, Bn, R=R, epi=4)))
+        for x, y in zip(*outs):
+            assert torch.equal(x, y)
+        tol = GEMM_TOL[mode]
+        assert nerr(outs[1][0], A.double() @ B.double().t()) <= tol
+        assert nerr(outs[1][3], A.double() @ Bn.double()) <= tol
+    finally:
+        _lib.check(lib.hsg_set_gemm_pair(1))
+        hb.set_gemm_mode(prev)
+
+
+@pytest.mark.parametrize("M,N1,N2", [(4099, 300, 512), (11817, 512, 300), (2000, 72, 300)])
+@pytest.mark.parametrize("colsum", [False, True])
+def test_weight_gradient_workspace_is_large_enough(M, N1, N2, colsum):
+    """hsg_gemm_tn_workspace_bytes must cover BOTH plans of the tensor-core product: without the column-sum column there
+    are fewer column tiles and therefore more splits (4 099 x 300 x 512: 12 against 9).  Round 1 sized for the
+    column-sum plan only and the other plan's partials ran past the buffer.  Here the workspace is exactly the advertised
+    size with a sentinel-filled guard behind it."""
+    import ctypes as C
+    from hetersumgraph_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(5)
+    A = torch.randn(M, N1, device="cuda")
+    B = torch.randn(M, N2, device="cuda")
+    nbytes = int(lib.hsg_gemm_tn_workspace_bytes(M, N1, N2))
+    guard = 8 << 20
+    buf = torch.full((nbytes + guard,), 0x5A, dtype=torch.uint8, device="cuda")
+    Cm = torch.empty(N1, N2, device="cuda")
+    cs = torch.empty(N1, device="cuda") if colsum else None
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hsg_gemm_tn(M, N1, N2, A.data_ptr(), N1, B.data_ptr(), N2, Cm.data_ptr(), N2,
+                               cs.data_ptr() if colsum else None, buf.data_ptr(), nbytes, C.c_void_p(st)))
+    torch.cuda.synchronize()
+    assert bool((buf[nbytes:] == 0x5A).all()), "the product wrote past its workspace"
+    assert nerr(Cm, A.double().t() @ B.double()) <= 3e-6
+    if colsum:
+        assert nerr(cs, A.double().sum(0)) <= 3e-6
