@@ -507,9 +507,7 @@ def run_ours(args):
         scaling_legs, grad_par = scaling_legs_run(args, dev, rank, world, dist, timed)
 
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+        _shutdown(dist, (gs_res, gs_e2e))
         return
 
     stress = None
@@ -581,9 +579,31 @@ def run_ours(args):
                                   "note": "informational (eager path), tolerance class 2e-2; not the headline"},
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    _shutdown(dist, (gs_res, gs_e2e))
+
+
+def _shutdown(dist, graphed_steps):
+    """End of a rank.  The captured step graphs contain ncclAllReduce nodes: they are destroyed and the device is drained
+    BEFORE the process group goes away (tearing the communicator down under live graphs left both ranks hanging in
+    destroy_process_group on the 2-GPU box: r02m), and the teardown itself is bounded - a rank that cannot finish it
+    within 20 s exits anyway, its line is already printed."""
+    sys.stdout.flush()
+    for gs in graphed_steps:
+        gs._invalidate()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    if dist is None:
+        return
+    dist.barrier()
+    torch.cuda.synchronize()
+    import threading
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def scaling_legs_run(args, dev, rank, world, dist, timed):
@@ -634,35 +654,9 @@ def scaling_legs_run(args, dev, rank, world, dist, timed):
 
     legs = {"strong_4096": leg(4096, 5), "weak_1024_per_gpu": leg(1024 * world, 5)}
 
-    # gradient parity on a 256-graph global batch
-    n_par = 256
-    exs_all = base[:n_par]
-    sf_all = torch.randn(sum(e.n_sent for e in exs_all) + 8, 64, generator=torch.Generator().manual_seed(11))
-    # sentence rows follow the examples: give every example its own slice so shards see the same features
-    offs = np.concatenate([[0], np.cumsum([e.n_sent for e in exs_all])])
-
-    def run(exs_sub, idxs):
-        tbs = syn.pack_token_batch(exs_sub)
-        order = list(tbs.order) if getattr(tbs, "order", None) is not None else list(range(len(exs_sub)))
-        rows = np.concatenate([np.arange(offs[idxs[j]], offs[idxs[j]] + exs_sub[j].n_sent) for j in order]) \
-            if len(exs_sub) else np.zeros(0, np.int64)
-        batch = HeteroBatch.from_token_batch(tbs, dev)
-        m, ar, _ = model_pair()
-        FusedTrainStep(m, n_par)(batch, sf_all[rows].to(dev))
-        return ar.flat.clone()
-
-    sh = shard_indices([e.n_sent for e in exs_all], [float(sum(len(x) for x in e.w2s)) for e in exs_all], world)
-    g_shard = run([exs_all[i] for i in sh[rank]], sh[rank])
-    if dist is not None:
-        dist.all_reduce(g_shard)
-    par = None
-    if rank == 0:
-        g_full = run(exs_all, list(range(n_par)))
-        err = float((g_shard - g_full).abs().max() / g_full.abs().max())
-        par = {"global_graphs": n_par, "ranks": world, "normalised_max_error": err, "bound": 1e-6,
-               "ok": bool(err <= 1e-6),
-               "what": "all-reduced flat gradient arena of the N shards (dist.shard_indices) vs rank 0 running the whole "
-                       "global batch alone, same parameters and sent_feature rows"}
+    # gradient parity on a 256-graph global batch (base[:256] is the same seeded batch)
+    from hetersumgraph_b200.dist import gradient_parity
+    par = gradient_parity(rank, world, dev, (lambda t: dist.all_reduce(t)) if dist is not None else None, 256, seed=3)
     return legs, par
 
 

@@ -388,6 +388,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
+      if (warp == 8 && lane == 0) trace(7, tl, rank);
       // Bias slice in shared memory, one copy per accumulator set: every epilogue warp writes the same values.  A warp
       // reaches this point for tile tl only after ALL epilogue warps released set `acc` for tile tl - 2, so nobody
       // still reads the copy being overwritten.
@@ -471,6 +472,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_rank(bar_tempty + 8 * acc, 0);              // hand the set back to the leader
+      if (warp == 8 && lane == 0) trace(8, tl, rank);
     }
     if (lane == 0) bulk_wait_all();                         // every store of this warp has reached global memory
     __syncwarp();

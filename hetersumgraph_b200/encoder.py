@@ -18,8 +18,8 @@ What runs where
     on chip for the whole sequence) + the library's GEMMs for the input products and all weight gradients -
     `LstmFn`.  Every graph's sentences are contiguous rows, so the pad / pack / unpack / per-graph Python loops of
     HiGraph.py:136-141,247-255 disappear.  `nn.LSTM` is kept as the PARAMETER CONTAINER (same state_dict keys and
-    initialisation as the reference); `use_cudnn_lstm=True` runs torch's own LSTM on a PackedSequence instead (the
-    call the reference makes; library code, for comparison only).
+    initialisation as the reference); its own forward (cuDNN) is never called by the package - the comparison with
+    torch's LSTM on a PackedSequence (the call the reference makes) lives in tests/test_gpu_encoder.py.
 No CPU fallback: every custom op raises without the sm_100a library.
 """
 import ctypes as C
@@ -88,7 +88,7 @@ class EncoderPlan:
 
     def _packed_order(self):
         """(batch_sizes on the host, perm, inv_perm): the time-major order of a PackedSequence over the per-graph sentence
-        lists - only the use_cudnn_lstm comparison path needs it, so it is built on first use."""
+        lists - only the comparison with torch's own LSTM in the tests needs it, so it is built on first use."""
         if self._packed is None:
             ptr, counts, S = self._ptr, self._counts, self.n_sent
             if np.any(counts[1:] > counts[:-1]):
@@ -388,8 +388,6 @@ class SentenceEncoder(nn.Module):
             raise NotImplementedError("the n-gram encoder assumes the frozen word embedding of the reference default "
                                       "(train.py:340-342)")
         self.sent_max_len = sent_max_len
-        self.lstm_allow_tf32 = False
-        self.use_cudnn_lstm = False
         self.sent_pos_embed = nn.Embedding.from_pretrained(sinusoid_table(doc_max_timesteps + 1, word_emb_dim,
                                                                           padding_idx=0), freeze=True)
         self.cnn_proj = nn.Linear(word_emb_dim, n_feature_size)
@@ -426,17 +424,11 @@ class SentenceEncoder(nn.Module):
     def lstm_feature(self, plan: EncoderPlan, ngram):
         """LSTM over every graph's sentence sequence (HiGraph.py:135-141), rows in batch order."""
         lstm = self.lstm
-        if not self.use_cudnn_lstm:
-            p_drop = float(lstm.dropout) if (self.training and lstm.num_layers > 1) else 0.0
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0.0 else 0     # CPU generator: no sync
-            cfg = (plan.n_graphs, lstm.hidden_size, lstm.num_layers, 2 if lstm.bidirectional else 1, p_drop, seed,
-                   self._targets(lstm._flat_weights))
-            return LstmFn.apply(ngram, plan.graph_sent_ptr, cfg, *lstm._flat_weights)
-        packed = torch.nn.utils.rnn.PackedSequence(ngram.index_select(0, plan.perm), plan.batch_sizes)
-        # cuDNN's RNN would otherwise run its products in TF32 (error class 1e-3, outside the fp32 bound of 1e-5)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.lstm_allow_tf32):
-            out, _ = self.lstm(packed)
-        return out.data.index_select(0, plan.inv_perm)
+        p_drop = float(lstm.dropout) if (self.training and lstm.num_layers > 1) else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0.0 else 0     # CPU generator: no sync
+        cfg = (plan.n_graphs, lstm.hidden_size, lstm.num_layers, 2 if lstm.bidirectional else 1, p_drop, seed,
+               self._targets(lstm._flat_weights))
+        return LstmFn.apply(ngram, plan.graph_sent_ptr, cfg, *lstm._flat_weights)
 
     def forward(self, plan: EncoderPlan):
         return self.encode(plan)

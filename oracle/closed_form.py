@@ -17,6 +17,11 @@ import torch
 import torch.nn.functional as F
 
 LEAKY_SLOPE = 0.01
+# test hook: when set to a list, every multi_head_cf call appends the smallest |pre-activation| of leaky_relu over its
+# edge logits.  leaky_relu has a kink at 0: a logit within rounding distance of 0 takes slope 1 in one arithmetic and
+# 0.01 in another, which no tolerance on the OUTPUT can absorb in the gradients; tests use this to know whether the
+# batch at hand contains such a logit.
+KINK_LOG = None
 
 
 def pack_layer(params, prefix, n_heads):
@@ -58,7 +63,10 @@ def multi_head_cf(h_src, n_dst, indptr, src, bins, extra_cnt, W, Wf, bf, a, T, a
     p = (z * a[:, :d].unsqueeze(0)).sum(-1)                                   # [N_src, H]
     dfeat = (T @ Wf.t() + bf).reshape(-1, H, d)                               # [10, H, d]
     q = (dfeat * a[:, 2 * d:].unsqueeze(0)).sum(-1)                           # [10, H]
-    e = F.leaky_relu(p[src] + q[bins], LEAKY_SLOPE)                           # [E, H]
+    pre_e = p[src] + q[bins]
+    if KINK_LOG is not None and pre_e.numel():
+        KINK_LOG.append(float(pre_e.detach().abs().min()))
+    e = F.leaky_relu(pre_e, LEAKY_SLOPE)                                      # [E, H]
     neg = torch.full((n_dst, H), float("-inf"), dtype=e.dtype)
     m = neg.scatter_reduce(0, dst.reshape(-1, 1).expand(-1, H), e, "amax", include_self=True)
     m = torch.where(extra > 0, torch.clamp(m, min=0.0), m)

@@ -38,7 +38,7 @@ def main():
     tr = {(int(e), int(it)): int(c) for e, it, c in ev if c}
     t0 = min(tr.values())
     names = {1: "tma0", 11: "tma1", 4: "land0", 14: "land1", 5: "cdone0", 15: "cdone1", 6: "arr0", 16: "arr1", 2: "mma_go",
-             3: "mma_commit"}
+             3: "mma_commit", 7: "epi_go0", 8: "epi_end0", 17: "epi_go1", 18: "epi_end1"}
     rows = []
     for it in range(0, 48):
         r = {"it": it}

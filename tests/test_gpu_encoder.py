@@ -166,14 +166,20 @@ def test_lstm_kernels_match_oracle(H, n_in, layers, bidir, lens):
         LstmFn.overlap_weight_grads = True
 
 
-def test_cudnn_lstm_option_agrees_with_kernels():
-    """use_cudnn_lstm=True (torch.nn.LSTM on a PackedSequence, the call the reference makes) gives the same features."""
+def test_lstm_kernels_agree_with_torch_lstm_on_a_packed_sequence():
+    """torch.nn.LSTM on a PackedSequence (cuDNN; the call the reference makes, HiGraph.py:136-141) gives the same LSTM
+    features as the package's recurrence kernels.  The library call lives HERE: the package has no cuDNN path."""
     z, params = fx.load_encoder_fixture(GOLD, "encoder_small.npz")
     enc = make_encoder(params, [int(v) for v in z["dims"]])
     plan = EncoderPlan(z["tokens"], z["graph_sent_ptr"], "cuda")
-    a = enc(plan)
-    enc.use_cudnn_lstm = True
-    b = enc(plan)
+    with torch.no_grad():
+        ngram = enc.ngram(plan)
+        a = enc.lstm_feature(plan, ngram)
+        packed = torch.nn.utils.rnn.PackedSequence(ngram.index_select(0, plan.perm), plan.batch_sizes)
+        # cuDNN's RNN would otherwise run its products in TF32 (error class 1e-3, outside the fp32 bound of 1e-5)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            out, _ = enc.lstm(packed)
+        b = out.data.index_select(0, plan.inv_perm)
     assert nerr(a, b) <= TOL
 
 

@@ -241,6 +241,7 @@ def test_bitwise_determinism():
 
 # ----------------------------------------------------------------------------- configs vs closed-form oracle
 GRAD_TOL = {"fp32": TOL, "tf32x3": TOL, "tf32": 5e-2}
+KINK_EPS = 5e-6     # |edge logit| below this: fp32 (3xTF32 products, error ~1e-6 of max|p|) may sit on the other side of 0
 FWD_TOL = {"fp32": TOL, "tf32x3": TOL, "tf32": 2e-2}
 
 
@@ -261,6 +262,69 @@ def test_large_batch_gradients_match_float64_closed_form():
     scratch/large_batch_debug.py); that is a property of the function, not of the kernels."""
     seed = int(os.environ.get("HSG_LARGE_BATCH_SEED", "7"))
     _check_against_closed_form("cnndm", False, 1, 160, seed, "tf32x3", torch.float64)
+
+
+@pytest.mark.parametrize("seed", [5, 6, 8, 9])
+def test_large_batch_gradients_other_seeds_with_kink_allowance(seed):
+    """The same 160-graph comparison on the batches the strict test above does not use.  Seeds 5, 6 and 8 contain an
+    edge logit within rounding distance of leaky_relu's kink (see above).  The fp64 oracle reports its smallest
+    |logit| (closed_form.KINK_LOG): a batch with none below KINK_EPS is compared at the full 1e-5 everywhere; otherwise
+    the forward must still hold 1e-5, at most `kink_rows` input-gradient rows may exceed 1e-5 (each <= 1e-3) and the
+    parameter gradients, all of which that edge feeds through dp / dq, are bounded at 1e-3."""
+    _check_against_closed_form("cnndm", False, 1, 160, seed, "tf32x3", torch.float64, kink_rows=2)
+
+
+@pytest.mark.parametrize("shape,hdsg,n_iter,seed", [("cnndm", False, 1, 0), ("nyt50", False, 3, 1),
+                                                    ("multinews", True, 1, 2)])
+def test_baseline_32_graph_configs_against_bucketed_port_without_device_masks(shape, hdsg, n_iter, seed):
+    """BASELINE.json's three 32-graph configurations, whole update loop, against `oracle/wswgat_ref.update_loop` - the
+    per-head, degree-bucketed port that is pinned bit-identically to the unmodified reference - evaluated on its OWN
+    ReLU branches (no device masks).  The forward is continuous in the pre-activations, so it must hold 1e-5 as is.
+    A gradient differs wherever the two arithmetics put an FFN unit with |pre-activation| ~ 1e-6 on different sides of
+    0; those units are counted separately (closed form with and without the device's active set) and the mask-free
+    gradient comparison is strict when there is none, bounded by 1e-3 otherwise; the strict all-gradient comparison on
+    the device's active set at this size follows."""
+    import hetersumgraph_b200.functional as fn
+    exs = syn.make_examples(32, shape, seed=seed, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
+    bg, _ = oracle_batch(exs, hdsg)
+    torch.manual_seed(4321)
+    m = hb.WSWGATUpdateLoop(n_iter=n_iter, atten_dropout_prob=0.0, ffn_dropout_prob=0.0)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    w, s = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+    cw, cs = torch.randn(batch.n_word, 300), torch.randn(batch.n_super, 64)
+    wg, sg = w.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    fn.RELU_MASK_CAPTURE = []
+    try:
+        gw, gs = m(batch, wg, sg)
+        masks = fn.RELU_MASK_CAPTURE
+    finally:
+        fn.RELU_MASK_CAPTURE = None
+    ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
+    wc, sc = w.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    ow, os_ = wr.update_loop(bg, wc, sc, params, n_iter)
+    assert nerr(gw, ow) <= TOL and nerr(gs, os_) <= TOL
+    ((ow * cw).sum() + (os_ * cs).sum()).backward()
+    # units on which the device and the oracle choose different ReLU branches
+    flips = []
+    with torch.no_grad():
+        cf.update_loop_cf(gb.derive_csc(bg), w, s, {k: v.detach() for k, v in params.items()}, n_iter, masks=masks,
+                          flips=flips)
+    n_flip, n_unit, pre = sum(f[0] for f in flips), sum(f[1] for f in flips), max(f[2] for f in flips)
+    assert n_flip <= 2e-5 * n_unit + 1 and pre <= 1e-5, (n_flip, n_unit, pre)
+    gtol = TOL if n_flip == 0 else 1e-3
+    assert nerr(wg.grad, wc.grad) <= gtol and nerr(sg.grad, sc.grad) <= gtol, (n_flip, nerr(wg.grad, wc.grad))
+    assert nerr(m._TFembed.weight.grad, params["_TFembed.weight"].grad) <= gtol
+    for pre_ in ("word2sent", "sent2word"):
+        mod = getattr(m, pre_)
+        H = mod.layer.num_heads
+        fc = torch.cat([params["%s.layer.heads.%d.fc.weight" % (pre_, k)].grad for k in range(H)], 0)
+        assert nerr(mod.layer.fc_weight.grad, fc) <= gtol, (pre_, n_flip)
+        assert nerr(mod.ffn.w_1.weight.grad, params[pre_ + ".ffn.w_1.weight"].grad) <= gtol, (pre_, n_flip)
+        assert nerr(mod.ffn.w_2.weight.grad, params[pre_ + ".ffn.w_2.weight"].grad) <= gtol, (pre_, n_flip)
+    # strict: forward and EVERY gradient on the device's active set, at the 32-graph size
+    _check_against_closed_form(shape, hdsg, n_iter, 32, seed, "tf32x3", torch.float32)
 
 
 def _check_against_closed_form(shape, hdsg, n_iter, n, seed, gemm_mode, oracle_dtype, kink_rows=0):
@@ -294,8 +358,15 @@ def _check_against_closed_form(shape, hdsg, n_iter, n, seed, gemm_mode, oracle_d
     ((gw * cw.cuda()).sum() + (gs * cs.cuda()).sum()).backward()
     wc, sc = w.clone().to(oracle_dtype).requires_grad_(True), s.clone().to(oracle_dtype).requires_grad_(True)
     flips = []
-    ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter, masks=masks, flips=flips)
+    cf.KINK_LOG = []
+    try:
+        ow, os_ = cf.update_loop_cf(csc, wc, sc, params, n_iter, masks=masks, flips=flips)
+        min_logit = min(cf.KINK_LOG) if cf.KINK_LOG else 1.0
+    finally:
+        cf.KINK_LOG = None
     ((ow * cw.to(oracle_dtype)).sum() + (os_ * cs.to(oracle_dtype)).sum()).backward()
+    if kink_rows and min_logit > KINK_EPS:
+        kink_rows = 0          # no edge logit near leaky_relu's kink in this batch: everything at full tolerance
     n_flip, n_unit = sum(f[0] for f in flips), sum(f[1] for f in flips)
     pre_at_flip = max(f[2] for f in flips)
     limit = {"fp32": (2e-5, 1e-5), "tf32x3": (2e-5, 1e-5), "tf32": (5e-3, 2e-2)}[gemm_mode]
@@ -327,9 +398,10 @@ def _check_against_closed_form(shape, hdsg, n_iter, n, seed, gemm_mode, oracle_d
             bad = d > gtol
             assert int(bad.sum()) <= kink_rows and float(d.max()) <= 1e-3, (name, int(bad.sum()), float(d.max()))
             continue
-        if kink_rows and (name == "TFembed" or name.endswith((".feat_fc", ".attn_fc", ".feat_fc_bias"))):
-            # the same edge enters these through dq / dp: sums that largely cancel (softmax-shift directions), so one
-            # flipped slope shows at ~1e-4 of the tensor's maximum; bounded, not compared at full tolerance
+        if kink_rows:
+            # the flipped slope of that edge changes dp of its source row and dq of its TF-IDF box by a factor 100, and
+            # through them every parameter gradient (seen: 1e-4 of the tensor's maximum on fc / feat_fc / attn_fc /
+            # TFembed, less on the FFN weights): bounded, not compared at full tolerance
             assert nerr(got, ref) <= 1e-3, (name, nerr(got, ref), gemm_mode)
             continue
         assert nerr(got, ref) <= gtol, (name, nerr(got, ref), gemm_mode)
