@@ -162,6 +162,7 @@ _PROTOS = {
     "hsg_set_bwd_overlap": (C.c_int, [_I]),
     "hsg_set_side_ctas": (C.c_int, [_I]),
     "hsg_set_tn_min_rows": (C.c_int, [_I]),
+    "hsg_set_tn_item_rows": (C.c_int, [_I]),
     "hsg_set_gemm_pair": (C.c_int, [_I]),
     "hsg_update_loop_plan": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopPlanC)]),
     "hsg_update_loop_fwd": (C.c_int, [C.POINTER(LoopArgsC), _P]),
@@ -185,6 +186,9 @@ _PROTOS = {
     "hsg_dropout_mask": (C.c_int, [_Z, C.c_float, C.c_ulonglong, C.c_uint, _P, _P]),
     "hsg_layernorm_fwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_layernorm_bwd_workspace_bytes": (_Z, [_I, _I]),
+    "hsg_ffn_rows_ok": (C.c_int, [_I, _I, _I]),
+    "hsg_ffn_rows_fwd": (C.c_int, [_I, _I, _I] + [_P] * 12),
+    "hsg_ffn_rows_bwd": (C.c_int, [_I, _I, _I] + [_P] * 12 + [_I, _P, _Z, _P]),
     "hsg_layernorm_bwd": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }
 
@@ -236,11 +240,12 @@ def require_device():
     _DEVICE_OK = True
 
 
-GEMM_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+GEMM_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3}
 
 
 def set_gemm_mode(mode):
-    """'fp32' (FFMA), 'tf32x3' (tcgen05, fp32-parity, default) or 'tf32' (tcgen05, single pass)."""
+    """'fp32' (FFMA), 'tf32x3' (tcgen05, fp32-parity, default), 'tf32' (tcgen05, single pass) or 'bf16' (tcgen05
+    kind::f16 on bf16-rounded operands, fp32 accumulation: the 2e-2 tolerance class)."""
     check(load().hsg_set_gemm_mode(GEMM_MODES[mode] if isinstance(mode, str) else int(mode)))
 
 

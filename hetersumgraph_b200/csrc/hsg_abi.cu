@@ -11,7 +11,7 @@ namespace hsg {
 static const char* kSlotNames[SLOT_COUNT] = {
     "build_count", "build_scan", "build_fill", "attn_prep_fwd", "attn_prep_bwd", "gemm_nt",
     "gemm_nn", "gemm_tn", "gemm_tn_reduce", "edge_fwd", "edge_bwd_prep", "edge_bwd",
-    "edge_bwd_dq", "layernorm_fwd", "layernorm_bwd", "layernorm_bwd_reduce", "head", "adam", "dropout", "s2s", "encoder", "lstm"};
+    "edge_bwd_dq", "layernorm_fwd", "layernorm_bwd", "layernorm_bwd_reduce", "head", "adam", "dropout", "s2s", "encoder", "lstm", "ffn_rows"};
 
 struct EventPair {
   cudaEvent_t a, b;

@@ -31,6 +31,7 @@ enum Slot {
   SLOT_S2S,
   SLOT_ENCODER,
   SLOT_LSTM,
+  SLOT_FFN_ROWS,
   SLOT_COUNT
 };
 

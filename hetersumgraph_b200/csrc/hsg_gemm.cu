@@ -21,7 +21,7 @@ int gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ld
 int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* R,
             int ldr, int epi, int precise, cudaStream_t s);
 int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* part, float* part_col,
-            int splits, int rows_per_split, int precise, cudaStream_t s);
+            int splits, int rows_per_split, int precise, cudaStream_t s, bool cta_per_item = false);
 int trace_ctl(int on, unsigned long long* host_out, int max_events);
 }  // namespace tc
 
@@ -50,6 +50,9 @@ static bool pair_enabled(int M) {
 
 // 0: FFMA exact fp32, 1: tcgen05 3xTF32 (fp32-parity, default), 2: tcgen05 single-pass TF32
 static std::atomic<int> g_gemm_mode{1};
+// arithmetic selector of the tensor-core kernels: 1 = 3xTF32 (fp32 parity), 0 = one TF32 pass, 2 = bf16 operands
+// (kind::f16, fp32 accumulation)
+static inline int tc_arith(int mode) { return mode == 1 ? 1 : (mode == 3 ? 2 : 0); }
 
 
 constexpr int BN = 64, BK = 16;
@@ -343,7 +346,35 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
 // the kernels' work, not by the small-kernel chain those products delay - so the defaults are "all SMs" and 256 rows.
 static std::atomic<int> g_tn_min_rows{256};
 
+// Short work items (hsg_set_tn_item_rows / HSG_TN_ITEM_ROWS, 0 = off): when the whole reduction fits in <= 48 splits of
+// `item_rows` rows, the product is cut into tiles x splits items of that length and launched with ONE CTA PER ITEM instead
+// of one persistent CTA per SM.  The weight-gradient products run on the low-priority side stream next to the serial
+// dx -> edge-backward chain; a persistent CTA keeps its SM (and all of its shared memory) for the whole product, so the
+// short kernels of that chain waited 40-50 us for an SM (CUPTI timeline r02t); with short items an SM is handed back
+// every few microseconds and the block scheduler gives it to the higher-priority stream first.
+static std::atomic<int> g_tn_item_rows{-1};
+static int tn_item_rows() {
+  int v = g_tn_item_rows.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("HSG_TN_ITEM_ROWS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    v = (v + 31) & ~31;
+    g_tn_item_rows.store(v);
+  }
+  return v;
+}
+static bool tn_short_items(int M) {
+  const int r = tn_item_rows();
+  return r > 0 && ceil_div(M, r) <= 48;
+}
+
 static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows, int cta_budget = 0) {
+  if (tn_short_items(M)) {
+    *rows = tn_item_rows();
+    *splits = ceil_div(M, *rows);
+    return;
+  }
   const int tiles = ceil_div(N1, 128) * ceil_div(N2 + (colsum ? 1 : 0), 128);
   const int sms = (cta_budget > 0 && cta_budget < 148) ? cta_budget : 148;
   int want = sms / tiles;   // floor: tiles * splits <= budget, ONE wave of the persistent kernel (ceil made 150 > 148)
@@ -368,6 +399,9 @@ static int tn_splits(int M, int N1, int N2) {
 static bool is_small(int M, int N, int K) {
   return 2.0 * (double)M * (double)N * (double)K < g_small_flops.load(std::memory_order_relaxed);
 }
+
+bool gemm_is_small(int M, int N, int K) { return is_small(M, N, K); }
+
 
 template <bool B_NT>
 static int launch_ffma(bool small, bool vec, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
@@ -402,7 +436,8 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
     if ((size_t)nsplit * ((size_t)N1 * N2 + N1) * sizeof(float) > ws_bytes) return HSG_ERR_WORKSPACE;
     part_col = part + (size_t)nsplit * N1 * N2;
     LaunchScope ls(SLOT_GEMM_TN, s);
-    int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, nsplit, rows, mode == 1, s);
+    int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, nsplit, rows, tc_arith(mode), s,
+                         tn_short_items(M));
     if (rc) return rc;
   } else if (M > 0) {
     int rows = ceil_div(M, nsplit);
@@ -449,8 +484,8 @@ int hsg_gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, in
   const int mode = g_gemm_mode.load(std::memory_order_relaxed);
   const bool small = is_small(M, N, K);
   if (mode != 0 && !small && vec && (ldc % 4 == 0)) {
-    if (pair_enabled(M)) return tc2::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, mode == 1, s);
-    return tc::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, mode == 1, s);
+    if (pair_enabled(M)) return tc2::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, tc_arith(mode), s);
+    return tc::gemm_nt(M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, tc_arith(mode), s);
   }
   return launch_ffma<true>(small, vec, M, N, K, A, lda, B, ldb, C, ldc, bias, R, ldr, epi, s);
 }
@@ -469,14 +504,20 @@ int hsg_gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, in
   const int mode = g_gemm_mode.load(std::memory_order_relaxed);
   const bool small = is_small(M, N, K);
   if (mode != 0 && !small && vec && (ldc % 4 == 0)) {
-    if (pair_enabled(M)) return tc2::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, mode == 1, s);
-    return tc::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, mode == 1, s);
+    if (pair_enabled(M)) return tc2::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, tc_arith(mode), s);
+    return tc::gemm_nn(M, N, K, A, lda, B, ldb, C, ldc, R, ldr, epi, tc_arith(mode), s);
   }
   return launch_ffma<false>(small, vec, M, N, K, A, lda, B, ldb, C, ldc, nullptr, R, ldr, epi, s);
 }
 
 int hsg_set_gemm_pair(int on) {
   g_pair.store(on ? 1 : 0);
+  return HSG_OK;
+}
+
+int hsg_set_tn_item_rows(int rows) {
+  if (rows < 0) return HSG_ERR_ARG;
+  g_tn_item_rows.store((rows + 31) & ~31);
   return HSG_OK;
 }
 
@@ -487,7 +528,7 @@ int hsg_set_tn_min_rows(int rows) {
 }
 
 int hsg_set_gemm_mode(int mode) {
-  if (mode < 0 || mode > 2) return HSG_ERR_ARG;
+  if (mode < 0 || mode > 3) return HSG_ERR_ARG;
   g_gemm_mode.store(mode);
   return HSG_OK;
 }

@@ -22,6 +22,7 @@
 // ReLU / residual / ReLU-mask before the global store.  Weight-gradient column sums come for free from an
 // extra all-ones B column.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -82,6 +83,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
+// bf16 x bf16 -> fp32 (kind::f16), K = 16 per instruction
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -108,6 +120,55 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// bf16 mode: fp32 accumulate, bf16 x bf16, both operands K-major (the converters transpose MN-major raw tiles)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);          // .x = a (low half), round to nearest even
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// ---- bf16 mode (hsg_set_gemm_mode(3)): operand conversion ---------------------------------------------------------
+// Both raw tile kinds are rewritten by the converter warps into ONE bf16 layout, K-major SWIZZLE_128B with only the
+// first 64 bytes (32 bf16) of every 128-byte row in use:   element (r, k) at  r*128 + (((k>>3) ^ (r&7)) << 4) + (k&7)*2.
+// The tensor core then reads it with the same descriptors as the fp32 K-major tiles (8-row groups 1024 B apart, a
+// k-step of 16 bf16 = 32 B inside the swizzled row), kind::f16, two k-steps per 32-deep k-block.
+// raw K-major tile (box {32 k, rows}, SWIZZLE_128B): one 16-byte chunk per work item, linear sweep
+__device__ __forceinline__ void bf16_from_kmajor(const char* raw, char* out, int rows, int ct, int nthreads) {
+  for (int id = ct; id < rows * 8; id += nthreads) {
+    const int r = id >> 3, c = (id & 7) ^ (r & 7);               // logical chunk c = fp32 elements 4c .. 4c+3 of row r
+    const float4 v = *reinterpret_cast<const float4*>(raw + id * 16);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8) = o;
+  }
+}
+// raw MN-major tile (boxes {32 mn, 32 k}, SWIZZLE_128B_ATOM_32B, atoms 4096 B apart): work item = (column mn, group of
+// 8 k); lanes walk consecutive mn, so the eight loads of a warp each read one 128-byte row (conflict-free) and the
+// 16-byte stores of a quarter warp fall into eight different chunk positions
+__device__ __forceinline__ void bf16_from_mnmajor(const char* raw, char* out, int mn_ext, int ct, int nthreads) {
+  for (int id = ct; id < mn_ext * 4; id += nthreads) {
+    const int g = id / mn_ext, m = id - g * mn_ext;
+    const char* col = raw + (m >> 5) * 4096 + (m & 7) * 4;
+    const int j = (m & 31) >> 3;
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = 8 * g + t;
+      f[t] = *reinterpret_cast<const float*>(col + k * 128 + ((j ^ (k & 3)) << 5));
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]);
+    o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + m * 128 + ((g ^ (m & 7)) << 4)) = o;
+  }
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -214,8 +275,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 warps x 32 x 33 floats
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool want_lo = precise != 0;
-  const bool use_conv = want_lo || ep.ones_col >= 0;     // converter warps touch the stage before the MMAs
+  const bool want_lo = precise == 1;                     // 3xTF32
+  const bool bf16 = precise == 2;                        // bf16 operands, one kind::f16 product
+  const bool use_conv = want_lo || bf16 || ep.ones_col >= 0;   // converter warps touch the stage before the MMAs
   // accumulator set a: main columns [a*acc_cols, +128), precise mode adds correction columns [.. +128, +256):
   // the tensor core's fp32 accumulation truncates, so the small hi*lo / lo*hi products get their own accumulator
   // (K/8 updates on the main one instead of 3K/8) and are added in the epilogue.
@@ -302,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // TMEM, so [B_hi | B_lo] is one operand and [main | corr] one accumulator: A_hi is read from shared memory
         // once instead of twice (the pipeline is shared-memory-bandwidth bound).  Columns n_mma..127 are scratch.
         const uint32_t idesc_wide = make_idesc(A_MN, B_MN, BN_MAX + ti.n_mma);
+        const uint32_t idesc_bf = make_idesc_bf16(ti.n_mma);
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait((use_conv ? bar_ready : bar_full) + 8 * slot, ph);
@@ -309,6 +372,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + slot * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
           const uint32_t b_hi = a_hi + 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+          if (bf16) {                                      // the converted tiles live where the lo planes would be
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              tc_mma_bf16(d_main, make_desc(a_lo + ks * 32u, 16u, 1024u, 2u), make_desc(b_lo + ks * 32u, 16u, 1024u, 2u),
+                          idesc_bf, (kb > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar_empty + 8 * slot);
+            trace(3, it);
+            continue;
+          }
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint32_t a_off = A_MN ? ks * 1024u : ks * 32u;
@@ -352,6 +424,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<float*>(st + 2 * TILE_BYTES + off) = 1.f;
             }
             asm volatile("bar.sync 1, %0;" ::"r"(NCONV) : "memory");
+          }
+          if (bf16) {
+            if (A_MN) bf16_from_mnmajor(st, st + TILE_BYTES, TM, ct, NCONV);
+            else      bf16_from_kmajor(st, st + TILE_BYTES, TM, ct, NCONV);
+            if (B_MN) bf16_from_mnmajor(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, nb_box, ct, NCONV);
+            else      bf16_from_kmajor(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, nb_box, ct, NCONV);
           }
           if (want_lo) {
             // (128 + nb_box) * 8 <= 2048 chunks of 16 B over 192 threads: up to 11 per thread, loads issued first
@@ -623,7 +701,7 @@ constexpr int K_CHUNK = 1024;
 
 template <bool A_MN, bool B_MN>
 static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, int K, int bn, int k_per_split,
-                  int precise, Epilogue ep, cudaStream_t s, int k_chunk = 0) {
+                  int precise, Epilogue ep, cudaStream_t s, int k_chunk = 0, bool cta_per_item = false) {
   if (!g_attr_done[which]) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
         cudaSuccess)
@@ -639,6 +717,11 @@ static int launch(int which, dim3 grid, Operand A, Operand B, int Md, int Nd, in
   if (!okA || !okB) return HSG_ERR_CUDA;
   const int m_tiles = (int)grid.x, n_tiles = (int)grid.y, n_items = m_tiles * n_tiles * (int)grid.z;
   int total = n_items, ctas = n_items < num_sms() ? n_items : num_sms();
+  if (cta_per_item) {
+    // short items on a low-priority stream: one CTA each, so that SMs return to the block scheduler every item
+    ctas = n_items;
+    if (k_per_split > k_chunk) k_chunk = 0;        // (items are planned <= K_CHUNK rows; never chunk across CTAs)
+  }
   if (k_chunk > 0) {
     // chunked items: CTA w must own every chunk of item w (its epilogue adds them up in place), i.e. exactly one CTA
     // per item; the plan keeps n_items within one wave, otherwise run unchunked
@@ -681,13 +764,14 @@ int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ld
 
 // part[z][N1][N2] (+ part_col[z][N1]) for z < splits; rows_per_split multiple of 32
 int gemm_tn(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* part, float* part_col,
-            int splits, int rows_per_split, int precise, cudaStream_t s) {
+            int splits, int rows_per_split, int precise, cudaStream_t s, bool cta_per_item) {
   Operand a{A, lda, N1, M}, b{B, ldb, N2, M};
   const int n_total = N2 + (part_col ? 1 : 0);
   const int bn = pick_bn(n_total);
   Epilogue ep{part, N2, (size_t)N1 * N2, nullptr, nullptr, 0, 0, part_col, part_col ? N2 : -1};
   dim3 grid(ceil_div(N1, TM), ceil_div(n_total, bn), splits);
-  return launch<true, true>(2, grid, a, b, N1, n_total, M, bn, rows_per_split, precise, ep, s, precise ? K_CHUNK : 0);
+  return launch<true, true>(2, grid, a, b, N1, n_total, M, bn, rows_per_split, precise, ep, s, precise ? K_CHUNK : 0,
+                            cta_per_item);
 }
 
 int trace_ctl(int on, unsigned long long* host_out, int max_events) {

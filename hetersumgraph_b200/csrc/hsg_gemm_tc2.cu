@@ -19,6 +19,7 @@
 // Arithmetic is identical to the single-CTA kernel product by product (same hi/lo split, same k order, separate
 // correction accumulator), so results are bit-identical to it; tests/test_gpu_parity.py runs both.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
 
@@ -112,6 +113,17 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
       : "memory");
 }
 
+// bf16 x bf16 -> fp32 (kind::f16), K = 16 per instruction, M = 256 over the pair
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -137,6 +149,44 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t make_idesc(bool b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(256 >> 4) << 24);
+}
+
+// bf16 mode (see hsg_gemm_tc.cu): both operands K-major bf16 in the first 64 bytes of SWIZZLE_128B rows
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void bf16_from_kmajor(const char* raw, char* out, int rows, int ct, int nthreads) {
+  for (int id = ct; id < rows * 8; id += nthreads) {
+    const int r = id >> 3, c = (id & 7) ^ (r & 7);
+    const float4 v = *reinterpret_cast<const float4*>(raw + id * 16);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + r * 128 + (((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8) = o;
+  }
+}
+__device__ __forceinline__ void bf16_from_mnmajor(const char* raw, char* out, int mn_ext, int ct, int nthreads) {
+  for (int id = ct; id < mn_ext * 4; id += nthreads) {
+    const int g = id / mn_ext, m = id - g * mn_ext;
+    const char* col = raw + (m >> 5) * 4096 + (m & 7) * 4;
+    const int j = (m & 31) >> 3;
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = 8 * g + t;
+      f[t] = *reinterpret_cast<const float*>(col + k * 128 + ((j ^ (k & 3)) << 5));
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]);
+    o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + m * 128 + ((g ^ (m & 7)) << 4)) = o;
+  }
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -173,6 +223,15 @@ __device__ __forceinline__ void trace(int ev, uint32_t it, uint32_t rank) {
     g_trace2[3 * i + 1] = it;
     g_trace2[3 * i + 2] = clock64();
   }
+}
+
+// per-CTA span of the traced launch: (globaltimer at entry, globaltimer at exit, SM id) - shows whether all 74 CTA
+// pairs of the persistent grid are co-resident or some start only after others have finished
+__device__ unsigned long long g_span2[3 * 160];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 struct Epilogue {
@@ -214,8 +273,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  if (g_trace2_on && tid == 0 && blockIdx.x < 160) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_span2[3 * blockIdx.x] = globaltimer_ns();
+    g_span2[3 * blockIdx.x + 2] = smid;
+  }
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const bool want_lo = precise != 0;
+  const bool want_lo = precise == 1;               // 3xTF32
+  const bool bf16 = precise == 2;                  // bf16 operands, one kind::f16 product
   const uint32_t acc_cols = want_lo ? 2u * BN_MAX : (uint32_t)BN_MAX;
   const uint32_t tmem_cols = 2u * acc_cols;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_ready = smem_u32(&bars[STAGES]),
@@ -288,6 +354,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_main = tmem_d + acc * acc_cols, d_corr = d_main + BN_MAX;
         const uint32_t idesc = make_idesc(B_MN, ti.n_mma);
+        const uint32_t idesc_bf = make_idesc_bf16(ti.n_mma);
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const uint32_t slot = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_ready + 8 * slot, ph);
@@ -295,6 +362,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + slot * STAGE_BYTES), a_lo = a_hi + A_TILE;
           const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_HALF;
+          if (bf16) {                                      // the converted tiles live where the lo planes would be
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks)
+              tc_mma_bf16_pair(d_main, make_desc(a_lo + ks * 32u, 16u, 1024u, 2u),
+                               make_desc(b_lo + ks * 32u, 16u, 1024u, 2u), idesc_bf, (kb > 0 || ks > 0) ? 1u : 0u);
+            tc_commit_pair(bar_empty + 8 * slot);
+            trace(3, it, rank);
+            continue;
+          }
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint32_t a_off = ks * 32u;
@@ -328,6 +404,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar_full + 8 * slot, ph);
         if (ct == 0) trace(4, it, rank);
         char* st = smem + slot * STAGE_BYTES;
+        if (bf16) {
+          bf16_from_kmajor(st, st + A_TILE, TM, ct, NCONV);
+          if (B_MN) bf16_from_mnmajor(st + 2 * A_TILE, st + 2 * A_TILE + B_HALF, nb_half_box, ct, NCONV);
+          else      bf16_from_kmajor(st + 2 * A_TILE, st + 2 * A_TILE + B_HALF, nb_half_box, ct, NCONV);
+        }
         if (want_lo) {
           // (128 + nb_half_box) * 8 <= 1536 chunks of 16 B over 192 threads: up to 8 per thread, loads issued first
           constexpr int CPT = (TM * 8 + (BN_MAX / 2) * 8 + NCONV - 1) / NCONV;
@@ -483,6 +564,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols));
   }
+  if (g_trace2_on && tid == 0 && blockIdx.x < 160) g_span2[3 * blockIdx.x + 1] = globaltimer_ns();
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -543,7 +625,24 @@ int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ld
   return launch<true>(1, A, lda, B, ldb, M, N, K, pick_bn(N), precise, ep, s);
 }
 
+// on == -2: copy the per-CTA spans (3 x 160 values) instead of the event trace; on == -3: returns the number of CTA
+// pairs of gemm_tc2_kernel<false> the device can hold at once (cudaOccupancyMaxActiveClusters)
 int trace_ctl(int on, unsigned long long* host_out, int max_events) {
+  if (on == -2) {
+    int n = 3 * 160 < max_events ? 3 * 160 : max_events;
+    if (host_out && n > 0) cudaMemcpyFromSymbol(host_out, g_span2, (size_t)n * sizeof(unsigned long long));
+    return n;
+  }
+  if (on == -3) {
+    cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (num_sms() / 2));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<false>, &cfg) != cudaSuccess) return -1;
+    return n;
+  }
   if (on >= 0) {
     static unsigned long long zeros[3 * 4096];
     cudaMemcpyToSymbol(g_trace2, zeros, sizeof(zeros));

@@ -62,6 +62,18 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
 int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,
                      float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
 
+// hsg_ffn.cu: whole position-wise FFN of a small node set in one launch each way (exact fp32); ffn_rows_ok tells
+// whether the shape qualifies.  Same outputs as gemm_nt + gemm_nt + layernorm_fwd / layernorm_bwd + gemm_nn + gemm_nn.
+bool ffn_rows_ok(int n, int F, int d_hid);
+int ffn_rows_fwd(int n, int F, int d_hid, const float* x, const float* w1, const float* b1, const float* w2,
+                 const float* b2, const float* gamma, const float* beta, float* hdn, float* r, float* y, float* stats,
+                 cudaStream_t s);
+int ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const float* stats, const float* gamma,
+                 const float* hdn, const float* w1, const float* w2, float* dr, float* dhp, float* dx, float* dgamma,
+                 float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+// hsg_gemm.cu: products below the small-product threshold (hsg_set_gemm_small_flops) run on FFMA tiles
+bool gemm_is_small(int M, int N, int K);
+
 // dq (+)= ...
 int edge_bwd_ex(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
                 const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s);

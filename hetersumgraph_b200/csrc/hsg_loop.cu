@@ -280,7 +280,9 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   }
   // sh, x = elu(sh) + origin, stat   (GATLayer.py:88-102,112-113; GAT.py:56-57)
   HSG_TRY(hsg_edge_fwd(csc, P.H, P.d, zp, ldz, st + L.q[k], origin, sh, x, stat, s));
-  // FFN (GATLayer.py:35-44)
+  // FFN (GATLayer.py:35-44); a small destination set (the sentence side) takes the one-launch row kernel
+  if (!L.drop_ffn && ffn_rows_ok(n_dst, F, P.d_hid))
+    return ffn_rows_fwd(n_dst, F, P.d_hid, x, P.w1, P.b1, P.w2, P.b2, P.gamma, P.beta, hdn, r, out, ln, s);
   HSG_TRY(hsg_gemm_nt(n_dst, P.d_hid, F, x, F, P.w1, F, hdn, P.d_hid, P.b1, nullptr, 0, HSG_EPI_BIAS | HSG_EPI_RELU, s));
   if (L.drop_ffn) {
     HSG_TRY(hsg_gemm_nt(n_dst, F, P.d_hid, hdn, P.d_hid, P.w2, P.d_hid, r, F, P.b2, nullptr, 0, HSG_EPI_BIAS, s));
@@ -315,16 +317,23 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     if (cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
     side_pending[k] = false;
   }
-  // LayerNorm
-  HSG_TRY(layernorm_bwd_ex(n_dst, F, dout, r, ln, P.gamma, dr, G.dgamma, G.dbeta, ws, ws_bytes, acc_ffn, s));
-  // FFN dropout: the residual path keeps dr, the W2 path sees dr * mask / (1-p)
+  const bool rows_kernel = !L.drop_ffn && ffn_rows_ok(n_dst, F, P.d_hid);
   const float* drm = dr;
-  if (L.drop_ffn) {
-    HSG_TRY(dropout_mul((size_t)n_dst * F, dr, sc + b.drm, make_drop(a->ffn_p, a->seed, stream_ffn(i), a->seed_dev), s));
-    drm = sc + b.drm;
+  if (rows_kernel) {
+    // small destination set: LayerNorm backward, dhp and dx in ONE launch (+ the dgamma / dbeta reduce)
+    HSG_TRY(ffn_rows_bwd(n_dst, F, P.d_hid, dout, r, ln, P.gamma, hdn, P.w1, P.w2, dr, dhp, dx, G.dgamma, G.dbeta, ws,
+                         ws_bytes, acc_ffn, s));
+  } else {
+    // LayerNorm
+    HSG_TRY(layernorm_bwd_ex(n_dst, F, dout, r, ln, P.gamma, dr, G.dgamma, G.dbeta, ws, ws_bytes, acc_ffn, s));
+    // FFN dropout: the residual path keeps dr, the W2 path sees dr * mask / (1-p)
+    if (L.drop_ffn) {
+      HSG_TRY(dropout_mul((size_t)n_dst * F, dr, sc + b.drm, make_drop(a->ffn_p, a->seed, stream_ffn(i), a->seed_dev), s));
+      drm = sc + b.drm;
+    }
+    // FFN: dhp = (drm . W2) * relu', dW2 = drm^T hdn, dW1 = dhp^T x, dx = dhp . W1 + dr
+    HSG_TRY(hsg_gemm_nn(n_dst, P.d_hid, F, drm, F, P.w2, P.d_hid, dhp, P.d_hid, hdn, P.d_hid, HSG_EPI_RELU_MASK, s));
   }
-  // FFN: dhp = (drm . W2) * relu', dW2 = drm^T hdn, dW1 = dhp^T x, dx = dhp . W1 + dr
-  HSG_TRY(hsg_gemm_nn(n_dst, P.d_hid, F, drm, F, P.w2, P.d_hid, dhp, P.d_hid, hdn, P.d_hid, HSG_EPI_RELU_MASK, s));
   if (sd) {
     if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->fork, 0) != cudaSuccess)
       return HSG_ERR_CUDA;
@@ -332,7 +341,8 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   const int budget = sd ? side_ctas() : 0;
   HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, wsw, ws_bytes, acc_ffn, s2, budget));
   HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
-  HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
+  if (!rows_kernel)
+    HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
   HSG_TRY(hsg_edge_bwd_prep(n_dst, P.H, P.d, dx, nullptr, sh, g, stat, s));
   HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, ws, ws_bytes, acc_aug, s));

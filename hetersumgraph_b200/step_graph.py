@@ -225,6 +225,11 @@ class GraphedTrainStep:
         self.stage = [None, None]                     # pinned host staging of each slot's token blob
         self.sf_dev = None
         self.sf_stage = [None, None]
+        # sent_feature of the NEXT step uploaded by this step's side branch (step(..., next_sent_feature=...)):
+        # pinned staging + device buffer per slot parity, and what each device buffer currently holds
+        self.sf_pref = [None, None]
+        self.sf_pstage = [None, None]
+        self._pref_tag = [None, None]
         self.loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
         self.side = torch.cuda.Stream(self.dev)
         self.cap_stream = torch.cuda.Stream(self.dev)
@@ -270,6 +275,18 @@ class GraphedTrainStep:
         self.sf_stage[self.i & 1][:n].copy_(sent_feature)   # host memcpy; the H2D is part of the step
         return True
 
+    def _stage_next_sf(self, q, nsf):
+        """host memcpy of the next step's sent_feature into the pinned staging buffer of parity q"""
+        n, w = nsf.shape
+        if self.sf_pref[q] is None or self.sf_pref[q].shape[0] < n or self.sf_pref[q].shape[1] != w:
+            cap = int(n * StaticBatchSlot.GROW) + 8
+            for k in (0, 1):
+                self.sf_pref[k] = torch.zeros(cap, w, dtype=torch.float32, device=self.dev)
+                self.sf_pstage[k] = torch.zeros(cap, w, dtype=torch.float32).pin_memory()
+            self._pref_tag = [None, None]
+            self._invalidate()
+        self.sf_pstage[q][:n].copy_(nsf)
+
     def prime(self, host):
         """Upload and build the first batch eagerly into slot 0."""
         s = 0
@@ -285,16 +302,19 @@ class GraphedTrainStep:
         self.i = 0
 
     # -- the step -------------------------------------------------------------------------------------------------
-    def _enqueue(self, p, batch, n_sf, sf_h2d, build_next, main):
+    def _enqueue(self, p, batch, n_sf, sf_h2d, build_next, main, use_pref=False, n_next_sf=0):
         """Everything of one step on `main` (current stream) + the side branch; returns (loss, logits, d_sf)."""
         side = self.side
         nxt = self.slots[1 - p]
-        if build_next:
+        if build_next or n_next_sf:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                nxt.enqueue_build(side, None if self.resident_tokens else self.stage[1 - p])
-                self.ev_totals[1 - p].record(side)
-        sf = self.sf_dev[:n_sf]
+                if n_next_sf:       # the next step's sent_feature travels first: ev_totals then also covers it
+                    self.sf_pref[1 - p][:n_next_sf].copy_(self.sf_pstage[1 - p][:n_next_sf], non_blocking=True)
+                if build_next:
+                    nxt.enqueue_build(side, None if self.resident_tokens else self.stage[1 - p])
+                    self.ev_totals[1 - p].record(side)
+        sf = self.sf_pref[p][:n_sf] if use_pref else self.sf_dev[:n_sf]
         if sf_h2d:
             sf.copy_(self.sf_stage[p][:n_sf], non_blocking=True)
         loss, logits, d_sf = self.fused(batch, sf)
@@ -302,12 +322,16 @@ class GraphedTrainStep:
             self.all_reduce(self.opt.g)
         self.opt.step_dev(zero_grad=True)
         self.loss_host[p].copy_(loss.detach().view(1), non_blocking=True)
-        if build_next:
+        if build_next or n_next_sf:
             main.wait_stream(side)
         self.ev_done[p].record(main)
         return loss, logits, d_sf
 
-    def step(self, next_host, sent_feature):
+    def step(self, next_host, sent_feature, next_sent_feature=None):
+        """next_sent_feature (optional, pinned or pageable HOST tensor): the sent_feature the NEXT call will pass; it is
+        uploaded by this step's side branch next to the next batch's tokens, so that the next step does not start with
+        an H2D copy on its critical path.  It must not be modified before that call, which has to pass the very same
+        tensor as `sent_feature`."""
         if self.cur is None:
             raise RuntimeError("GraphedTrainStep: call prime(host) with the first batch before step()")
         p = self.i & 1
@@ -324,9 +348,18 @@ class GraphedTrainStep:
                 nslot.dtb._blob.copy_(next_host["blob"], non_blocking=True)
                 nslot.loaded = next_host
         n_sf = sent_feature.shape[0]
-        sf_h2d = self._stage_sf(sent_feature)
+        tag = (sent_feature.data_ptr(), tuple(sent_feature.shape))
+        use_pref = (not sent_feature.is_cuda) and self._pref_tag[p] == tag
+        sf_h2d = False if use_pref else self._stage_sf(sent_feature)
+        n_next_sf = 0
+        if next_sent_feature is not None and not next_sent_feature.is_cuda and build_next:
+            self._stage_next_sf(1 - p, next_sent_feature)
+            n_next_sf = int(next_sent_feature.shape[0])
+            self._pref_tag[1 - p] = (next_sent_feature.data_ptr(), tuple(next_sent_feature.shape))
+        else:
+            self._pref_tag[1 - p] = None
         gens = (self.slots[0].generation, self.slots[1].generation)
-        key = (p, ckey, nkey, n_sf, sf_h2d, gens)
+        key = (p, ckey, nkey, n_sf, sf_h2d, gens, use_pref, n_next_sf)
         main = torch.cuda.current_stream(self.dev)
         ent = self.graphs.get(key) if self.capture else None
         if ent is None:
@@ -339,7 +372,7 @@ class GraphedTrainStep:
                 cs = self.cap_stream
                 cs.wait_stream(main)
                 with torch.cuda.graph(g, pool=self.pool, stream=cs, capture_error_mode="thread_local"):
-                    outs = self._enqueue(p, batch, n_sf, sf_h2d, build_next, cs)
+                    outs = self._enqueue(p, batch, n_sf, sf_h2d, build_next, cs, use_pref, n_next_sf)
                 if self.pool is None:
                     self.pool = g.pool()
                 main.wait_stream(cs)
@@ -347,7 +380,7 @@ class GraphedTrainStep:
                 self.graphs[key] = ent
                 self.launches_per_step = lib.hsg_launch_count() - l0
             else:
-                outs = self._enqueue(p, batch, n_sf, sf_h2d, build_next, main)
+                outs = self._enqueue(p, batch, n_sf, sf_h2d, build_next, main, use_pref, n_next_sf)
                 self.eager_steps += 1
                 self.launches_per_step = lib.hsg_launch_count() - l0
         if ent is not None:

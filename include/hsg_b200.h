@@ -178,7 +178,11 @@ int hsg_attn_prep_bwd(int H, int d, int in_dim, int feat_dim, int ld_rows,
  *   0  FFMA, exact fp32
  *   1  tcgen05.mma kind::tf32 with a 3-product hi/lo split ("3xTF32", ~2^-21 relative) - default; this is the
  *      fp32-parity mode (BASELINE.json bound 1e-5)
- *   2  tcgen05.mma kind::tf32, single product (bound 2e-2, the "bf16 projections" class of BASELINE.json)
+ *   2  tcgen05.mma kind::tf32, single product (bound 2e-2)
+ *   3  bf16 projection mode: tcgen05.mma kind::f16 on bf16 operands (the fp32 tiles are rounded to bf16 by the
+ *      converter warps on their way to the tensor core), fp32 accumulation in TMEM - the "bf16 projections <= 2e-2"
+ *      class of BASELINE.json's north_star for fc (module/GATLayer.py:110,146) and the FFN linears (:38); activations
+ *      and weights stay fp32 in HBM, so results of every other kernel are unchanged
  * Shapes the tensor-core path cannot take (K or a leading dimension not a multiple of 4) fall back to mode 0. */
 int hsg_set_gemm_mode(int mode);
 int hsg_get_gemm_mode(void);
@@ -269,6 +273,21 @@ int hsg_layernorm_fwd(int N, int D, const float* r, const float* gamma, const fl
 size_t hsg_layernorm_bwd_workspace_bytes(int N, int D);
 int hsg_layernorm_bwd(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma,
                       float* dr, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* Whole PositionwiseFeedForward.forward (module/GATLayer.py:35-44) of a SMALL node set in ONE launch each way
+ * (exact fp32): y = LayerNorm(W2 relu(W1 x + b1) + b2 + x), leaving hdn [n, d_hid], r [n, F] and stats [n, 2] behind
+ * exactly as hsg_gemm_nt + hsg_gemm_nt + hsg_layernorm_fwd would; the backward produces dr, dhp, dx and
+ * (accumulate != 0: adds to) dgamma / dbeta; the weight-gradient products dW2 = dr^T hdn, dW1 = dhp^T x stay with
+ * hsg_gemm_tn.  hsg_ffn_rows_ok: 1 when the shape qualifies (F == 64, d_hid % 64 == 0, d_hid <= 1024, n below the
+ * small-product threshold of hsg_set_gemm_small_flops) - the sentence side of the 32-graph step; the update-loop
+ * entry points pick it by themselves, anything else returns HSG_ERR_SHAPE here.  ws as for hsg_layernorm_bwd. */
+int hsg_ffn_rows_ok(int n, int F, int d_hid);
+int hsg_ffn_rows_fwd(int n, int F, int d_hid, const float* x, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* gamma, const float* beta, float* hdn, float* r, float* y,
+                     float* stats, void* stream);
+int hsg_ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const float* stats, const float* gamma,
+                     const float* hdn, const float* w1, const float* w2, float* dr, float* dhp, float* dx,
+                     float* dgamma, float* dbeta, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Coarse-grained entry points: every kernel of ONE WSWGAT application (module/GAT.py:45-59), forward or
@@ -385,6 +404,10 @@ int hsg_set_side_ctas(int n);
 int hsg_set_gemm_pair(int on);
 /* shortest reduction range (rows) one split of a tensor-core weight-gradient product may have (default 256) */
 int hsg_set_tn_min_rows(int rows);
+/* rows > 0 (or HSG_TN_ITEM_ROWS): weight-gradient products whose reduction fits in <= 48 splits of `rows` rows are cut
+ * into tiles x splits items of that length and launched with one CTA per item instead of one persistent CTA per SM, so
+ * that the SMs go back to the block scheduler (and to the higher-priority main stream) every item; 0: persistent plan. */
+int hsg_set_tn_item_rows(int rows);
 /* Sizes/offsets for the given dimensions (pointers inside `a` are not read). */
 int hsg_update_loop_plan(const hsg_loop_args* a, hsg_loop_plan* plan);
 int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream);

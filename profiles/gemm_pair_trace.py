@@ -48,6 +48,17 @@ def main():
         rows.append(r)
     for r in rows:
         print(json.dumps(r))
+    # per-CTA spans: are all CTA pairs co-resident?
+    sp = (C.c_ulonglong * (3 * 160))()
+    lib.hsg_gemm_pair_trace(-2, sp, 3 * 160)
+    a = np.frombuffer(sp, dtype=np.uint64).reshape(-1, 3).astype(np.int64)
+    a = a[a[:, 0] > 0]
+    if len(a):
+        t0 = a[:, 0].min()
+        print(json.dumps({"max_active_clusters": lib.hsg_gemm_pair_trace(-3, None, 0), "ctas": len(a),
+                          "start_us": [round((x - t0) / 1e3, 1) for x in a[:, 0].tolist()],
+                          "end_us": [round((x - t0) / 1e3, 1) for x in a[:, 1].tolist()],
+                          "smid": a[:, 2].tolist()}))
 
 
 if __name__ == "__main__":

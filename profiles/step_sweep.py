@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SETTERS = {"side_ctas": "hsg_set_side_ctas", "tn_min_rows": "hsg_set_tn_min_rows", "pdl": "hsg_set_pdl",
-           "overlap": "hsg_set_bwd_overlap", "gemm_mode": "hsg_set_gemm_mode"}
+           "overlap": "hsg_set_bwd_overlap", "gemm_mode": "hsg_set_gemm_mode", "tn_item_rows": "hsg_set_tn_item_rows",
+           "small_flops": "hsg_set_gemm_small_flops"}
 
 
 def main():

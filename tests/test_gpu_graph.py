@@ -40,8 +40,11 @@ def _hosts(hdsg, shapes):
 
 
 @pytest.mark.parametrize("hdsg,p_drop,sf_on_host", [(False, 0.0, True), (False, 0.0, False), (True, 0.0, True),
-                                                    (False, 0.1, True)])
+                                                    (False, 0.1, True), (False, 0.0, "prefetch")])
 def test_replayed_step_is_bit_equal_to_eager(hdsg, p_drop, sf_on_host):
+    """sf_on_host == "prefetch": the host sent_feature of step i+1 is handed to step i (next_sent_feature) and uploaded
+    by its side branch; the eager run of that case uses the plain host path, so the comparison also shows that the
+    prefetched rows are the right ones."""
     from hetersumgraph_b200.step_graph import GraphedTrainStep
     hosts = _hosts(hdsg, [(6, 51), (6, 52), (6, 53)])
     tb0 = hosts[0][1]
@@ -59,7 +62,8 @@ def test_replayed_step_is_bit_equal_to_eager(hdsg, p_drop, sf_on_host):
         for i, k in enumerate(seq):
             nxt = hosts[seq[i + 1]][0] if i + 1 < len(seq) else None
             sf = hosts[k][2] if sf_on_host else hosts[k][2].cuda()
-            loss_h, logits, d_sf = gs.step(nxt, sf)
+            nsf = hosts[seq[i + 1]][2] if (sf_on_host == "prefetch" and capture and i + 1 < len(seq)) else None
+            loss_h, logits, d_sf = gs.step(nxt, sf, next_sent_feature=nsf)
             loss = gs.sync_loss()
             rec.append((loss, logits.clone(), d_sf.clone(), arena.flat_param.data.clone(), opt.m.clone(), opt.v.clone()))
         base_seed = model.loop.__dict__.get("_base_seed")
