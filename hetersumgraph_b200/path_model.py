@@ -106,8 +106,12 @@ class FusedTrainStep:
             raise NotImplementedError("FusedTrainStep assumes the frozen word embedding of the reference default")
         self.model, self.n_graphs_global = model, n_graphs_global
 
-    def __call__(self, g: HeteroBatch, sent_feature: torch.Tensor):
+    def __call__(self, g: HeteroBatch, sent_feature: torch.Tensor, hooks=None):
+        """hooks: optional dict of callables invoked between the enqueue phases of the step ("after_forward": every
+        forward kernel of the update loop is enqueued; "after_head": loss forward + backward enqueued) - the step graph
+        forks its build-of-the-next-batch branch there instead of at the very start."""
         from .functional import SentenceLossFn, UpdateLoopFn
+        hooks = hooks or {}
         m = self.model
         loop = m.loop
         prev = loop.fuse_grad_accumulation
@@ -131,10 +135,14 @@ class FusedTrainStep:
                 super_feature = DocInitFn.forward(c0, g, sent_feature, m.dn_feature_proj.weight)
             c1 = _Ctx([False, False, False, True] + [False] * len(tensors))
             _, super_state = UpdateLoopFn.forward(c1, g, cfg, word_feature, super_feature, *tensors)
+            if "after_forward" in hooks:
+                hooks["after_forward"]()
             c2 = _Ctx([False] * 7)
             loss, logits = SentenceLossFn.forward(c2, g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
                                                   m.wh.weight, m.wh.bias, g.labels)
             d_state = SentenceLossFn.backward(c2, None, None)[3]
+            if "after_head" in hooks:
+                hooks["after_head"]()
             d_sent_feature = UpdateLoopFn.backward(c1, None, d_state)[3]
             if m.hdsg:
                 _, d_sent_feature, dW = DocInitFn.backward(c0, d_sent_feature)

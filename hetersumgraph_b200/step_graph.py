@@ -242,6 +242,11 @@ class GraphedTrainStep:
         self.eager_steps = 0
         self.replays = 0
         self.launches_per_step = None
+        # where the build branch forks off the main branch: "start", "after_forward" or "after_head" (see _enqueue)
+        import os
+        self.fork_at = os.environ.get("HSG_BUILD_FORK", "start")
+        if self.fork_at not in ("start", "after_forward", "after_head"):
+            raise ValueError("HSG_BUILD_FORK must be start, after_forward or after_head")
         # dropout under replay: masks are keyed by the optimizer's device step counter
         model.loop.seed_dev = opt.device_step_counter()
 
@@ -306,18 +311,32 @@ class GraphedTrainStep:
         """Everything of one step on `main` (current stream) + the side branch; returns (loss, logits, d_sf)."""
         side = self.side
         nxt = self.slots[1 - p]
-        if build_next or n_next_sf:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                if n_next_sf:       # the next step's sent_feature travels first: ev_totals then also covers it
-                    self.sf_pref[1 - p][:n_next_sf].copy_(self.sf_pstage[1 - p][:n_next_sf], non_blocking=True)
-                if build_next:
-                    nxt.enqueue_build(side, None if self.resident_tokens else self.stage[1 - p])
-                    self.ev_totals[1 - p].record(side)
+
+        def fork_build():
+            # side branch: [H2D of the next step's sent_feature], [H2D of its token blob], build.  WHERE it forks off
+            # the main branch is a knob (HSG_BUILD_FORK): the builder is one CTA per graph for ~130 us and, started at
+            # the top of the step, shares the GPU with the two word-side FFN products of the forward (33 us alone, 50 /
+            # 63 us under it - CUPTI timeline r02t).  Forking after the forward or after the loss was measured and is
+            # NOT faster (0.650 ms at the top, 0.660 / 0.665 ms later - gpurun r02x): the step is bound by the summed
+            # SM-time of its kernels, not by where the builder overlaps, so the default stays "start".
+            if build_next or n_next_sf:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    if n_next_sf:       # the next step's sent_feature travels first: ev_totals then also covers it
+                        self.sf_pref[1 - p][:n_next_sf].copy_(self.sf_pstage[1 - p][:n_next_sf], non_blocking=True)
+                    if build_next:
+                        nxt.enqueue_build(side, None if self.resident_tokens else self.stage[1 - p])
+                        self.ev_totals[1 - p].record(side)
+
+        hooks = {}
+        if self.fork_at == "start":
+            fork_build()
+        else:
+            hooks[self.fork_at] = fork_build
         sf = self.sf_pref[p][:n_sf] if use_pref else self.sf_dev[:n_sf]
         if sf_h2d:
             sf.copy_(self.sf_stage[p][:n_sf], non_blocking=True)
-        loss, logits, d_sf = self.fused(batch, sf)
+        loss, logits, d_sf = self.fused(batch, sf, hooks)
         if self.all_reduce is not None:
             self.all_reduce(self.opt.g)
         self.opt.step_dev(zero_grad=True)
