@@ -29,81 +29,10 @@
 #include "hsg_common.cuh"
 #include "hsg_internal.cuh"
 #include "hsg_edge_layout.cuh"
+#include "hsg_edge_cfg.cuh"
 
 namespace hsg {
 
-template <int H_, int D_>
-struct EdgeCfg {
-  static constexpr int H = H_, D = D_, F = H_ * D_;
-  static constexpr int VEC = (D_ % 4 == 0) ? 4 : ((D_ % 2 == 0) ? 2 : 1);
-  static constexpr int NV = D_ / VEC;                       // vectors per head
-  static constexpr int LPH = edge_lph(H_, NV);              // lanes per head (hsg_edge_layout.cuh)
-  static constexpr int VPL = (NV + LPH - 1) / LPH;          // vectors per lane
-  static constexpr int GROUP = H_ * LPH;                    // lanes per edge row
-  static constexpr int EPS = 32 / GROUP;                    // edge rows per warp step
-  static constexpr int NE = VPL * VEC;                      // elements per lane
-  static constexpr int FP = VPL * GROUP * VEC;              // permuted row width
-  // a lane's elements are original columns k*D + VEC*(l + LPH*i) + t: with LPH == 1 (lane owns its whole head) or
-  // VPL == 1 every lane vector is a contiguous piece of the row; otherwise row I/O is staged through shared memory
-  static constexpr bool STAGED = VPL > 1 && LPH > 1;
-  static_assert(H_ <= 32 && LPH >= 1 && EPS >= 1, "bad edge config");
-  static_assert(!STAGED || (EPS == 1 && F % 4 == 0), "staged epilogue assumes one row per warp step");
-};
-
-template <int VEC>
-__device__ __forceinline__ void ld_vec(const float* p, float* out) {
-  if (VEC == 4) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-  } else if (VEC == 2) {
-    float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    out[0] = v.x; out[1] = v.y;
-  } else {
-    out[0] = __ldg(p);
-  }
-}
-
-template <int VEC>
-__device__ __forceinline__ void st_vec(float* p, const float* v) {
-  if (VEC == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  } else if (VEC == 2) {
-    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-  } else {
-    p[0] = v[0];
-  }
-}
-
-// sum over the LPH lanes that own one head (lanes [base, base+LPH) of the warp)
-template <int LPH>
-__device__ __forceinline__ float head_sum(float v, int lane, int l) {
-  if ((LPH & (LPH - 1)) == 0) {
-#pragma unroll
-    for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  } else {
-    const int base = lane - l;
-    float s = v;
-#pragma unroll
-    for (int o = 1; o < LPH; ++o) {
-      int src = base + ((l + o) % LPH);
-      s += __shfl_sync(0xffffffffu, v, src & 31);
-    }
-    return s;
-  }
-}
-
-constexpr int EDGE_WARPS = 8;
-constexpr int EDGE_THREADS = EDGE_WARPS * 32;
-
-// ---------------------------------------------------------------------------
-// forward.  U = edge rows gathered back-to-back per group before any is consumed (memory-level parallelism):
-// large for high-degree destinations (supernodes), small for low-degree ones (words) where it only costs registers.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float elu1(float o) {            // F.elu, alpha = 1 (GAT.py:56), branch-free
-  const float e = __expf(fminf(o, 0.f)) - 1.f;
-  return o > 0.f ? o : e;
-}
 
 template <int H, int D, int U>
 __global__ void __launch_bounds__(EDGE_THREADS, (EdgeCfg<H, D>::NE <= 8) ? 4 : 3)
@@ -277,7 +206,7 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
             float o[C::VEC];
 #pragma unroll
             for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
-            st_vec<C::VEC>(sh + off, o);
+            if (sh != nullptr) st_vec<C::VEC>(sh + off, o);
             if (x != nullptr) {
               float xo[C::VEC];
 #pragma unroll
@@ -307,7 +236,7 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
         if (c4 < C::F / 4) {
           const float4 o = *reinterpret_cast<const float4*>(st_row + 4 * c4);
           const size_t off = (size_t)v * C::F + 4 * c4;
-          *reinterpret_cast<float4*>(sh + off) = o;
+          if (sh != nullptr) *reinterpret_cast<float4*>(sh + off) = o;
           if (x != nullptr)
             *reinterpret_cast<float4*>(x + off) =
                 make_float4(og[i].x + elu1(o.x), og[i].y + elu1(o.y), og[i].z + elu1(o.z), og[i].w + elu1(o.w));
@@ -476,7 +405,7 @@ edge_fwd_rowpar_kernel(int n_dst, const int32_t* __restrict__ indptr, const int3
           float o[C::VEC];
 #pragma unroll
           for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
-          st_vec<C::VEC>(sh + off, o);
+          if (sh != nullptr) st_vec<C::VEC>(sh + off, o);
           if (x != nullptr) {
             float xo[C::VEC];
 #pragma unroll
@@ -1335,6 +1264,12 @@ __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, c
   if (threadIdx.x == 0) dq[i] = accumulate ? dq[i] + red[0] : red[0];
 }
 
+int edge_dq_reduce(int nblocks, int nq, const float* dq_part, float* dq, int accumulate, cudaStream_t s) {
+  LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
+  launch_k(edge_bwd_dq_kernel, dim3(nq), dim3(128), 0, s, nblocks, nq, dq_part, dq, accumulate);
+  return check_launch();
+}
+
 constexpr int EDGE_MAX_BLOCKS = 148 * 32;  // upper bound of the grid (sizes the dq partial workspace)
 constexpr int EDGE_DEFAULT_BLOCKS = 148 * 8;
 
@@ -1539,10 +1474,10 @@ int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, con
                  float* sh, float* x, float* stat, void* stream) {
   if (!csc || csc->n_dst < 0) return HSG_ERR_ARG;
   if (csc->n_dst == 0) return HSG_OK;                 // empty destination set (row pointers may be NULL)
-  if (!zp || !q || !sh || !stat) return HSG_ERR_ARG;
+  if (!zp || !q || !stat || (!sh && !x)) return HSG_ERR_ARG;   // sh may be NULL (segment backward recomputes it)
   if (x != nullptr && origin == nullptr) return HSG_ERR_ARG;
   if (!csc->indptr || (csc->n_edges > 0 && (!csc->nbr || !csc->bin))) return HSG_ERR_ARG;
-  if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(sh) || (x && (!aligned16(x) || !aligned16(origin))))
+  if (!layout_ok(H, d, ldz) || !aligned16(zp) || (sh && !aligned16(sh)) || (x && (!aligned16(x) || !aligned16(origin))))
     return HSG_ERR_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
 #define X(HH, DD) \

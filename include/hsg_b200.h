@@ -118,6 +118,15 @@ typedef struct {
   const int32_t* nbr;     /* [E] source ROW (rank among unit==0 resp. unit==1 nodes) */
   const uint8_t* bin;     /* [E] tffrac */
   const int32_t* extra;   /* [n_dst] in-edges that are not word<->supernode edges (e=0, z_src=0); may be NULL */
+  /* Optional block-diagonal structure of a batch of disjoint graphs (dgl.batch, dataloader.py:480): segment g owns
+   * the destination rows [seg_dst_ptr[g], seg_dst_ptr[g+1]) and the source rows [seg_src_ptr[g], seg_src_ptr[g+1])
+   * and every edge stays inside its segment (the builder's word_ptr / super_ptr).  n_seg = 0: not known - the
+   * segment-resident kernels (hsg_edge_bwd_seg) are then never picked.  seg_max_src / seg_max_dst: host-side upper
+   * bounds of the rows of one segment (0 = unknown); a segment that breaks the bound gets NaN results (fails
+   * loudly in the numbers, never writes out of bounds). */
+  const int32_t* seg_dst_ptr;  /* [n_seg+1] device */
+  const int32_t* seg_src_ptr;  /* [n_seg+1] device */
+  int32_t n_seg, seg_max_src, seg_max_dst, reserved2;
 } hsg_csc;
 
 typedef struct {
@@ -262,6 +271,20 @@ int hsg_set_edge_bwd_async(int mode);
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q,
                  const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
                  void* ws, size_t ws_bytes, void* stream);
+
+/* K5-seg: segment-resident backward (csrc/hsg_edge_seg.cu) for a CSC that carries its block-diagonal structure
+ * (seg_* fields of hsg_csc) and a layout with one lane group per warp and F % 4 == 0 (the S2W default (6,50)): a CTA
+ * owns whole graphs, their source rows [z | p] and accumulators [dz | dp] live in shared memory, the destination
+ * side streams through bulk-copied 16-row tiles of dx.  Takes the layer's FORWARD csc and dx itself: sh is
+ * recomputed from stat = (m, den), so hsg_edge_fwd may be called with sh = NULL and hsg_edge_bwd_prep is not
+ * needed; same dzp / dq as hsg_edge_bwd_prep + hsg_edge_bwd up to summation order (fixed: bitwise reproducible).
+ * hsg_edge_bwd_seg_ok: 1 when the csc / shape qualifies.  hsg_set_edge_seg: what the update loop picks: -1 auto
+ * (>= 512 segments), 0 never, 1 whenever it qualifies; set it before the forward of a step. */
+int hsg_set_edge_seg(int mode);
+int hsg_edge_bwd_seg_ok(const hsg_csc* csc, int H, int d, int ldz);
+int hsg_edge_bwd_seg(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
+                     const float* dx /* [n_dst,F] */, const float* stat, float* dzp, float* dq /* [10,H] */,
+                     void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K4  position-wise FFN pieces (GATLayer.py:35-44); the two products use hsg_gemm_*.
