@@ -925,6 +925,17 @@ def _time_edge_kernels(batch, label, dev, pk, flush, iters):
         nb = {"edge_fwd": accounting.edge_fwd_bytes(E, csc.n_src, csc.n_dst, H, d),
               "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
               "edge_bwd": accounting.edge_bwd_bytes(E, csc.n_src, csc.n_dst, H, d)}
+        if lib.hsg_edge_bwd_prep_rc_ok(H, d, ldz):
+            # the recomputing path (csrc/hsg_edge_rc.cu; what the update loop takes from 65 536 destination rows on):
+            # the forward does not store sh, the backward prep recomputes it from (m, den) and the source rows
+            fns["edge_fwd_no_sh"] = lambda: _lib.check(lib.hsg_edge_fwd(
+                C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(), None, x.data_ptr(),
+                stat.data_ptr(), st))
+            fns["edge_bwd_prep_rc"] = lambda: _lib.check(lib.hsg_edge_bwd_prep_rc(
+                C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(), g.data_ptr(), stat.data_ptr(),
+                st))
+            nb["edge_fwd_no_sh"] = accounting.edge_fwd_bytes_survey(E, csc.n_src, csc.n_dst, H, d)
+            nb["edge_bwd_prep_rc"] = accounting.edge_bwd_prep_rc_bytes(E, csc.n_src, csc.n_dst, H, d)
         out += _edge_rows(fns, nb, label, kind, H, d, E, csc, pk, flush, iters)
         del zp, origin, sh, x, g, dzp
     return out
@@ -958,15 +969,17 @@ def _edge_rows(fns, nb, label, kind, H, d, E, csc, pk, flush, iters):
         row = {"input": label, "kernel": name, "layer": kind, "heads": H, "head_dim": d, "pairs": E,
                "n_src": csc.n_src, "n_dst": csc.n_dst, "ms": ms, "algorithmic_MB": nb[name] / 1e6,
                "GBps": gbs, "frac_of_hbm_peak": gbs / pk["hbm"], "l2": "flushed before every launch"}
-        if name == "edge_fwd":
+        if name in ("edge_fwd", "edge_fwd_no_sh"):
             row["survey_MB"] = b_fwd / 1e6
             row["frac_survey"] = b_fwd / (ms * 1e-3) / 1e9 / pk["hbm"]
         rows.append(row)
     if "edge_bwd" in ms_of:
-        ms_pair = ms_of["edge_bwd"] + ms_of.get("edge_bwd_prep", 0.0)
-        rows.append({"input": label, "kernel": "edge_bwd_prep+edge_bwd", "layer": kind, "heads": H, "head_dim": d,
-                     "pairs": E, "ms": ms_pair, "survey_MB": b_bwd / 1e6,
-                     "frac_survey": b_bwd / (ms_pair * 1e-3) / 1e9 / pk["hbm"]})
+        for prep in ("edge_bwd_prep", "edge_bwd_prep_rc"):
+            if prep in ms_of:
+                ms_pair = ms_of["edge_bwd"] + ms_of[prep]
+                rows.append({"input": label, "kernel": prep + "+edge_bwd", "layer": kind, "heads": H, "head_dim": d,
+                             "pairs": E, "ms": ms_pair, "survey_MB": b_bwd / 1e6,
+                             "frac_survey": b_bwd / (ms_pair * 1e-3) / 1e9 / pk["hbm"]})
     return rows
 
 
@@ -1012,49 +1025,15 @@ def large_shard_leg(dev, pk, n_graphs=2048, iters=10):
 def stress_leg(dev, pk, scale=4, iters=10, flush=None):
     """Edge kernels on the stress graph of SURVEY 8-d (x1, x4, x16), each timed alone with CUDA events, L2 flushed before
     every launch."""
-    import ctypes as C
-
     import hetersumgraph_b200 as hb
-    from hetersumgraph_b200 import _lib, accounting
     from hetersumgraph_b200 import synthetic as syn
-    from hetersumgraph_b200.functional import _Workspace
-    lib = _lib.load()
     if flush is None:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_word, n_super, n_edges = 262144 * scale, 32768 * scale, 1048576 * scale
     word, sup, bins, extra = syn.stress_edges(n_word, n_super, n_edges, seed=4, extra=64)
     (sip, ssrc, sbin, _), (wip, wsrc, wbin, _) = hb.csc_pair_from_edges(word, sup, bins, n_word, n_super)
     batch = hb.HeteroBatch.from_csc_arrays(sip, ssrc, sbin, extra, wip, wsrc, wbin, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    out = []
-    for kind, H, d in (("W2S", 8, 8), ("S2W", 6, 50)):
-        csc, csc_t = batch.csc(kind)
-        F = H * d
-        fp, ldz = _lib.edge_layout(H, d)
-        zp = torch.randn(csc.n_src, ldz, device=dev)
-        q = torch.randn(10, H, device=dev)
-        origin = torch.randn(csc.n_dst, F, device=dev)
-        sh = torch.empty(csc.n_dst, F, device=dev)
-        x = torch.empty(csc.n_dst, F, device=dev)
-        stat = torch.empty(csc.n_dst, 3 * H, device=dev)
-        g = torch.empty(csc.n_dst, fp, device=dev)
-        dzp = torch.empty(csc.n_src, ldz, device=dev)
-        dq = torch.empty(10, H, device=dev)
-        ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
-        fns = {
-            "edge_fwd": lambda: _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(),
-                                                            origin.data_ptr(), sh.data_ptr(), x.data_ptr(),
-                                                            stat.data_ptr(), st)),
-            "edge_bwd_prep": lambda: _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None,
-                                                                      sh.data_ptr(), g.data_ptr(), stat.data_ptr(), st)),
-            "edge_bwd": lambda: _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(),
-                                                            g.data_ptr(), stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(),
-                                                            ws.data_ptr(), ws.numel(), st))}
-        nb = {"edge_fwd": accounting.edge_fwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d),
-              "edge_bwd_prep": accounting.edge_bwd_prep_bytes(csc.n_dst, H, d),
-              "edge_bwd": accounting.edge_bwd_bytes(n_edges, csc.n_src, csc.n_dst, H, d)}
-        out += _edge_rows(fns, nb, "stress graph x%d" % scale, kind, H, d, n_edges, csc, pk, flush, iters)
-        del zp, origin, sh, x, g, dzp
+    out = _time_edge_kernels(batch, "stress graph x%d" % scale, dev, pk, flush, iters)
     del batch
     torch.cuda.empty_cache()
     return out

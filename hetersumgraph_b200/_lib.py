@@ -31,9 +31,7 @@ class GraphOffsetsC(C.Structure):
 
 class CscC(C.Structure):
     _fields_ = [("n_dst", C.c_int32), ("n_src", C.c_int32), ("n_edges", C.c_int32), ("reserved", C.c_int32),
-                ("indptr", C.c_void_p), ("nbr", C.c_void_p), ("bin", C.c_void_p), ("extra", C.c_void_p),
-                ("seg_dst_ptr", C.c_void_p), ("seg_src_ptr", C.c_void_p), ("n_seg", C.c_int32),
-                ("seg_max_src", C.c_int32), ("seg_max_dst", C.c_int32), ("reserved2", C.c_int32)]
+                ("indptr", C.c_void_p), ("nbr", C.c_void_p), ("bin", C.c_void_p), ("extra", C.c_void_p)]
 
 
 class GraphOutC(C.Structure):
@@ -145,9 +143,9 @@ _PROTOS = {
     "hsg_edge_bwd_prep": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd_workspace_bytes": (_Z, [_I]),
     "hsg_set_edge_rowpar": (C.c_int, [_I]),
-    "hsg_set_edge_seg": (C.c_int, [_I]),
-    "hsg_edge_bwd_seg_ok": (C.c_int, [C.POINTER(CscC), _I, _I, _I]),
-    "hsg_edge_bwd_seg": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "hsg_set_edge_recompute": (C.c_int, [_I]),
+    "hsg_edge_bwd_prep_rc_ok": (C.c_int, [_I, _I, _I]),
+    "hsg_edge_bwd_prep_rc": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "hsg_set_edge_fwd_rowpar": (C.c_int, [_I]),
     "hsg_set_edge_blockrow": (C.c_int, [_I]),
     "hsg_set_edge_bwd_async": (C.c_int, [_I]),

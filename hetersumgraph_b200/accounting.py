@@ -27,6 +27,13 @@ def edge_bwd_prep_bytes(n_dst, H, d):
     return 3 * n_dst * F * 4 + n_dst * H * 4   # dx, sh read; g written; s written
 
 
+def edge_bwd_prep_rc_bytes(E, n_src, n_dst, H, d):
+    """recomputing prep (csrc/hsg_edge_rc.cu): dx read, g written, the forward CSC, (m, den) read, s written, the source
+    rows [z | p] once."""
+    F = H * d
+    return 2 * n_dst * F * 4 + E * 5 + n_dst * 4 + n_dst * H * 12 + n_src * (F + H) * 4
+
+
 def edge_bwd_bytes(E, n_src, n_dst, H, d):
     """source-centric pass: rows = forward sources (n_src), gathered rows = forward destinations (n_dst)."""
     F = H * d

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libhsg_b200.so")
-SOURCES = ["hsg_abi.cu", "hsg_builder.cu", "hsg_prep.cu", "hsg_gemm.cu", "hsg_gemm_small.cu", "hsg_gemm_tc.cu", "hsg_gemm_tc2.cu", "hsg_edge.cu", "hsg_edge_seg.cu", "hsg_ffn.cu", "hsg_wswgat.cu", "hsg_loop.cu", "hsg_head.cu", "hsg_dropout.cu", "hsg_s2s.cu", "hsg_encoder.cu", "hsg_lstm.cu"]
+SOURCES = ["hsg_abi.cu", "hsg_builder.cu", "hsg_prep.cu", "hsg_gemm.cu", "hsg_gemm_small.cu", "hsg_gemm_tc.cu", "hsg_gemm_tc2.cu", "hsg_edge.cu", "hsg_edge_rc.cu", "hsg_ffn.cu", "hsg_wswgat.cu", "hsg_loop.cu", "hsg_head.cu", "hsg_dropout.cu", "hsg_s2s.cu", "hsg_encoder.cu", "hsg_lstm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
 

@@ -152,14 +152,14 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
           lgv[uu] = ok[uu] ? leaky(pe[uu] + q_s[bb[uu] * H + k]) : -CUDART_INF_F;
           mx = fmaxf(mx, lgv[uu]);
         }
-        const float sc = (m == mx) ? 1.f : __expf(m - mx);   // m == mx also covers -inf == -inf (no row seen yet)
+        const float sc = (m == mx) ? 1.f : exp_fast(m - mx);   // m == mx also covers -inf == -inf (no row seen yet)
         den *= sc;
 #pragma unroll
         for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
         m = mx;
 #pragma unroll
         for (int uu = 0; uu < U; ++uu) {
-          const float w = ok[uu] ? __expf(lgv[uu] - mx) : 0.f;
+          const float w = ok[uu] ? exp_fast(lgv[uu] - mx) : 0.f;
           den += w;
 #pragma unroll
           for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
@@ -173,8 +173,8 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
       const float m2 = __shfl_sync(0xffffffffu, m, src);
       const float d2 = __shfl_sync(0xffffffffu, den, src);
       const float mn = fmaxf(m, m2);
-      const float s1 = (m == -CUDART_INF_F) ? 0.f : __expf(m - mn);
-      const float s2 = (m2 == -CUDART_INF_F) ? 0.f : __expf(m2 - mn);
+      const float s1 = (m == -CUDART_INF_F) ? 0.f : exp_fast(m - mn);
+      const float s2 = (m2 == -CUDART_INF_F) ? 0.f : exp_fast(m2 - mn);
       // only group 0 accumulates: the other groups must keep their own partial state for later reads
       if (grp == 0) den = den * s1 + d2 * s2;
 #pragma unroll
@@ -189,8 +189,8 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
       den = xcnt > 0.f ? xcnt : 1.f;
     } else {
       mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
-      const float sc = __expf(m - mf);
-      den = den * sc + xcnt * __expf(-mf);
+      const float sc = exp_fast(m - mf);
+      den = den * sc + xcnt * exp_fast(-mf);
       inv = sc / den;
     }
     if (grp == 0 && l == 0) {
@@ -371,14 +371,14 @@ edge_fwd_rowpar_kernel(int n_dst, const int32_t* __restrict__ indptr, const int3
         lgv[uu] = ok[uu] ? leaky(pe[uu] + q_s[bb[uu] * H + k]) : -CUDART_INF_F;
         mx = fmaxf(mx, lgv[uu]);
       }
-      const float sc = (m == mx) ? 1.f : __expf(m - mx);
+      const float sc = (m == mx) ? 1.f : exp_fast(m - mx);
       den *= sc;
 #pragma unroll
       for (int i = 0; i < C::NE; ++i) acc[i] *= sc;
       m = mx;
 #pragma unroll
       for (int uu = 0; uu < U; ++uu) {
-        const float w = ok[uu] ? __expf(lgv[uu] - mx) : 0.f;
+        const float w = ok[uu] ? exp_fast(lgv[uu] - mx) : 0.f;
         den += w;
 #pragma unroll
         for (int i = 0; i < C::NE; ++i) acc[i] = fmaf(w, zv[uu][i], acc[i]);
@@ -389,8 +389,8 @@ edge_fwd_rowpar_kernel(int n_dst, const int32_t* __restrict__ indptr, const int3
       den = xcnt > 0.f ? xcnt : 1.f;
     } else {
       mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
-      const float sc = __expf(m - mf);
-      den = den * sc + xcnt * __expf(-mf);
+      const float sc = exp_fast(m - mf);
+      den = den * sc + xcnt * exp_fast(-mf);
       inv = sc / den;
     }
     if (row_on) {
@@ -478,7 +478,7 @@ edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __res
             if (dx != nullptr) {
               ld_vec<C::VEC>(dx + off, gi);
 #pragma unroll
-              for (int t = 0; t < C::VEC; ++t) gi[t] *= (s_[t] > 0.f ? 1.f : __expf(s_[t]));
+              for (int t = 0; t < C::VEC; ++t) gi[t] *= (s_[t] > 0.f ? 1.f : exp_fast(s_[t]));
             } else {
               ld_vec<C::VEC>(dsh + off, gi);
             }
@@ -499,10 +499,10 @@ edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __res
             const float4 s4 = ps[i];
             float4 g4 = pg[i];
             if (dx != nullptr) {
-              g4.x *= (s4.x > 0.f ? 1.f : __expf(s4.x));
-              g4.y *= (s4.y > 0.f ? 1.f : __expf(s4.y));
-              g4.z *= (s4.z > 0.f ? 1.f : __expf(s4.z));
-              g4.w *= (s4.w > 0.f ? 1.f : __expf(s4.w));
+              g4.x *= (s4.x > 0.f ? 1.f : exp_fast(s4.x));
+              g4.y *= (s4.y > 0.f ? 1.f : exp_fast(s4.y));
+              g4.z *= (s4.z > 0.f ? 1.f : exp_fast(s4.z));
+              g4.w *= (s4.w > 0.f ? 1.f : exp_fast(s4.w));
             }
             *reinterpret_cast<float4*>(g_row + 4 * c4) = g4;
             *reinterpret_cast<float4*>(s_row + 4 * c4) = s4;
@@ -651,7 +651,7 @@ edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __
           if (ok[uu]) {
             const float pre = pu + q_s[bb[uu] * H + k];
             const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-            const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
+            const float alpha = __fdividef(exp_fast(lg - mk[uu]), dk[uu]);
             const float de = alpha * (t - sk[uu]);
             const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -823,7 +823,7 @@ edge_bwd_rowpar_kernel(int n_src, const int32_t* __restrict__ indptr, const int3
         if (ok[uu]) {
           const float pre = pu + q_s[bb[uu] * H + k];
           const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-          const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
+          const float alpha = __fdividef(exp_fast(lg - mk[uu]), dk[uu]);
           const float de = alpha * (t - sk[uu]);
           const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -960,7 +960,7 @@ edge_bwd_blockrow_kernel(int n_src, const int32_t* __restrict__ indptr, const in
           if (ok[uu]) {
             const float pre = pu + q_s[bb[uu] * H + k];
             const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-            const float alpha = __fdividef(__expf(lg - mk[uu]), dk[uu]);
+            const float alpha = __fdividef(exp_fast(lg - mk[uu]), dk[uu]);
             const float de = alpha * (t - sk[uu]);
             const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll
@@ -1223,7 +1223,7 @@ edge_bwd_async_kernel(int n_src, const int32_t* __restrict__ indptr, const int32
       if (lane_on) {
         const float pre = pu + q_s[bb * H + k];
         const float lg = pre > 0.f ? pre : HSG_LEAKY_SLOPE * pre;
-        const float alpha = __fdividef(__expf(lg - mk), dk);
+        const float alpha = __fdividef(exp_fast(lg - mk), dk);
         const float de = alpha * (t - sk);
         const float dpre = pre > 0.f ? de : HSG_LEAKY_SLOPE * de;
 #pragma unroll

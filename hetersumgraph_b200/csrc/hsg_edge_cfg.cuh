@@ -76,8 +76,17 @@ constexpr int EDGE_THREADS = EDGE_WARPS * 32;
 // forward.  U = edge rows gathered back-to-back per group before any is consumed (memory-level parallelism):
 // large for high-degree destinations (supernodes), small for low-degree ones (words) where it only costs registers.
 // ---------------------------------------------------------------------------
+// exp(x) as ONE multiply + MUFU.EX2 (flush-to-zero).  __expf is the same approximation plus a range fix-up for
+// results below 2^-126 that none of the edge kernels' arguments needs - three more instructions per call, which the
+// per-ELEMENT calls of the wide S2W rows (issue-bound kernels) pay ten times per lane and row.
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 __device__ __forceinline__ float elu1(float o) {            // F.elu, alpha = 1 (GAT.py:56), branch-free
-  const float e = __expf(fminf(o, 0.f)) - 1.f;
+  const float e = exp_fast(fminf(o, 0.f)) - 1.f;
   return o > 0.f ? o : e;
 }
 

@@ -78,14 +78,8 @@ bool gemm_is_small(int M, int N, int K);
 int edge_bwd_ex(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
                 const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s);
 
-// hsg_edge.cu: dq (+)= sum over blocks of dq_part[block, nq], fixed order
-int edge_dq_reduce(int nblocks, int nq, const float* dq_part, float* dq, int accumulate, cudaStream_t s);
-// hsg_edge_seg.cu: segment-resident backward (csc = the layer's FORWARD CSC with its segment fields set; dx instead
-// of g: sh is recomputed).  edge_bwd_seg_use: whether the update loop takes this path (then the forward skips sh).
-bool edge_bwd_seg_use(const hsg_csc* csc_fwd, int H, int d, int ldz);
-int edge_bwd_seg_ex(const hsg_csc* csc_fwd, int H, int d, const float* zp, int ldz, const float* q, const float* dx,
-                    const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq,
-                    cudaStream_t s);
+// hsg_edge_rc.cu: whether the update loop recomputes sh in the backward prep (then the forward does not store it)
+bool edge_recompute_use(const hsg_csc* csc_fwd, int H, int d, int ldz);
 
 // dW, dWf, dbf, da, dT (+)= ...   (acc_params: the four layer parameters; acc_T: the shared TF-IDF table)
 int attn_prep_bwd_ex(int H, int d, int in_dim, int feat_dim, int ld_rows, const float* W, const float* Wf,

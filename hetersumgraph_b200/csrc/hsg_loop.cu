@@ -278,9 +278,9 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     HSG_TRY(hsg_gemm_nt(n_src, ldz, P.in_dim, neighbor, P.in_dim, st + L.waug[k], P.in_dim, zp, ldz, nullptr, nullptr,
                         0, 0, s));
   }
-  // sh, x = elu(sh) + origin, stat   (GATLayer.py:88-102,112-113; GAT.py:56-57); the segment-resident backward
-  // recomputes sh from stat, so the forward does not store it on that path
-  if (edge_bwd_seg_use(csc, P.H, P.d, ldz)) sh = nullptr;
+  // sh, x = elu(sh) + origin, stat   (GATLayer.py:88-102,112-113; GAT.py:56-57); when the backward prep recomputes sh
+  // (hsg_edge_rc.cu) the forward does not store it
+  if (edge_recompute_use(csc, P.H, P.d, ldz)) sh = nullptr;
   HSG_TRY(hsg_edge_fwd(csc, P.H, P.d, zp, ldz, st + L.q[k], origin, sh, x, stat, s));
   // FFN (GATLayer.py:35-44); a small destination set (the sentence side) takes the one-launch row kernel
   if (!L.drop_ffn && ffn_rows_ok(n_dst, F, P.d_hid))
@@ -347,12 +347,11 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
   const hsg_csc* csc_f = k == 0 ? a->csc_super : a->csc_word;
-  if (edge_bwd_seg_use(csc_f, P.H, P.d, ldz)) {
-    HSG_TRY(edge_bwd_seg_ex(csc_f, P.H, P.d, zp, ldz, st + L.q[k], dx, stat, dzp, dq, ws, ws_bytes, acc_aug, s));
-  } else {
+  if (edge_recompute_use(csc_f, P.H, P.d, ldz))
+    HSG_TRY(hsg_edge_bwd_prep_rc(csc_f, P.H, P.d, zp, ldz, st + L.q[k], dx, g, stat, s));
+  else
     HSG_TRY(hsg_edge_bwd_prep(n_dst, P.H, P.d, dx, nullptr, sh, g, stat, s));
-    HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, ws, ws_bytes, acc_aug, s));
-  }
+  HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, ws, ws_bytes, acc_aug, s));
   // projection backward
   int rc;
   if (L.drop_attn) {

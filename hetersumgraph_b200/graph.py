@@ -76,9 +76,7 @@ class DeviceTokenBatch:
             t = t.pin_memory()
         S, L = tb.tokens.shape
         per_graph = np.diff(tb.graph_sent_ptr)
-        per_super = per_graph + (np.diff(tb.graph_doc_ptr) if tb.hdsg else 0)     # supernode rows of a graph
         meta = dict(S=int(S), L=int(L), max_sent=int(per_graph.max()) if tb.n_graphs > 0 else 0,
-                    max_super=int(per_super.max()) if tb.n_graphs > 0 else 0,
                     n_doc=int(tb.graph_doc_ptr[-1]) if tb.hdsg else 0, n_doc_tok=int(tb.doc_tok_ptr[-1]) if tb.hdsg else 0,
                     vocab=int(tb.filter_bitmap.shape[0]) * 32, n_graphs=int(tb.n_graphs), hdsg=bool(tb.hdsg))
         nbytes = sum(v[1] for v in layout.values())
@@ -124,7 +122,6 @@ class DeviceTokenBatch:
         d.graph_doc_ptr = d.sent_doc = d.doc_tok_ptr = d.doc_tokens = d.doc_bin = d.sent_graph = d.sent_local = None
         d.doc_graph = d.doc_local = d.sent_doc_g = d.doc_graph32 = None
         d.n_sent = meta["S"]
-        d.max_super = meta.get("max_super", 0)
         if tb.hdsg:
             d.graph_doc_ptr, d.sent_doc, d.doc_tok_ptr = view("graph_doc_ptr"), view("sent_doc"), view("doc_tok_ptr")
             d.doc_tokens, d.doc_bin = view("doc_tokens"), view("doc_bin")
@@ -178,22 +175,12 @@ class HeteroBatch:
     graph_sent_ptr: Optional[torch.Tensor] = None        # [B+1] sentence offsets per graph
     n_total_nodes: int = 0
     n_total_edges: int = 0
-    # host-side upper bounds of one graph's rows (0 = unknown): with them the CSCs carry the batch's block-diagonal
-    # structure (word_ptr / super_ptr) and the segment-resident kernels may be picked (csrc/hsg_edge_seg.cu)
-    max_super_per_graph: int = 0
-    max_word_per_graph: int = 0
 
     def __post_init__(self):
-        seg = self.n_graphs > 0 and self.word_ptr.numel() == self.n_graphs + 1 and \
-            self.super_ptr.numel() == self.n_graphs + 1
-        nseg = self.n_graphs if seg else 0
-        wp, sp = (_ptr(self.word_ptr), _ptr(self.super_ptr)) if seg else (None, None)
         self._csc_super = _lib.CscC(self.n_super, self.n_word, self.n_pair, 0, _ptr(self.super_indptr),
-                                    _ptr(self.super_src), _ptr(self.super_bin), _ptr(self.super_extra),
-                                    sp, wp, nseg, self.max_word_per_graph, self.max_super_per_graph, 0)
+                                    _ptr(self.super_src), _ptr(self.super_bin), _ptr(self.super_extra))
         self._csc_word = _lib.CscC(self.n_word, self.n_super, self.n_pair, 0, _ptr(self.word_indptr),
-                                   _ptr(self.word_src), _ptr(self.word_bin), _ptr(self.word_extra),
-                                   wp, sp, nseg, self.max_super_per_graph, self.max_word_per_graph, 0)
+                                   _ptr(self.word_src), _ptr(self.word_bin), _ptr(self.word_extra))
 
     # ---- reference-facing helpers ------------------------------------------------
     def set_tfidf_embedding(self, weight: torch.Tensor):
@@ -350,8 +337,7 @@ class HeteroBatch:
             super_indptr=out["super_indptr"], super_src=out["super_src"][:n_pair],
             super_bin=out["super_bin"][:n_pair], super_eid=out["super_eid"][:n_pair],
             word_indptr=out["word_indptr"], word_src=out["word_src"][:n_pair], word_bin=out["word_bin"][:n_pair],
-            word_eid=out["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge,
-            max_super_per_graph=getattr(dtb, "max_super", 0))
+            word_eid=out["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge)
         hb._keepalive = (dtb, ws, status, a32, a8, c["totals_dev"])
         hb.labels = dtb.labels
         hb.graph_sent_ptr = dtb.graph_sent_ptr

@@ -111,7 +111,7 @@ class StaticBatchSlot:
             self.generation += 1
         m = host["meta"]
         lay = tuple((k, v[0], v[1]) for k, v in host["layout"].items())
-        self._bkey = (m["n_graphs"], m["S"], m["L"], m["max_sent"], m.get("max_super", 0), m["n_doc"], m["n_doc_tok"], m["hdsg"], hash(lay))
+        self._bkey = (m["n_graphs"], m["S"], m["L"], m["max_sent"], m["n_doc"], m["n_doc_tok"], m["hdsg"], hash(lay))
         return self._bkey
 
     def enqueue_build(self, stream, blob_host=None):
@@ -179,8 +179,7 @@ class StaticBatchSlot:
             super_src=a["super_src"][:max(n_pair, 1)][:n_pair] if n_pair else a["super_src"][:0],
             super_bin=a["super_bin"][:n_pair], super_eid=a["super_eid"][:n_pair],
             word_indptr=a["word_indptr"][:n_word + 1], word_src=a["word_src"][:n_pair], word_bin=a["word_bin"][:n_pair],
-            word_eid=a["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge,
-            max_super_per_graph=getattr(dtb, "max_super", 0))
+            word_eid=a["word_eid"][:n_pair], n_total_nodes=n_node, n_total_edges=n_edge)
         # zero-size slices of a live buffer keep a valid base pointer, which is what the C side expects for empty sets
         hb._keepalive = (dtb, self)
         hb.labels = dtb.labels

@@ -118,15 +118,6 @@ typedef struct {
   const int32_t* nbr;     /* [E] source ROW (rank among unit==0 resp. unit==1 nodes) */
   const uint8_t* bin;     /* [E] tffrac */
   const int32_t* extra;   /* [n_dst] in-edges that are not word<->supernode edges (e=0, z_src=0); may be NULL */
-  /* Optional block-diagonal structure of a batch of disjoint graphs (dgl.batch, dataloader.py:480): segment g owns
-   * the destination rows [seg_dst_ptr[g], seg_dst_ptr[g+1]) and the source rows [seg_src_ptr[g], seg_src_ptr[g+1])
-   * and every edge stays inside its segment (the builder's word_ptr / super_ptr).  n_seg = 0: not known - the
-   * segment-resident kernels (hsg_edge_bwd_seg) are then never picked.  seg_max_src / seg_max_dst: host-side upper
-   * bounds of the rows of one segment (0 = unknown); a segment that breaks the bound gets NaN results (fails
-   * loudly in the numbers, never writes out of bounds). */
-  const int32_t* seg_dst_ptr;  /* [n_seg+1] device */
-  const int32_t* seg_src_ptr;  /* [n_seg+1] device */
-  int32_t n_seg, seg_max_src, seg_max_dst, reserved2;
 } hsg_csc;
 
 typedef struct {
@@ -244,7 +235,7 @@ int hsg_edge_perm(int H, int d, int col);
  * 0 never, 1 whenever the layout allows.  Same results up to summation order (tested). */
 int hsg_set_edge_fwd_rowpar(int mode);
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
-                 const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F] */,
+                 const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F]; NULL: not stored (x != NULL) */,
                  float* x /* [n_dst,F] or NULL */, float* stat /* [n_dst,3H] */, void* stream);
 /* K5a: g = dx * elu'(sh) (or g = dsh when dx == NULL) written lane-interleaved [n_dst, fp]; s[v,k] = g_v[k] . sh_v[k]. */
 int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx /* or NULL */, const float* dsh /* or NULL */,
@@ -272,19 +263,19 @@ int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, c
                  const float* g, const float* stat, float* dzp, float* dq /* [10,H] */,
                  void* ws, size_t ws_bytes, void* stream);
 
-/* K5-seg: segment-resident backward (csrc/hsg_edge_seg.cu) for a CSC that carries its block-diagonal structure
- * (seg_* fields of hsg_csc) and a layout with one lane group per warp and F % 4 == 0 (the S2W default (6,50)): a CTA
- * owns whole graphs, their source rows [z | p] and accumulators [dz | dp] live in shared memory, the destination
- * side streams through bulk-copied 16-row tiles of dx.  Takes the layer's FORWARD csc and dx itself: sh is
- * recomputed from stat = (m, den), so hsg_edge_fwd may be called with sh = NULL and hsg_edge_bwd_prep is not
- * needed; same dzp / dq as hsg_edge_bwd_prep + hsg_edge_bwd up to summation order (fixed: bitwise reproducible).
- * hsg_edge_bwd_seg_ok: 1 when the csc / shape qualifies.  hsg_set_edge_seg: what the update loop picks: -1 auto
- * (>= 512 segments), 0 never, 1 whenever it qualifies; set it before the forward of a step. */
-int hsg_set_edge_seg(int mode);
-int hsg_edge_bwd_seg_ok(const hsg_csc* csc, int H, int d, int ldz);
-int hsg_edge_bwd_seg(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
-                     const float* dx /* [n_dst,F] */, const float* stat, float* dzp, float* dq /* [10,H] */,
-                     void* ws, size_t ws_bytes, void* stream);
+/* K5a': backward prep that RECOMPUTES sh from the saved softmax state instead of reading it (csrc/hsg_edge_rc.cu):
+ * walks the layer's FORWARD csc, gathers the few source rows [z | p] of every destination (L1 / L2 resident on
+ * word rows), forms sh, g = dx * elu'(sh) (lane-interleaved [n_dst, fp]) and s = g . sh (stat[:, 2H:3H]).  With it
+ * hsg_edge_fwd is called with sh = NULL: the forward's store of sh and the prep's read of it - 2 x n_dst x F x 4
+ * bytes that SURVEY.md 8(d)'s algorithmic byte counts do not contain - disappear.  Layouts with one lane group per
+ * warp and F % 4 == 0 (the S2W default (6,50)); hsg_edge_bwd_prep_rc_ok tells.  Same g / s as hsg_edge_bwd_prep up to
+ * the rounding of the recomputed sh (<= 2e-6 normalised, tested).  hsg_set_edge_recompute: what the update loop
+ * picks: -1 auto (>= 65 536 destination rows with at most 2 in-edges on average), 0 never, 1 whenever the layout
+ * allows; set it before the forward. */
+int hsg_set_edge_recompute(int mode);
+int hsg_edge_bwd_prep_rc_ok(int H, int d, int ldz);
+int hsg_edge_bwd_prep_rc(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
+                         const float* dx /* [n_dst,F] */, float* g /* [n_dst,fp] */, float* stat, void* stream);
 
 /* ------------------------------------------------------------------------
  * K4  position-wise FFN pieces (GATLayer.py:35-44); the two products use hsg_gemm_*.

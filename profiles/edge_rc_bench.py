@@ -1,6 +1,5 @@
-"""Edge kernels of the S2W layer on a data-parallel shard (n cnndm graphs): the general path (forward storing sh,
-bwd-prep, source-centric backward) against the segment-resident path (forward without sh, hsg_edge_bwd_seg), each
-kernel timed alone with CUDA events, L2 flushed before every launch.  Fractions are of the measured HBM peak over
+"""Edge kernels of the S2W layer on a data-parallel shard (n cnndm graphs): the path that saves sh (forward storing sh,
+bwd-prep reading it) against the recomputing path (forward without sh, hsg_edge_bwd_prep_rc), each kernel timed alone with CUDA events, L2 flushed before every launch.  Fractions are of the measured HBM peak over
 SURVEY.md 8(d)'s B_fwd / B_bwd.
 
     python profiles/edge_seg_bench.py [--graphs 2048] [--iters 10] [--ncu KERNEL]   (--ncu: run one kernel only)
@@ -66,12 +65,12 @@ def main():
         "edge_bwd": lambda: _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(),
                                                         g.data_ptr(), stat.data_ptr(), dzp.data_ptr(), dq.data_ptr(),
                                                         ws.data_ptr(), ws.numel(), st)),
-        "edge_bwd_seg": lambda: _lib.check(lib.hsg_edge_bwd_seg(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(),
-                                                                origin.data_ptr(), stat.data_ptr(), dzp.data_ptr(),
-                                                                dq.data_ptr(), ws.data_ptr(), ws.numel(), st))}
+        "edge_bwd_prep_rc": lambda: _lib.check(lib.hsg_edge_bwd_prep_rc(C.byref(csc), H, d, zp.data_ptr(), ldz,
+                                                                        q.data_ptr(), origin.data_ptr(), g.data_ptr(),
+                                                                        stat.data_ptr(), st))}
     b_fwd = accounting.edge_fwd_bytes_survey(E, csc.n_src, csc.n_dst, H, d)
     b_bwd = accounting.edge_bwd_bytes_survey(E, csc.n_src, csc.n_dst, H, d)
-    out = {"graphs": a.graphs, "n_dst": csc.n_dst, "n_src": csc.n_src, "pairs": E, "max_super": batch.max_super_per_graph,
+    out = {"graphs": a.graphs, "n_dst": csc.n_dst, "n_src": csc.n_src, "pairs": E,
            "survey_fwd_MB": b_fwd / 1e6, "survey_bwd_MB": b_bwd / 1e6, "hbm_peak": hbm, "ms": {}}
     fns["edge_fwd"]()
     for name, fn in fns.items():
@@ -98,8 +97,8 @@ def main():
             out["frac_survey"][name] = fr(b_fwd, ms[name])
     if "edge_bwd" in ms and "edge_bwd_prep" in ms:
         out["frac_survey"]["edge_bwd_prep+edge_bwd"] = fr(b_bwd, ms["edge_bwd"] + ms["edge_bwd_prep"])
-    if "edge_bwd_seg" in ms:
-        out["frac_survey"]["edge_bwd_seg"] = fr(b_bwd, ms["edge_bwd_seg"])
+    if "edge_bwd" in ms and "edge_bwd_prep_rc" in ms:
+        out["frac_survey"]["edge_bwd_prep_rc+edge_bwd"] = fr(b_bwd, ms["edge_bwd"] + ms["edge_bwd_prep_rc"])
     print(json.dumps(out))
 
 

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"workspace" in lib.hsg_strerror(-4)
     assert lib.hsg_profile_num_slots() > 0
     # struct layouts agree with the header (pointer-size sanity)
-    assert ctypes.sizeof(_lib.CscC) == 16 + 4 * 8 + 2 * 8 + 16
+    assert ctypes.sizeof(_lib.CscC) == 16 + 4 * 8
     assert ctypes.sizeof(_lib.TokenBatchC) == 32 + 9 * 8
     assert ctypes.sizeof(_lib.GraphOutC) == 16 + 5 * 8 + 15 * 8
 
