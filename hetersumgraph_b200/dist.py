@@ -78,6 +78,26 @@ def gradient_parity(rank, world, dev, all_reduce=None, n_global=256, seed=3):
     the ranks by `shard_indices` (module/dataloader.py:479-480 order + snake deal); every rank runs the fused train
     step (loss scaled by 1/n_global) on its shard, the flat gradient arenas are summed by `all_reduce` (NCCL), and
     rank 0 compares the sum with its own run of the WHOLE batch.  Returns the report dict on rank 0, None elsewhere."""
+    from . import _lib
+    from . import synthetic as syn
+    from .graph import HeteroBatch
+    from .path_model import FusedTrainStep, HSGPath
+    # Kernel selection is pinned for the comparison: every product goes to the tensor-core path.  A shard and the whole
+    # batch otherwise fall on different sides of the size thresholds (the exact-fp32 small-product / one-launch FFN
+    # kernels below 3e8 flops, 3xTF32 above; the recomputing edge prep from 65 536 rows on): each is inside the fp32
+    # class, but their ~1e-7 differences flip single ReLU units at their kink - measured at 256 graphs on 2 ranks:
+    # 1.3e-5 on 48 of 433 k gradient elements, 1e-7 with the selection pinned (scratch/shard_parity.py).
+    lib = _lib.load()
+    lib.hsg_set_gemm_small_flops(0.0)
+    lib.hsg_set_edge_recompute(0)
+    try:
+        return _gradient_parity(rank, world, dev, all_reduce, n_global, seed)
+    finally:
+        lib.hsg_set_gemm_small_flops(3e8)
+        lib.hsg_set_edge_recompute(-1)
+
+
+def _gradient_parity(rank, world, dev, all_reduce, n_global, seed):
     from . import synthetic as syn
     from .graph import HeteroBatch
     from .path_model import FusedTrainStep, HSGPath
@@ -110,5 +130,5 @@ def gradient_parity(rank, world, dev, all_reduce=None, n_global=256, seed=3):
     return {"global_graphs": n_global, "ranks": world, "normalised_max_error": err, "bound": GRAD_PARITY_BOUND,
             "survey_estimate": 1e-6, "ok": bool(err <= GRAD_PARITY_BOUND),
             "what": "all-reduced flat gradient arena of the N shards (dist.shard_indices) vs rank 0 running the whole "
-                    "global batch alone, same parameters and sent_feature rows; bound = fp32 reassociation of the "
-                    "row sums (see hetersumgraph_b200/dist.py)"}
+                    "global batch alone, same parameters and sent_feature rows, kernel selection pinned (every product "
+                    "on the tensor-core path: see gradient_parity); bound = fp32 reassociation of the row sums"}
