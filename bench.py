@@ -1034,6 +1034,18 @@ def stress_leg(dev, pk, scale=4, iters=10, flush=None):
     (sip, ssrc, sbin, _), (wip, wsrc, wbin, _) = hb.csc_pair_from_edges(word, sup, bins, n_word, n_super)
     batch = hb.HeteroBatch.from_csc_arrays(sip, ssrc, sbin, extra, wip, wsrc, wbin, device=dev)
     out = _time_edge_kernels(batch, "stress graph x%d" % scale, dev, pk, flush, iters)
+    # what the kernels REALLY move on a random graph whose gathered set exceeds L2 (ncu capture, profiles/traffic.json):
+    # every gather is a DRAM miss, so SURVEY 8(d)'s compulsory count (each source row once) is out of reach there
+    try:
+        seen = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("stress_x%d" % scale, {})
+    except (OSError, ValueError):
+        seen = {}
+    for row in out:
+        cap = seen.get("%s/%s" % (row.get("layer"), row.get("kernel")))
+        if cap:
+            nbytes = cap["dram_read"] + cap["dram_write"]
+            row["ncu_dram_MB"] = nbytes / 1e6
+            row["frac_of_hbm_peak_ncu_bytes"] = nbytes / (row["ms"] * 1e-3) / 1e9 / pk["hbm"]
     del batch
     torch.cuda.empty_cache()
     return out
