@@ -179,6 +179,92 @@ class MultiHeadFn(torch.autograd.Function):
         return None, None, None, None, dh, dW, dWf, dbf, da, dT
 
 
+_ROW_HEAD = {}
+
+
+def _waug_row_head(H, d, device):
+    """head of every row of W_aug (rows = lane-interleaved columns of z, then the H rows of p, then zero padding)"""
+    key = (H, d, str(device))
+    if key not in _ROW_HEAD:
+        lib = _lib.load()
+        fp, ldz = _lib.edge_layout(H, d)
+        rh = [0] * ldz
+        for c in range(H * d):
+            rh[lib.hsg_edge_perm(H, d, c)] = c // d
+        for k in range(H):
+            rh[fp + k] = k
+        _ROW_HEAD[key] = torch.tensor(rh, dtype=torch.long, device=device)
+    return _ROW_HEAD[key]
+
+
+class MultiHeadDropFn(torch.autograd.Function):
+    """MultiHeadLayer.forward(g, h) in TRAINING mode with input dropout p > 0 on its own: every head projects its OWN
+    dropout(h) (GATStackLayer.py:56).  Same construction as the update loop's dropout path (hsg_dropout.cu): the H
+    masked copies of the input side by side, [n_src, H in], times the head-blocked weight [ldz, H in]; masks from the
+    library generator (stream 0 = attention input of application 0, element ((head n_src) + row) in + col)."""
+
+    @staticmethod
+    def forward(ctx, batch, kind, H, d, h_src, W, Wf, bf, a, T, p, seed):
+        _lib.require_device()
+        lib = _lib.load()
+        csc, _ = batch.csc(kind)
+        h_src, W, Wf, a, T = (_f32c(t) for t in (h_src, W, Wf, a, T))
+        bf = _f32c(bf) if bf is not None else None
+        n_src, in_dim = h_src.shape
+        if n_src != csc.n_src:
+            raise ValueError("%s: input has %d rows, graph has %d source nodes" % (kind, n_src, csc.n_src))
+        dev = h_src.device
+        fp, ldz = _lib.edge_layout(H, d)
+        W_aug = torch.empty(ldz, in_dim, dtype=torch.float32, device=dev)
+        q = torch.empty(_N_BINS, H, dtype=torch.float32, device=dev)
+        _lib.check(lib.hsg_attn_prep_fwd(H, d, in_dim, Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a), _p(T), _p(W_aug),
+                                         _p(q), _st()))
+        mult = _keep_mult(H * n_src * in_dim, p, seed, 0, dev).view(H, n_src, in_dim)
+        a_exp = (h_src.unsqueeze(0) * mult).permute(1, 0, 2).reshape(n_src, H * in_dim).contiguous()
+        row_head = _waug_row_head(H, d, dev)
+        w_blk = torch.zeros(ldz, H, in_dim, dtype=torch.float32, device=dev)
+        w_blk[torch.arange(ldz, device=dev), row_head] = W_aug
+        w_blk = w_blk.view(ldz, H * in_dim)
+        zp = gemm_nt(a_exp, w_blk)
+        sh = torch.empty(csc.n_dst, H * d, dtype=torch.float32, device=dev)
+        stat = torch.empty(csc.n_dst, 3 * H, dtype=torch.float32, device=dev)
+        _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, _p(zp), ldz, _p(q), None, _p(sh), None, _p(stat), _st()))
+        ctx.batch, ctx.kind, ctx.H, ctx.d, ctx.has_bf = batch, kind, H, d, bf is not None
+        ctx.save_for_backward(W, Wf, bf if bf is not None else W.new_empty(0), a, T, q, zp, sh, stat, mult, a_exp, w_blk)
+        return sh
+
+    @staticmethod
+    def backward(ctx, dsh):
+        lib = _lib.load()
+        W, Wf, bf, a, T, q, zp, sh, stat, mult, a_exp, w_blk = ctx.saved_tensors
+        bf = bf if ctx.has_bf else None
+        H, d = ctx.H, ctx.d
+        _, csc_t = ctx.batch.csc(ctx.kind)
+        dev = zp.device
+        n_dst, n_src, ldz = sh.shape[0], zp.shape[0], zp.shape[1]
+        in_dim = W.shape[1]
+        fp, _ = _lib.edge_layout(H, d)
+        g = torch.empty(n_dst, fp, dtype=torch.float32, device=dev)
+        stat = stat.clone()
+        _lib.check(lib.hsg_edge_bwd_prep(n_dst, H, d, None, _p(_f32c(dsh)), _p(sh), _p(g), _p(stat), _st()))
+        dzp = torch.empty(n_src, ldz, dtype=torch.float32, device=dev)
+        dq = torch.empty(_N_BINS, H, dtype=torch.float32, device=dev)
+        ws = _Workspace.get(lib.hsg_edge_bwd_workspace_bytes(H), dev, "edge")
+        _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, _p(zp), ldz, _p(q), _p(g), _p(stat), _p(dzp), _p(dq), _p(ws),
+                                    ws.numel(), _st()))
+        d_exp = gemm_nn(dzp, w_blk)                                                   # [n_src, H in]
+        dh = (d_exp.view(n_src, H, in_dim).permute(1, 0, 2) * mult).sum(0)
+        dw_blk, _ = gemm_tn(dzp, a_exp)                                               # [ldz, H in]
+        row_head = _waug_row_head(H, d, dev)
+        dW_aug = dw_blk.view(ldz, H, in_dim)[torch.arange(ldz, device=dev), row_head].contiguous()
+        dW, dWf = torch.empty_like(W), torch.empty_like(Wf)
+        dbf = torch.empty_like(bf) if bf is not None else None
+        da, dT = torch.empty_like(a), torch.empty_like(T)
+        _lib.check(lib.hsg_attn_prep_bwd(H, d, in_dim, Wf.shape[1], ldz, _p(W), _p(Wf), _p(bf), _p(a), _p(T),
+                                         _p(dW_aug), _p(dq), _p(dW), _p(dWf), _p(dbf), _p(da), _p(dT), _st()))
+        return None, None, None, None, dh, dW, dWf, dbf, da, dT, None, None
+
+
 class S2SFn(torch.autograd.Function):
     """MultiHeadSGATLayer.forward(g, h) (GATStackLayer.py:36-44) -> cat of the heads' sh, or, with `origin`,
     elu(.) + origin (GAT.py:56-57 for layerType "S2S")."""
@@ -274,6 +360,52 @@ class FFNFn(torch.autograd.Function):
     def backward(ctx, dout):
         x, w1, w2, gamma, hdn, r, stats = ctx.saved_tensors
         return _ffn_backward(_f32c(dout), x, w1, w2, gamma, hdn, r, stats)
+
+
+def _keep_mult(n, p, seed, stream_id, device):
+    """multipliers keep / (1 - p) of the library's counter-based mask (hsg_dropout.cu), element indices 0..n-1"""
+    return dropout_keep_mask(n, p, seed, stream_id, device).to(torch.float32).mul_(1.0 / (1.0 - p))
+
+
+class FFNDropFn(torch.autograd.Function):
+    """PositionwiseFeedForward.forward in TRAINING mode with dropout p > 0 on its own (GATLayer.py:35-44:
+    LayerNorm(x + dropout(w_2 relu(w_1 x)))).  Inside WSWGAT / the update loop the mask is applied by the kernels
+    (hsg_update_loop_fwd); this stand-alone form uses the same mask generator (stream 1 = FFN of application 0,
+    element row * F + col) and the same GEMM / LayerNorm entry points, with two elementwise torch ops for the mask."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, p, seed):
+        _lib.require_device()
+        lib = _lib.load()
+        x, w1, b1, w2, b2, gamma, beta = (_f32c(t) for t in (x, w1, b1, w2, b2, gamma, beta))
+        N, D = x.shape
+        hdn = gemm_nt(x, w1, bias=b1, epi=EPI_BIAS | EPI_RELU)
+        y = gemm_nt(hdn, w2, bias=b2, epi=EPI_BIAS)
+        mult = _keep_mult(N * D, p, seed, 1, x.device).view(N, D)
+        r = torch.addcmul(x, y, mult)
+        out = torch.empty_like(r)
+        stats = torch.empty(N, 2, dtype=torch.float32, device=x.device)
+        _lib.check(lib.hsg_layernorm_fwd(N, D, _p(r), _p(gamma), _p(beta), _p(out), _p(stats), _st()))
+        ctx.save_for_backward(x, w1, w2, gamma, hdn, r, stats, mult)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, w1, w2, gamma, hdn, r, stats, mult = ctx.saved_tensors
+        N, D = x.shape
+        dout = _f32c(dout)
+        dr = torch.empty_like(r)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        ws = _Workspace.get(lib.hsg_layernorm_bwd_workspace_bytes(N, D), x.device, "ln")
+        _lib.check(lib.hsg_layernorm_bwd(N, D, _p(dout), _p(r), _p(stats), _p(gamma), _p(dr), _p(dgamma), _p(dbeta),
+                                         _p(ws), ws.numel(), _st()))
+        drm = dr * mult                                    # the w_2 path sees the mask, the residual path does not
+        dhp = gemm_nn(drm, w2, R=hdn, epi=EPI_RELU_MASK)
+        dw2, db2 = gemm_tn(drm, hdn, want_colsum=True)
+        dw1, db1 = gemm_tn(dhp, x, want_colsum=True)
+        dx = gemm_nn(dhp, w1, R=dr, epi=EPI_ADD)
+        return dx, dw1, db1, dw2, db2, dgamma, dbeta, None, None
 
 
 # --------------------------------------------------------------------------------------------

@@ -17,7 +17,8 @@ import math
 import torch
 import torch.nn as nn
 
-from .functional import AttnPrepFn, FFNFn, MultiHeadFn, S2SFn, UpdateLoopFn, WSWGATCoreFn
+from .functional import (AttnPrepFn, FFNDropFn, FFNFn, MultiHeadDropFn, MultiHeadFn, S2SFn, UpdateLoopFn,
+                         WSWGATCoreFn)
 
 
 class WSGATLayer:
@@ -104,10 +105,12 @@ class PositionwiseFeedForward(nn.Module):
                 self.layer_norm.weight, self.layer_norm.bias)
 
     def forward(self, x):
-        _check_dropout(self, self.dropout.p, "FFN")
         squeeze = x.dim() == 3
         x2 = x.reshape(-1, x.shape[-1])
-        out = FFNFn.apply(x2, *self.packed())
+        if self.training and self.dropout.p > 0.0:     # on its own (inside WSWGAT the kernels apply the mask)
+            out = FFNDropFn.apply(x2, *self.packed(), float(self.dropout.p), _next_dropout_seed())
+        else:
+            out = FFNFn.apply(x2, *self.packed())
         return out.reshape(x.shape) if squeeze else out
 
 
@@ -179,10 +182,13 @@ class MultiHeadLayer(nn.Module):
                     unexpected_keys.append(key)
 
     def forward(self, g, h):
-        _check_dropout(self, self.dropout.p, "attention-input")
         if g.tfidfembed_weight is None:
             raise RuntimeError("HeteroBatch has no TF-IDF embedding table: call g.set_tfidf_embedding(_TFembed.weight) "
                                "(counterpart of HSumGraph.set_wnfeature, HiGraph.py:150-151)")
+        if self.training and self.dropout.p > 0.0:     # on its own (inside WSWGAT the kernels apply the masks)
+            return MultiHeadDropFn.apply(g, self.kind, self.num_heads, self.out_dim, h, self.fc_weight,
+                                         self.feat_fc_weight, self.feat_fc_bias, self.attn_fc_weight,
+                                         g.tfidfembed_weight, float(self.dropout.p), _next_dropout_seed())
         return MultiHeadFn.apply(g, self.kind, self.num_heads, self.out_dim, h, self.fc_weight, self.feat_fc_weight,
                                  self.feat_fc_bias, self.attn_fc_weight, g.tfidfembed_weight)
 
@@ -261,7 +267,6 @@ class WSWGAT(nn.Module):
     def forward(self, g, w, s, prepared=None):
         if self.layerType == "S2S":
             assert torch.equal(w, s)                                           # GAT.py:51
-            _check_dropout(self.ffn, self.ffn.dropout.p, "FFN")
             return self.ffn(self.layer(g, s, origin=w))
         if self.layerType == "W2S":
             origin, neighbor = s, w

@@ -701,6 +701,81 @@ def test_standalone_wswgat_module_with_dropout():
         assert nerr(got, want) <= TOL, kind
 
 
+def test_standalone_ffn_training_dropout():
+    """PositionwiseFeedForward called on its own in training mode with p > 0 (GATLayer.py:35-44):
+    LayerNorm(x + dropout(w_2 relu(w_1 x))) with the library's mask, forward and every gradient against torch."""
+    import hetersumgraph_b200.functional as fn
+    import hetersumgraph_b200.modules as md
+    torch.manual_seed(2)
+    ffn = hb.PositionwiseFeedForward(64, 512, 0.3).cuda().train()
+    x = torch.randn(700, 64, device="cuda", requires_grad=True)
+    cot = torch.randn(700, 64, device="cuda")
+    torch.manual_seed(77)
+    seed = md._next_dropout_seed()
+    torch.manual_seed(77)                                   # the module draws the same seed
+    fn.RELU_MASK_CAPTURE = None
+    y = ffn(x)
+    (y * cot).sum().backward()
+    got = [y.detach(), x.grad.clone()] + [p.grad.clone() for p in ffn.parameters()]
+    mult = fn.dropout_keep_mask(700 * 64, 0.3, seed, 1).float().view(700, 64) / 0.7
+    assert 0.6 < float((mult > 0).float().mean()) < 0.8
+    w1, b1, w2, b2, gamma, beta = [t.detach().double().requires_grad_(True) for t in ffn.packed()]
+    xd = x.detach().double().requires_grad_(True)
+    inner = torch.relu(xd @ w1.t() + b1) @ w2.t() + b2
+    ref = torch.nn.functional.layer_norm(xd + inner * mult.double(), (64,), gamma, beta, 1e-5)
+    (ref * cot.double()).sum().backward()
+    want = [ref.detach(), xd.grad, w1.grad.view_as(ffn.w_1.weight), b1.grad, w2.grad.view_as(ffn.w_2.weight), b2.grad,
+            gamma.grad, beta.grad]
+    for a, b in zip(got, want):
+        assert nerr(a, b) <= TOL, nerr(a, b)
+    ffn.eval()                                              # evaluation mode: no mask
+    assert nerr(ffn(x.detach()), torch.nn.functional.layer_norm(
+        xd + (torch.relu(xd @ w1.t() + b1) @ w2.t() + b2), (64,), gamma, beta, 1e-5).detach()) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["W2S", "S2W"])
+def test_standalone_multihead_layer_training_dropout(kind):
+    """MultiHeadLayer called on its own in training mode with p > 0: every head aggregates ITS OWN dropout(h)
+    (GATStackLayer.py:56).  Heads are independent, so head k of the result must equal head k of the p = 0 layer fed
+    with the k-th masked input - forward and every gradient."""
+    import hetersumgraph_b200.functional as fn
+    import hetersumgraph_b200.modules as md
+    exs = syn.make_examples(5, "tiny", seed=43)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs))
+    T = torch.randn(10, 50, device="cuda", requires_grad=True)
+    batch.set_tfidf_embedding(T)
+    in_dim, d, H, n_src, n_dst = (300, 8, 8, batch.n_word, batch.n_super) if kind == "W2S" else \
+        (64, 50, 6, batch.n_super, batch.n_word)
+    torch.manual_seed(4)
+    lay = hb.MultiHeadLayer(in_dim, d, H, 0.25, 50, layer=hb.WSGATLayer if kind == "W2S" else hb.SWGATLayer).cuda()
+    h = torch.randn(n_src, in_dim, device="cuda", requires_grad=True)
+    cot = torch.randn(n_dst, H * d, device="cuda")
+    params = list(lay.parameters()) + [T]
+
+    def grads():
+        out = [h.grad.clone()] + [p.grad.clone() for p in params]
+        h.grad = None
+        for p in params:
+            p.grad = None
+        return out
+
+    lay.train()
+    torch.manual_seed(91)
+    seed = md._next_dropout_seed()
+    torch.manual_seed(91)
+    got = lay(batch, h)
+    (got * cot).sum().backward()
+    got_g = grads()
+    mult = fn.dropout_keep_mask(H * n_src * in_dim, 0.25, seed, 0).float().view(H, n_src, in_dim) / 0.75
+    lay.eval()
+    want = torch.cat([lay(batch, h * mult[k])[:, k * d:(k + 1) * d] for k in range(H)], dim=1)
+    (want * cot).sum().backward()
+    want_g = grads()
+    assert nerr(got, want) <= TOL
+    for a, b in zip(got_g, want_g):
+        assert nerr(a, b) <= TOL, nerr(a, b)
+
+
 @pytest.mark.parametrize("kind,H,d", [("W2S", 8, 8), ("S2W", 6, 50)])
 def test_edge_bwd_row_mappings_agree(kind, H, d):
     """hsg_edge_bwd's row mappings - warp per row with the groups sharing the row's edge list (baseline), each group

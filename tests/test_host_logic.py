@@ -104,11 +104,16 @@ def test_reference_error_behaviour():
     # training-mode dropout is implemented in the sm_100a kernels: without a GPU the call fails loudly (no fallback)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         m(batch, torch.randn(1, 300), torch.randn(1, 64))
-    # the bare sub-layers do not carry dropout on their own (the reference only runs them inside WSWGAT)
-    with pytest.raises(NotImplementedError, match="dropout"):
+    # the bare sub-layers carry their training-mode dropout on their own too (GATStackLayer.py:56, GATLayer.py:41):
+    # same kernels, so without a GPU they fail just as loudly
+    with pytest.raises(RuntimeError, match="no CUDA device"):
         m.layer(batch, torch.randn(1, 300))
-    with pytest.raises(NotImplementedError, match="dropout"):
+    with pytest.raises(RuntimeError, match="no CUDA device"):
         m.ffn(torch.randn(1, 1, 64))
+    # the never-instantiated S2S layer type keeps its input dropout unimplemented (HiGraph.py:57-76 builds no S2S)
+    s2s = hb.MultiHeadSGATLayer(64, 8, 8, 0.1).train()
+    with pytest.raises(NotImplementedError, match="dropout"):
+        s2s(batch, torch.randn(1, 64))
 
 
 def test_generator_shapes_and_determinism():
