@@ -143,6 +143,7 @@ _PROTOS = {
     "hsg_edge_bwd_prep": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "hsg_edge_bwd_workspace_bytes": (_Z, [_I]),
     "hsg_set_edge_rowpar": (C.c_int, [_I]),
+    "hsg_set_edge_fwd_lowdeg": (C.c_int, [_I]),
     "hsg_set_edge_recompute": (C.c_int, [_I]),
     "hsg_edge_bwd_prep_rc_ok": (C.c_int, [_I, _I, _I]),
     "hsg_edge_bwd_prep_rc": (C.c_int, [C.POINTER(CscC), _I, _I, _P, _I, _P, _P, _P, _P, _P]),

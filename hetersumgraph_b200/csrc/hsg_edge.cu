@@ -255,6 +255,193 @@ edge_fwd_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __
 }
 
 // ---------------------------------------------------------------------------
+// forward over WIDE rows of LOW degree (the word rows of the S2W layer: 300 floats, 1-3 in-edges; layouts with one
+// lane group per warp and the staged epilogue).  ncu on the 2 048-graph shard showed edge_fwd_kernel<6,50,1> neither
+// bandwidth- nor occupancy-bound there: half of the samples wait on the ONE source-row gather a row issues and
+// consumes in the same iteration, and a row costs 390 instructions (chunk loops, id shuffles, the online-softmax
+// rescale).  Here the software pipeline is one stage deeper - row pointers three rows ahead, the ids of the first two
+// in-edges two rows ahead (broadcast loads, no shuffles), their source rows [z | p] and the destination's origin row
+// ONE ROW AHEAD in registers - and rows of at most two in-edges take a straight-line path (both logits, one maximum,
+// no rescale); further edges of a row are folded in by the online update one at a time.  Same results as
+// edge_fwd_kernel up to the summation order inside a row.
+// ---------------------------------------------------------------------------
+template <int H, int D>
+__global__ void __launch_bounds__(EDGE_THREADS, 2)
+edge_fwd_lowdeg_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
+                       const uint8_t* __restrict__ bin, const int32_t* __restrict__ extra,
+                       const float* __restrict__ zp, int ldz, const float* __restrict__ q,
+                       const float* __restrict__ origin, float* __restrict__ sh, float* __restrict__ x,
+                       float* __restrict__ stat) {
+  pdl_prologue();
+  using C = EdgeCfg<H, D>;
+  static_assert(C::EPS == 1 && C::STAGED, "one lane group per warp, staged row I/O");
+  constexpr int OV = (C::F / 4 + 31) / 32;                 // float4 per lane of a raw row
+  constexpr int NE = C::NE;
+  __shared__ float q_s[HSG_N_BINS * H];
+  __shared__ __align__(16) float stage[EDGE_WARPS * C::F];
+  for (int i = threadIdx.x; i < HSG_N_BINS * H; i += blockDim.x) q_s[i] = q[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int gl = lane % C::GROUP;
+  const int k = gl / C::LPH;       // head owned by this lane
+  const int l = gl % C::LPH;
+  const bool lane_on = lane < C::GROUP;
+  float* st_row = stage + wib * C::F;
+
+  auto load_ip = [&](int vr, int& b_, int& e_) {
+    b_ = 0;
+    e_ = 0;
+    if (vr < n_dst) {
+      b_ = __ldg(indptr + vr);
+      e_ = __ldg(indptr + vr + 1);
+    }
+  };
+  auto load_ids = [&](int b_, int e_, int* us, int* bs) {   // first two in-edges: every lane reads the same words
+    us[0] = us[1] = 0;
+    bs[0] = bs[1] = 0;
+    if (b_ < e_) {
+      us[0] = __ldg(nbr + b_);
+      bs[0] = __ldg(bin + b_);
+    }
+    if (b_ + 1 < e_) {
+      us[1] = __ldg(nbr + b_ + 1);
+      bs[1] = __ldg(bin + b_ + 1);
+    }
+  };
+  auto gather = [&](int u, float* zz, float& pp, bool on) { // [z | p] of source row u in the lane layout
+    pp = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) zz[i] = 0.f;
+    if (lane_on && on) {
+      const float* row = zp + (size_t)u * ldz;
+      pp = __ldg(row + C::FP + k);
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i)
+        if (l + C::LPH * i < C::NV) ld_vec<C::VEC>(row + (i * C::GROUP + gl) * C::VEC, zz + i * C::VEC);
+    }
+  };
+  auto load_origin = [&](int vr, float4* og) {
+#pragma unroll
+    for (int i = 0; i < OV; ++i) {
+      const int c4 = lane + 32 * i;
+      og[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (x != nullptr && vr < n_dst && c4 < C::F / 4)
+        og[i] = __ldg(reinterpret_cast<const float4*>(origin + (size_t)vr * C::F) + c4);
+    }
+  };
+
+  int v = warp;
+  int beg, end, begn, endn, beg2, end2;
+  int us[2], bs[2], usn[2], bsn[2];
+  float z0[NE], z1[NE], p0, p1;
+  float4 og[OV];
+  load_ip(v, beg, end);
+  load_ip(v + nwarps, begn, endn);
+  load_ip(v + 2 * nwarps, beg2, end2);
+  load_ids(beg, end, us, bs);
+  load_ids(begn, endn, usn, bsn);
+  load_origin(v, og);
+  gather(us[0], z0, p0, end > beg);
+  gather(us[1], z1, p1, end > beg + 1);
+  while (v < n_dst) {
+    int beg3, end3, us2[2], bs2[2];
+    load_ip(v + 3 * nwarps, beg3, end3);
+    load_ids(beg2, end2, us2, bs2);
+    const float xcnt = extra ? (float)__ldg(extra + v) : 0.f;
+    const int deg = end - beg;
+    // ---- softmax over the in-edges: the first two from the prefetched rows, straight line ----
+    float m = -CUDART_INF_F, den = 0.f;
+    float acc[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) acc[i] = 0.f;
+    if (deg > 0) {
+      const float lg0 = leaky(p0 + q_s[bs[0] * H + k]);
+      const float lg1 = deg > 1 ? leaky(p1 + q_s[bs[1] * H + k]) : -CUDART_INF_F;
+      m = fmaxf(lg0, lg1);
+      const float w0 = exp_fast(lg0 - m), w1 = exp_fast(lg1 - m);      // exp(-inf) = 0 for a missing second edge
+      den = w0 + w1;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) acc[i] = fmaf(w1, z1[i], w0 * z0[i]);
+      for (int e = beg + 2; e < end; ++e) {                // further in-edges (rare on word rows): online update
+        float zt[NE], pt;
+        gather(__ldg(nbr + e), zt, pt, true);
+        const float lg = leaky(pt + q_s[(int)__ldg(bin + e) * H + k]);
+        const float mx = fmaxf(m, lg);
+        const float sc = exp_fast(m - mx), w = exp_fast(lg - mx);
+        den = den * sc + w;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) acc[i] = fmaf(w, zt[i], acc[i] * sc);
+        m = mx;
+      }
+    }
+    // the next row's source rows and origin start their way now (its ids were fetched one iteration ago)
+    float4 ogc[OV];
+#pragma unroll
+    for (int i = 0; i < OV; ++i) ogc[i] = og[i];
+    gather(usn[0], z0, p0, endn > begn);
+    gather(usn[1], z1, p1, endn > begn + 1);
+    load_origin(v + nwarps, og);
+
+    float mf = 0.f, inv = 0.f;
+    if (m == -CUDART_INF_F) {  // no word<->supernode in-edge: DGL's zero fill (or softmax over z = 0 extras)
+      den = xcnt > 0.f ? xcnt : 1.f;
+    } else {
+      mf = xcnt > 0.f ? fmaxf(m, 0.f) : m;
+      const float sc = exp_fast(m - mf);
+      den = den * sc + xcnt * exp_fast(-mf);
+      inv = sc / den;
+    }
+    if (lane_on) {
+      if (l == 0) {
+        stat[(size_t)v * 3 * H + k] = mf;
+        stat[(size_t)v * 3 * H + H + k] = den;
+      }
+#pragma unroll
+      for (int i = 0; i < C::VPL; ++i) {
+        if (l + C::LPH * i < C::NV) {
+          float o[C::VEC];
+#pragma unroll
+          for (int t = 0; t < C::VEC; ++t) o[t] = acc[i * C::VEC + t] * inv;
+          st_vec<C::VEC>(st_row + k * D + C::VEC * (l + C::LPH * i), o);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < OV; ++i) {                         // coalesced 128-bit row stores
+      const int c4 = lane + 32 * i;
+      if (c4 < C::F / 4) {
+        const float4 o = *reinterpret_cast<const float4*>(st_row + 4 * c4);
+        const size_t off = (size_t)v * C::F + 4 * c4;
+        if (sh != nullptr) *reinterpret_cast<float4*>(sh + off) = o;
+        if (x != nullptr)
+          *reinterpret_cast<float4*>(x + off) = make_float4(ogc[i].x + elu1(o.x), ogc[i].y + elu1(o.y),
+                                                            ogc[i].z + elu1(o.z), ogc[i].w + elu1(o.w));
+      }
+    }
+    __syncwarp();
+    v += nwarps;
+    beg = begn;
+    end = endn;
+    begn = beg2;
+    endn = end2;
+    beg2 = beg3;
+    end2 = end3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      us[i] = usn[i];
+      bs[i] = bsn[i];
+      usn[i] = us2[i];
+      bsn[i] = bs2[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // forward, ROW-PARALLEL: every GROUP-lane group of a warp walks ITS OWN destination row (EPS rows per warp in flight,
 // U gathered rows each).  No merge of partial softmax states, no index shuffles: on the W2S default (8,8) (one lane
 // per head, four rows per warp) this executes ~2.5x fewer instructions per edge than the shared-row mapping, which
@@ -1304,6 +1491,8 @@ static int edge_grid(int n_rows_steps, int cap = EDGE_DEFAULT_BLOCKS) {
   X(8, 8) X(6, 50) X(8, 16) X(6, 16) X(8, 32) X(6, 32) X(4, 4) X(6, 8) X(4, 16) X(1, 64) X(16, 4) X(2, 32) X(4, 32) X(12, 25)
 
 static std::atomic<int> g_fwd_rowpar{-1};   // -1 auto (many rows), 0 never, 1 whenever the layout allows
+static std::atomic<int> g_fwd_lowdeg{-1};   // -1 auto (many low-degree wide rows), 0 never, 1 whenever the layout allows
+constexpr int FWD_LOWDEG_MIN_ROWS = 16384;
 constexpr int FWD_ROWPAR_MIN_ROWS = 16384;
 
 template <int H, int D>
@@ -1336,6 +1525,15 @@ static int launch_fwd(const hsg_csc* c, const float* zp, int ldz, const float* q
   if (rowpar && launch_fwd_rowpar<H, D>(edge_grid(ceil_div(c->n_dst, C::EPS)), deep_row, c, zp, ldz, q, origin, sh, x,
                                         stat, s))
     return check_launch();
+  if constexpr (C::EPS == 1 && C::STAGED) {
+    // wide rows of low degree in numbers (the word rows of a shard): the pipelined straight-line kernel
+    const int ld = g_fwd_lowdeg.load(std::memory_order_relaxed);
+    if (ld == 1 || (ld < 0 && !deep && c->n_dst >= FWD_LOWDEG_MIN_ROWS)) {
+      launch_k(edge_fwd_lowdeg_kernel<H, D>, dim3(edge_grid(c->n_dst, EDGE_MAX_BLOCKS)), dim3(EDGE_THREADS), 0, s,
+               c->n_dst, c->indptr, c->nbr, c->bin, c->extra, zp, ldz, q, origin, sh, x, stat);
+      return check_launch();
+    }
+  }
   if (deep)
     launch_k(edge_fwd_kernel<H, D, UHI>, dim3(edge_grid(c->n_dst, C::STAGED ? EDGE_MAX_BLOCKS : EDGE_DEFAULT_BLOCKS)), dim3(EDGE_THREADS), 0, s, c->n_dst, c->indptr, c->nbr, c->bin,
                                                                            c->extra, zp, ldz, q, origin, sh, x, stat);
@@ -1502,6 +1700,11 @@ int hsg_edge_bwd_prep(int n_dst, int H, int d, const float* dx, const float* dsh
 
 int hsg_set_edge_rowpar(int mode) {
   g_rowpar.store(mode < 0 ? -1 : (mode ? 1 : 0));
+  return HSG_OK;
+}
+
+int hsg_set_edge_fwd_lowdeg(int mode) {
+  g_fwd_lowdeg.store(mode < 0 ? -1 : (mode ? 1 : 0));
   return HSG_OK;
 }
 

@@ -234,6 +234,11 @@ int hsg_edge_perm(int H, int d, int col);
  * destination row when there are >= 16 384 rows - large shards; the groups share one row's edge list otherwise),
  * 0 never, 1 whenever the layout allows.  Same results up to summation order (tested). */
 int hsg_set_edge_fwd_rowpar(int mode);
+/* Forward mapping for WIDE rows of LOW degree (layouts with one lane group per warp and the staged epilogue, e.g. the
+ * S2W default (6,50) on word rows): source rows and the origin row prefetched one destination ahead, straight-line
+ * softmax for rows of at most two in-edges.  -1 auto (>= 16 384 destination rows of average in-degree <= 4), 0 never,
+ * 1 whenever the layout allows.  Same results up to summation order (tested). */
+int hsg_set_edge_fwd_lowdeg(int mode);
 int hsg_edge_fwd(const hsg_csc* csc, int H, int d, const float* zp, int ldz, const float* q,
                  const float* origin /* [n_dst,F] or NULL */, float* sh /* [n_dst,F]; NULL: not stored (x != NULL) */,
                  float* x /* [n_dst,F] or NULL */, float* stat /* [n_dst,3H] */, void* stream);

@@ -60,6 +60,9 @@ def main():
                                                         origin.data_ptr(), sh.data_ptr(), x.data_ptr(), stat.data_ptr(), st)),
         "edge_fwd_no_sh": lambda: _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(),
                                                               origin.data_ptr(), None, x.data_ptr(), stat.data_ptr(), st)),
+        "edge_fwd_no_sh_general": lambda: (lib.hsg_set_edge_fwd_lowdeg(0), _lib.check(lib.hsg_edge_fwd(
+            C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(), None, x.data_ptr(),
+            stat.data_ptr(), st)), lib.hsg_set_edge_fwd_lowdeg(-1)),
         "edge_bwd_prep": lambda: _lib.check(lib.hsg_edge_bwd_prep(csc.n_dst, H, d, origin.data_ptr(), None, sh.data_ptr(),
                                                                   g.data_ptr(), stat.data_ptr(), st)),
         "edge_bwd": lambda: _lib.check(lib.hsg_edge_bwd(C.byref(csc_t), H, d, zp.data_ptr(), ldz, q.data_ptr(),
@@ -92,7 +95,7 @@ def main():
     ms = out["ms"]
     fr = lambda b, t: b / (t * 1e-3) / 1e9 / hbm  # noqa: E731
     out["frac_survey"] = {}
-    for name in ("edge_fwd", "edge_fwd_no_sh"):
+    for name in ("edge_fwd", "edge_fwd_no_sh", "edge_fwd_no_sh_general"):
         if name in ms:
             out["frac_survey"][name] = fr(b_fwd, ms[name])
     if "edge_bwd" in ms and "edge_bwd_prep" in ms:

@@ -102,3 +102,43 @@ def test_update_loop_same_results_with_either_prep(n_iter, hdsg):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     for x, y in zip(b, a):
         assert nerr(x, y) <= 3e-6, nerr(x, y)
+
+
+@pytest.mark.parametrize("shape,hdsg,n,kind", [("cnndm", False, 40, "S2W"), ("multinews", True, 24, "S2W"),
+                                               ("nyt50", False, 64, "S2W"), ("cnndm", False, 12, "W2S")])
+def test_lowdeg_forward_equals_general_forward(shape, hdsg, n, kind):
+    """edge_fwd_lowdeg_kernel (rows prefetched one destination ahead, straight-line softmax up to two in-edges, online
+    update beyond) against edge_fwd_kernel on the (6,50) layout: word rows (S2W) and, to exercise long edge lists and
+    the implicit extra in-edges, the supernode rows of the other direction."""
+    lib = _lib.load()
+    exs = syn.make_examples(n, shape, seed=13, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
+    csc, _ = batch.csc(kind)
+    H, d = 6, 50
+    _, ldz = _lib.edge_layout(H, d)
+    torch.manual_seed(1)
+    dev = "cuda"
+    zp = torch.randn(csc.n_src, ldz, device=dev)
+    q = torch.randn(10, H, device=dev)
+    origin = torch.randn(csc.n_dst, H * d, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.hsg_set_edge_fwd_lowdeg(mode)
+            sh = torch.full((csc.n_dst, H * d), float("nan"), device=dev)
+            x = torch.full((csc.n_dst, H * d), float("nan"), device=dev)
+            stat = torch.zeros(csc.n_dst, 3 * H, device=dev)
+            _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(),
+                                        sh.data_ptr(), x.data_ptr(), stat.data_ptr(), st))
+            outs.append((sh, x, stat[:, :2 * H].clone()))
+        x_only = torch.full((csc.n_dst, H * d), float("nan"), device=dev)       # sh = NULL, x only
+        stat = torch.zeros(csc.n_dst, 3 * H, device=dev)
+        _lib.check(lib.hsg_edge_fwd(C.byref(csc), H, d, zp.data_ptr(), ldz, q.data_ptr(), origin.data_ptr(), None,
+                                    x_only.data_ptr(), stat.data_ptr(), st))
+    finally:
+        lib.hsg_set_edge_fwd_lowdeg(-1)
+    for a, b in zip(outs[1], outs[0]):
+        assert torch.isfinite(a).all()
+        assert nerr(a, b) <= 2e-6, nerr(a, b)
+    assert torch.equal(x_only, outs[1][1])
