@@ -189,3 +189,65 @@ def seeded_state_dict(shapes, seed, keep=()):
 
 
 FROZEN_MODEL_KEYS = ("sent_pos_embed.weight", "ngram_enc.position_embedding.weight")
+
+
+def time_verbatim_reference(exs, tb, hdsg, n_iter, steps=1):
+    """B-ref of BASELINE.md 3 (test infrastructure; build container only - needs /root/reference): the reference's OWN
+    WSWGAT modules (module/GAT.py:45-59 over GATStackLayer.py / GATLayer.py) run UNMODIFIED on the DGL-0.4-semantics
+    shim, fwd+bwd of the update loop (HiGraph.py:98-106) on the given batch, dropout 0, at 1 thread and at all host
+    threads.  Graph construction (reference CreateGraph on the shim) is timed separately, once."""
+    import importlib.util
+    import os
+    import time
+
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("hsg_make_golden", os.path.join(root, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)                     # installs the shim, imports the reference from /root/reference
+    from hetersumgraph_b200 import synthetic as syn
+    filt = set(syn.filter_ids().tolist())
+    t0 = time.time()
+    graphs = [(mg.ref_graph_hdsg if hdsg else mg.ref_graph_hsg)(e, filt) for e in exs]
+    BG = mg.shim.batch([graphs[i] for i in tb.order])
+    build_s = time.time() - t0
+    ga = mg.shim_to_arrays(BG)
+    torch.manual_seed(1234)
+    w2s = mg.WSWGAT(300, 64, 8, 0.0, 512, 0.0, 50, "W2S").train()
+    s2w = mg.WSWGAT(64, 300, 6, 0.0, 512, 0.0, 50, "S2W").train()
+    T = torch.nn.Embedding(10, 50)
+    nw, ns = int((ga.unit == 0).sum()), int((ga.unit == 1).sum())
+    w = torch.randn(nw, 300, requires_grad=True)
+    s = torch.randn(ns, 64, requires_grad=True)
+    cw, cs = torch.randn(nw, 300) / len(exs), torch.randn(ns, 64) / len(exs)
+    params = list(w2s.parameters()) + list(s2w.parameters()) + list(T.parameters())
+
+    base_n, base_e = set(BG.ndata.keys()), set(BG.edata.keys())
+
+    def step():
+        for p in params + [w, s]:
+            p.grad = None
+        # a fresh step starts from the graph as the data loader delivers it: fields written by the previous step
+        # (tfidfembed, e, ...) carry that step's autograd history
+        for view, base in ((BG.ndata, base_n), (BG.edata, base_e)):
+            for key in [k for k in view.keys() if k not in base]:
+                view.pop(key)
+        ws_, ss_ = mg.run_reference_loop(BG, w2s, s2w, T, w, s, n_iter)
+        ((ws_ * cw).sum() + (ss_ * cs).sum()).backward()
+
+    out = {"what": "reference WSWGAT modules verbatim on the DGL-0.4-semantics shim (real DGL not installable), update "
+                   "loop fwd+bwd, dropout 0", "graphs": len(exs), "word_nodes": nw, "supernodes": ns,
+           "graph_build_s_once": build_s, "host_cores": os.cpu_count()}
+    all_threads = torch.get_num_threads()
+    try:
+        for label, nt in (("threads_1", 1), ("threads_all", os.cpu_count() or all_threads)):
+            torch.set_num_threads(nt)
+            step()
+            t0 = time.time()
+            for _ in range(steps):
+                step()
+            sec = (time.time() - t0) / steps
+            out[label] = {"threads": nt, "s_per_step": sec, "graphs_per_s": len(exs) / sec}
+    finally:
+        torch.set_num_threads(all_threads)
+    return out
