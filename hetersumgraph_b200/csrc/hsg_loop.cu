@@ -423,17 +423,30 @@ int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   float* st = a->state;
   // attention prep: once per layer (parameters only)
-  for (int k = 0; k < 2; ++k) {
+  // The prep of the kind application 0 needs runs on the caller's stream; the other kind's (first needed by
+  // application 1) runs on the side stream next to application 0 and is joined before application 1.
+  SideRes* sd = (overlap_enabled() && L.n_apps > 1) ? side_res() : nullptr;
+  const int k_first = L.kind(0);
+  for (int kk = 0; kk < 2; ++kk) {
+    const int k = kk == 0 ? k_first : (k_first ^ 1);
     if (!L.has[k]) continue;
     const hsg_layer_params& P = layer(a, k);
+    cudaStream_t sp = s;
+    if (kk == 1 && sd) {
+      if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
+        return HSG_ERR_CUDA;
+      sp = sd->stream;
+    }
     HSG_TRY(hsg_attn_prep_fwd(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, st + L.waug[k],
-                              st + L.q[k], stream));
-    if (L.drop_attn) HSG_TRY(wblk_build(P.H, P.d, P.in_dim, L.ldz[k], st + L.waug[k], st + L.wblk[k], s));
+                              st + L.q[k], (void*)sp));
+    if (L.drop_attn) HSG_TRY(wblk_build(P.H, P.d, P.in_dim, L.ldz[k], st + L.waug[k], st + L.wblk[k], sp));
+    if (kk == 1 && sd && cudaEventRecord(sd->done[k], sp) != cudaSuccess) return HSG_ERR_CUDA;
   }
   const float* word = a->word_feature;
   const float* sup = a->super_feature;
   for (int i = 0; i < L.n_apps; ++i) {
     const int k = L.kind(i);
+    if (i == 1 && sd && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
     HSG_TRY(app_fwd(a, L, i, k == 0 ? word : sup, k == 0 ? sup : word, s));
     float* out = st + L.app_start(i) + L.app[k].out;
     if (k == 0) sup = out; else word = out;
@@ -465,6 +478,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
   int done[2] = {0, 0};
   SideRes* sd = overlap_enabled() ? side_res() : nullptr;
   bool side_pending[2] = {false, false};
+  bool prep_done[2] = {false, false};
   void* ws2 = reinterpret_cast<char*>(b->ws) + L.ws_half;
   for (int i = L.n_apps - 1; i >= 0; --i) {
     const int k = L.kind(i);
@@ -494,14 +508,33 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
     ++done[k];
     gst[k] = dx;
     gst[k ^ 1] = dnb;
+    if (i == 1) {
+      // application 1 is the LAST one of its kind in this backward order: its layer's (dW_aug, dq) are complete.  The
+      // attention-prep backward of that layer runs now - on the side stream, next to application 0 - instead of at
+      // the end of the step; the other layer's follows application 0 and ADDS its share of dT (two terms: the sum
+      // does not depend on the order).
+      cudaStream_t sp = s;
+      if (sd) {
+        if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
+          return HSG_ERR_CUDA;
+        sp = sd->stream;
+      }
+      HSG_TRY(attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
+                               sc + L.dq[k], G.dW, G.dWf, G.dbf, G.da, b->dT, acc, acc, sp));
+      prep_done[k] = true;
+      if (sd) {
+        if (cudaEventRecord(sd->done[k], sp) != cudaSuccess) return HSG_ERR_CUDA;
+        side_pending[k] = true;
+      }
+    }
   }
   if (sd)                                               // join: every weight gradient is complete from here on
     for (int k = 0; k < 2; ++k)
       if (side_pending[k] && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
   // attention-prep backward: (dW_aug, dq) summed over the applications -> fc / feat_fc / attn_fc / TF-IDF table
-  int t_written = 0;
+  int t_written = (prep_done[0] || prep_done[1]) ? 1 : 0;
   for (int k = 0; k < 2; ++k) {
-    if (!L.has[k]) continue;
+    if (!L.has[k] || prep_done[k]) continue;
     const hsg_layer_params& P = layer(a, k);
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
     HSG_TRY(attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
