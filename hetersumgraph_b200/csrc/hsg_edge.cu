@@ -1433,14 +1433,19 @@ edge_bwd_async_kernel(int n_src, const int32_t* __restrict__ indptr, const int32
   }
 }
 
-// dq[i] = sum over blocks, fixed order: one CTA per output, strided partial sums + smem tree
-__global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, const float* __restrict__ dq_part,
-                                                          float* __restrict__ dq, int accumulate) {
+// dq[i] = sum over the per-block partials of nseg launches (segment j at dq_part + j * seg_stride), fixed order: one
+// CTA per output, strided partial sums + smem tree
+__global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nseg, int nblocks, size_t seg_stride, int nq,
+                                                          const float* __restrict__ dq_part, float* __restrict__ dq,
+                                                          int accumulate) {
   pdl_prologue();
   __shared__ float red[128];
   const int i = blockIdx.x;
   float s = 0.f;
-  for (int b = threadIdx.x; b < nblocks; b += 128) s += dq_part[(size_t)b * nq + i];
+  for (int j = 0; j < nseg; ++j) {
+    const float* part = dq_part + (size_t)j * seg_stride;
+    for (int b = threadIdx.x; b < nblocks; b += 128) s += part[(size_t)b * nq + i];
+  }
   red[threadIdx.x] = s;
   __syncthreads();
 #pragma unroll
@@ -1451,9 +1456,10 @@ __global__ void __launch_bounds__(128) edge_bwd_dq_kernel(int nblocks, int nq, c
   if (threadIdx.x == 0) dq[i] = accumulate ? dq[i] + red[0] : red[0];
 }
 
-int edge_dq_reduce(int nblocks, int nq, const float* dq_part, float* dq, int accumulate, cudaStream_t s) {
+int edge_dq_reduce(int nseg, int nblocks, size_t seg_stride, int nq, const float* dq_part, float* dq, int accumulate,
+                   cudaStream_t s) {
   LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
-  launch_k(edge_bwd_dq_kernel, dim3(nq), dim3(128), 0, s, nblocks, nq, dq_part, dq, accumulate);
+  launch_k(edge_bwd_dq_kernel, dim3(nq), dim3(128), 0, s, nseg, nblocks, seg_stride, nq, dq_part, dq, accumulate);
   return check_launch();
 }
 
@@ -1600,7 +1606,7 @@ static bool launch_bwd_async(int* blocks_out, const hsg_csc* c, const float* zp,
 
 template <int H, int D>
 static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g, const float* stat,
-                      float* dzp, float* dq, float* ws, int accumulate_dq, cudaStream_t s) {
+                      float* dzp, float* dq, float* ws, int accumulate_dq, cudaStream_t s, int* defer_blocks) {
   using C = EdgeCfg<H, D>;
   constexpr int UHI = C::NE <= 4 ? 4 : 2, ULO = C::NE <= 4 ? 2 : 1;
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
@@ -1630,10 +1636,11 @@ static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q
     int rc = check_launch();
     if (rc) return rc;
   }
-  LaunchScope ls(SLOT_EDGE_BWD_DQ, s);
-  const int nq = HSG_N_BINS * H;
-  launch_k(edge_bwd_dq_kernel, dim3(nq), dim3(128), 0, s, blocks, nq, ws, dq, accumulate_dq);
-  return check_launch();
+  if (defer_blocks) {                                   // the caller reduces the partials of several launches at once
+    *defer_blocks = blocks;
+    return HSG_OK;
+  }
+  return edge_dq_reduce(1, blocks, 0, HSG_N_BINS * H, ws, dq, accumulate_dq, s);
 }
 
 static bool layout_ok(int H, int d, int ldz) {
@@ -1727,20 +1734,23 @@ size_t hsg_edge_bwd_workspace_bytes(int H) { return (size_t)EDGE_MAX_BLOCKS * HS
 
 int hsg_edge_bwd(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
                  const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, void* stream) {
-  return edge_bwd_ex(csc_t, H, d, zp, ldz, q, g, stat, dzp, dq, ws, ws_bytes, 0, (cudaStream_t)stream);
+  return edge_bwd_ex(csc_t, H, d, zp, ldz, q, g, stat, dzp, dq, ws, ws_bytes, 0, (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"
 
 namespace hsg {
 int edge_bwd_ex(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
-                const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s) {
-  if (!csc_t || !zp || !q || !g || !stat || !dzp || !dq || !ws || csc_t->n_dst < 0) return HSG_ERR_ARG;
+                const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s,
+                int* defer_blocks) {
+  if (!csc_t || !zp || !q || !g || !stat || !dzp || (!dq && !defer_blocks) || !ws || csc_t->n_dst < 0)
+    return HSG_ERR_ARG;
   if (ws_bytes < hsg_edge_bwd_workspace_bytes(H)) return HSG_ERR_WORKSPACE;
   if (!layout_ok(H, d, ldz) || !aligned16(zp) || !aligned16(g) || !aligned16(dzp)) return HSG_ERR_ALIGN;
   if (csc_t->n_dst > 0 && (!csc_t->indptr || (csc_t->n_edges > 0 && (!csc_t->nbr || !csc_t->bin)))) return HSG_ERR_ARG;
 #define X(HH, DD) \
-  if (H == HH && d == DD) return launch_bwd<HH, DD>(csc_t, zp, ldz, q, g, stat, dzp, dq, (float*)ws, accumulate_dq, s);
+  if (H == HH && d == DD) \
+    return launch_bwd<HH, DD>(csc_t, zp, ldz, q, g, stat, dzp, dq, (float*)ws, accumulate_dq, s, defer_blocks);
   HSG_EDGE_CONFIGS(X)
 #undef X
   return HSG_ERR_SHAPE;

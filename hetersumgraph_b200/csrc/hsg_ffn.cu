@@ -193,9 +193,11 @@ layernorm_bwd_kernel(int N, int D, const float* __restrict__ dy, const float* __
   }
 }
 
-// dgamma / dbeta = column sums of the per-block partials; 32 columns x 32 row groups per CTA, fixed order
-// (row group r sums blocks r, r+32, ... ; the 32 group sums are then added in order)
-__global__ void __launch_bounds__(1024) layernorm_bwd_reduce_kernel(int nblocks, int D, const float* __restrict__ part,
+// dgamma / dbeta = column sums of the per-block partials of nseg launches (segment j at part + j * seg_stride);
+// 32 columns x 32 row groups per CTA, fixed order (row group r sums rows r, r+32, ... of the concatenated segments;
+// the 32 group sums are then added in order)
+__global__ void __launch_bounds__(1024) layernorm_bwd_reduce_kernel(int nseg, int nblocks, size_t seg_stride, int D,
+                                                                    const float* __restrict__ part,
                                                                     float* __restrict__ dgamma,
                                                                     float* __restrict__ dbeta, int accumulate) {
   pdl_prologue();
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(1024) layernorm_bwd_reduce_kernel(int nblocks,
   const int i = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (i < 2 * D)
-    for (int b = ty; b < nblocks; b += 32) s += part[(size_t)b * 2 * D + i];
+    for (int b = ty; b < nseg * nblocks; b += 32)
+      s += part[(size_t)(b / nblocks) * seg_stride + (size_t)(b % nblocks) * 2 * D + i];
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && i < 2 * D) {
@@ -609,9 +612,19 @@ int layernorm_fwd_dropres(int N, int D, float* r, const float* resid, DropCfg dc
   return check_launch();
 }
 
+int ln_partials_reduce(int nseg, int nblocks, size_t seg_stride, int D, const float* part, float* dgamma, float* dbeta,
+                       int accumulate, cudaStream_t s) {
+  LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
+  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * D, 32)), dim3(1024), 0, s, nseg, nblocks, seg_stride, D, part,
+           dgamma, dbeta, accumulate);
+  return check_launch();
+}
+
 int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,
-                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
-  if (N < 0 || D <= 0 || !dy || !r || !stats || !gamma || !dr || !dgamma || !dbeta || !ws) return HSG_ERR_ARG;
+                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s,
+                     int* defer_blocks) {
+  if (N < 0 || D <= 0 || !dy || !r || !stats || !gamma || !dr || (!defer_blocks && (!dgamma || !dbeta)) || !ws)
+    return HSG_ERR_ARG;
   if (D % 4 != 0 || D > 512) return HSG_ERR_SHAPE;
   if (ws_bytes < hsg_layernorm_bwd_workspace_bytes(N, D)) return HSG_ERR_WORKSPACE;
   if (!aligned16(dy) || !aligned16(r) || !aligned16(dr) || !aligned16(gamma)) return HSG_ERR_ALIGN;
@@ -630,9 +643,11 @@ int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float*
     int rc = check_launch();
     if (rc) return rc;
   }
-  LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * D, 32)), dim3(1024), 0, s, grid, D, part, dgamma, dbeta, accumulate);
-  return check_launch();
+  if (defer_blocks) {                                   // the caller reduces the partials of several launches at once
+    *defer_blocks = grid;
+    return HSG_OK;
+  }
+  return ln_partials_reduce(1, grid, 0, D, part, dgamma, dbeta, accumulate, s);
 }
 
 
@@ -666,8 +681,9 @@ int ffn_rows_fwd(int n, int F, int d_hid, const float* x, const float* w1, const
 
 int ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const float* stats, const float* gamma,
                  const float* hdn, const float* w1, const float* w2, float* dr, float* dhp, float* dx, float* dgamma,
-                 float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
-  if (!dy || !r || !stats || !gamma || !hdn || !w1 || !w2 || !dr || !dhp || !dx || !dgamma || !dbeta || !ws)
+                 float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s, int* defer_blocks) {
+  if (!dy || !r || !stats || !gamma || !hdn || !w1 || !w2 || !dr || !dhp || !dx ||
+      (!defer_blocks && (!dgamma || !dbeta)) || !ws)
     return HSG_ERR_ARG;
   if (!ffn_rows_ok(n, F, d_hid)) return HSG_ERR_SHAPE;
   if (ws_bytes < hsg_layernorm_bwd_workspace_bytes(n, F)) return HSG_ERR_WORKSPACE;
@@ -686,9 +702,11 @@ int ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const
     int rc = check_launch();
     if (rc) return rc;
   }
-  LaunchScope ls(SLOT_LN_BWD_REDUCE, s);
-  launch_k(layernorm_bwd_reduce_kernel, dim3(ceil_div(2 * F, 32)), dim3(1024), 0, s, nblocks, F, part, dgamma, dbeta, accumulate);
-  return check_launch();
+  if (defer_blocks) {
+    *defer_blocks = nblocks;
+    return HSG_OK;
+  }
+  return ln_partials_reduce(1, nblocks, 0, F, part, dgamma, dbeta, accumulate, s);
 }
 
 }  // namespace hsg

@@ -59,8 +59,15 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
                float* colsum, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s, int cta_budget = 0);
 
 // dgamma / dbeta (+)= ...
+// defer_blocks != NULL (here, in ffn_rows_bwd and in edge_bwd_ex): the kernel leaves its per-block partials in `ws`,
+// the fixed-order reduce is NOT launched and *defer_blocks tells how many partial rows there are - the update loop
+// reduces the partials of all applications of a layer with ONE launch, off the critical chain.
 int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float* stats, const float* gamma, float* dr,
-                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s,
+                     int* defer_blocks = nullptr);
+// dgamma / dbeta (+)= column sums of nseg x nblocks partial rows (segment j at part + j * seg_stride floats)
+int ln_partials_reduce(int nseg, int nblocks, size_t seg_stride, int D, const float* part, float* dgamma, float* dbeta,
+                       int accumulate, cudaStream_t s);
 
 // hsg_ffn.cu: whole position-wise FFN of a small node set in one launch each way (exact fp32); ffn_rows_ok tells
 // whether the shape qualifies.  Same outputs as gemm_nt + gemm_nt + layernorm_fwd / layernorm_bwd + gemm_nn + gemm_nn.
@@ -70,13 +77,17 @@ int ffn_rows_fwd(int n, int F, int d_hid, const float* x, const float* w1, const
                  cudaStream_t s);
 int ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const float* stats, const float* gamma,
                  const float* hdn, const float* w1, const float* w2, float* dr, float* dhp, float* dx, float* dgamma,
-                 float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+                 float* dbeta, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s, int* defer_blocks = nullptr);
 // hsg_gemm.cu: products below the small-product threshold (hsg_set_gemm_small_flops) run on FFMA tiles
 bool gemm_is_small(int M, int N, int K);
 
 // dq (+)= ...
 int edge_bwd_ex(const hsg_csc* csc_t, int H, int d, const float* zp, int ldz, const float* q, const float* g,
-                const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s);
+                const float* stat, float* dzp, float* dq, void* ws, size_t ws_bytes, int accumulate_dq, cudaStream_t s,
+                int* defer_blocks = nullptr);
+// hsg_edge.cu: dq (+)= sum of nseg x nblocks partial rows (segment j at dq_part + j * seg_stride floats), fixed order
+int edge_dq_reduce(int nseg, int nblocks, size_t seg_stride, int nq, const float* dq_part, float* dq, int accumulate,
+                   cudaStream_t s);
 
 // hsg_edge_rc.cu: whether the update loop recomputes sh in the backward prep (then the forward does not store it)
 bool edge_recompute_use(const hsg_csc* csc_fwd, int H, int d, int ldz);

@@ -114,6 +114,8 @@ AppOff app_layout(const hsg_layer_params& P, int ldz, int n_src, int n_dst) {
 
 struct KindBuf {            // backward scratch of one kind (dst = its destination node type)
   size_t dr, dhp, g, dx, dzp, gstate, drm, dA, dWblk;
+  size_t ln_part, dq_part;  // per-block partials of (dgamma, dbeta) / dq, one slot per application of the kind
+  size_t ln_stride, dq_stride;
 };
 
 struct Layout {
@@ -195,7 +197,7 @@ int make_layout(const hsg_loop_args* a, Layout* L) {
   for (int k = 0; k < 2; ++k) {
     KindBuf& b = L->kb[k];
     L->dWaug[k] = L->dq[k] = off;
-    b = KindBuf{off, off, off, off, off, off, off, off, off};
+    b = KindBuf{off, off, off, off, off, off, off, off, off, off, off, 0, 0};
     if (!L->has[k]) continue;
     const hsg_layer_params& P = layer(a, k);
     const size_t F = (size_t)P.H * P.d, nd = (size_t)L->n_dst[k], ns = (size_t)L->n_src[k];
@@ -212,6 +214,12 @@ int make_layout(const hsg_loop_args* a, Layout* L) {
       b.dA = off;    off += r4(ns * P.H * P.in_dim);
       b.dWblk = off; off += r4((size_t)L->ldz[k] * P.H * P.in_dim);
     }
+    // deferred reduces: every application of the kind leaves its partial rows in its own slot
+    const int n_k = (L->n_apps + (L->start == k ? 1 : 0)) / 2;           // applications of this kind
+    b.ln_stride = r4(hsg_layernorm_bwd_workspace_bytes((int)nd, (int)F) / sizeof(float) + 1);
+    b.dq_stride = r4(hsg_edge_bwd_workspace_bytes(P.H) / sizeof(float) + 1);
+    b.ln_part = off; off += (size_t)n_k * b.ln_stride;
+    b.dq_part = off; off += (size_t)n_k * b.dq_stride;
     zero_out = mx(zero_out, r4(nd * F));
   }
   L->zero_out = off; off += zero_out;
@@ -300,7 +308,8 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
 // earlier application of the same kind still has side work in flight on this kind's scratch buffers.
 int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbor, const float* dout, float* dx,
             float* dnb, const float* dnb_add, float* sc, int acc_aug, const hsg_layer_grads& G, int acc_ffn, void* ws,
-            size_t ws_bytes, void* ws2, SideRes* sd, bool* side_pending, cudaStream_t s) {
+            size_t ws_bytes, void* ws2, SideRes* sd, bool* side_pending, int slot, int* ln_blocks, int* dq_blocks,
+            cudaStream_t s) {
   const int k = L.kind(i);
   const hsg_layer_params& P = layer(a, k);
   const AppOff& o = L.app[k];
@@ -321,13 +330,20 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   }
   const bool rows_kernel = !L.drop_ffn && ffn_rows_ok(n_dst, F, P.d_hid);
   const float* drm = dr;
+  // (dgamma, dbeta) and dq leave the kernels as per-block partials in this application's slot; the fixed-order reduces
+  // run once per layer after its last application (hsg_update_loop_bwd), not here on the critical chain
+  void* ln_ws = sc + b.ln_part + (size_t)slot * b.ln_stride;
+  const size_t ln_ws_bytes = b.ln_stride * sizeof(float);
+  void* dq_ws = sc + b.dq_part + (size_t)slot * b.dq_stride;
+  const size_t dq_ws_bytes = b.dq_stride * sizeof(float);
   if (rows_kernel) {
     // small destination set: LayerNorm backward, dhp and dx in ONE launch (+ the dgamma / dbeta reduce)
-    HSG_TRY(ffn_rows_bwd(n_dst, F, P.d_hid, dout, r, ln, P.gamma, hdn, P.w1, P.w2, dr, dhp, dx, G.dgamma, G.dbeta, ws,
-                         ws_bytes, acc_ffn, s));
+    HSG_TRY(ffn_rows_bwd(n_dst, F, P.d_hid, dout, r, ln, P.gamma, hdn, P.w1, P.w2, dr, dhp, dx, G.dgamma, G.dbeta, ln_ws,
+                         ln_ws_bytes, acc_ffn, s, ln_blocks));
   } else {
     // LayerNorm
-    HSG_TRY(layernorm_bwd_ex(n_dst, F, dout, r, ln, P.gamma, dr, G.dgamma, G.dbeta, ws, ws_bytes, acc_ffn, s));
+    HSG_TRY(layernorm_bwd_ex(n_dst, F, dout, r, ln, P.gamma, dr, G.dgamma, G.dbeta, ln_ws, ln_ws_bytes, acc_ffn, s,
+                             ln_blocks));
     // FFN dropout: the residual path keeps dr, the W2 path sees dr * mask / (1-p)
     if (L.drop_ffn) {
       HSG_TRY(dropout_mul((size_t)n_dst * F, dr, sc + b.drm, make_drop(a->ffn_p, a->seed, stream_ffn(i), a->seed_dev), s));
@@ -351,7 +367,8 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     HSG_TRY(hsg_edge_bwd_prep_rc(csc_f, P.H, P.d, zp, ldz, st + L.q[k], dx, g, stat, s));
   else
     HSG_TRY(hsg_edge_bwd_prep(n_dst, P.H, P.d, dx, nullptr, sh, g, stat, s));
-  HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, ws, ws_bytes, acc_aug, s));
+  HSG_TRY(edge_bwd_ex(csc_t, P.H, P.d, zp, ldz, st + L.q[k], g, stat, dzp, dq, dq_ws, dq_ws_bytes, acc_aug, s,
+                      dq_blocks));
   // projection backward
   int rc;
   if (L.drop_attn) {
@@ -383,6 +400,20 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     side_pending[k] = true;
   }
   return HSG_OK;
+}
+
+// Everything of layer `k` that waits for its LAST application in backward order: the fixed-order reduces of the
+// (dgamma, dbeta) and dq partials of its n_k applications (one launch each), then the attention-prep backward
+// (dW_aug, dq) -> fc / feat_fc / attn_fc / TF-IDF table.
+int finish_kind(const hsg_loop_args* a, const Layout& L, int k, int n_k, int ln_blocks, int dq_blocks, float* sc,
+                const hsg_layer_grads& G, float* dT, int acc_params, int acc_T, cudaStream_t s) {
+  const hsg_layer_params& P = layer(a, k);
+  const KindBuf& b = L.kb[k];
+  const int F = P.H * P.d;
+  HSG_TRY(ln_partials_reduce(n_k, ln_blocks, b.ln_stride, F, sc + b.ln_part, G.dgamma, G.dbeta, acc_params, s));
+  HSG_TRY(edge_dq_reduce(n_k, dq_blocks, b.dq_stride, HSG_N_BINS * P.H, sc + b.dq_part, sc + L.dq[k], 0, s));
+  return attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
+                          sc + L.dq[k], G.dW, G.dWf, G.dbf, G.da, dT, acc_params, acc_T, s);
 }
 
 }  // namespace
@@ -479,6 +510,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
   SideRes* sd = overlap_enabled() ? side_res() : nullptr;
   bool side_pending[2] = {false, false};
   bool prep_done[2] = {false, false};
+  int ln_blocks[2] = {0, 0}, dq_blocks[2] = {0, 0};
   void* ws2 = reinterpret_cast<char*>(b->ws) + L.ws_half;
   for (int i = L.n_apps - 1; i >= 0; --i) {
     const int k = L.kind(i);
@@ -503,8 +535,12 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
       dnb = ext_neighbor;                              // NULL: not wanted (e.g. frozen embedding) - product skipped
     }
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
+    int lnb = 0, dqb = 0;
     HSG_TRY(app_bwd(a, L, i, neighbor, dout, dx, dnb, gst[k ^ 1], sc, done[k] > 0, G, acc || done[k] > 0, b->ws,
-                    L.ws_half, ws2, sd, side_pending, s));
+                    L.ws_half, ws2, sd, side_pending, done[k], &lnb, &dqb, s));
+    if (done[k] > 0 && (lnb != ln_blocks[k] || dqb != dq_blocks[k])) return HSG_ERR_SHAPE;   // same launch per kind
+    ln_blocks[k] = lnb;
+    dq_blocks[k] = dqb;
     ++done[k];
     gst[k] = dx;
     gst[k ^ 1] = dnb;
@@ -519,8 +555,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
           return HSG_ERR_CUDA;
         sp = sd->stream;
       }
-      HSG_TRY(attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
-                               sc + L.dq[k], G.dW, G.dWf, G.dbf, G.da, b->dT, acc, acc, sp));
+      HSG_TRY(finish_kind(a, L, k, done[k], ln_blocks[k], dq_blocks[k], sc, G, b->dT, acc, acc, sp));
       prep_done[k] = true;
       if (sd) {
         if (cudaEventRecord(sd->done[k], sp) != cudaSuccess) return HSG_ERR_CUDA;
@@ -537,8 +572,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
     if (!L.has[k] || prep_done[k]) continue;
     const hsg_layer_params& P = layer(a, k);
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
-    HSG_TRY(attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
-                             sc + L.dq[k], G.dW, G.dWf, G.dbf, G.da, b->dT, acc, acc || t_written, s));
+    HSG_TRY(finish_kind(a, L, k, done[k], ln_blocks[k], dq_blocks[k], sc, G, b->dT, acc, acc || t_written, s));
     t_written = 1;
   }
   return HSG_OK;
