@@ -727,7 +727,7 @@ edge_bwd_prep_kernel(int n_dst, const float* __restrict__ dx, const float* __res
 // backward, source-centric over the transposed structure
 // ---------------------------------------------------------------------------
 template <int H, int D, int U>
-__global__ void __launch_bounds__(EDGE_THREADS, (EdgeCfg<H, D>::NE <= 4) ? 4 : 3)
+__global__ void __launch_bounds__(EDGE_THREADS, (EdgeCfg<H, D>::NE <= 4) ? 4 : ((U * EdgeCfg<H, D>::NE > 24) ? 2 : 3))
 edge_bwd_kernel(int n_src, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
                 const uint8_t* __restrict__ bin, const float* __restrict__ zp, int ldz, const float* __restrict__ q,
                 const float* __restrict__ g, const float* __restrict__ stat, float* __restrict__ dzp,
@@ -1463,6 +1463,9 @@ int edge_dq_reduce(int nseg, int nblocks, size_t seg_stride, int nq, const float
   return check_launch();
 }
 
+#ifndef HSG_BWD_UHI_WIDE
+#define HSG_BWD_UHI_WIDE 2
+#endif
 constexpr int EDGE_MAX_BLOCKS = 148 * 32;  // upper bound of the grid (sizes the dq partial workspace)
 constexpr int EDGE_DEFAULT_BLOCKS = 148 * 8;
 
@@ -1608,7 +1611,7 @@ template <int H, int D>
 static int launch_bwd(const hsg_csc* c, const float* zp, int ldz, const float* q, const float* g, const float* stat,
                       float* dzp, float* dq, float* ws, int accumulate_dq, cudaStream_t s, int* defer_blocks) {
   using C = EdgeCfg<H, D>;
-  constexpr int UHI = C::NE <= 4 ? 4 : 2, ULO = C::NE <= 4 ? 2 : 1;
+  constexpr int UHI = C::NE <= 4 ? 4 : (HSG_BWD_UHI_WIDE), ULO = C::NE <= 4 ? 2 : 1;
   const bool deep = (double)c->n_edges > 4.0 * C::EPS * (double)c->n_dst;
   const int rp = g_rowpar.load(std::memory_order_relaxed);
   const bool rowpar = C::EPS > 1 && !C::STAGED && (rp == 1 || (rp < 0 && !deep));
