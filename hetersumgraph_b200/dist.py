@@ -86,7 +86,7 @@ def gradient_parity(rank, world, dev, all_reduce=None, n_global=256, seed=3):
     # batch otherwise fall on different sides of the size thresholds (the exact-fp32 small-product / one-launch FFN
     # kernels below 3e8 flops, 3xTF32 above; the recomputing edge prep from 65 536 rows on): each is inside the fp32
     # class, but their ~1e-7 differences flip single ReLU units at their kink - measured at 256 graphs on 2 ranks:
-    # 1.3e-5 on 48 of 433 k gradient elements, 1e-7 with the selection pinned (scratch/shard_parity.py).
+    # 1.3e-5 on 48 of 433 k gradient elements, 1e-7 with the selection pinned (profiles/shard_parity.py).
     lib = _lib.load()
     lib.hsg_set_gemm_small_flops(0.0)
     lib.hsg_set_edge_recompute(0)
