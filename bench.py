@@ -326,11 +326,24 @@ def run_ours(args):
     sf_host = torch.randn(n_sent_rows, 64, generator=gen).pin_memory()
 
     all_reduce = (lambda t: dist.all_reduce(t)) if dist is not None else None
+    # N > 1: gradient all-reduce + Adam + zero_grad as ONE kernel over NVLink peer memory (dist.PeerAllReduceAdam);
+    # NCCL all-reduce + Adam kernel when symmetric memory is not available (or HSG_PEER_REDUCE=0)
+    fused_reduce, reduce_how = None, ("nccl all_reduce + adam kernel" if dist is not None else "single GPU: adam kernel")
+    if dist is not None and os.environ.get("HSG_PEER_REDUCE", "1") != "0":
+        from hetersumgraph_b200.dist import PeerAllReduceAdam
+        try:
+            if PeerAllReduceAdam.available():
+                fused_reduce = PeerAllReduceAdam(opt)
+                reduce_how = "fused peer-memory all-reduce + adam kernel (hsg_allreduce_adam_step)"
+        except Exception as e:           # every rank takes the same branch: the constructor is collective
+            reduce_how += " (peer path unavailable: %s)" % repr(e)[:120]
     use_graph = not args.no_graph
     # `value` leg: token blob and sent_feature resident in HBM before the timed region; `e2e` leg: both come from
     # pinned host memory every step (H2D inside the step), the loss goes back to pinned host memory every step
-    gs_res = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=True)
-    gs_e2e = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=False)
+    gs_res = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=True,
+                              fused_reduce=fused_reduce)
+    gs_e2e = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=False,
+                              fused_reduce=fused_reduce)
     gs_res.prime(host)
     gs_e2e.prime(host)
     gs_res._stage_sf(sf_host.to(dev))
@@ -424,7 +437,8 @@ def run_ours(args):
     # operands, fp32 TMEM accumulation): the same graph-replayed step, reported NEXT TO the fp32-parity headline
     hb.set_gemm_mode("bf16")
     ms_bf16_eager = timed(step_eager, args.steps, 5)
-    gs_bf = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=True)
+    gs_bf = GraphedTrainStep(model, opt, bitmap_dev, n_graphs_global, all_reduce, capture=use_graph, resident_tokens=True,
+                             fused_reduce=fused_reduce)
     gs_bf.prime(host)
     gs_bf._stage_sf(sf_dev)
     sf_bf = gs_bf.sf_dev[:n_sent_rows]
@@ -596,8 +610,9 @@ def run_ours(args):
         "config": base_config(args, cfg_idx, n_iter),
         "details": {"l2": "flushed between steps (256 MiB memset outside the timed events)",
                     "step": ("one cudaGraphLaunch per step (step_graph.GraphedTrainStep): build of batch i+1 on a forked "
-                             "branch + embedding gather, update loop fwd, loss, update loop bwd, %sAdam+zero_grad of batch i"
-                             % ("NCCL all-reduce, " if world > 1 else "")) if use_graph else "eager enqueue (--no-graph)",
+                             "branch + embedding gather, update loop fwd, loss, update loop bwd, gradient reduce + "
+                             "Adam + zero_grad of batch i") if use_graph else "eager enqueue (--no-graph)",
+                    "gradient_reduce": reduce_how,
                     "graph_replays_resident_e2e": replays,
                     "prewarm_steps_per_leg": PREWARM,
                     "build": "device-side (K0), double-buffered slots: batch i+1 is built while batch i computes; exactly one build per timed step",

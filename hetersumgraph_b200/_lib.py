@@ -183,6 +183,9 @@ _PROTOS = {
                                 _P]),
     "hsg_adam_step_dev": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _I, C.c_float, _P,
                                     _Z, _P]),
+    "hsg_allreduce_adam_buffer_floats": (_Z, [_Z, _I]),
+    "hsg_allreduce_adam_step": (C.c_int, [_Z, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _I, _I,
+                                          _P]),
     "hsg_embed_gather": (C.c_int, [_I, _I, _P, _P, _P, _P]),
     "hsg_s2s_fwd": (C.c_int, [C.POINTER(S2SGraphC), _P, _P, _P, _P, _P, _P, _P]),
     "hsg_s2s_bwd_workspace_bytes": (_Z, [_I, _I, _I]),

@@ -244,6 +244,128 @@ adam_dev_kernel(size_t n, float* __restrict__ p, float* __restrict__ g, float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient all-reduce + Adam in ONE kernel over NVLink peer memory (data-parallel ranks of one box; replaces
+// ncclAllReduce + adam_dev_kernel, train.py:131-135 under DistributedDataParallel-style training).  The 433 k-float
+// arena is latency-, not bandwidth-bound: NCCL needs ~75 us for it inside the step graph, this kernel ~15-25 us.
+//   every rank owns a symmetric buffer  [ flags: world x u64 | recv: 2 parities x world slots x n floats ];
+//   phase 1  PUSH: the rank's gradient arena is stored into slot `rank` of EVERY rank's recv area (parity = step & 1;
+//            plain 128-bit stores through the peer mappings) and the arena is zeroed in the same sweep - nobody else
+//            ever reads it, so no exit barrier is needed before the next step accumulates into it;
+//   phase 2  the last block to finish publishes flag[rank] = step on every rank (fence.sys + st.release.sys);
+//   phase 3  every block waits until all `world` flags of its own rank show this step (ld.acquire.sys);
+//   phase 4  REDUCE + UPDATE from LOCAL memory: g = sum over slots in rank order (a fixed order: every rank computes
+//            bit-identical sums, so the replicas stay bit-identical), then the Adam update of adam_dev_kernel.
+// Step s + 2 reuses the parity of step s; a rank can only push for s + 2 after the barrier of s + 1, which every peer
+// passes after finishing its phase 4 of step s (program order) - the slots are free by then.
+// All blocks of the grid must be co-resident (phase 3 spins): the launcher sizes the grid to one block per SM.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int PEER_FLAG_FLOATS = 64;                       // 256 bytes of flags in front of the recv area
+
+__global__ void __launch_bounds__(256)
+allreduce_adam_kernel(size_t n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                      float* __restrict__ v, float lr, float beta1, float beta2, float eps,
+                      unsigned long long* __restrict__ state, float* const* __restrict__ peer, int rank, int world) {
+  pdl_prologue();
+  __shared__ int last_flag;
+  const unsigned long long t = state[0] + 1ull;           // this step (the same number on every rank)
+  const size_t par_off = (size_t)PEER_FLAG_FLOATS + (size_t)(t & 1ull) * world * n;
+  const size_t tid = blockIdx.x * (size_t)256 + threadIdx.x, nthr = (size_t)gridDim.x * 256;
+  const size_t n4 = n / 4;
+  // ---- phase 1: push + zero ----
+  {
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (size_t i = tid; i < n4; i += nthr) {
+      const float4 x = g4[i];
+      for (int r = 0; r < world; ++r)
+        reinterpret_cast<float4*>(peer[r] + par_off + (size_t)rank * n)[i] = x;
+      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (size_t i = 4 * n4 + tid; i < n; i += nthr) {
+      const float x = g[i];
+      for (int r = 0; r < world; ++r) peer[r][par_off + (size_t)rank * n + i] = x;
+      g[i] = 0.f;
+    }
+  }
+  // ---- phase 2: the last block publishes this rank's flag on every rank ----
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long ticket = atomicAdd(&state[1], 1ull);
+    last_flag = ticket == (unsigned long long)gridDim.x - 1ull;
+  }
+  __syncthreads();
+  if (last_flag) {
+    if (threadIdx.x == 0) state[1] = 0ull;
+    __threadfence_system();
+    if ((int)threadIdx.x < world)
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(peer[threadIdx.x]) + rank, t);
+  }
+  // ---- phase 3: wait for every rank's push ----
+  if ((int)threadIdx.x < world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(peer[rank]) + threadIdx.x;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys_u64(f) < t)
+      if (++spins > (1ull << 28)) __trap();               // a rank that never arrives: fail loudly, do not hang
+  }
+  __syncthreads();
+  // ---- phase 4: reduce the local slots in rank order + Adam ----
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float* recv = peer[rank] + par_off;
+  auto upd = [&](float gi, float& pi, float& mi_, float& vi_) {
+    const float mi = beta1 * mi_ + (1.f - beta1) * gi;
+    const float vi = beta2 * vi_ + (1.f - beta2) * gi * gi;
+    mi_ = mi;
+    vi_ = vi;
+    pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  };
+  {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (size_t i = tid; i < n4; i += nthr) {
+      float4 s = __ldcg(reinterpret_cast<const float4*>(recv) + i);
+      for (int r = 1; r < world; ++r) {
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(recv + (size_t)r * n) + i);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+      float4 pp = p4[i], mm = m4[i], vv = v4[i];
+      upd(s.x, pp.x, mm.x, vv.x);
+      upd(s.y, pp.y, mm.y, vv.y);
+      upd(s.z, pp.z, mm.z, vv.z);
+      upd(s.w, pp.w, mm.w, vv.w);
+      p4[i] = pp;
+      m4[i] = mm;
+      v4[i] = vv;
+    }
+    for (size_t i = 4 * n4 + tid; i < n; i += nthr) {
+      float s = __ldcg(recv + i);
+      for (int r = 1; r < world; ++r) s += __ldcg(recv + (size_t)r * n + i);
+      upd(s, p[i], m[i], v[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&state[2], 1ull);
+    if (ticket == (unsigned long long)gridDim.x - 1ull) {
+      state[2] = 0ull;
+      state[0] = t;
+      __threadfence();
+    }
+  }
+}
+
 // out[i, :] = table[ids[i], :]   (the word-embedding lookup of set_wnfeature, HiGraph.py:147-148), float4 rows
 __global__ void __launch_bounds__(256)
 embed_gather_kernel(int n, int dim4, const int32_t* __restrict__ ids, const float4* __restrict__ table,
@@ -377,6 +499,29 @@ int hsg_adam_step_dev(size_t n, float* param, float* grad, float* exp_avg, float
   if (blocks > 1184) blocks = 1184;
   launch_k(adam_dev_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2,
            eps, sumsq, max_grad_norm, step_state, zero_grad);
+  return check_launch();
+}
+
+size_t hsg_allreduce_adam_buffer_floats(size_t n, int world) {
+  return (size_t)PEER_FLAG_FLOATS + 2 * (size_t)(world > 0 ? world : 1) * n;
+}
+
+int hsg_allreduce_adam_step(size_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                            float beta1, float beta2, float eps, unsigned long long* step_state,
+                            float* const* peer_bufs, int rank, int world, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step_state || !peer_bufs) return HSG_ERR_ARG;
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return HSG_ERR_ARG;
+  if (n % 4 != 0) return HSG_ERR_SHAPE;                    // the receive slots are n floats apart: 128-bit accesses
+  if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq)) return HSG_ERR_ALIGN;
+  if (n == 0) return HSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  LaunchScope ls(SLOT_ADAM, s);
+  size_t blocks = (n / 4 + 255) / 256;
+  const size_t cap = (size_t)num_sms();                    // phase 3 spins: every block must be resident
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  launch_k(allreduce_adam_kernel, dim3((unsigned)blocks), dim3(256), 0, s, n, param, grad, exp_avg, exp_avg_sq, lr, beta1,
+           beta2, eps, step_state, peer_bufs, rank, world);
   return check_launch();
 }
 

@@ -34,7 +34,8 @@ class FlatGradArena:
 
     def __init__(self, params, flatten_params=False):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        n_used = sum(p.numel() for p in self.params)
+        n = (n_used + 3) // 4 * 4          # 16-byte multiple: the peer all-reduce (PeerAllReduceAdam) moves 128-bit words
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
@@ -46,7 +47,7 @@ class FlatGradArena:
             # parameters become views of one buffer as well: the optimizer then updates ONE tensor with ONE fused
             # kernel (Adam is element-wise, so this is the same arithmetic as per-tensor Adam)
             with torch.no_grad():
-                buf = torch.empty(n, dtype=torch.float32, device=dev)
+                buf = torch.zeros(n, dtype=torch.float32, device=dev)
                 off = 0
                 for p in self.params:
                     buf[off:off + p.numel()].copy_(p.reshape(-1))
@@ -132,3 +133,56 @@ def _gradient_parity(rank, world, dev, all_reduce, n_global, seed):
             "what": "all-reduced flat gradient arena of the N shards (dist.shard_indices) vs rank 0 running the whole "
                     "global batch alone, same parameters and sent_feature rows, kernel selection pinned (every product "
                     "on the tensor-core path: see gradient_parity); bound = fp32 reassociation of the row sums"}
+
+
+class PeerAllReduceAdam:
+    """Gradient all-reduce + Adam + zero_grad of a `functional.FusedAdam` in ONE kernel over NVLink peer memory
+    (`hsg_allreduce_adam_step`, csrc/hsg_head.cu) instead of `dist.all_reduce` (NCCL) followed by `step_dev`: the
+    433 k-float arena of the path is latency-bound, NCCL costs ~75 us per step for it at any rank count, the fused
+    kernel a fraction of that.  The receive buffers come from torch's symmetric-memory allocator (peer mappings of one
+    box); `available()` tells whether that works here, callers fall back to NCCL + `step_dev` otherwise.
+
+        fused = PeerAllReduceAdam(opt)          # collective: every rank of the default group
+        ...backward...; fused.step()            # instead of all_reduce(opt.g); opt.step_dev(zero_grad=True)
+    """
+
+    def __init__(self, opt, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        if opt.max_grad_norm > 0.0:
+            raise ValueError("PeerAllReduceAdam: gradient clipping needs the global norm after the reduce - use NCCL + step_dev")
+        self.opt = opt
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        lib = _lib.load()
+        n = opt.g.numel()
+        if n % 4 != 0:
+            raise ValueError("PeerAllReduceAdam: arena of %d floats is not a 16-byte multiple (use dist.FlatGradArena)" % n)
+        dev = opt.g.device
+        self.buf = symm_mem.empty(int(lib.hsg_allreduce_adam_buffer_floats(n, self.world)), dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.state = opt.device_step_counter()              # [0] completed steps (shared with step_dev), [1..3] tickets
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)                            # every rank's buffer is zeroed before anybody pushes
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except Exception:
+            return False
+
+    def step(self):
+        from . import _lib
+        from .functional import _p, _st
+        o = self.opt
+        _lib.check(_lib.load().hsg_allreduce_adam_step(o.p.numel(), _p(o.p), _p(o.g), _p(o.m), _p(o.v), o.lr, o.betas[0],
+                                                       o.betas[1], o.eps, self.state.data_ptr(), self.peers.data_ptr(),
+                                                       self.rank, self.world, _st()))
+

@@ -830,9 +830,9 @@ class FusedAdam:
                                              self.ws.data_ptr(), self.ws.numel(), _st()))
 
     def device_step_counter(self):
-        """[2] int64 on the device: [0] = completed steps (starts at the host count), [1] = kernel-internal ticket."""
+        """[4] int64 on the device: [0] = completed steps (starts at the host count), [1..3] = kernel-internal tickets."""
         if self.step_state is None:
-            self.step_state = torch.tensor([self.t, 0], dtype=torch.int64, device=self.p.device)
+            self.step_state = torch.tensor([self.t, 0, 0, 0], dtype=torch.int64, device=self.p.device)
         return self.step_state
 
     def step_dev(self, zero_grad=True):

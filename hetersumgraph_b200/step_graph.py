@@ -211,13 +211,14 @@ class GraphedTrainStep:
     model.loop.fuse_grad_accumulation must be on a dist.FlatGradArena whose arena is `opt.g`."""
 
     def __init__(self, model, opt, filter_bitmap_dev, n_graphs_global=None, all_reduce=None, capture=True,
-                 resident_tokens=False, max_graphs=16):
+                 resident_tokens=False, max_graphs=16, fused_reduce=None):
         from .path_model import FusedTrainStep
         self.model, self.opt = model, opt
         self.dev = opt.p.device
         self.fused = FusedTrainStep(model, n_graphs_global)
         self.bitmap = filter_bitmap_dev
         self.all_reduce = all_reduce
+        self.fused_reduce = fused_reduce              # dist.PeerAllReduceAdam: replaces all_reduce + opt.step_dev
         self.capture = capture
         self.resident_tokens = resident_tokens        # True: the token blob is not re-copied per step (bench `value` leg)
         self.max_graphs = max_graphs
@@ -337,9 +338,12 @@ class GraphedTrainStep:
         if sf_h2d:
             sf.copy_(self.sf_stage[p][:n_sf], non_blocking=True)
         loss, logits, d_sf = self.fused(batch, sf, hooks)
-        if self.all_reduce is not None:
-            self.all_reduce(self.opt.g)
-        self.opt.step_dev(zero_grad=True)
+        if self.fused_reduce is not None:                  # all-reduce + Adam + zero_grad in one kernel over peer memory
+            self.fused_reduce.step()
+        else:
+            if self.all_reduce is not None:
+                self.all_reduce(self.opt.g)
+            self.opt.step_dev(zero_grad=True)
         self.loss_host[p].copy_(loss.detach().view(1), non_blocking=True)
         if build_next or n_next_sf:
             main.wait_stream(side)

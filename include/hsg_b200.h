@@ -480,6 +480,18 @@ int hsg_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
 int hsg_adam_step_dev(size_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
                       float beta2, float eps, unsigned long long* step_state, int zero_grad, float max_grad_norm,
                       void* ws, size_t ws_bytes, void* stream);
+/* Gradient all-reduce (sum over the data-parallel ranks of one box) + Adam + zero_grad in ONE kernel over NVLink peer
+ * memory (csrc/hsg_head.cu: push into every rank's receive slots, system-scope flags, reduce in rank order from local
+ * memory): replaces ncclAllReduce + hsg_adam_step_dev for the small (latency-bound) gradient arena of the path.
+ * Every rank owns a symmetric buffer of hsg_allreduce_adam_buffer_floats(n, world) floats, ZEROED once before the
+ * first step; peer_bufs is a DEVICE array of the `world` base pointers (peer mappings, rank order, own buffer
+ * included).  step_state: [4] device u64, [0] = completed steps (the same on every rank), the rest kernel-internal and
+ * zero.  n must keep 16-byte alignment of the slots (n % 4 == 0).  Every rank must enqueue the call once per step;
+ * bit-identical results on all ranks (fixed summation order). */
+size_t hsg_allreduce_adam_buffer_floats(size_t n, int world);
+int hsg_allreduce_adam_step(size_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                            float beta1, float beta2, float eps, unsigned long long* step_state,
+                            float* const* peer_bufs, int rank, int world, void* stream);
 /* out[i, :] = table[ids[i], :]: the frozen word-embedding lookup of set_wnfeature (HiGraph.py:147-148).  dim % 4 == 0. */
 int hsg_embed_gather(int n, int dim, const int32_t* ids, const float* table, float* out, void* stream);
 
