@@ -74,7 +74,17 @@ def make_workload(args, rank):
     if args.global_batch > 0:
         world = int(os.environ.get("WORLD_SIZE", "1"))
         args.graphs_per_gpu = max(1, args.global_batch // world)
-    exs = syn.make_examples(args.graphs_per_gpu, shape, seed=seed + 1000 * rank, hdsg=hdsg)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # ONE seeded global batch of graphs_per_gpu x N graphs, dealt to the ranks the way the data-parallel reference
+        # would (dist.shard_indices: module/dataloader.py:479 order + snake deal balanced by edge count); its first
+        # graphs_per_gpu graphs are the N = 1 batch
+        from hetersumgraph_b200.dist import shard_indices
+        exs_all = syn.make_examples(args.graphs_per_gpu * world, shape, seed=seed, hdsg=hdsg)
+        sh = shard_indices([e.n_sent for e in exs_all], [float(sum(len(x) for x in e.w2s)) for e in exs_all], world)
+        exs = [exs_all[i] for i in sh[rank]]
+    else:
+        exs = syn.make_examples(args.graphs_per_gpu, shape, seed=seed, hdsg=hdsg)
     tb = syn.pack_token_batch(exs, hdsg=hdsg)
     return exs, tb, hdsg, n_iter, cfg_idx
 
@@ -613,6 +623,9 @@ def run_ours(args):
                              "branch + embedding gather, update loop fwd, loss, update loop bwd, gradient reduce + "
                              "Adam + zero_grad of batch i") if use_graph else "eager enqueue (--no-graph)",
                     "gradient_reduce": reduce_how,
+                    "batch": ("one seeded global batch of %d graphs dealt to the %d ranks by dist.shard_indices "
+                              "(dataloader.py:479 order + snake deal)" % (n_graphs_global, world)) if world > 1
+                             else "one seeded batch",
                     "graph_replays_resident_e2e": replays,
                     "prewarm_steps_per_leg": PREWARM,
                     "build": "device-side (K0), double-buffered slots: batch i+1 is built while batch i computes; exactly one build per timed step",
