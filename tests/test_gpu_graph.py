@@ -131,7 +131,7 @@ def test_adam_device_step_matches_torch():
         assert float(g.abs().max()) == 0.0
         assert float((mine - ref).abs().max() / ref.abs().max()) <= 1e-6
     st = fa.device_step_counter().tolist()
-    assert st == [6, 0]
+    assert st[:2] == [6, 0]      # [0] completed steps, [1] ticket back at 0; [2..3] belong to the peer-reduce kernel
 
 
 def test_embed_gather_bit_exact():
