@@ -37,7 +37,8 @@ namespace {
 // same kernels, same per-buffer order, bitwise identical results.
 struct SideRes {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, dzp = nullptr, done[2] = {nullptr, nullptr};
+  cudaStream_t stream2 = nullptr;                   // finish_kind of the layer whose applications are done first
+  cudaEvent_t fork = nullptr, dzp = nullptr, done[2] = {nullptr, nullptr}, fin = nullptr;
   bool ok = false;
 };
 static SideRes g_side[32];
@@ -55,6 +56,15 @@ int side_ctas() {
     g_side_ctas.store(v);
   }
   return v;
+}
+
+// HSG_TAIL_ON_MAIN=0: round-2 session-3 placement (last dzp product and the first finish_kind on the one side stream)
+bool tail_on_main() {
+  static const int v = [] {
+    const char* e = getenv("HSG_TAIL_ON_MAIN");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v != 0;
 }
 
 bool overlap_enabled() {
@@ -78,7 +88,9 @@ SideRes* side_res() {
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
     if (cudaStreamCreateWithPriority(&r.stream, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&r.stream2, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
     bool good = cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&r.fin, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r.dzp, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r.done[0], cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r.done[1], cudaEventDisableTiming) == cudaSuccess;
@@ -383,12 +395,16 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     HSG_TRY(gemm_tn_ex(n_src, ldz, KW, dzp, ldz, aexp, KW, sc + b.dWblk, KW, nullptr, ws, ws_bytes, 0, s));
     rc = wblk_gather(P.H, P.d, P.in_dim, ldz, sc + b.dWblk, dW_aug, acc_aug, s);
   } else {
-    if (sd) {
+    // the chain ends here when no d_neighbor is wanted (application 0 over a frozen embedding): the caller's stream
+    // has nothing left to run, so this product stays on it (own workspace half) instead of queueing behind the FFN
+    // weight gradients of the side stream
+    const bool tn_on_main = sd && !dnb && tail_on_main();
+    if (sd && !tn_on_main) {
       if (cudaEventRecord(sd->dzp, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->dzp, 0) != cudaSuccess)
         return HSG_ERR_CUDA;
     }
-    HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr, wsw, ws_bytes,
-                       acc_aug, s2, budget));
+    HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr,
+                       tn_on_main ? ws : wsw, ws_bytes, acc_aug, tn_on_main ? s : s2, tn_on_main ? 0 : budget));
     rc = HSG_OK;
     if (dnb)
       rc = hsg_gemm_nn(n_src, P.in_dim, ldz, dzp, ldz, st + L.waug[k], P.in_dim, dnb, P.in_dim, dnb_add, P.in_dim,
@@ -510,6 +526,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
   SideRes* sd = overlap_enabled() ? side_res() : nullptr;
   bool side_pending[2] = {false, false};
   bool prep_done[2] = {false, false};
+  bool fin_pending = false;
   int ln_blocks[2] = {0, 0}, dq_blocks[2] = {0, 0};
   void* ws2 = reinterpret_cast<char*>(b->ws) + L.ws_half;
   for (int i = L.n_apps - 1; i >= 0; --i) {
@@ -550,22 +567,31 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
       // the end of the step; the other layer's follows application 0 and ADDS its share of dT (two terms: the sum
       // does not depend on the order).
       cudaStream_t sp = s;
+      const bool own = sd && tail_on_main();         // its own branch: does not delay application 0's weight gradients
       if (sd) {
-        if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(sd->stream, sd->fork, 0) != cudaSuccess)
+        sp = own ? sd->stream2 : sd->stream;
+        if (cudaEventRecord(sd->fork, s) != cudaSuccess || cudaStreamWaitEvent(sp, sd->fork, 0) != cudaSuccess)
           return HSG_ERR_CUDA;
-        sp = sd->stream;
+        if (own && side_pending[k] && cudaStreamWaitEvent(sp, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
       }
       HSG_TRY(finish_kind(a, L, k, done[k], ln_blocks[k], dq_blocks[k], sc, G, b->dT, acc, acc, sp));
       prep_done[k] = true;
       if (sd) {
-        if (cudaEventRecord(sd->done[k], sp) != cudaSuccess) return HSG_ERR_CUDA;
-        side_pending[k] = true;
+        if (own) {
+          if (cudaEventRecord(sd->fin, sp) != cudaSuccess) return HSG_ERR_CUDA;
+          fin_pending = true;
+        } else {
+          if (cudaEventRecord(sd->done[k], sp) != cudaSuccess) return HSG_ERR_CUDA;
+          side_pending[k] = true;
+        }
       }
     }
   }
-  if (sd)                                               // join: every weight gradient is complete from here on
+  if (sd) {                                             // join: every weight gradient is complete from here on
     for (int k = 0; k < 2; ++k)
       if (side_pending[k] && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
+    if (fin_pending && cudaStreamWaitEvent(s, sd->fin, 0) != cudaSuccess) return HSG_ERR_CUDA;
+  }
   // attention-prep backward: (dW_aug, dq) summed over the applications -> fc / feat_fc / attn_fc / TF-IDF table
   int t_written = (prep_done[0] || prep_done[1]) ? 1 : 0;
   for (int k = 0; k < 2; ++k) {

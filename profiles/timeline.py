@@ -46,12 +46,12 @@ def main():
             gs.step(host, sfr)
         torch.cuda.synchronize()
     evs = []
-    for e in prof.events():
-        if e.device_type == torch.autograd.DeviceType.CUDA:
-            evs.append((e.time_range.start, e.time_range.end - e.time_range.start, e.name[:70], getattr(e, "device_index", 0)))
+    for e in prof.profiler.kineto_results.events():
+        if str(e.device_type()).endswith("CUDA"):
+            evs.append((e.start_ns() / 1e3, e.duration_ns() / 1e3, e.name()[:70], int(e.device_resource_id())))
     evs.sort()
     t0 = evs[0][0] if evs else 0
-    out = [{"t_us": round(s - t0, 2), "dur_us": round(d, 2), "name": n} for s, d, n, _ in evs]
+    out = [{"t_us": round(s - t0, 2), "dur_us": round(d, 2), "name": n, "stream": st} for s, d, n, st in evs]
     print(json.dumps({"graphs": n_graphs, "capture": capture, "events": out}))
 
 
