@@ -370,7 +370,12 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   }
   const int budget = sd ? side_ctas() : 0;
   HSG_TRY(gemm_tn_ex(n_dst, F, P.d_hid, drm, F, hdn, P.d_hid, G.dw2, P.d_hid, G.db2, wsw, ws_bytes, acc_ffn, s2, budget));
-  HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
+  // end of the chain (no d_neighbor wanted) over a small destination set: the side stream would run the two FFN weight
+  // gradients one after the other while the caller's stream idles behind its last projection product; dW1 follows
+  // that product on the caller's stream instead (same kernel, same operands: the placement changes no bit)
+  const bool dw1_on_main = sd && !dnb && rows_kernel && !L.drop_attn && tail_on_main();
+  if (!dw1_on_main)
+    HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
   if (!rows_kernel)
     HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
@@ -403,8 +408,11 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
       if (cudaEventRecord(sd->dzp, s) != cudaSuccess || cudaStreamWaitEvent(s2, sd->dzp, 0) != cudaSuccess)
         return HSG_ERR_CUDA;
     }
+    if (tn_on_main && cudaEventRecord(sd->dzp, s) != cudaSuccess) return HSG_ERR_CUDA;   // edge backward done (dq partials)
     HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr,
                        tn_on_main ? ws : wsw, ws_bytes, acc_aug, tn_on_main ? s : s2, tn_on_main ? 0 : budget));
+    if (dw1_on_main)
+      HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, ws, ws_bytes, acc_ffn, s, 0));
     rc = HSG_OK;
     if (dnb)
       rc = hsg_gemm_nn(n_src, P.in_dim, ldz, dzp, ldz, st + L.waug[k], P.in_dim, dnb, P.in_dim, dnb_add, P.in_dim,
@@ -421,13 +429,18 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
 // Everything of layer `k` that waits for its LAST application in backward order: the fixed-order reduces of the
 // (dgamma, dbeta) and dq partials of its n_k applications (one launch each), then the attention-prep backward
 // (dW_aug, dq) -> fc / feat_fc / attn_fc / TF-IDF table.
+// parts: 1 = the two reduces (need the layer's edge / LayerNorm backward kernels only), 2 = attention-prep backward
+// (needs dq and the layer's complete dW_aug)
 int finish_kind(const hsg_loop_args* a, const Layout& L, int k, int n_k, int ln_blocks, int dq_blocks, float* sc,
-                const hsg_layer_grads& G, float* dT, int acc_params, int acc_T, cudaStream_t s) {
+                const hsg_layer_grads& G, float* dT, int acc_params, int acc_T, cudaStream_t s, int parts = 3) {
   const hsg_layer_params& P = layer(a, k);
   const KindBuf& b = L.kb[k];
   const int F = P.H * P.d;
-  HSG_TRY(ln_partials_reduce(n_k, ln_blocks, b.ln_stride, F, sc + b.ln_part, G.dgamma, G.dbeta, acc_params, s));
-  HSG_TRY(edge_dq_reduce(n_k, dq_blocks, b.dq_stride, HSG_N_BINS * P.H, sc + b.dq_part, sc + L.dq[k], 0, s));
+  if (parts & 1) {
+    HSG_TRY(ln_partials_reduce(n_k, ln_blocks, b.ln_stride, F, sc + b.ln_part, G.dgamma, G.dbeta, acc_params, s));
+    HSG_TRY(edge_dq_reduce(n_k, dq_blocks, b.dq_stride, HSG_N_BINS * P.H, sc + b.dq_part, sc + L.dq[k], 0, s));
+  }
+  if (!(parts & 2)) return HSG_OK;
   return attn_prep_bwd_ex(P.H, P.d, P.in_dim, P.feat_dim, L.ldz[k], P.W, P.Wf, P.bf, P.a, a->T, sc + L.dWaug[k],
                           sc + L.dq[k], G.dW, G.dWf, G.dbf, G.da, dT, acc_params, acc_T, s);
 }
@@ -587,6 +600,21 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
       }
     }
   }
+  // the reduces of the layer application 0 belongs to wait for its edge backward only (event dzp, recorded when the last
+  // projection product stayed on this stream): they run on the second branch next to that product
+  int early_reduce = -1;
+  if (sd && tail_on_main() && !L.drop_attn && L.n_apps > 0) {
+    const int k0 = L.kind(0);
+    const bool dnb0 = (k0 == 0 ? b->d_word_feature : b->d_super_feature) != nullptr;
+    if (!dnb0 && !prep_done[k0]) {
+      const hsg_layer_grads& G = k0 == 0 ? b->w2s : b->s2w;
+      if (cudaStreamWaitEvent(sd->stream2, sd->dzp, 0) != cudaSuccess) return HSG_ERR_CUDA;
+      HSG_TRY(finish_kind(a, L, k0, done[k0], ln_blocks[k0], dq_blocks[k0], sc, G, b->dT, acc, acc, sd->stream2, 1));
+      if (cudaEventRecord(sd->fin, sd->stream2) != cudaSuccess) return HSG_ERR_CUDA;
+      fin_pending = true;
+      early_reduce = k0;
+    }
+  }
   if (sd) {                                             // join: every weight gradient is complete from here on
     for (int k = 0; k < 2; ++k)
       if (side_pending[k] && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;
@@ -598,7 +626,8 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
     if (!L.has[k] || prep_done[k]) continue;
     const hsg_layer_params& P = layer(a, k);
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
-    HSG_TRY(finish_kind(a, L, k, done[k], ln_blocks[k], dq_blocks[k], sc, G, b->dT, acc, acc || t_written, s));
+    HSG_TRY(finish_kind(a, L, k, done[k], ln_blocks[k], dq_blocks[k], sc, G, b->dT, acc, acc || t_written, s,
+                        k == early_reduce ? 2 : 3));
     t_written = 1;
   }
   return HSG_OK;
