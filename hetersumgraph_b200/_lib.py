@@ -75,7 +75,8 @@ class LoopArgsC(C.Structure):
                 ("w2s", LayerParamsC), ("s2w", LayerParamsC),
                 ("T", C.c_void_p), ("word_feature", C.c_void_p), ("super_feature", C.c_void_p),
                 ("state", C.c_void_p), ("state_floats", C.c_size_t),
-                ("attn_p", C.c_float), ("ffn_p", C.c_float), ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p)]
+                ("attn_p", C.c_float), ("ffn_p", C.c_float), ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p),
+                ("input_ready", C.c_void_p)]
 
 
 class LoopPlanC(C.Structure):
@@ -174,6 +175,7 @@ _PROTOS = {
     "hsg_head_workspace_bytes": (_Z, [_I, _I]),
     "hsg_head_fwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _Z, _P]),
     "hsg_head_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "hsg_head_fwd_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "hsg_doc_mean": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P]),
     "hsg_super_assemble": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P, _P]),
     "hsg_doc_init_bwd": (C.c_int, [C.POINTER(DocMapC), _P, _P, _P, _P, _P]),

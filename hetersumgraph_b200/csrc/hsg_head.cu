@@ -139,6 +139,125 @@ head_bwd_reduce_kernel(int nblocks, int n_out, const float* __restrict__ part, f
   }
 }
 
+// ---- forward + backward in ONE launch (training step: d L / d loss = 1) ------------------------------------------
+// Same block shape as the two kernels above (8 sentences per block: warp w does head_fwd_kernel's work for sentence
+// i0 + w, then thread j does head_bwd_kernel's column j over the block's sentences from the shared-memory copy of
+// dlogits); head_reduce_both_kernel then runs head_loss_reduce_kernel's and head_bwd_reduce_kernel's reductions with
+// their exact summation trees.  Every output is bit-identical to hsg_head_fwd + hsg_head_bwd(gout = NULL); four launches
+// of the serial chain between the update loop's forward and backward become two.  (Both reductions inside the first
+// kernel, by the block that takes the last ticket, was measured: 130 outputs x 127 partials on one block's 8 warps is a
+// chain of dependent L2 reads, +20 us per step.)
+__global__ void __launch_bounds__(256)
+head_fwd_bwd_kernel(hsg_head_args a, float* __restrict__ logits, float* __restrict__ dlogits,
+                    float* __restrict__ row_loss, float* __restrict__ d_state, float* __restrict__ part) {
+  pdl_prologue();
+  __shared__ float s_d[HEAD_ROWS_PER_BLOCK][2];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int width = a.hidden * (a.two_part ? 2 : 1);
+  const int i0 = blockIdx.x * HEAD_ROWS_PER_BLOCK, i1 = min(a.n_sent, i0 + HEAD_ROWS_PER_BLOCK);
+  {
+    const int i = i0 + wrp;
+    if (i < a.n_sent) {
+      const int srow = a.sent_row ? a.sent_row[i] : i;
+      float l0 = 0.f, l1 = 0.f;
+      for (int j = lane; j < a.hidden; j += 32) {
+        const float sv = a.state[(size_t)srow * a.hidden + j];
+        l0 = fmaf(sv, a.wh_w[j], l0);
+        l1 = fmaf(sv, a.wh_w[width + j], l1);
+      }
+      if (a.two_part) {
+        const int drow = a.doc_row[i];
+        for (int j = lane; j < a.hidden; j += 32) {
+          const float sv = a.state[(size_t)drow * a.hidden + j];
+          l0 = fmaf(sv, a.wh_w[a.hidden + j], l0);
+          l1 = fmaf(sv, a.wh_w[width + a.hidden + j], l1);
+        }
+      }
+      l0 = warp_sum(l0) + a.wh_b[0];
+      l1 = warp_sum(l1) + a.wh_b[1];
+      if (lane == 0) {
+        const int y = (int)a.labels[i];
+        const float mx = fmaxf(l0, l1);
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+        const float lse = mx + logf(e0 + e1);
+        const float inv = 1.f / (e0 + e1);
+        logits[2 * i] = l0;
+        logits[2 * i + 1] = l1;
+        row_loss[i] = lse - (y ? l1 : l0);
+        const float d0 = a.inv_graphs * (e0 * inv - (y == 0 ? 1.f : 0.f));
+        const float d1 = a.inv_graphs * (e1 * inv - (y == 1 ? 1.f : 0.f));
+        dlogits[2 * i] = d0;
+        dlogits[2 * i + 1] = d1;
+        s_d[wrp][0] = d0;
+        s_d[wrp][1] = d1;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int j = threadIdx.x;
+    float w0 = 0.f, w1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const float wc0 = j < width ? a.wh_w[j] : 0.f, wc1 = j < width ? a.wh_w[width + j] : 0.f;
+    for (int i = i0; i < i1; ++i) {
+      const float d0 = s_d[i - i0][0], d1 = s_d[i - i0][1];
+      if (j < width) {
+        const int srow = a.sent_row ? a.sent_row[i] : i;
+        const int row = j < a.hidden ? srow : a.doc_row[i];
+        const int jj = j < a.hidden ? j : j - a.hidden;
+        const float f = a.state[(size_t)row * a.hidden + jj];
+        w0 = fmaf(d0, f, w0);
+        w1 = fmaf(d1, f, w1);
+        if (j < a.hidden) d_state[(size_t)srow * a.hidden + j] = d0 * wc0 + d1 * wc1;
+      }
+      b0 += d0;
+      b1 += d1;
+    }
+    float* p = part + (size_t)blockIdx.x * (2 * width + 2);
+    if (j < width) {
+      p[j] = w0;
+      p[width + j] = w1;
+    }
+    if (j == 0) {
+      p[2 * width] = b0;
+      p[2 * width + 1] = b1;
+    }
+  }
+}
+
+// both fixed-order reductions of the head in one launch: block 0 = head_loss_reduce_kernel's tree over its 1024 virtual
+// threads (4 per thread), blocks 1.. = head_bwd_reduce_kernel (one warp per output)
+__global__ void __launch_bounds__(256)
+head_reduce_both_kernel(int n, const float* __restrict__ row_loss, float scale, float* __restrict__ loss, int nblocks,
+                        int n_out, const float* __restrict__ part, float* __restrict__ d_w, float* __restrict__ d_b,
+                        int accumulate) {
+  pdl_prologue();
+  if (blockIdx.x == 0) {
+    __shared__ float red[1024];
+    for (int v = threadIdx.x; v < 1024; v += 256) {
+      float sm = 0.f;
+      for (int i = v; i < n; i += 1024) sm += row_loss[i];
+      red[v] = sm;
+    }
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+      for (int v = threadIdx.x; v < o; v += 256) red[v] += red[v + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = red[0] * scale;
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int i = ((blockIdx.x - 1) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_out) return;
+  float sm = 0.f;
+  for (int b = lane; b < nblocks; b += 32) sm += part[(size_t)b * n_out + i];
+  sm = warp_sum(sm);
+  if (lane == 0) {
+    float* o = i < n_out - 2 ? d_w + i : d_b + (i - (n_out - 2));
+    *o = accumulate ? *o + sm : sm;
+  }
+}
+
 // one warp per graph: out[g, rank] = local sentence index with the rank-th largest class-1 logit (ties: lower index
 // first), -1 padded.  n is at most a few hundred, so rank counting is cheaper than a sort.
 __global__ void __launch_bounds__(256)
@@ -443,6 +562,33 @@ int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout
   }
   const int n_out = 2 * width + 2;
   launch_k(head_bwd_reduce_kernel, dim3(ceil_div(n_out, 8)), dim3(256), 0, s, blocks, n_out, part, d_wh_w, d_wh_b, accumulate);
+  return check_launch();
+}
+
+int hsg_head_fwd_bwd(const hsg_head_args* a, float* logits, float* dlogits, float* loss, float* d_state, float* d_wh_w,
+                     float* d_wh_b, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  if (!head_args_ok(a) || !logits || !dlogits || !loss || !d_state || !d_wh_w || !d_wh_b || !ws) return HSG_ERR_ARG;
+  if (a->n_sent <= 0) {                                  // nothing to fuse: the two calls handle the empty batch
+    const int rc = hsg_head_fwd(a, logits, dlogits, loss, ws, ws_bytes, stream);
+    if (rc != HSG_OK) return rc;
+    return hsg_head_bwd(a, dlogits, nullptr, d_state, d_wh_w, d_wh_b, accumulate, ws, ws_bytes, stream);
+  }
+  const int width = a->hidden * (a->two_part ? 2 : 1);
+  if (ws_bytes < hsg_head_workspace_bytes(a->n_sent, width)) return HSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* row_loss = reinterpret_cast<float*>(ws);
+  float* part = row_loss + a->n_sent;
+  const int blocks = ceil_div(a->n_sent, HEAD_ROWS_PER_BLOCK);
+  LaunchScope ls(SLOT_HEAD, s);
+  if (a->sent_row || a->two_part) {
+    if (cudaMemsetAsync(d_state, 0, (size_t)a->n_super * a->hidden * sizeof(float), s) != cudaSuccess) return HSG_ERR_CUDA;
+  }
+  launch_k(head_fwd_bwd_kernel, dim3(blocks), dim3(256), 0, s, *a, logits, dlogits, row_loss, d_state, part);
+  if (a->two_part && a->n_graphs > 0)
+    launch_k(head_bwd_doc_kernel, dim3(a->n_graphs), dim3(256), 0, s, *a, (const float*)dlogits, (const float*)nullptr, d_state);
+  const int n_out = 2 * width + 2;
+  launch_k(head_reduce_both_kernel, dim3(1 + ceil_div(n_out, 8)), dim3(256), 0, s, a->n_sent, (const float*)row_loss,
+           a->inv_graphs, loss, blocks, n_out, (const float*)part, d_wh_w, d_wh_b, accumulate);
   return check_launch();
 }
 

@@ -67,6 +67,24 @@ bool tail_on_main() {
   return v != 0;
 }
 
+// tuning knobs of the tail (measured defaults): SMs the last projection product may occupy on the caller's
+// stream (0 = all), and whether dW1 of the last application follows it there
+int tail_tn_ctas() {
+  static const int v = [] {
+    const char* e = getenv("HSG_TAIL_TN_CTAS");
+    const int x = e ? atoi(e) : 0;
+    return x < 0 ? 0 : x;
+  }();
+  return v;
+}
+bool tail_dw1_main() {
+  static const int v = [] {
+    const char* e = getenv("HSG_TAIL_DW1_MAIN");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v != 0;
+}
+
 bool overlap_enabled() {
   int v = g_overlap.load(std::memory_order_relaxed);
   if (v < 0) {
@@ -373,7 +391,7 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   // end of the chain (no d_neighbor wanted) over a small destination set: the side stream would run the two FFN weight
   // gradients one after the other while the caller's stream idles behind its last projection product; dW1 follows
   // that product on the caller's stream instead (same kernel, same operands: the placement changes no bit)
-  const bool dw1_on_main = sd && !dnb && rows_kernel && !L.drop_attn && tail_on_main();
+  const bool dw1_on_main = sd && !dnb && rows_kernel && !L.drop_attn && tail_on_main() && tail_dw1_main();
   if (!dw1_on_main)
     HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
   if (!rows_kernel)
@@ -410,7 +428,7 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
     }
     if (tn_on_main && cudaEventRecord(sd->dzp, s) != cudaSuccess) return HSG_ERR_CUDA;   // edge backward done (dq partials)
     HSG_TRY(gemm_tn_ex(n_src, ldz, P.in_dim, dzp, ldz, neighbor, P.in_dim, dW_aug, P.in_dim, nullptr,
-                       tn_on_main ? ws : wsw, ws_bytes, acc_aug, tn_on_main ? s : s2, tn_on_main ? 0 : budget));
+                       tn_on_main ? ws : wsw, ws_bytes, acc_aug, tn_on_main ? s : s2, tn_on_main ? tail_tn_ctas() : budget));
     if (dw1_on_main)
       HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, ws, ws_bytes, acc_ffn, s, 0));
     rc = HSG_OK;
@@ -504,6 +522,7 @@ int hsg_update_loop_fwd(const hsg_loop_args* a, void* stream) {
   }
   const float* word = a->word_feature;
   const float* sup = a->super_feature;
+  if (a->input_ready && cudaStreamWaitEvent(s, (cudaEvent_t)a->input_ready, 0) != cudaSuccess) return HSG_ERR_CUDA;
   for (int i = 0; i < L.n_apps; ++i) {
     const int k = L.kind(i);
     if (i == 1 && sd && cudaStreamWaitEvent(s, sd->done[k], 0) != cudaSuccess) return HSG_ERR_CUDA;

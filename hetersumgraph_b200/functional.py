@@ -609,6 +609,8 @@ class UpdateLoopFn(torch.autograd.Function):
         args.attn_p, args.ffn_p, args.seed = float(cfg.get("attn_p", 0.0)), float(cfg.get("ffn_p", 0.0)), int(cfg.get("seed", 0))
         sd = cfg.get("seed_dev")                    # device step counter mixed into the dropout key (CUDA-graph replay)
         args.seed_dev = sd.data_ptr() if sd is not None else None
+        ev = cfg.get("input_ready")                 # torch.cuda.Event recorded on the stream that produces the inputs
+        args.input_ready = ev.cuda_event if ev is not None else None
         pkey = (n_apps, start, n_word, n_super, args.attn_p > 0, args.ffn_p > 0, sig[1:])
         pent = cache.get("plan") if cache is not None else None
         if pent is not None and pent[0] == pkey:
@@ -755,6 +757,38 @@ class SentenceLossFn(torch.autograd.Function):
         if ctx.grad_targets is not None:
             return None, None, None, d_state, None, None, None
         return None, None, None, d_state, d_w, d_b, None
+
+
+def head_fwd_bwd(batch, n_graphs_global, grad_targets, state, wh_w, wh_b, labels):
+    """(loss, logits, d_state) of SentenceLossFn forward + backward with d L / d loss = 1 in ONE launch
+    (hsg_head_fwd_bwd; train.py:114-121): bit-identical to the two calls, d wh ADDED into grad_targets = (d_w, d_b)."""
+    _lib.require_device()
+    lib = _lib.load()
+    state, wh_w, wh_b = _f32c(state), _f32c(wh_w), _f32c(wh_b)
+    n_super, hidden = state.shape
+    two_part = 1 if wh_w.shape[1] == 2 * hidden else 0
+    if wh_w.shape[0] != 2 or wh_w.shape[1] != hidden * (1 + two_part):
+        raise ValueError("wh weight must be [2, hidden] (HSG) or [2, 2*hidden] (HDSG)")
+    n_sent = labels.shape[0]
+    labels = labels.contiguous()
+    if labels.dtype != torch.int64:
+        raise TypeError("labels must be int64")
+    sent_row = batch.sent_row
+    if sent_row is None and n_sent != n_super:
+        raise ValueError("HSG batch: %d labels for %d sentence nodes" % (n_sent, n_super))
+    doc_row = batch.sent_doc_row.int() if two_part else None
+    gptr = batch.graph_sent_ptr
+    args = _lib.HeadArgsC(n_sent, n_super, hidden, two_part, batch.n_graphs, 0, _p(state), _p(sent_row), _p(doc_row),
+                          _p(gptr), _p(wh_w), _p(wh_b), _p(labels), 1.0 / float(n_graphs_global), 0.0)
+    dev = state.device
+    out = torch.empty(4 * n_sent + 4, dtype=torch.float32, device=dev)
+    logits, dlogits, loss = out[:2 * n_sent].view(n_sent, 2), out[2 * n_sent:4 * n_sent], out[4 * n_sent:4 * n_sent + 1]
+    d_state = torch.empty_like(state)
+    d_w, d_b = grad_targets
+    ws = _Workspace.get(lib.hsg_head_workspace_bytes(n_sent, hidden * (1 + two_part)), dev, "head")
+    _lib.check(lib.hsg_head_fwd_bwd(C.byref(args), _p(logits), _p(dlogits), _p(loss), _p(d_state), _p(d_w), _p(d_b), 1,
+                                    ws.data_ptr(), ws.numel(), _st()))
+    return loss.view(()), logits, d_state
 
 
 class DocInitFn(torch.autograd.Function):

@@ -11,6 +11,8 @@ sentence encoder (module/Encoder.py, HiGraph.py:112-161) is out of the hot-path 
   loss   = mean_graphs sum_sentences CE               train.py:114-119
   top-m  = per graph topk(logit[:,1], m)              Tester.py:128
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -105,6 +107,11 @@ class FusedTrainStep:
         if model._embed.weight.requires_grad:
             raise NotImplementedError("FusedTrainStep assumes the frozen word embedding of the reference default")
         self.model, self.n_graphs_global = model, n_graphs_global
+        # measured (gpurun r02x): as its own root of the step graph the gather starts ~9 us AFTER the attention prep, the
+        # first projection begins at the same time either way (0.6031 ms per step on and off) - off by default
+        self.gather_overlap = os.environ.get("HSG_GATHER_OVERLAP", "0") == "1"
+        self._gstream = self._gevent = None
+        self.fused_head = os.environ.get("HSG_FUSED_HEAD", "1") != "0"
 
     def __call__(self, g: HeteroBatch, sent_feature: torch.Tensor, hooks=None):
         """hooks: optional dict of callables invoked between the enqueue phases of the step ("after_forward": every
@@ -125,7 +132,22 @@ class FusedTrainStep:
         n = self.n_graphs_global if self.n_graphs_global is not None else g.n_graphs
         with torch.no_grad():
             from .functional import embed_gather
-            word_feature = embed_gather(g.word_wid, m._embed.weight)     # own kernel: no stock ATen launch on the step
+            # own kernel (no stock ATen launch on the step), on a forked stream: the update loop's parameter-only
+            # attention prep runs next to it and application 0 waits for the event (hsg_loop_args.input_ready)
+            if self.gather_overlap:
+                cur = torch.cuda.current_stream(g.word_wid.device)
+                if self._gstream is None:
+                    self._gstream = torch.cuda.Stream(device=g.word_wid.device)
+                    self._gevent = torch.cuda.Event()
+                word_feature = torch.empty(g.word_wid.shape[0], m._embed.weight.shape[1], dtype=torch.float32,
+                                           device=g.word_wid.device)
+                self._gstream.wait_stream(cur)
+                with torch.cuda.stream(self._gstream):
+                    embed_gather(g.word_wid, m._embed.weight, out=word_feature)
+                self._gevent.record(self._gstream)
+                cfg = dict(cfg, input_ready=self._gevent)
+            else:
+                word_feature = embed_gather(g.word_wid, m._embed.weight)
             super_feature = sent_feature
             if m.hdsg:                                   # HiGraph.py:196-203,231-244
                 from .functional import DocInitFn
@@ -137,10 +159,15 @@ class FusedTrainStep:
             _, super_state = UpdateLoopFn.forward(c1, g, cfg, word_feature, super_feature, *tensors)
             if "after_forward" in hooks:
                 hooks["after_forward"]()
-            c2 = _Ctx([False] * 7)
-            loss, logits = SentenceLossFn.forward(c2, g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
-                                                  m.wh.weight, m.wh.bias, g.labels)
-            d_state = SentenceLossFn.backward(c2, None, None)[3]
+            if self.fused_head:                           # loss forward + backward in one launch (bit-identical)
+                from .functional import head_fwd_bwd
+                loss, logits, d_state = head_fwd_bwd(g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
+                                                     m.wh.weight, m.wh.bias, g.labels)
+            else:
+                c2 = _Ctx([False] * 7)
+                loss, logits = SentenceLossFn.forward(c2, g, n, (m.wh.weight.grad, m.wh.bias.grad), super_state,
+                                                      m.wh.weight, m.wh.bias, g.labels)
+                d_state = SentenceLossFn.backward(c2, None, None)[3]
             if "after_head" in hooks:
                 hooks["after_head"]()
             d_sent_feature = UpdateLoopFn.backward(c1, None, d_state)[3]

@@ -382,6 +382,11 @@ typedef struct {
    * graph replays identical kernel arguments every step; with this pointer (advanced by hsg_adam_step_dev) every
    * replay still draws fresh masks, identical in forward and backward of the same step. */
   const unsigned long long* seed_dev;
+  /* optional cudaEvent_t (NULL: none): word_feature / super_feature are being produced on ANOTHER stream (e.g. the
+   * embedding gather, HiGraph.py:147-148) and this event marks their completion.  hsg_update_loop_fwd enqueues the
+   * parameter-only attention prep first and makes `stream` wait for the event right before application 0, so the two
+   * overlap; backward ignores it. */
+  void* input_ready;
 } hsg_loop_args;
 
 typedef struct {
@@ -465,6 +470,10 @@ int hsg_head_fwd(const hsg_head_args* a, float* logits, float* dlogits, float* l
 /* gout: device scalar d L / d loss, or NULL (= 1).  d_state [n_super, hidden] is fully written. */
 int hsg_head_bwd(const hsg_head_args* a, const float* dlogits, const float* gout, float* d_state, float* d_wh_w,
                  float* d_wh_b, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* hsg_head_fwd followed by hsg_head_bwd(gout = NULL) in one launch (the training step, train.py:114-121, where the
+ * loss is the root of backward); every output is bit-identical to the two calls. */
+int hsg_head_fwd_bwd(const hsg_head_args* a, float* logits, float* dlogits, float* loss, float* d_state, float* d_wh_w,
+                     float* d_wh_b, int accumulate, void* ws, size_t ws_bytes, void* stream);
 /* out_idx [n_graphs, m]: local sentence indices by descending class-1 logit (ties: lower index first), -1 padded */
 int hsg_topm(const float* logits, const int32_t* graph_sent_ptr, int n_graphs, int m, int32_t* out_idx, void* stream);
 /* torch.optim.Adam semantics (no amsgrad / weight decay) on flat fp32 arrays, `step` counts from 1.

@@ -563,6 +563,36 @@ def test_fused_loss_matches_reference_loss(hdsg):
         assert nerr(a, b) <= TOL, nerr(a, b)
 
 
+@pytest.mark.parametrize("hdsg", [False, True])
+@pytest.mark.parametrize("n_graphs,shape", [(6, "tiny"), (32, "cnndm")])
+def test_one_launch_head_is_bit_identical_to_forward_then_backward(hdsg, n_graphs, shape):
+    """hsg_head_fwd_bwd (what the fused training step launches) against hsg_head_fwd + hsg_head_bwd(gout = NULL): loss,
+    logits, d_state and the ACCUMULATED d wh, bit for bit; twice in a row (the ticket counter returns to zero)."""
+    from hetersumgraph_b200.functional import SentenceLossFn, head_fwd_bwd
+    from hetersumgraph_b200.path_model import _Ctx
+    if hdsg and shape == "cnndm":
+        shape = "multinews"
+    exs = syn.make_examples(n_graphs, shape, seed=3, hdsg=hdsg)
+    batch = hb.HeteroBatch.from_token_batch(syn.pack_token_batch(exs, hdsg=hdsg))
+    torch.manual_seed(5)
+    n_super = batch.n_super
+    state = torch.randn(n_super, 64, device="cuda")
+    w = torch.randn(2, 128 if hdsg else 64, device="cuda") * 0.3
+    b = torch.randn(2, device="cuda")
+    g0 = (torch.randn_like(w), torch.randn_like(b))
+    for rep in range(2):
+        ta = (g0[0].clone(), g0[1].clone())
+        c = _Ctx([False] * 7)
+        loss_a, logits_a = SentenceLossFn.forward(c, batch, 7, ta, state, w, b, batch.labels)
+        d_a = SentenceLossFn.backward(c, None, None)[3]
+        tb = (g0[0].clone(), g0[1].clone())
+        loss_b, logits_b, d_b = head_fwd_bwd(batch, 7, tb, state, w, b, batch.labels)
+        torch.cuda.synchronize()
+        assert torch.equal(loss_a, loss_b) and torch.equal(logits_a, logits_b) and torch.equal(d_a, d_b)
+        assert torch.equal(ta[0], tb[0]) and torch.equal(ta[1], tb[1])
+        assert float((ta[0] - g0[0]).abs().max()) > 0.0
+
+
 def test_topm_bit_exact_vs_torch_topk():
     from hetersumgraph_b200.functional import topm
     rng = np.random.default_rng(0)
