@@ -281,7 +281,7 @@ __device__ __forceinline__ void fs_issue_group(float* ring, const float* __restr
 
 #define FS_FMA4x4(ACC, A, B)                                                              \
   do {                                                                                    \
-    _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_) {                                    \
+    _Pragma("unroll") for (int u_ = 0; u_ < U; ++u_) {                                    \
       _Pragma("unroll") for (int t_ = 0; t_ < 4; ++t_) {                                  \
         ACC[u_][t_] = fmaf(A[u_].x, B[t_].x, ACC[u_][t_]);                                \
         ACC[u_][t_] = fmaf(A[u_].y, B[t_].y, ACC[u_][t_]);                                \
@@ -291,6 +291,10 @@ __device__ __forceinline__ void fs_issue_group(float* ring, const float* __restr
     }                                                                                     \
   } while (0)
 
+// U = rows per thread, R = 4 U rows per CTA: 16 rows (U = 4) by default, 8 rows (U = 2) for small node sets (fs_rows:
+// more, shorter CTAs; the weights are re-streamed from L2 by twice as many CTAs).  Every output keeps its summation
+// order, so results do not depend on U (except the per-CTA dgamma / dbeta partials of the backward).
+template <int U>
 __global__ void __launch_bounds__(FS_THREADS)
 ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __restrict__ w1,
                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -303,22 +307,23 @@ ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __r
   float* hs = rs + FS_ROWS * FS_F;                       // [16][Dh]
   float* ring = hs + (size_t)FS_ROWS * Dh;               // [8][64][68]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rq = tid >> 6;                               // rows 4 rq .. 4 rq + 3
-  const int row0 = blockIdx.x * FS_ROWS;
+  constexpr int R = 4 * U;                               // rows of this CTA
+  const int rq = tid >> 6;                               // rows U rq .. U rq + U - 1
+  const int row0 = blockIdx.x * R;
   const int nch = Dh / FS_CH, ngrp = nch / FS_GRP;       // groups per matrix
   fs_issue_group(ring, w1, w2, true, 0, nch, Dh, tid);
   fs_issue_group(ring, w1, w2, true, 1, nch, Dh, tid);
   {
     const int rr = tid >> 4, c4 = tid & 15;              // 16 rows x 16 float4
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + rr < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)(row0 + rr) * FS_F) + c4);
+    if (rr < R && row0 + rr < n) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)(row0 + rr) * FS_F) + c4);
     *reinterpret_cast<float4*>(xs + rr * FS_F + 4 * c4) = v;
   }
   // second product: thread = (4 output columns cq + 16 t, k quarter kq of every chunk, 4 rows)
   const int cq = tid & 15, kq = (tid >> 4) & 3;
-  float acc2[4][4];
+  float acc2[U][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < U; ++u)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc2[u][t] = 0.f;
   for (int gi = 0; gi < 2 * ngrp; ++gi) {
@@ -328,25 +333,25 @@ ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __r
     if (gi < ngrp) {
       // ---- hdn = relu(x W1^T + b1): hidden units 256 gi + 64 t + jq, t = 0..3 (slot t holds W1 rows 256 gi + 64 t ..) ----
       const int jq = tid & 63;
-      float acc[4][4];
+      float acc[U][4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float bj = __ldg(b1 + gi * FS_GRP * FS_CH + FS_CH * t + jq);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u][t] = bj;
+        for (int u = 0; u < U; ++u) acc[u][t] = bj;
       }
 #pragma unroll 2
       for (int c4 = 0; c4 < FS_F / 4; ++c4) {
-        float4 xv[4], wv[4];
+        float4 xv[U], wv[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) wv[t] = *reinterpret_cast<const float4*>(grp + t * FS_SLOT_FLOATS + jq * FS_WLD + 4 * c4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xv[u] = *reinterpret_cast<const float4*>(xs + (4 * rq + u) * FS_F + 4 * c4);   // broadcast
+        for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const float4*>(xs + (U * rq + u) * FS_F + 4 * c4);   // broadcast
         FS_FMA4x4(acc, xv, wv);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int rr = 4 * rq + u;
+      for (int u = 0; u < U; ++u) {
+        const int rr = U * rq + u;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int j = gi * FS_GRP * FS_CH + FS_CH * t + jq;
@@ -364,12 +369,12 @@ ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __r
 #pragma unroll 2
         for (int k4 = 0; k4 < 4; ++k4) {
           const int kl = 16 * kq + 4 * k4;
-          float4 hv[4], wv[4];
+          float4 hv[U], wv[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) wv[t] = *reinterpret_cast<const float4*>(ws + (cq + 16 * t) * FS_WLD + kl);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            hv[u] = *reinterpret_cast<const float4*>(hs + (size_t)(4 * rq + u) * Dh + kbase + FS_CH * sl + kl);
+          for (int u = 0; u < U; ++u)
+            hv[u] = *reinterpret_cast<const float4*>(hs + (size_t)(U * rq + u) * Dh + kbase + FS_CH * sl + kl);
           FS_FMA4x4(acc2, hv, wv);
         }
       }
@@ -381,26 +386,28 @@ ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __r
   {
     float* ps = ring;                                    // [4 kq][16 rows][64 c]
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) ps[(kq * FS_ROWS + 4 * rq + u) * FS_F + cq + 16 * t] = acc2[u][t];
+      for (int t = 0; t < 4; ++t) ps[(kq * R + U * rq + u) * FS_F + cq + 16 * t] = acc2[u][t];
     __syncthreads();
     const int rr = tid >> 4, c4 = tid & 15;
-    float4 o = __ldg(reinterpret_cast<const float4*>(b2) + c4);
-    const float4 xv = *reinterpret_cast<const float4*>(xs + rr * FS_F + 4 * c4);
+    if (rr < R) {
+      float4 o = __ldg(reinterpret_cast<const float4*>(b2) + c4);
+      const float4 xv = *reinterpret_cast<const float4*>(xs + rr * FS_F + 4 * c4);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 pv = *reinterpret_cast<const float4*>(ps + (q * FS_ROWS + rr) * FS_F + 4 * c4);
-      o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+      for (int q = 0; q < 4; ++q) {
+        const float4 pv = *reinterpret_cast<const float4*>(ps + (q * R + rr) * FS_F + 4 * c4);
+        o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+      }
+      o.x += xv.x; o.y += xv.y; o.z += xv.z; o.w += xv.w;
+      *reinterpret_cast<float4*>(rs + rr * FS_F + 4 * c4) = o;
+      if (row0 + rr < n) *reinterpret_cast<float4*>(r + (size_t)(row0 + rr) * FS_F + 4 * c4) = o;
     }
-    o.x += xv.x; o.y += xv.y; o.z += xv.z; o.w += xv.w;
-    *reinterpret_cast<float4*>(rs + rr * FS_F + 4 * c4) = o;
-    if (row0 + rr < n) *reinterpret_cast<float4*>(r + (size_t)(row0 + rr) * FS_F + 4 * c4) = o;
   }
   __syncthreads();
   // ---- LayerNorm: warp w normalises rows w and w + 8 (same formulas as layernorm_fwd_kernel) ----
 #pragma unroll
-  for (int h2 = 0; h2 < FS_ROWS / 8; ++h2) {
+  for (int h2 = 0; h2 < R / 8; ++h2) {
     const int rr = warp + 8 * h2, row = row0 + rr;
     const float v0 = rs[rr * FS_F + lane], v1 = rs[rr * FS_F + lane + 32];
     const float mean = warp_sum(v0 + v1) * (1.f / (float)FS_F);
@@ -417,6 +424,7 @@ ffn_rows_fwd_kernel(int n, int Dh, const float* __restrict__ x, const float* __r
   }
 }
 
+template <int U>
 __global__ void __launch_bounds__(FS_THREADS)
 ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __restrict__ r,
                     const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ hdn,
@@ -429,8 +437,9 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
   float* dhs = pg + FS_ROWS * FS_F;                      // [16][Dh]; its head doubles as the dbeta staging area
   float* ring = dhs + (size_t)FS_ROWS * Dh;              // [8][64][68]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int R = 4 * U;
   const int rq = tid >> 6;
-  const int row0 = blockIdx.x * FS_ROWS;
+  const int row0 = blockIdx.x * R;
   const int nch = Dh / FS_CH, ngrp = nch / FS_GRP;
   // weight stream of this pass: W2 column chunks, then W1 row chunks; the first two groups travel during the LayerNorm part
   fs_issue_group(ring, w1, w2, false, 0, nch, Dh, tid);
@@ -438,7 +447,7 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
   float* pb = dhs;                                       // [16][64] dbeta terms (dhs is written only after the barriers below)
   // ---- LayerNorm backward: warp w owns rows w and w + 8 ----
 #pragma unroll
-  for (int h2 = 0; h2 < FS_ROWS / 8; ++h2) {
+  for (int h2 = 0; h2 < R / 8; ++h2) {
     const int rr = warp + 8 * h2, row = row0 + rr;
     float mean = 0.f, rstd = 0.f, dv[2] = {0.f, 0.f}, rv[2] = {0.f, 0.f};
     if (row < n) {
@@ -476,14 +485,14 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
     const float* src = tid < FS_F ? pg + tid : pb + (tid - FS_F);
     float sacc = 0.f;
 #pragma unroll
-    for (int w = 0; w < FS_ROWS; ++w) sacc += src[w * FS_F];
+    for (int w = 0; w < R; ++w) sacc += src[w * FS_F];
     part[(size_t)blockIdx.x * 2 * FS_F + tid] = sacc;
   }
   // (the barrier at the top of the first loop pass separates these reads of pb from the writes to dhs)
   const int cq = tid & 15, kq = (tid >> 4) & 3;
-  float accx[4][4];
+  float accx[U][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < U; ++u)
 #pragma unroll
     for (int t = 0; t < 4; ++t) accx[u][t] = 0.f;
   for (int gi = 0; gi < 2 * ngrp; ++gi) {
@@ -494,20 +503,20 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
       // ---- dhp = (dr W2) * relu'(hdn): thread = hidden units j = 256 gi + 4 jq .. + 3 (slot jq / 16, columns 4 (jq % 16) ..) ----
       const int jq = tid & 63;
       const float* ws = grp + (jq >> 4) * FS_SLOT_FLOATS + 4 * (jq & 15);
-      float acc[4][4];
+      float acc[U][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[u][t] = 0.f;
 #pragma unroll 2
       for (int c4 = 0; c4 < FS_F / 4; ++c4) {
-        float4 dv[4], wv[4];                              // wv[e] = W2[4 c4 + e][j .. j + 3]
+        float4 dv[U], wv[4];                              // wv[e] = W2[4 c4 + e][j .. j + 3]
 #pragma unroll
         for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float4*>(ws + (4 * c4 + e) * FS_WLD);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dv[u] = *reinterpret_cast<const float4*>(drs + (4 * rq + u) * FS_F + 4 * c4);   // broadcast
+        for (int u = 0; u < U; ++u) dv[u] = *reinterpret_cast<const float4*>(drs + (U * rq + u) * FS_F + 4 * c4);   // broadcast
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           acc[u][0] = fmaf(dv[u].x, wv[0].x, acc[u][0]); acc[u][1] = fmaf(dv[u].x, wv[0].y, acc[u][1]);
           acc[u][2] = fmaf(dv[u].x, wv[0].z, acc[u][2]); acc[u][3] = fmaf(dv[u].x, wv[0].w, acc[u][3]);
           acc[u][0] = fmaf(dv[u].y, wv[1].x, acc[u][0]); acc[u][1] = fmaf(dv[u].y, wv[1].y, acc[u][1]);
@@ -520,8 +529,8 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
       }
       const int j = gi * FS_GRP * FS_CH + 4 * jq;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int rr = 4 * rq + u;
+      for (int u = 0; u < U; ++u) {
+        const int rr = U * rq + u;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + rr < n) {
           const float4 hm = __ldg(reinterpret_cast<const float4*>(hdn + (size_t)(row0 + rr) * Dh + j));
@@ -541,14 +550,14 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
 #pragma unroll 2
         for (int k4 = 0; k4 < 4; ++k4) {
           const int kl = 16 * kq + 4 * k4;
-          float4 dv[4], wv[4];                            // wv[e] = W1[k + e][4 cq .. + 3]
+          float4 dv[U], wv[4];                            // wv[e] = W1[k + e][4 cq .. + 3]
 #pragma unroll
           for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float4*>(ws + (kl + e) * FS_WLD);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            dv[u] = *reinterpret_cast<const float4*>(dhs + (size_t)(4 * rq + u) * Dh + kbase + FS_CH * sl + kl);
+          for (int u = 0; u < U; ++u)
+            dv[u] = *reinterpret_cast<const float4*>(dhs + (size_t)(U * rq + u) * Dh + kbase + FS_CH * sl + kl);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < U; ++u) {
             accx[u][0] = fmaf(dv[u].x, wv[0].x, accx[u][0]); accx[u][1] = fmaf(dv[u].x, wv[0].y, accx[u][1]);
             accx[u][2] = fmaf(dv[u].x, wv[0].z, accx[u][2]); accx[u][3] = fmaf(dv[u].x, wv[0].w, accx[u][3]);
             accx[u][0] = fmaf(dv[u].y, wv[1].x, accx[u][0]); accx[u][1] = fmaf(dv[u].y, wv[1].y, accx[u][1]);
@@ -568,18 +577,20 @@ ffn_rows_bwd_kernel(int n, int Dh, const float* __restrict__ dy, const float* __
   {
     float* ps = ring;                                    // [4 kq][16 rows][64 c]
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      *reinterpret_cast<float4*>(ps + (kq * FS_ROWS + 4 * rq + u) * FS_F + 4 * cq) =
+    for (int u = 0; u < U; ++u)
+      *reinterpret_cast<float4*>(ps + (kq * R + U * rq + u) * FS_F + 4 * cq) =
           make_float4(accx[u][0], accx[u][1], accx[u][2], accx[u][3]);
     __syncthreads();
     const int rr = tid >> 4, c4 = tid & 15;
-    float4 o = *reinterpret_cast<const float4*>(drs + rr * FS_F + 4 * c4);
+    if (rr < R) {
+      float4 o = *reinterpret_cast<const float4*>(drs + rr * FS_F + 4 * c4);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 pv = *reinterpret_cast<const float4*>(ps + (q * FS_ROWS + rr) * FS_F + 4 * c4);
-      o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+      for (int q = 0; q < 4; ++q) {
+        const float4 pv = *reinterpret_cast<const float4*>(ps + (q * R + rr) * FS_F + 4 * c4);
+        o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+      }
+      if (row0 + rr < n) *reinterpret_cast<float4*>(dx + (size_t)(row0 + rr) * FS_F + 4 * c4) = o;
     }
-    if (row0 + rr < n) *reinterpret_cast<float4*>(dx + (size_t)(row0 + rr) * FS_F + 4 * c4) = o;
   }
 }
 
@@ -651,10 +662,25 @@ int layernorm_bwd_ex(int N, int D, const float* dy, const float* r, const float*
 }
 
 
+// rows per CTA (HSG_FFN_ROWS_PER_CTA = 8 / 16 forces one).  Measured at n = 1 009 (gpurun r02x): alone, 8 rows per CTA
+// take 14.6 / 15.9 us forward / backward against 17.4 / 17.4 us - a CTA is bound by the latency of its shared-memory
+// reads at two warps per scheduler (ncu: 37 % issue, short-scoreboard stalls), not by its FMA count - but inside the
+// 32-graph step the 127 CTAs share SMs with the side-stream products and the step does not move (0.604 against 0.602
+// ms); 8 rows are used while they leave half of the SMs to the other streams.
+static int fs_rows(int n) {
+  static const int forced = [] {
+    const char* e = getenv("HSG_FFN_ROWS_PER_CTA");
+    const int v = e ? atoi(e) : 0;
+    return (v == 8 || v == 16) ? v : 0;
+  }();
+  if (forced) return forced;
+  return ceil_div(n, 8) <= 74 ? 8 : FS_ROWS;
+}
+
 // fused small-node-set FFN (see ffn_rows_fwd_kernel)
 bool ffn_rows_ok(int n, int F, int d_hid) {
   if (n <= 0 || F != FS_F || d_hid <= 0 || d_hid > FS_MAX_DH || d_hid % (FS_GRP * FS_CH) != 0) return false;
-  if (ceil_div(n, FS_ROWS) > FS_MAX_BLOCKS) return false;           // dgamma / dbeta partials fit the LayerNorm workspace
+  if (ceil_div(n, fs_rows(n)) > FS_MAX_BLOCKS) return false;        // dgamma / dbeta partials fit the LayerNorm workspace
   return gemm_is_small(n, d_hid, F);                                // same latency-vs-throughput threshold as the GEMMs
 }
 
@@ -670,12 +696,19 @@ int ffn_rows_fwd(int n, int F, int d_hid, const float* x, const float* w1, const
   if (!aligned16(x) || !aligned16(w1) || !aligned16(w2)) return HSG_ERR_ALIGN;
   static bool attr_done = false;
   if (!attr_done) {
-    if (!fs_attr((const void*)ffn_rows_fwd_kernel, fs_smem_floats(FS_MAX_DH) * sizeof(float))) return HSG_ERR_CUDA;
+    if (!fs_attr((const void*)ffn_rows_fwd_kernel<4>, fs_smem_floats(FS_MAX_DH) * sizeof(float)) ||
+        !fs_attr((const void*)ffn_rows_fwd_kernel<2>, fs_smem_floats(FS_MAX_DH) * sizeof(float)))
+      return HSG_ERR_CUDA;
     attr_done = true;
   }
   LaunchScope ls(SLOT_FFN_ROWS, s);
-  launch_k(ffn_rows_fwd_kernel, dim3(ceil_div(n, FS_ROWS)), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s, n,
-           d_hid, x, w1, b1, w2, b2, gamma, beta, hdn, r, y, stats);
+  const int rows = fs_rows(n);
+  if (rows == 8)
+    launch_k(ffn_rows_fwd_kernel<2>, dim3(ceil_div(n, 8)), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s, n,
+             d_hid, x, w1, b1, w2, b2, gamma, beta, hdn, r, y, stats);
+  else
+    launch_k(ffn_rows_fwd_kernel<4>, dim3(ceil_div(n, FS_ROWS)), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s,
+             n, d_hid, x, w1, b1, w2, b2, gamma, beta, hdn, r, y, stats);
   return check_launch();
 }
 
@@ -690,15 +723,22 @@ int ffn_rows_bwd(int n, int F, int d_hid, const float* dy, const float* r, const
   if (!aligned16(w1) || !aligned16(w2)) return HSG_ERR_ALIGN;
   static bool attr_done = false;
   if (!attr_done) {
-    if (!fs_attr((const void*)ffn_rows_bwd_kernel, fs_smem_floats(FS_MAX_DH) * sizeof(float))) return HSG_ERR_CUDA;
+    if (!fs_attr((const void*)ffn_rows_bwd_kernel<4>, fs_smem_floats(FS_MAX_DH) * sizeof(float)) ||
+        !fs_attr((const void*)ffn_rows_bwd_kernel<2>, fs_smem_floats(FS_MAX_DH) * sizeof(float)))
+      return HSG_ERR_CUDA;
     attr_done = true;
   }
   float* part = reinterpret_cast<float*>(ws);
-  const int nblocks = ceil_div(n, FS_ROWS);
+  const int rows = fs_rows(n);
+  const int nblocks = ceil_div(n, rows);
   {
     LaunchScope ls(SLOT_FFN_ROWS, s);
-    launch_k(ffn_rows_bwd_kernel, dim3(nblocks), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s, n, d_hid, dy,
-             r, stats, gamma, hdn, w1, w2, dr, dhp, dx, part);
+    if (rows == 8)
+      launch_k(ffn_rows_bwd_kernel<2>, dim3(nblocks), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s, n, d_hid,
+               dy, r, stats, gamma, hdn, w1, w2, dr, dhp, dx, part);
+    else
+      launch_k(ffn_rows_bwd_kernel<4>, dim3(nblocks), dim3(FS_THREADS), fs_smem_floats(d_hid) * sizeof(float), s, n, d_hid,
+               dy, r, stats, gamma, hdn, w1, w2, dr, dhp, dx, part);
     int rc = check_launch();
     if (rc) return rc;
   }

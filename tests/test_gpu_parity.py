@@ -167,6 +167,51 @@ def test_ffn_matches_torch(N, D, Dh):
         assert nerr(a, b) <= TOL
 
 
+@pytest.mark.parametrize("n", [1009, 37, 590, 593, 2500])
+def test_one_launch_ffn_rows_both_cta_shapes_match_float64(n):
+    """hsg_ffn_rows_fwd / _bwd (the sentence-side FFN of the update loop, GATLayer.py:35-44) at 8 rows per CTA (n <= 592)
+    and 16 rows per CTA, straight through the C ABI, against the float64 formulas: hdn, r, y, stats / dr, dhp, dx and the
+    (dgamma, dbeta) partials reduced by the library."""
+    import ctypes as C
+    from hetersumgraph_b200 import _lib
+    lib = _lib.load()
+    F_, Dh = 64, 512
+    assert lib.hsg_ffn_rows_ok(n, F_, Dh) == 1
+    torch.manual_seed(n)
+    dev = "cuda"
+    x = torch.randn(n, F_, device=dev)
+    w1, b1 = torch.randn(Dh, F_, device=dev) * 0.1, torch.randn(Dh, device=dev) * 0.1
+    w2, b2 = torch.randn(F_, Dh, device=dev) * 0.1, torch.randn(F_, device=dev) * 0.1
+    gamma, beta = torch.rand(F_, device=dev) + 0.5, torch.randn(F_, device=dev) * 0.1
+    dy = torch.randn(n, F_, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    ws = torch.empty(lib.hsg_layernorm_bwd_workspace_bytes(n, F_) + 1024, dtype=torch.uint8, device=dev)
+    hdn, r, y, stats = (torch.full((n, Dh), float("nan"), device=dev), torch.full((n, F_), float("nan"), device=dev),
+                        torch.full((n, F_), float("nan"), device=dev), torch.full((n, 2), float("nan"), device=dev))
+    _lib.check(lib.hsg_ffn_rows_fwd(n, F_, Dh, p(x), p(w1), p(b1), p(w2), p(b2), p(gamma), p(beta), p(hdn), p(r), p(y),
+                                    p(stats), st))
+    dr, dhp, dx = (torch.full((n, F_), float("nan"), device=dev), torch.full((n, Dh), float("nan"), device=dev),
+                   torch.full((n, F_), float("nan"), device=dev))
+    dg, db = torch.zeros(F_, device=dev), torch.zeros(F_, device=dev)
+    _lib.check(lib.hsg_ffn_rows_bwd(n, F_, Dh, p(dy), p(r), p(stats), p(gamma), p(hdn), p(w1), p(w2), p(dr), p(dhp), p(dx),
+                                    p(dg), p(db), 0, p(ws), ws.numel(), st))
+    torch.cuda.synchronize()
+    X = x.double().requires_grad_(True)
+    G = gamma.double().requires_grad_(True)
+    Bt = beta.double().requires_grad_(True)
+    H = torch.relu(X @ w1.double().t() + b1.double())
+    Rr = H @ w2.double().t() + b2.double() + X
+    Y = torch.nn.functional.layer_norm(Rr, (F_,), G, Bt, 1e-5)     # HSG_LN_EPS = nn.LayerNorm default
+    H.retain_grad()
+    Rr.retain_grad()
+    (Y * dy.double()).sum().backward()
+    mask = (hdn > 0).double()
+    for got, want in ((hdn, H), (r, Rr), (y, Y), (stats[:, 0], Rr.mean(1)), (dr, Rr.grad), (dhp, H.grad * mask),
+                      (dx, X.grad), (dg, G.grad), (db, Bt.grad)):
+        assert nerr(got, want.detach()) <= TOL, nerr(got, want.detach())
+
+
 # ----------------------------------------------------------------------------- whole path vs golden
 def _load_fixture(name):
     z = dict(np.load(os.path.join(GOLD, name)))
