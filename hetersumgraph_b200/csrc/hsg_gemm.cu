@@ -318,7 +318,43 @@ gemm_tn_kernel(int M, int N1, int N2, const float* __restrict__ A, int lda, cons
   if (do_col && tid < TB && n1_0 + tid < N1) part_col[(size_t)z * N1 + n1_0 + tid] = csum;
 }
 
-__global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* __restrict__ part,
+// Column sums of A [M, N1] over row chunks of `rows` rows: part_col[chunk][c] = sum of A[row][c] in row order per row
+// lane (8 lanes: rows l, l + 8, ...), the 8 lane sums added in order.  Used instead of the ones column of the
+// tensor-core product when that column would open a new column of output tiles (N2 a multiple of 128: the FFN's
+// dW2 = dr^T hdn with db2, 300 x 512 + 1 -> 15 tiles instead of 12, 57 us instead of 41 us per launch at 11 817 rows).
+constexpr int CS_LANES = 8;
+__global__ void __launch_bounds__(128 * CS_LANES)
+colsum_part_kernel(int M, int N1, const float* __restrict__ A, int lda, int rows, float* __restrict__ part_col) {
+  pdl_prologue();
+  __shared__ float red[CS_LANES][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + tx;
+  const int r0 = blockIdx.x * rows, r1 = min(M, r0 + rows);
+  float sm = 0.f;
+  if (c < N1) {
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += CS_LANES) sm += __ldg(A + (size_t)r * lda + c);
+  }
+  red[ty][tx] = sm;
+  __syncthreads();
+  if (ty == 0 && c < N1) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < CS_LANES; ++l) t += red[l][tx];
+    part_col[(size_t)blockIdx.x * N1 + c] = t;
+  }
+}
+constexpr int CS_MAX_PARTS = 592;
+static void colsum_plan(int M, int* parts, int* rows) {
+  int r = 256;
+  if (ceil_div(M, r) > CS_MAX_PARTS) r = ceil_div(ceil_div(M, CS_MAX_PARTS), 8) * 8;
+  *rows = r;
+  *parts = ceil_div(M, r);
+}
+
+// part_col: [ncol][N1] column-sum partials (ncol == nsplit when the product kernel wrote them, its own count when
+// colsum_part_kernel did)
+__global__ void gemm_tn_reduce_kernel(int nsplit, int ncol, int N1, int N2, const float* __restrict__ part,
                                       const float* __restrict__ part_col, float* __restrict__ C, int ldc,
                                       float* __restrict__ colsum, int accumulate) {
   pdl_prologue();
@@ -332,7 +368,7 @@ __global__ void gemm_tn_reduce_kernel(int nsplit, int N1, int N2, const float* _
     } else if (colsum != nullptr) {
       int c = i - total;
       float s = 0.f;
-      for (int z = 0; z < nsplit; ++z) s += part_col[(size_t)z * N1 + c];
+      for (int z = 0; z < ncol; ++z) s += part_col[(size_t)z * N1 + c];
       colsum[c] = accumulate ? colsum[c] + s : s;
     }
   }
@@ -367,6 +403,15 @@ static int tn_item_rows() {
 static bool tn_short_items(int M) {
   const int r = tn_item_rows();
   return r > 0 && ceil_div(M, r) <= 48;
+}
+
+// HSG_TN_COLSUM_APART=0: keep the ones column inside the product even when it opens a new column of tiles
+static bool colsum_apart() {
+  static const int v = [] {
+    const char* e = getenv("HSG_TN_COLSUM_APART");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v != 0;
 }
 
 static void tn_plan_tc(int M, int N1, int N2, bool colsum, int* splits, int* rows, int cta_budget = 0) {
@@ -430,14 +475,24 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
   float* part_col = part + (size_t)nsplit * N1 * N2;
   const int mode = g_gemm_mode.load(std::memory_order_relaxed);
   const bool vec_tc = (N1 % 4 == 0) && (N2 % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && aligned16(A) && aligned16(B);
+  int ncol = -1;                                      // column-sum partials: -1 = one per split, written by the product
   if (M > 0 && mode != 0 && vec_tc) {
     int rows = 0;
-    tn_plan_tc(M, N1, N2, colsum != nullptr, &nsplit, &rows, cta_budget);
-    if ((size_t)nsplit * ((size_t)N1 * N2 + N1) * sizeof(float) > ws_bytes) return HSG_ERR_WORKSPACE;
+    // the ones column would be the only column of a fifth (ninth, ...) column of tiles: sum the columns of A apart
+    const bool col_apart = colsum != nullptr && (N2 % 128 == 0) && colsum_apart();
+    tn_plan_tc(M, N1, N2, colsum != nullptr && !col_apart, &nsplit, &rows, cta_budget);
+    int crows = 0, cparts = 0;
+    if (col_apart) colsum_plan(M, &cparts, &crows);
+    if (((size_t)nsplit * (size_t)N1 * N2 + (size_t)(col_apart ? cparts : nsplit) * N1) * sizeof(float) > ws_bytes)
+      return HSG_ERR_WORKSPACE;
     part_col = part + (size_t)nsplit * N1 * N2;
     LaunchScope ls(SLOT_GEMM_TN, s);
-    int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, colsum ? part_col : nullptr, nsplit, rows, tc_arith(mode), s,
-                         tn_short_items(M));
+    if (col_apart) {
+      launch_k(colsum_part_kernel, dim3(cparts, ceil_div(N1, 128)), dim3(128 * CS_LANES), 0, s, M, N1, A, lda, crows, part_col);
+      ncol = cparts;
+    }
+    int rc = tc::gemm_tn(M, N1, N2, A, lda, B, ldb, part, (colsum && !col_apart) ? part_col : nullptr, nsplit, rows,
+                         tc_arith(mode), s, tn_short_items(M));
     if (rc) return rc;
   } else if (M > 0) {
     int rows = ceil_div(M, nsplit);
@@ -459,7 +514,8 @@ int gemm_tn_ex(int M, int N1, int N2, const float* A, int lda, const float* B, i
     int total = N1 * N2 + N1;
     int blocks = ceil_div(total, 256);
     if (blocks > 1184) blocks = 1184;
-    launch_k(gemm_tn_reduce_kernel, dim3(blocks), dim3(256), 0, s, nsplit, N1, N2, part, part_col, C, ldc, colsum, accumulate);
+    launch_k(gemm_tn_reduce_kernel, dim3(blocks), dim3(256), 0, s, nsplit, ncol < 0 ? nsplit : ncol, N1, N2, part, part_col, C,
+             ldc, colsum, accumulate);
   }
   return check_launch();
 }
@@ -555,7 +611,10 @@ size_t hsg_gemm_tn_workspace_bytes(int M, int N1, int N2) {
     tn_plan_tc(M, N1, N2, cs != 0, &s_tc, &rows_tc);
     if ((size_t)s_tc > s) s = (size_t)s_tc;
   }
-  return s * ((size_t)N1 * N2 + N1) * sizeof(float) + 16;
+  int cparts = 0, crows = 0;
+  colsum_plan(M, &cparts, &crows);                   // column sums taken apart (colsum_part_kernel)
+  if ((size_t)cparts < s) cparts = (int)s;
+  return (s * (size_t)N1 * N2 + (size_t)cparts * N1) * sizeof(float) + 16;
 }
 
 int hsg_gemm_tn_acc(int M, int N1, int N2, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
