@@ -67,6 +67,21 @@ bool tail_on_main() {
   return v != 0;
 }
 
+// A weight-gradient product whose launch is postponed to the tail of the step (see hsg_update_loop_bwd)
+struct DeferredTN {
+  bool set = false;
+  int M = 0, N1 = 0, N2 = 0, lda = 0, ldb = 0, ldc = 0, acc = 0;
+  const float *A = nullptr, *B = nullptr;
+  float *C = nullptr, *colsum = nullptr;
+};
+bool tail_defer_dw1() {
+  static const int v = [] {
+    const char* e = getenv("HSG_TAIL_DEFER_DW1");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v != 0;
+}
+
 // tuning knobs of the tail (measured defaults): SMs the last projection product may occupy on the caller's
 // stream (0 = all), and whether dW1 of the last application follows it there
 int tail_tn_ctas() {
@@ -339,7 +354,7 @@ int app_fwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
 int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbor, const float* dout, float* dx,
             float* dnb, const float* dnb_add, float* sc, int acc_aug, const hsg_layer_grads& G, int acc_ffn, void* ws,
             size_t ws_bytes, void* ws2, SideRes* sd, bool* side_pending, int slot, int* ln_blocks, int* dq_blocks,
-            cudaStream_t s) {
+            cudaStream_t s, DeferredTN* defer = nullptr) {
   const int k = L.kind(i);
   const hsg_layer_params& P = layer(a, k);
   const AppOff& o = L.app[k];
@@ -392,8 +407,14 @@ int app_bwd(const hsg_loop_args* a, const Layout& L, int i, const float* neighbo
   // gradients one after the other while the caller's stream idles behind its last projection product; dW1 follows
   // that product on the caller's stream instead (same kernel, same operands: the placement changes no bit)
   const bool dw1_on_main = sd && !dnb && rows_kernel && !L.drop_attn && tail_on_main() && tail_dw1_main();
-  if (!dw1_on_main)
+  if (defer && sd && !rows_kernel) {                // launched by the caller at the tail of the step (side stream)
+    defer->set = true;
+    defer->M = n_dst; defer->N1 = P.d_hid; defer->N2 = F;
+    defer->A = dhp; defer->lda = P.d_hid; defer->B = x; defer->ldb = F;
+    defer->C = G.dw1; defer->ldc = F; defer->colsum = G.db1; defer->acc = acc_ffn;
+  } else if (!dw1_on_main) {
     HSG_TRY(gemm_tn_ex(n_dst, P.d_hid, F, dhp, P.d_hid, x, F, G.dw1, F, G.db1, wsw, ws_bytes, acc_ffn, s2, budget));
+  }
   if (!rows_kernel)
     HSG_TRY(hsg_gemm_nn(n_dst, F, P.d_hid, dhp, P.d_hid, P.w1, F, dx, F, dr, F, HSG_EPI_ADD, s));
   // edge backward (d origin = dx, GAT.py:57)
@@ -559,6 +580,7 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
   bool side_pending[2] = {false, false};
   bool prep_done[2] = {false, false};
   bool fin_pending = false;
+  DeferredTN deferred;
   int ln_blocks[2] = {0, 0}, dq_blocks[2] = {0, 0};
   void* ws2 = reinterpret_cast<char*>(b->ws) + L.ws_half;
   for (int i = L.n_apps - 1; i >= 0; --i) {
@@ -585,8 +607,19 @@ int hsg_update_loop_bwd(const hsg_loop_args* a, const hsg_loop_bwd_args* b, void
     }
     const hsg_layer_grads& G = k == 0 ? b->w2s : b->s2w;
     int lnb = 0, dqb = 0;
+    // HSG_TAIL_DEFER_DW1=1: the big dW1 product of application 1 (the last of its kind) waits for application 0's edge
+    // backward and runs next to the tail's small kernels instead of next to application 0's chain
+    const bool defer_here = i == 1 && sd && tail_on_main() && tail_defer_dw1() && !L.drop_attn && !L.drop_ffn &&
+                            (L.kind(0) == 0 ? b->d_word_feature : b->d_super_feature) == nullptr;
     HSG_TRY(app_bwd(a, L, i, neighbor, dout, dx, dnb, gst[k ^ 1], sc, done[k] > 0, G, acc || done[k] > 0, b->ws,
-                    L.ws_half, ws2, sd, side_pending, done[k], &lnb, &dqb, s));
+                    L.ws_half, ws2, sd, side_pending, done[k], &lnb, &dqb, s, defer_here ? &deferred : nullptr));
+    if (i == 0 && deferred.set) {
+      if (cudaStreamWaitEvent(sd->stream, sd->dzp, 0) != cudaSuccess) return HSG_ERR_CUDA;
+      HSG_TRY(gemm_tn_ex(deferred.M, deferred.N1, deferred.N2, deferred.A, deferred.lda, deferred.B, deferred.ldb,
+                         deferred.C, deferred.ldc, deferred.colsum, ws2, L.ws_half, deferred.acc, sd->stream, 0));
+      if (cudaEventRecord(sd->done[k], sd->stream) != cudaSuccess) return HSG_ERR_CUDA;
+      side_pending[k] = true;
+    }
     if (done[k] > 0 && (lnb != ln_blocks[k] || dqb != dq_blocks[k])) return HSG_ERR_SHAPE;   // same launch per kind
     ln_blocks[k] = lnb;
     dq_blocks[k] = dqb;
