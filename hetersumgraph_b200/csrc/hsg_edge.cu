@@ -448,8 +448,11 @@ edge_fwd_lowdeg_kernel(int n_dst, const int32_t* __restrict__ indptr, const int3
 // ncu showed issue-bound on large shards.  Used when there are enough rows to fill the machine (hsg_edge_fwd picks).
 // Same arithmetic per row as edge_fwd_kernel with one group (edges in CSC order, one rescale per U rows).
 // ---------------------------------------------------------------------------
+#ifndef HSG_ROWPAR_4CTA_MAX
+#define HSG_ROWPAR_4CTA_MAX 16
+#endif
 template <int H, int D, int U>
-__global__ void __launch_bounds__(EDGE_THREADS, (U * EdgeCfg<H, D>::NE <= 16) ? 4 : 3)
+__global__ void __launch_bounds__(EDGE_THREADS, (U * EdgeCfg<H, D>::NE <= HSG_ROWPAR_4CTA_MAX) ? 4 : 3)
 edge_fwd_rowpar_kernel(int n_dst, const int32_t* __restrict__ indptr, const int32_t* __restrict__ nbr,
                        const uint8_t* __restrict__ bin, const int32_t* __restrict__ extra,
                        const float* __restrict__ zp, int ldz, const float* __restrict__ q,
