@@ -173,6 +173,7 @@ _PROTOS = {
     "hsg_update_loop_fwd": (C.c_int, [C.POINTER(LoopArgsC), _P]),
     "hsg_update_loop_bwd": (C.c_int, [C.POINTER(LoopArgsC), C.POINTER(LoopBwdArgsC), _P]),
     "hsg_head_workspace_bytes": (_Z, [_I, _I]),
+    "hsg_abi_sizeof": (_Z, [_I]),
     "hsg_head_fwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _Z, _P]),
     "hsg_head_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "hsg_head_fwd_bwd": (C.c_int, [C.POINTER(HeadArgsC), _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

@@ -106,6 +106,28 @@ extern "C" {
 
 int hsg_version(void) { return HSG_ABI_VERSION; }
 
+// sizeof of the i-th argument structure of the header, in declaration order (binding self-check: a foreign-function
+// binding compares its own layout with these before the first call); 0 past the end
+size_t hsg_abi_sizeof(int i) {
+  switch (i) {
+    case 0: return sizeof(hsg_token_batch);
+    case 1: return sizeof(hsg_graph_offsets);
+    case 2: return sizeof(hsg_csc);
+    case 3: return sizeof(hsg_graph_out);
+    case 4: return sizeof(hsg_wswgat_fwd_args);
+    case 5: return sizeof(hsg_wswgat_bwd_args);
+    case 6: return sizeof(hsg_layer_params);
+    case 7: return sizeof(hsg_layer_grads);
+    case 8: return sizeof(hsg_loop_args);
+    case 9: return sizeof(hsg_loop_plan);
+    case 10: return sizeof(hsg_loop_bwd_args);
+    case 11: return sizeof(hsg_head_args);
+    case 12: return sizeof(hsg_s2s_graph);
+    case 13: return sizeof(hsg_doc_map);
+    default: return 0;
+  }
+}
+
 const char* hsg_strerror(int status) {
   switch (status) {
     case HSG_OK: return "ok";

@@ -48,6 +48,9 @@ typedef enum {
 } hsg_status;
 
 int hsg_version(void);
+/* sizeof of the i-th argument structure below, in declaration order (hsg_token_batch = 0 ... hsg_doc_map = 13), 0 past
+ * the end: lets a binding (ctypes / cgo / JNI) check its own struct layouts against the library's before the first call. */
+size_t hsg_abi_sizeof(int i);
 const char* hsg_strerror(int status);
 /* 0 when the current device can run the sm_100a kernels, HSG_ERR_ARCH otherwise. */
 int hsg_device_check(void);

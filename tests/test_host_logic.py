@@ -36,6 +36,24 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.GraphOutC) == 16 + 5 * 8 + 15 * 8
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    """Every argument structure of include/hsg_b200.h, in declaration order, against the ctypes mirror in _lib.py: the
+    sizes the compiled library reports (hsg_abi_sizeof) are the sizes the binding passes, and the header declares exactly
+    these structures."""
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hsg_b200.h")).read()
+    declared = [n for n in re.findall(r"^\}\s*(hsg_[a-z0-9_]+);", header, flags=re.M) if n != "hsg_status"]
+    mirror = [_lib.TokenBatchC, _lib.GraphOffsetsC, _lib.CscC, _lib.GraphOutC, _lib.WswgatFwdArgsC, _lib.WswgatBwdArgsC,
+              _lib.LayerParamsC, _lib.LayerGradsC, _lib.LoopArgsC, _lib.LoopPlanC, _lib.LoopBwdArgsC, _lib.HeadArgsC,
+              _lib.S2SGraphC, _lib.DocMapC]
+    assert declared == ["hsg_token_batch", "hsg_graph_offsets", "hsg_csc", "hsg_graph_out", "hsg_wswgat_fwd_args",
+                        "hsg_wswgat_bwd_args", "hsg_layer_params", "hsg_layer_grads", "hsg_loop_args", "hsg_loop_plan",
+                        "hsg_loop_bwd_args", "hsg_head_args", "hsg_s2s_graph", "hsg_doc_map"]
+    for i, (name, cls) in enumerate(zip(declared, mirror)):
+        assert lib.hsg_abi_sizeof(i) == ctypes.sizeof(cls), (name, lib.hsg_abi_sizeof(i), ctypes.sizeof(cls))
+    assert lib.hsg_abi_sizeof(len(mirror)) == 0
+
+
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     assert lib.hsg_gemm_nt(4, 4, 4, None, 4, None, 4, None, 4, None, None, 0, 0, None) == -1
