@@ -245,9 +245,13 @@ class GraphedTrainStep:
         self.launches_per_step = None
         # where the build branch forks off the main branch: "start", "after_forward" or "after_head" (see _enqueue)
         import os
-        self.fork_at = os.environ.get("HSG_BUILD_FORK", "start")
-        if self.fork_at not in ("start", "after_forward", "after_head"):
-            raise ValueError("HSG_BUILD_FORK must be start, after_forward or after_head")
+        # Default (measured on the 32-graph step, gpurun r02v, three runs each): with the tokens resident the builder starts
+        # at the top of the step (0.590 against 0.606 ms); when the branch begins with the H2D copy of the next batch the
+        # builder would start ~25 us later and sit on both word-side FFN products of the forward - forking after the
+        # forward is then faster end to end (53.4 k against 52.4 k graphs/s from host buffers)
+        self.fork_at = os.environ.get("HSG_BUILD_FORK", "start" if resident_tokens else "after_forward")
+        if self.fork_at not in ("start", "after_forward", "after_head", "split"):
+            raise ValueError("HSG_BUILD_FORK must be start, after_forward, after_head or split")
         # dropout under replay: masks are keyed by the optimizer's device step counter
         model.loop.seed_dev = opt.device_step_counter()
 
@@ -317,21 +321,42 @@ class GraphedTrainStep:
             # side branch: [H2D of the next step's sent_feature], [H2D of its token blob], build.  WHERE it forks off
             # the main branch is a knob (HSG_BUILD_FORK): the builder is one CTA per graph for ~130 us and, started at
             # the top of the step, shares the GPU with the two word-side FFN products of the forward (33 us alone, 50 /
-            # 63 us under it - CUPTI timeline r02t).  Forking after the forward or after the loss was measured and is
-            # NOT faster (0.650 ms at the top, 0.660 / 0.665 ms later - gpurun r02x): the step is bound by the summed
-            # SM-time of its kernels, not by where the builder overlaps, so the default stays "start".
+            # 63 us under it - CUPTI timeline r02t).  With resident tokens forking after the forward or after the loss is
+            # NOT faster (0.590 ms at the top, 0.606 / 0.605 ms later - gpurun r02v); from host buffers it is (see the
+            # default in __init__).  "split": H2D copies at the top, builder after the forward.
             if build_next or n_next_sf:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    if n_next_sf:       # the next step's sent_feature travels first: ev_totals then also covers it
-                        self.sf_pref[1 - p][:n_next_sf].copy_(self.sf_pstage[1 - p][:n_next_sf], non_blocking=True)
+                    if not copied[0]:
+                        fork_copy_body()
                     if build_next:
-                        nxt.enqueue_build(side, None if self.resident_tokens else self.stage[1 - p])
+                        nxt.enqueue_build(side, None)
                         self.ev_totals[1 - p].record(side)
+
+        copied = [False]
+
+        def fork_copy_body():
+            # (on the side stream) the next step's sent_feature travels first: ev_totals then also covers it
+            if n_next_sf:
+                self.sf_pref[1 - p][:n_next_sf].copy_(self.sf_pstage[1 - p][:n_next_sf], non_blocking=True)
+            if build_next and not self.resident_tokens:
+                blob = nxt.dtb._blob
+                blob.copy_(self.stage[1 - p][:blob.numel()], non_blocking=True)
+            copied[0] = True
+
+        def fork_copy():
+            # "split": the H2D copies leave at the top of the step (copy engine, no SM), the builder forks later
+            if (build_next and not self.resident_tokens) or n_next_sf:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    fork_copy_body()
 
         hooks = {}
         if self.fork_at == "start":
             fork_build()
+        elif self.fork_at == "split":
+            fork_copy()
+            hooks["after_forward"] = fork_build
         else:
             hooks[self.fork_at] = fork_build
         sf = self.sf_pref[p][:n_sf] if use_pref else self.sf_dev[:n_sf]
