@@ -500,6 +500,16 @@ int hsg_build_fill(const hsg_token_batch* tb, const hsg_graph_out* out, void* ws
       return HSG_ERR_CUDA;
     configured = smem;
   }
+  // The builder runs next to the step's tensor-core products (one ~180 KB CTA per SM).  An SM keeps the shared-memory
+  // carve-out of the kernel it is running: with the maximum carve-out requested here a GEMM CTA can join a builder CTA
+  // on the same SM instead of waiting for it to finish.
+  static bool carve = false;
+  if (!carve) {
+    cudaFuncSetAttribute(build_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(build_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(build_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve = true;
+  }
   LaunchScope ls(SLOT_BUILD_FILL, s);
   launch_k(build_fill_kernel, dim3(tb->n_graphs), dim3(BLD_THREADS), smem, s, *tb, w, *out, cap_tok, cap_sup);
   return check_launch();

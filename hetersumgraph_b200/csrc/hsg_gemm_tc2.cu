@@ -6,7 +6,7 @@
 // 768 tensor-core cycles) and holds only three 64 KB stages.  Here two CTAs of a cluster share ONE 256 x BN tile:
 // each CTA stages its own 128 rows of A but only HALF of the B tile (BN/2 rows / columns), the other half is read by
 // the pair's MMA straight from the peer's shared memory.  Per CTA and k-block: TMA write 24 KB, hi/lo sweep 48 KB,
-// operand reads 72 KB = 144 KB, 24 KB from L2 instead of 32, and a stage is 48 KB, so FOUR stages are in flight.
+// operand reads 72 KB = 144 KB, 24 KB from L2 instead of 32, and a stage is 48 KB (four stages fit; three are used - see HSG_TC2_STAGES below).
 //
 //   * both CTAs: one thread issues TMA loads of the CTA's own A rows and B half into its own shared memory;
 //     converter warps split the landed tiles into hi (= the raw tile: kind::tf32 truncates) and lo = x - hi;
@@ -40,7 +40,18 @@ constexpr int NEPI_WARPS = 4;
 constexpr int A_TILE = TM * 128;                 // 16 KB
 constexpr int B_HALF = (BN_MAX / 2) * 128;       // 8 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_HALF;   // A_raw | A_lo | B_raw | B_lo = 48 KB
-constexpr int STAGES = 4;
+// Three stages and a 112-register cap (no spills; HSG_TC2_STAGES=4 -DHSG_TC2_MAXREG=0 restores the first version): the
+// kernel's own time is the same as with four stages and 151 registers (32.7-33.8 us on the four FFN shapes at 11 817
+// rows; +-6 % per shape at 731 k rows, equal in sum), but a 178 KB / 43 k-register CTA leaves room on its SM for a CTA of
+// the graph builder (build_fill: 40 KB, 10 k registers), which otherwise holds 32 SMs for ~130 us next to the word-side
+// FFN products: FFN-2 of the forward 46 -> 40 us inside the step, e2e 53.3 -> 54.2 k graphs/s (gpurun r02u).
+#ifndef HSG_TC2_STAGES
+#define HSG_TC2_STAGES 3
+#endif
+#ifndef HSG_TC2_MAXREG
+#define HSG_TC2_MAXREG 112
+#endif
+constexpr int STAGES = HSG_TC2_STAGES;
 constexpr int EPI_BUF = 32 * 128;                                // one 32 x 32 fp32 chunk, SWIZZLE_128B rows of 128 B
 constexpr int EPI_BYTES = NEPI_WARPS * 2 * EPI_BUF;              // two chunks in flight per epilogue warp
 constexpr int BARS_BYTES = 256;                                  // barriers + TMEM slot
@@ -260,7 +271,11 @@ __device__ __forceinline__ TileInfo tile_info(int t, int n_tiles, int Nd, int bn
 }
 
 template <bool B_MN>
+#if HSG_TC2_MAXREG > 0
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(HSG_TC2_MAXREG)
+#else
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+#endif
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, int Md, int Nd, int K,
                 int bn, int nb_half_box, int n_tiles, int total_tiles, int precise, Epilogue ep) {
