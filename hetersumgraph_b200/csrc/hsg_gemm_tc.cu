@@ -265,7 +265,19 @@ __device__ __forceinline__ TileInfo tile_info(int t, int m_tiles, int n_tiles, i
 }
 
 template <bool A_MN, bool B_MN>
+// Register cap (HSG_TC_MAXREG, 0 = none, the default): at 168 registers x 384 threads a CTA of this kernel takes the
+// whole register file of its SM, so while a weight-gradient product runs on the side stream no CTA of the caller's
+// chain can be placed next to it.  Measured with a cap of 112 (gpurun r02t): edge_bwd_blockrow then does run next to the
+// dW2 product (62 -> 17.5 us in the step), but the cluster kernel and ffn_rows_bwd behind it (shared memory) still wait
+// for whole CTAs to retire, and the capped kernel spills (40 B) and is 6 % slower: step 0.6045 against 0.589 ms.
+#ifndef HSG_TC_MAXREG
+#define HSG_TC_MAXREG 0
+#endif
+#if HSG_TC_MAXREG > 0
+__global__ void __maxnreg__(HSG_TC_MAXREG)
+#else
 __global__ void __launch_bounds__(THREADS, 1)
+#endif
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int Md, int Nd,
                int K, int bn, int nb_box, int k_per_split, int m_tiles, int n_tiles, int total_tiles, int precise,
                int k_chunk, int n_items, Epilogue ep) {
