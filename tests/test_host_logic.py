@@ -189,3 +189,25 @@ def test_encoder_plan_host_logic():
     assert plan.perm[plan.inv_perm].tolist() == list(range(7))
     with pytest.raises(ValueError):
         EncoderPlan(tokens, np.asarray([0, 1, 7]), "cpu").perm   # a PackedSequence needs batch order (cuDNN option only)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU and prints ONE JSON line
+    with the contract's keys: impl, the metric / unit / config of our arm, cpu_baseline of this run, e2e = the line's own
+    value with zero H2D / D2H bytes."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--graphs-per-gpu", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("HSG train graphs/sec") and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert set(d["config"]) == {"workload", "graphs_per_gpu", "n_iter", "dropout"} and d["config"]["graphs_per_gpu"] == 2
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
